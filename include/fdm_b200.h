@@ -1,0 +1,263 @@
+/*
+ * fdm_b200.h — C-ABI of libfdm_sm100.so: hand-written sm_100a kernels for the FDM latent video
+ * denoising hot path (UNetVideoModel.forward + DDPM step math).
+ *
+ * The reference (plai-group/latent-flexible-video-diffusion-modeling) has NO FFI/plugin boundary:
+ * every op below replaces a stock PyTorch call site inside improved_diffusion/{unet,rpe,nn,
+ * gaussian_diffusion,respace}.py (cited per entry point, paths relative to the reference root).
+ * The Python host in latent-flexible-video-diffusion-modeling_b200/improved_diffusion/ binds these
+ * symbols with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers owned by the caller
+ *    (PyTorch caching allocator); the library allocates nothing persistent.
+ *  - every entry point is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *    never synchronises the device.  Return value: 0 = ok, <0 = FDM_ERR_* (see fdm_status_string).
+ *  - activations are channels-last: [N frames][H][W][C]; frame n = b*T + t.
+ *  - dtype codes: FDM_F32 = 0, FDM_BF16 = 1 ("operand" tensors feeding tensor-core GEMMs are bf16 in
+ *    bf16 mode and fp32 in the exact fp32 mode; residual stream, statistics, softmax are always fp32).
+ *  - GroupNorm statistics buffers are [N][C] pairs (sum, sum of squares), fp32, accumulated with
+ *    atomics by the producing kernel; the caller zeroes them (one memset per forward).
+ */
+#ifndef FDM_B200_H_
+#define FDM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDM_ABI_VERSION 1
+
+enum { FDM_F32 = 0, FDM_BF16 = 1 };
+
+enum {
+  FDM_OK = 0,
+  FDM_ERR_BAD_ARG = -1,      /* null pointer / inconsistent sizes */
+  FDM_ERR_UNSUPPORTED = -2,  /* shape or dtype outside what the kernels implement */
+  FDM_ERR_CUDA = -3,         /* a CUDA runtime/driver call failed (launch error, bad arch, ...) */
+  FDM_ERR_NO_DEVICE = -4     /* no sm_100 device */
+};
+
+int fdm_abi_version(void);
+const char* fdm_status_string(int status);
+/* last CUDA error string seen by this thread inside the library (diagnostics only) */
+const char* fdm_last_cuda_error(void);
+/* sizeof() of every argument struct, so the host binding can verify its mirror (index = order below) */
+size_t fdm_struct_size(int which);
+
+/* ------------------------------------------------------------------------------------------------
+ * A1  input preparation — unet.py:439-449
+ *   xin[n,h,w,c<C] = x*(1-obs[n]) + x0*obs[n];  xin[n,h,w,C] = obs[n]
+ *   x, x0: [N][C][H][W] fp32 (the reference's NCHW frames); xin: [N][H][W][C+1] fp32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x;
+  const float* x0;
+  const float* obs_mask; /* [N] */
+  float* xin;
+  int32_t N, C, H, W;
+} fdm_input_prep_args; /* which = 0 */
+int fdm_input_prep(const fdm_input_prep_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A3/A5/A6/A11  convolution / linear as implicit GEMM — nn.Conv2d call sites unet.py:76,108,155,169,
+ * 176-180,313,402 and nn.Linear sites rpe.py:111-112 (qkv, proj_out).
+ *   y[n,oh,ow,co] = bias[co] + sum_seg sum_{r,s,ci} A_seg[n, ih, iw, ci] * W_seg[r,s,ci,co]  (+ resid)
+ *   segment 0: ksize in {1,3}, stride in {1,2}, optional nearest x2 upsample folded into the gather
+ *              (F.interpolate + conv, unet.py:85-87); segment 1 (optional): a 1x1 conv over a second
+ *              input with the same spatial size as the output (the ResBlock skip_connection, :180).
+ *   Weight layouts:  engine FDM_CONV_SIMT: fp32 [tap][ci][co];  engine FDM_CONV_TC: bf16 [tap][co][ci_pad]
+ *   (ci_pad = ci rounded up to 64), both produced by the host from PyTorch's [co][ci][kh][kw].
+ *   Outputs (any subset): y_f32 [.,Cout] fp32; y_op [.,Cout] in op_dtype; stats (sum,sumsq per frame,
+ *   channel); out_nchw: y_f32 is written as [N][Cout][Ho][Wo] (the head conv producing eps).
+ * ---------------------------------------------------------------------------------------------- */
+enum { FDM_CONV_SIMT = 0, FDM_CONV_TC = 1 };
+typedef struct {
+  const void* a0;   /* segment-0 input  [N][Hin][Win][C0], a_dtype */
+  const void* w0;   /* segment-0 weights */
+  const void* a1;   /* segment-1 input  [N][Ho][Wo][C1] or NULL */
+  const void* w1;   /* segment-1 weights (1x1) or NULL */
+  const float* bias;  /* [Cout] (sum of both segments' biases) or NULL */
+  const float* resid; /* [N][Ho][Wo][Cout] fp32 or NULL */
+  float* y_f32;
+  void* y_op;
+  float* stats;     /* [N][Cout][2] or NULL */
+  int32_t N, Hin, Win, C0, C1, Cout;
+  int32_t ksize, stride, upsample;
+  int32_t a_dtype, op_dtype, out_nchw, engine;
+} fdm_conv_args; /* which = 1 */
+int fdm_conv(const fdm_conv_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A4/A5  GroupNorm(32) apply (+FiLM) (+SiLU) — nn.py:12-19, unet.py:153-154,165-166,199-203,400-401,
+ * rpe.py:113,136 (spatial attention norm).  The input may be the channel concat of two tensors
+ * (th.cat skip connection, unet.py:460) which is never materialised in fp32.
+ *   v = (x - mean_g) * rstd_g * gamma + beta;  if film: v = v*(1+film[b][c]) + film[b][C+c];  if silu: v*=sigmoid(v)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* xa;      /* [N][HW][Ca] */
+  const float* xb;      /* [N][HW][Cb] or NULL */
+  const float* stats_a; /* [N][Ca][2] */
+  const float* stats_b; /* [N][Cb][2] or NULL */
+  const float* gamma;   /* [Ca+Cb] */
+  const float* beta;
+  const float* film;    /* [B][film_stride] rows: scale at [film_off + c], shift at [film_off + C + c]; or NULL */
+  void* out_op;         /* [N][HW][C] op_dtype or NULL */
+  float* out_f32;       /* [N][HW][C] or NULL */
+  void* raw_op;         /* [N][HW][C] op_dtype copy of the un-normalised concat, or NULL */
+  int32_t N, HW, Ca, Cb, T;   /* T = frames per video (b = n / T) */
+  int32_t film_stride, film_off;
+  int32_t silu, op_dtype;
+  float eps;
+} fdm_gn_apply_args; /* which = 2 */
+int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A8(1)  temporal GroupNorm — rpe.py:135-137: statistics over (C/32 channels x T frames) per (b, pixel)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x;   /* [B*T][HW][C] */
+  const float* gamma;
+  const float* beta;
+  float* out_f32;   /* [B*T][HW][C] */
+  void* out_op;     /* same, op_dtype */
+  int32_t B, T, HW, C, op_dtype;
+  float eps;
+} fdm_temporal_gn_args; /* which = 3 */
+int fdm_temporal_gn(const fdm_temporal_gn_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A2/A5/A9  conditioning path (depends only on t and frame_indices, computed once per step)
+ *   fdm_timestep_embedding — nn.py:105-123 (cos | sin)
+ *   fdm_grouped_linear     — nn.Linear sites unet.py:304-308 (time_embed), :159 (emb_layers of all
+ *                            ResBlocks in one launch), rpe.py:12,14 (RPENet linears of all attention blocks)
+ *   fdm_rpe_hidden         — rpe.py:21-30: SiLU(W_t·temb[b]+b_t + W_d·phi(fi[b,t]-fi[b,s]) + b_d)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* t;         /* [B] model timesteps (already rescaled, respace.py:118-124), or NULL when t_index is given */
+  const int64_t* t_index; /* [B] diffusion step index, or NULL */
+  const float* t_table;   /* [num_timesteps] model timestep per step index (timestep_map[i]*1000/N), used with t_index */
+  const float* freqs;     /* [dim/2] exp(-ln(max_period)*i/half), computed by the host exactly as nn.py:116-118 does (on CPU) */
+  float* out;             /* [B][dim] */
+  int32_t B, dim;
+} fdm_timestep_embedding_args; /* which = 4 */
+int fdm_timestep_embedding(const fdm_timestep_embedding_args* a, void* stream);
+
+typedef struct {
+  const float* x; /* [M][K] row stride ldx */
+  const float* w; /* [Nout][K] (PyTorch Linear layout) */
+  const float* b; /* [Nout] or NULL */
+  float* y;       /* [M][Nout] row stride ldy */
+  int32_t M, K, Nout, ldx, ldy;
+  int32_t silu_in; /* apply SiLU to x on load */
+} fdm_linear_problem; /* which = 13 */
+typedef struct {
+  const fdm_linear_problem* problems; /* DEVICE array */
+  int32_t count;
+  int32_t max_M, max_Nout; /* grid sizing */
+} fdm_grouped_linear_args; /* which = 5 */
+int fdm_grouped_linear(const fdm_grouped_linear_args* a, void* stream);
+
+typedef struct {
+  const float* wd;  /* [C][3] embed_distances.weight */
+  const float* bd;  /* [C] */
+  float* hidden;    /* [B][T][T][C] */
+  int32_t C, te_off; /* this net's W_t·temb + b_t lives at te[b][te_off .. te_off+C) */
+} fdm_rpe_hidden_problem; /* which = 14 */
+typedef struct {
+  const float* te;              /* [B][te_stride] */
+  const int64_t* frame_indices; /* [B][T] */
+  const fdm_rpe_hidden_problem* problems; /* DEVICE array, one per RPENet */
+  int32_t B, T, te_stride, count, max_C;
+} fdm_rpe_hidden_args; /* which = 6 */
+int fdm_rpe_hidden(const fdm_rpe_hidden_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A8  temporal attention core with in-kernel RPE and the two-group mask — rpe.py:139-170
+ *   qkv: [B*T][HW][3C] (q|k|v, each [heads][F]);  Rq,Rk,Rv: [B][T][T][C] fp32 (R[b,t,s,h,f]);
+ *   mask: [B][T] (1/0 group id);  out: [B*T][HW][C] op_dtype
+ * A10 spatial attention core — same code path with no RPE / no mask; sequence = pixels of one frame
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* qkv;
+  const float* Rq;
+  const float* Rk;
+  const float* Rv;
+  const float* mask;
+  void* out;
+  int32_t B, T, HW, C, heads;
+  int32_t qkv_dtype, out_dtype;
+} fdm_attn_temporal_args; /* which = 7 */
+int fdm_attn_temporal(const fdm_attn_temporal_args* a, void* stream);
+
+typedef struct {
+  const void* qkv; /* [N][L][3C] */
+  void* out;       /* [N][L][C] */
+  int32_t N, L, C, heads;
+  int32_t qkv_dtype, out_dtype;
+} fdm_attn_spatial_args; /* which = 8 */
+int fdm_attn_spatial(const fdm_attn_spatial_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A6  nearest x2 upsample + cast to operand dtype (F.interpolate, unet.py:85) and plain cast
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x; /* [N][H][W][C] */
+  void* out;      /* [N][H*f][W*f][C], f = upsample ? 2 : 1 */
+  int32_t N, H, W, C, upsample, op_dtype;
+} fdm_cast_args; /* which = 9 */
+int fdm_cast(const fdm_cast_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A16-A18  fused DDPM posterior update — gaussian_diffusion.py:305-310,341-346,228-231,396-400
+ *   coef: DEVICE table [num_timesteps][8] fp32 built once from the float64 numpy tables:
+ *     {sqrt_recip_acp, sqrt_recipm1_acp, post_coef1, post_coef2, exp(0.5*log_var)*[t!=0], 0,0,0}
+ *   xs = a*x - b*eps; clip; mean = c1*xs + c2*x; sample = mean + sigma*noise
+ *   x, eps, noise, sample, pred_xstart: [B][per_video] fp32 (any layout, elementwise); t: [B] int64
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x;
+  const float* eps;
+  const float* noise;
+  const float* coef;
+  const int64_t* t;
+  float* sample;
+  float* pred_xstart; /* or NULL */
+  int64_t per_video;
+  int32_t B, clip;
+} fdm_ddpm_step_args; /* which = 10 */
+int fdm_ddpm_step(const fdm_ddpm_step_args* a, void* stream);
+
+/* A20/A21  q_sample (gaussian_diffusion.py:200-218) and masked squared-error means (:787-788, nn.py:86-92)
+ *   coef2: DEVICE table [num_timesteps][2] = {sqrt_acp, sqrt_one_minus_acp}
+ *   mse[b] = mean_{all elems}((noise-eps)^2 * m1[b,frame]); eval[b] likewise with m2;  masks [B][T] or NULL */
+typedef struct {
+  const float* x0;
+  const float* noise;
+  const float* coef2;
+  const int64_t* t;
+  float* x_t;
+  int64_t per_video;
+  int32_t B;
+} fdm_q_sample_args; /* which = 11 */
+int fdm_q_sample(const fdm_q_sample_args* a, void* stream);
+
+typedef struct {
+  const float* eps;
+  const float* noise;
+  const float* m1;
+  const float* m2;
+  float* mse;   /* [B], zeroed by caller */
+  float* eval;  /* [B], zeroed by caller */
+  int64_t per_frame; /* C*H*W */
+  int32_t B, T;
+} fdm_masked_mse_args; /* which = 12 */
+int fdm_masked_mse(const fdm_masked_mse_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDM_B200_H_ */

@@ -1,0 +1,273 @@
+// Elementwise / small kernels: input preparation, casts, the fused DDPM posterior update, q_sample,
+// masked MSE, and the per-step conditioning path (timestep embedding, grouped small linears, RPENet hidden).
+#include "common.cuh"
+
+namespace fdm {
+
+// ---------------- A1 input prep (unet.py:439-449): NCHW frames -> NHWC (+indicator channel) ----------
+__global__ void input_prep_kernel(const float* __restrict__ x, const float* __restrict__ x0,
+                                  const float* __restrict__ obs, float* __restrict__ xin, int N, int C, int HW) {
+  // one thread per (n, pixel); reads are coalesced across pixels per channel plane
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * HW) return;
+  int n = (int)(i / HW), px = (int)(i - (long long)n * HW);
+  float m = obs[n];
+  const float* xs = x + (size_t)n * C * HW + px;
+  const float* x0s = x0 + (size_t)n * C * HW + px;
+  float* o = xin + (size_t)i * (C + 1);
+  for (int c = 0; c < C; ++c) o[c] = xs[(size_t)c * HW] * (1.f - m) + x0s[(size_t)c * HW] * m;
+  o[C] = m;
+}
+
+// ---------------- A6 nearest x2 upsample + cast (unet.py:85) ------------------------------------------
+template <typename OT>
+__global__ void cast_kernel(const float* __restrict__ x, OT* __restrict__ out, int N, int H, int W, int C, int up) {
+  const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
+  const int quads = C / 4;
+  long long total = (long long)N * Ho * Wo * quads;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % quads);
+    long long pix = i / quads;
+    int ow = (int)(pix % Wo);
+    long long r = pix / Wo;
+    int oh = (int)(r % Ho), n = (int)(r / Ho);
+    int ih = up ? oh >> 1 : oh, iw = up ? ow >> 1 : ow;
+    float4 v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W + iw) * C + q * 4);
+    OpType<OT>::store4(out + (size_t)pix * C + q * 4, v);
+  }
+}
+
+// ---------------- A16-A18 fused DDPM posterior update -------------------------------------------------
+__global__ void ddpm_step_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
+                                 const float4* __restrict__ noise, const float* __restrict__ coef,
+                                 const int64_t* __restrict__ t, float4* __restrict__ sample,
+                                 float4* __restrict__ pred, long long per_video4, int B, int clip) {
+  long long total = per_video4 * B;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(i / per_video4);
+    const float* c = coef + (size_t)t[b] * 8;
+    const float ca = c[0], cb = c[1], c1 = c[2], c2 = c[3], sg = c[4];
+    float4 xv = x[i], ev = eps[i], nv = noise[i];
+    float xin[4] = {xv.x, xv.y, xv.z, xv.w}, e[4] = {ev.x, ev.y, ev.z, ev.w}, nz[4] = {nv.x, nv.y, nv.z, nv.w};
+    float s[4], ps[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // same association as the reference: (a*x) - (b*eps); c1*xs + c2*x; mean + sigma*noise — no FMA contraction
+      float xs = __fsub_rn(__fmul_rn(ca, xin[j]), __fmul_rn(cb, e[j]));
+      if (clip) xs = fminf(fmaxf(xs, -1.f), 1.f);
+      float mean = __fadd_rn(__fmul_rn(c1, xs), __fmul_rn(c2, xin[j]));
+      s[j] = __fadd_rn(mean, __fmul_rn(sg, nz[j]));
+      ps[j] = xs;
+    }
+    sample[i] = make_float4(s[0], s[1], s[2], s[3]);
+    if (pred != nullptr) pred[i] = make_float4(ps[0], ps[1], ps[2], ps[3]);
+  }
+}
+
+// ---------------- A20 q_sample ------------------------------------------------------------------------
+__global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise,
+                                const float* __restrict__ coef2, const int64_t* __restrict__ t,
+                                float4* __restrict__ xt, long long per_video4, int B) {
+  long long total = per_video4 * B;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(i / per_video4);
+    const float a = coef2[(size_t)t[b] * 2], s = coef2[(size_t)t[b] * 2 + 1];
+    float4 xv = x0[i], nv = noise[i];
+    xt[i] = make_float4(__fadd_rn(__fmul_rn(a, xv.x), __fmul_rn(s, nv.x)), __fadd_rn(__fmul_rn(a, xv.y), __fmul_rn(s, nv.y)),
+                        __fadd_rn(__fmul_rn(a, xv.z), __fmul_rn(s, nv.z)), __fadd_rn(__fmul_rn(a, xv.w), __fmul_rn(s, nv.w)));
+  }
+}
+
+// ---------------- A21 masked MSE means: grid (chunks, B*T) --------------------------------------------
+__global__ void masked_mse_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
+                                  const float* __restrict__ m1, const float* __restrict__ m2,
+                                  float* __restrict__ mse, float* __restrict__ evl, long long per_frame, int T) {
+  const int f = blockIdx.y, b = f / T;
+  const float* e = eps + (size_t)f * per_frame;
+  const float* n = noise + (size_t)f * per_frame;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += (long long)gridDim.x * blockDim.x) {
+    float d = n[i] - e[i];
+    s += d * d;
+  }
+  s = warp_sum(s);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      const float inv = 1.f / ((float)per_frame * (float)T);
+      atomicAdd(mse + b, v * (m1 ? m1[f] : 1.f) * inv);
+      atomicAdd(evl + b, v * (m2 ? m2[f] : 1.f) * inv);
+    }
+  }
+}
+
+// ---------------- A2 timestep embedding (nn.py:105-123) -----------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, const int64_t* __restrict__ t_index,
+                                          const float* __restrict__ t_table, const float* __restrict__ freqs,
+                                          float* __restrict__ out, int B, int dim) {
+  const int half = dim / 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  int b = i / half, k = i - b * half;
+  const float tv = t_index != nullptr ? t_table[t_index[b]] : t[b];
+  float arg = tv * freqs[k];
+  out[(size_t)b * dim + k] = cosf(arg);
+  out[(size_t)b * dim + half + k] = sinf(arg);
+  if ((dim & 1) && k == 0) out[(size_t)b * dim + dim - 1] = 0.f;
+}
+
+// ---------------- grouped small linear: y = act(x) W^T + b,  M small (<= a few thousand) ---------------
+// block (32 x 8): each warp computes 1 output column for up to 32... simple mapping: thread = (row m, col n)
+// tile 16 rows x 64 cols per block, K streamed through shared memory in chunks of 32.
+constexpr int GL_TM = 16, GL_TN = 64, GL_TK = 32;
+__global__ void __launch_bounds__(256) grouped_linear_kernel(const fdm_linear_problem* __restrict__ probs) {
+  const fdm_linear_problem pr = probs[blockIdx.z];
+  const int m0 = blockIdx.y * GL_TM, n0 = blockIdx.x * GL_TN;
+  if (m0 >= pr.M || n0 >= pr.Nout) return;
+  __shared__ float xs[GL_TM][GL_TK + 1];
+  __shared__ float ws[GL_TN][GL_TK + 1];
+  const int tid = threadIdx.x;
+  const int tn = tid & 63, tm = tid >> 6;  // each thread: column tn, rows tm*4 .. tm*4+3
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < pr.K; k0 += GL_TK) {
+    for (int i = tid; i < GL_TM * GL_TK; i += 256) {
+      int r = i / GL_TK, k = i - r * GL_TK;
+      float v = 0.f;
+      if (m0 + r < pr.M && k0 + k < pr.K) {
+        v = pr.x[(size_t)(m0 + r) * pr.ldx + k0 + k];
+        if (pr.silu_in) v = silu_precise(v);
+      }
+      xs[r][k] = v;
+    }
+    for (int i = tid; i < GL_TN * GL_TK; i += 256) {
+      int r = i / GL_TK, k = i - r * GL_TK;
+      ws[r][k] = (n0 + r < pr.Nout && k0 + k < pr.K) ? pr.w[(size_t)(n0 + r) * pr.K + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < GL_TK; ++k) {
+      float w = ws[tn][k];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(xs[tm * 4 + i][k], w, acc[i]);
+    }
+    __syncthreads();
+  }
+  if (n0 + tn < pr.Nout) {
+    float bias = pr.b ? pr.b[n0 + tn] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m = m0 + tm * 4 + i;
+      if (m < pr.M) pr.y[(size_t)m * pr.ldy + n0 + tn] = acc[i] + bias;
+    }
+  }
+}
+
+// ---------------- A9 RPENet hidden layer (rpe.py:21-30) -----------------------------------------------
+__global__ void rpe_hidden_kernel(const float* __restrict__ te, const int64_t* __restrict__ fi,
+                                  const fdm_rpe_hidden_problem* __restrict__ probs, int B, int T, int te_stride) {
+  const fdm_rpe_hidden_problem pr = probs[blockIdx.y];
+  const int C = pr.C;
+  long long total = (long long)B * T * T * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    int s = (int)(r % T);
+    r /= T;
+    int t = (int)(r % T), b = (int)(r / T);
+    float d = (float)(fi[(size_t)b * T + t] - fi[(size_t)b * T + s]);
+    float f0 = logf(1.f + fmaxf(d, 0.f)), f1 = logf(1.f + fmaxf(-d, 0.f)), f2 = d == 0.f ? 1.f : 0.f;
+    // embed_distances(feats) = f0*w0 + f1*w1 + f2*w2 + bd, then + (W_t temb + b_t)
+    float e = fmaf(f2, pr.wd[c * 3 + 2], fmaf(f1, pr.wd[c * 3 + 1], f0 * pr.wd[c * 3])) + pr.bd[c];
+    e += te[(size_t)b * te_stride + pr.te_off + c];
+    pr.hidden[i] = silu_precise(e);
+  }
+}
+
+static inline int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  long long cap = 148LL * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace fdm
+
+using namespace fdm;
+
+extern "C" int fdm_input_prep(const fdm_input_prep_args* a, void* stream) {
+  FDM_REQUIRE(a && a->x && a->x0 && a->obs_mask && a->xin, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->N > 0 && a->C > 0 && a->H > 0 && a->W > 0, FDM_ERR_BAD_ARG);
+  long long total = (long long)a->N * a->H * a->W;
+  input_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->x, a->x0, a->obs_mask, a->xin, a->N, a->C, a->H * a->W);
+  return check_launch();
+}
+
+extern "C" int fdm_cast(const fdm_cast_args* a, void* stream) {
+  FDM_REQUIRE(a && a->x && a->out, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->C % 4 == 0 && a->N > 0, FDM_ERR_UNSUPPORTED);
+  long long total = (long long)a->N * a->H * a->W * (a->upsample ? 4 : 1) * (a->C / 4);
+  int g = grid_for(total, 256);
+  if (a->op_dtype == FDM_BF16)
+    cast_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(a->x, (__nv_bfloat16*)a->out, a->N, a->H, a->W, a->C, a->upsample);
+  else
+    cast_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(a->x, (float*)a->out, a->N, a->H, a->W, a->C, a->upsample);
+  return check_launch();
+}
+
+extern "C" int fdm_ddpm_step(const fdm_ddpm_step_args* a, void* stream) {
+  FDM_REQUIRE(a && a->x && a->eps && a->noise && a->coef && a->t && a->sample, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->per_video % 4 == 0 && a->B > 0, FDM_ERR_UNSUPPORTED);
+  long long pv4 = a->per_video / 4;
+  ddpm_step_kernel<<<grid_for(pv4 * a->B, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)a->x, (const float4*)a->eps, (const float4*)a->noise, a->coef, a->t, (float4*)a->sample,
+      (float4*)a->pred_xstart, pv4, a->B, a->clip);
+  return check_launch();
+}
+
+extern "C" int fdm_q_sample(const fdm_q_sample_args* a, void* stream) {
+  FDM_REQUIRE(a && a->x0 && a->noise && a->coef2 && a->t && a->x_t, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->per_video % 4 == 0 && a->B > 0, FDM_ERR_UNSUPPORTED);
+  long long pv4 = a->per_video / 4;
+  q_sample_kernel<<<grid_for(pv4 * a->B, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)a->x0, (const float4*)a->noise, a->coef2, a->t, (float4*)a->x_t, pv4, a->B);
+  return check_launch();
+}
+
+extern "C" int fdm_masked_mse(const fdm_masked_mse_args* a, void* stream) {
+  FDM_REQUIRE(a && a->eps && a->noise && a->mse && a->eval, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->B > 0 && a->T > 0 && a->per_frame > 0, FDM_ERR_BAD_ARG);
+  int chunks = (int)((a->per_frame + 256 * 8 - 1) / (256 * 8));
+  if (chunks > 64) chunks = 64;
+  dim3 grid(chunks, a->B * a->T);
+  masked_mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a->eps, a->noise, a->m1, a->m2, a->mse, a->eval, a->per_frame, a->T);
+  return check_launch();
+}
+
+extern "C" int fdm_timestep_embedding(const fdm_timestep_embedding_args* a, void* stream) {
+  FDM_REQUIRE(a && a->freqs && a->out && a->B > 0 && a->dim >= 2, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->t != nullptr || (a->t_index != nullptr && a->t_table != nullptr), FDM_ERR_BAD_ARG);
+  int total = a->B * (a->dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a->t, a->t_index, a->t_table, a->freqs, a->out, a->B, a->dim);
+  return check_launch();
+}
+
+extern "C" int fdm_grouped_linear(const fdm_grouped_linear_args* a, void* stream) {
+  FDM_REQUIRE(a && a->problems && a->count > 0 && a->max_M > 0 && a->max_Nout > 0, FDM_ERR_BAD_ARG);
+  dim3 grid((a->max_Nout + GL_TN - 1) / GL_TN, (a->max_M + GL_TM - 1) / GL_TM, a->count);
+  FDM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, FDM_ERR_UNSUPPORTED);
+  grouped_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a->problems);
+  return check_launch();
+}
+
+extern "C" int fdm_rpe_hidden(const fdm_rpe_hidden_args* a, void* stream) {
+  FDM_REQUIRE(a && a->te && a->frame_indices && a->problems && a->count > 0 && a->max_C > 0, FDM_ERR_BAD_ARG);
+  long long total = (long long)a->B * a->T * a->T * a->max_C;
+  int gx = grid_for(total, 256);
+  if (gx > 592) gx = 592;
+  dim3 grid(gx, a->count);
+  rpe_hidden_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a->te, a->frame_indices, a->problems, a->B, a->T, a->te_stride);
+  return check_launch();
+}

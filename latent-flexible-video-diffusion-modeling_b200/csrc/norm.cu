@@ -1,0 +1,159 @@
+// GroupNorm(32) kernels: fused apply (+FiLM)(+SiLU) over a virtual channel concat, and the temporal
+// GroupNorm of the attention block whose statistics span (C/32 channels x T frames) per (b, pixel).
+// Reference: nn.py:12-19,95-102; unet.py:153-154,165-166,199-203,400-401,460; rpe.py:113,135-137.
+// HBM-bound: 128-bit loads/stores, one read of x, one write per requested output.
+#include "common.cuh"
+
+namespace fdm {
+
+struct GnParams {
+  const float* xa; const float* xb; const float* sa; const float* sb;
+  const float* gamma; const float* beta; const float* film;
+  void* out_op; float* out_f32; void* raw_op;
+  int N, HW, Ca, Cb, C, T, film_stride, film_off, silu, pix_per_block;
+  float eps;
+};
+
+// grid: (ceil(HW / pix_per_block), N); block: (C/4) * ppi threads  (ppi pixels per iteration)
+template <typename OT>
+__global__ void gn_apply_kernel(GnParams p) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int n = blockIdx.y;
+  const int C = p.C, cpg = C / 32;
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    float s = 0.f, ss = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      int c = g * cpg + j;
+      const float* st = c < p.Ca ? p.sa + ((size_t)n * p.Ca + c) * 2 : p.sb + ((size_t)n * p.Cb + (c - p.Ca)) * 2;
+      s += st[0];
+      ss += st[1];
+    }
+    float cnt = (float)cpg * (float)p.HW;
+    float mean = s / cnt;
+    float var = fmaxf(ss / cnt - mean * mean, 0.f);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  const int quads = C / 4;
+  const int q = threadIdx.x % quads, pl = threadIdx.x / quads, ppi = blockDim.x / quads;
+  const int c = q * 4;
+  float mul[4], add[4];  // v = x*mul + add, folding mean/rstd/gamma/beta/FiLM
+  {
+    const int b = n / p.T;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int g = (c + j) / cpg;
+      float ga = p.gamma[c + j] * s_rstd[g];
+      float be = p.beta[c + j] - s_mean[g] * ga;
+      if (p.film != nullptr) {
+        const float* f = p.film + (size_t)b * p.film_stride + p.film_off;
+        float sc = 1.f + f[c + j], sh = f[C + c + j];
+        ga *= sc;
+        be = be * sc + sh;
+      }
+      mul[j] = ga;
+      add[j] = be;
+    }
+  }
+  const bool from_a = c < p.Ca;  // Ca, Cb are multiples of 4: a quad never straddles the concat boundary
+  const float* src = from_a ? p.xa + (size_t)n * p.HW * p.Ca + c : p.xb + (size_t)n * p.HW * p.Cb + (c - p.Ca);
+  const int sstride = from_a ? p.Ca : p.Cb;
+  const int p0 = blockIdx.x * p.pix_per_block;
+  const int p1 = min(p0 + p.pix_per_block, p.HW);
+  for (int px = p0 + pl; px < p1; px += ppi) {
+    float4 x = *reinterpret_cast<const float4*>(src + (size_t)px * sstride);
+    float v[4] = {x.x * mul[0] + add[0], x.y * mul[1] + add[1], x.z * mul[2] + add[2], x.w * mul[3] + add[3]};
+    if (p.silu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = silu_precise(v[j]);
+    }
+    size_t o = ((size_t)n * p.HW + px) * C + c;
+    float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
+    if (p.out_op != nullptr) OpType<OT>::store4(reinterpret_cast<OT*>(p.out_op) + o, v4);
+    if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = v4;
+    if (p.raw_op != nullptr) OpType<OT>::store4(reinterpret_cast<OT*>(p.raw_op) + o, x);
+  }
+}
+
+struct TgnParams {
+  const float* x; const float* gamma; const float* beta; float* out_f32; void* out_op;
+  int B, T, HW, C;
+  float eps;
+};
+
+// one warp per (b, pixel); lane g owns group g (cpg consecutive channels) across all T frames
+template <typename OT>
+__global__ void temporal_gn_kernel(TgnParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.B * p.HW) return;
+  const int b = warp / p.HW, px = warp - b * p.HW;
+  const int cpg = p.C / 32, c0 = lane * cpg;
+  const size_t fstride = (size_t)p.HW * p.C;
+  const float* base = p.x + ((size_t)b * p.T * p.HW + px) * p.C + c0;
+  float s = 0.f, ss = 0.f;
+  for (int t = 0; t < p.T; ++t) {
+    const float* r = base + t * fstride;
+    for (int j = 0; j < cpg; ++j) {
+      float v = r[j];
+      s += v;
+      ss += v * v;
+    }
+  }
+  const float cnt = (float)(cpg * p.T);
+  const float mean = s / cnt;
+  const float rstd = rsqrtf(fmaxf(ss / cnt - mean * mean, 0.f) + p.eps);
+  for (int t = 0; t < p.T; ++t) {
+    const float* r = base + t * fstride;
+    size_t o = ((size_t)(b * p.T + t) * p.HW + px) * p.C + c0;
+    for (int j = 0; j < cpg; ++j) {
+      float v = (r[j] - mean) * rstd * p.gamma[c0 + j] + p.beta[c0 + j];
+      if (p.out_f32 != nullptr) p.out_f32[o + j] = v;
+      if (p.out_op != nullptr) OpType<OT>::store(reinterpret_cast<OT*>(p.out_op) + o + j, v);
+    }
+  }
+}
+
+}  // namespace fdm
+
+extern "C" int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream) {
+  using namespace fdm;
+  FDM_REQUIRE(a && a->xa && a->stats_a && a->gamma && a->beta, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE((a->xb == nullptr) == (a->stats_b == nullptr), FDM_ERR_BAD_ARG);
+  GnParams p;
+  p.xa = a->xa; p.xb = a->xb; p.sa = a->stats_a; p.sb = a->stats_b; p.gamma = a->gamma; p.beta = a->beta;
+  p.film = a->film; p.out_op = a->out_op; p.out_f32 = a->out_f32; p.raw_op = a->raw_op;
+  p.N = a->N; p.HW = a->HW; p.Ca = a->Ca; p.Cb = a->xb ? a->Cb : 0; p.C = p.Ca + p.Cb; p.T = a->T > 0 ? a->T : 1;
+  p.film_stride = a->film_stride; p.film_off = a->film_off; p.silu = a->silu; p.eps = a->eps;
+  FDM_REQUIRE(p.C % 32 == 0 && p.Ca % 4 == 0 && p.Cb % 4 == 0 && p.C <= 4096, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(a->N > 0 && a->HW > 0, FDM_ERR_BAD_ARG);
+  const int quads = p.C / 4;
+  FDM_REQUIRE(quads <= 1024, FDM_ERR_UNSUPPORTED);
+  int ppi = quads >= 256 ? 1 : 256 / quads;
+  if (ppi > a->HW) ppi = a->HW;
+  const int threads = quads * ppi;
+  // aim for >= ~4 waves of 148 SMs when the tensor is large, but keep >= 4 iterations per block
+  int ppb = ppi * 4;
+  while ((long long)a->N * ((a->HW + ppb - 1) / ppb) > 148LL * 16 && ppb < a->HW) ppb *= 2;
+  p.pix_per_block = ppb;
+  dim3 grid((a->HW + ppb - 1) / ppb, a->N);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->op_dtype == FDM_BF16) gn_apply_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(p);
+  else gn_apply_kernel<float><<<grid, threads, 0, st>>>(p);
+  return check_launch();
+}
+
+extern "C" int fdm_temporal_gn(const fdm_temporal_gn_args* a, void* stream) {
+  using namespace fdm;
+  FDM_REQUIRE(a && a->x && a->gamma && a->beta && (a->out_f32 || a->out_op), FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->C % 32 == 0 && a->B > 0 && a->T > 0 && a->HW > 0, FDM_ERR_UNSUPPORTED);
+  TgnParams p{a->x, a->gamma, a->beta, a->out_f32, a->out_op, a->B, a->T, a->HW, a->C, a->eps};
+  const long long warps = (long long)a->B * a->HW;
+  const int threads = 256;
+  const int blocks = (int)((warps * 32 + threads - 1) / threads);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->op_dtype == FDM_BF16) temporal_gn_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(p);
+  else temporal_gn_kernel<float><<<blocks, threads, 0, st>>>(p);
+  return check_launch();
+}

@@ -1,0 +1,118 @@
+"""
+ctypes binding of libfdm_sm100.so (the C-ABI declared in include/fdm_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, this module raises.  The
+structures below mirror the header field by field; `verify_struct_sizes()` cross-checks every
+ctypes mirror against `fdm_struct_size()` exported by the library (runs on CPU, no GPU needed).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfdm_sm100.so")
+
+F32, BF16 = 0, 1
+CONV_SIMT, CONV_TC = 0, 1
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+def _S(name, fields):
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+InputPrepArgs = _S("InputPrepArgs", [("x", vp), ("x0", vp), ("obs_mask", vp), ("xin", vp),
+                                     ("N", i32), ("C", i32), ("H", i32), ("W", i32)])
+ConvArgs = _S("ConvArgs", [("a0", vp), ("w0", vp), ("a1", vp), ("w1", vp), ("bias", vp), ("resid", vp),
+                           ("y_f32", vp), ("y_op", vp), ("stats", vp),
+                           ("N", i32), ("Hin", i32), ("Win", i32), ("C0", i32), ("C1", i32), ("Cout", i32),
+                           ("ksize", i32), ("stride", i32), ("upsample", i32),
+                           ("a_dtype", i32), ("op_dtype", i32), ("out_nchw", i32), ("engine", i32)])
+GnApplyArgs = _S("GnApplyArgs", [("xa", vp), ("xb", vp), ("stats_a", vp), ("stats_b", vp), ("gamma", vp), ("beta", vp),
+                                 ("film", vp), ("out_op", vp), ("out_f32", vp), ("raw_op", vp),
+                                 ("N", i32), ("HW", i32), ("Ca", i32), ("Cb", i32), ("T", i32),
+                                 ("film_stride", i32), ("film_off", i32), ("silu", i32), ("op_dtype", i32), ("eps", f32)])
+TemporalGnArgs = _S("TemporalGnArgs", [("x", vp), ("gamma", vp), ("beta", vp), ("out_f32", vp), ("out_op", vp),
+                                       ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("op_dtype", i32), ("eps", f32)])
+TimestepEmbeddingArgs = _S("TimestepEmbeddingArgs", [("t", vp), ("t_index", vp), ("t_table", vp), ("freqs", vp), ("out", vp),
+                                                     ("B", i32), ("dim", i32)])
+LinearProblem = _S("LinearProblem", [("x", vp), ("w", vp), ("b", vp), ("y", vp),
+                                     ("M", i32), ("K", i32), ("Nout", i32), ("ldx", i32), ("ldy", i32), ("silu_in", i32)])
+GroupedLinearArgs = _S("GroupedLinearArgs", [("problems", vp), ("count", i32), ("max_M", i32), ("max_Nout", i32)])
+RpeHiddenProblem = _S("RpeHiddenProblem", [("wd", vp), ("bd", vp), ("hidden", vp), ("C", i32), ("te_off", i32)])
+RpeHiddenArgs = _S("RpeHiddenArgs", [("te", vp), ("frame_indices", vp), ("problems", vp),
+                                     ("B", i32), ("T", i32), ("te_stride", i32), ("count", i32), ("max_C", i32)])
+AttnTemporalArgs = _S("AttnTemporalArgs", [("qkv", vp), ("Rq", vp), ("Rk", vp), ("Rv", vp), ("mask", vp), ("out", vp),
+                                           ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("heads", i32),
+                                           ("qkv_dtype", i32), ("out_dtype", i32)])
+AttnSpatialArgs = _S("AttnSpatialArgs", [("qkv", vp), ("out", vp), ("N", i32), ("L", i32), ("C", i32), ("heads", i32),
+                                         ("qkv_dtype", i32), ("out_dtype", i32)])
+CastArgs = _S("CastArgs", [("x", vp), ("out", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32),
+                           ("upsample", i32), ("op_dtype", i32)])
+DdpmStepArgs = _S("DdpmStepArgs", [("x", vp), ("eps", vp), ("noise", vp), ("coef", vp), ("t", vp), ("sample", vp),
+                                   ("pred_xstart", vp), ("per_video", i64), ("B", i32), ("clip", i32)])
+QSampleArgs = _S("QSampleArgs", [("x0", vp), ("noise", vp), ("coef2", vp), ("t", vp), ("x_t", vp),
+                                 ("per_video", i64), ("B", i32)])
+MaskedMseArgs = _S("MaskedMseArgs", [("eps", vp), ("noise", vp), ("m1", vp), ("m2", vp), ("mse", vp), ("eval", vp),
+                                     ("per_frame", i64), ("B", i32), ("T", i32)])
+
+# index = `which` of fdm_struct_size (include/fdm_b200.h)
+STRUCTS = [InputPrepArgs, ConvArgs, GnApplyArgs, TemporalGnArgs, TimestepEmbeddingArgs, GroupedLinearArgs,
+           RpeHiddenArgs, AttnTemporalArgs, AttnSpatialArgs, CastArgs, DdpmStepArgs, QSampleArgs, MaskedMseArgs,
+           LinearProblem, RpeHiddenProblem]
+
+ENTRY_POINTS = ["fdm_input_prep", "fdm_conv", "fdm_gn_apply", "fdm_temporal_gn", "fdm_timestep_embedding",
+                "fdm_grouped_linear", "fdm_rpe_hidden", "fdm_attn_temporal", "fdm_attn_spatial", "fdm_cast",
+                "fdm_ddpm_step", "fdm_q_sample", "fdm_masked_mse"]
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libfdm_sm100.so (built in-tree by `make -C csrc` / __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} is missing: build it with `make -C {os.path.join(os.path.dirname(_HERE), 'csrc')}`; "
+                              "there is no CPU / PyTorch fallback for the FDM hot path")
+        L = C.CDLL(LIB_PATH)
+        L.fdm_abi_version.restype = C.c_int
+        L.fdm_status_string.restype = C.c_char_p
+        L.fdm_status_string.argtypes = [C.c_int]
+        L.fdm_last_cuda_error.restype = C.c_char_p
+        L.fdm_struct_size.restype = C.c_size_t
+        L.fdm_struct_size.argtypes = [C.c_int]
+        for name in ENTRY_POINTS:
+            fn = getattr(L, name)
+            fn.restype = C.c_int
+            fn.argtypes = [vp, vp]
+        if L.fdm_abi_version() != 1:
+            raise NativeError(f"libfdm_sm100.so ABI {L.fdm_abi_version()} != 1")
+        _lib = L
+    return _lib
+
+
+def verify_struct_sizes():
+    L = lib()
+    for which, st in enumerate(STRUCTS):
+        n = L.fdm_struct_size(which)
+        if n != C.sizeof(st):
+            raise NativeError(f"struct #{which} {st.__name__}: library says {n} bytes, ctypes mirror {C.sizeof(st)}")
+    return True
+
+
+def check(rc, what):
+    if rc != 0:
+        L = lib()
+        msg = L.fdm_status_string(rc).decode()
+        if rc == -3:
+            msg += ": " + L.fdm_last_cuda_error().decode()
+        raise NativeError(f"{what} failed: {msg}")
+
+
+def call(name, args, stream):
+    check(getattr(lib(), name)(C.byref(args), C.c_void_p(stream)), name)

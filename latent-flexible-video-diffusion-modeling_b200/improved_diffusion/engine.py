@@ -1,0 +1,539 @@
+"""
+DenoiserEngine — compiles UNetVideoModel.forward (reference unet.py:428-464 + rpe.py:133-174) into a flat
+schedule of libfdm_sm100.so kernel launches over a static HBM arena, one schedule ("plan") per input shape.
+
+Design (B200-first, not a module walk):
+  * activations are channels-last [N=B*T][H][W][C]; the residual stream, GroupNorm statistics and softmax
+    are fp32; tensors that feed GEMMs ("operands") are bf16 in precision="bf16" and fp32 in "fp32".
+  * GroupNorm statistics are produced by the epilogue of the kernel that writes the tensor (atomics into
+    [N][C] sum/sumsq), so GN+SiLU(+FiLM) is ONE read + ONE write; th.cat skip connections are never
+    materialised in fp32 (the GN kernel reads two sources); the 1x1 skip conv of a ResBlock is a second
+    K-segment of its out-conv; permute/reshape copies of FactorizedAttentionBlock disappear (kernels index
+    the [B*T][HW][C] layout directly).
+  * everything that depends only on (t, frame_indices) — time MLP, all FiLM projections, all RPENet tables —
+    is computed once per step up front in 6 launches.
+  * the plan owns every intermediate buffer (liveness-packed arena), so a step is replayable as a CUDA graph.
+"""
+import ctypes as C
+
+import torch as th
+import torch.nn as nn
+
+from . import _native as N_
+from .nn import timestep_freqs
+
+
+class Buf:
+    """A region of the plan's arena (or of its statistics arena)."""
+    __slots__ = ("name", "nbytes", "offset", "first", "last", "persistent", "arena")
+
+    def __init__(self, name, nbytes, persistent=False, arena="main"):
+        self.name, self.nbytes, self.persistent, self.arena = name, (int(nbytes) + 255) // 256 * 256, persistent, arena
+        self.offset, self.first, self.last = None, None, None
+
+
+class Plan:
+    def __init__(self, engine, B, T, H, W):
+        self.engine, self.B, self.T, self.H, self.W = engine, B, T, H, W
+        self.ops = []        # (entry point name, struct class, {field: python value | Buf | tensor | (Buf, byte offset)})
+        self.bufs = []
+        self.keep = []       # tensors that must outlive the plan (weights views, problem arrays)
+        self.calls = None    # [(fn, byref(struct))] after finalize()
+        self.stats_bytes = 0
+        self.graphs = {}     # CUDA graphs captured over this plan (see gaussian_diffusion._graph_sampler)
+
+    # ---- buffers
+    def buf(self, name, nbytes, persistent=False):
+        b = Buf(name, nbytes, persistent)
+        self.bufs.append(b)
+        return b
+
+    def stats(self, name, n, c):
+        b = Buf(name, n * c * 2 * 4, True, "stats")
+        b.offset = self.stats_bytes
+        self.stats_bytes += b.nbytes
+        return b
+
+    def op(self, fn, cls, **fields):
+        idx = len(self.ops)
+        for v in fields.values():
+            b = v[0] if isinstance(v, tuple) else v
+            if isinstance(b, Buf) and b.arena == "main":
+                b.first = idx if b.first is None else b.first
+                b.last = idx
+        self.ops.append((fn, cls, fields))
+
+    # ---- liveness-based packing (first-fit over a free list), then struct materialisation
+    def finalize(self, device):
+        free, top = [], 0  # free: [(offset, size)]
+        release = {}
+        for b in self.bufs:
+            if b.first is None:
+                b.first = b.last = 0
+            if not b.persistent:
+                release.setdefault(b.last, []).append(b)
+        order = sorted(self.bufs, key=lambda b: (0 if b.persistent else 1, b.first))
+        # persistent buffers first, at the bottom of the arena
+        for b in order:
+            if b.persistent:
+                b.offset, top = top, top + b.nbytes
+        by_first = {}
+        for b in self.bufs:
+            if not b.persistent:
+                by_first.setdefault(b.first, []).append(b)
+        for i in range(len(self.ops)):
+            for b in by_first.get(i, []):
+                slot = next((k for k, (o, s) in enumerate(free) if s >= b.nbytes), None)
+                if slot is None:
+                    b.offset, top = top, top + b.nbytes
+                else:
+                    o, s = free.pop(slot)
+                    b.offset = o
+                    if s > b.nbytes:
+                        free.append((o + b.nbytes, s - b.nbytes))
+            for b in release.get(i, []):
+                free.append((b.offset, b.nbytes))
+                free.sort()
+                merged = []
+                for o, s in free:  # coalesce neighbours
+                    if merged and merged[-1][0] + merged[-1][1] == o:
+                        merged[-1] = (merged[-1][0], merged[-1][1] + s)
+                    else:
+                        merged.append((o, s))
+                free = merged
+        self.arena = th.empty(max(top, 256), dtype=th.uint8, device=device)
+        self.stats_arena = th.zeros(max(self.stats_bytes, 256) // 4, dtype=th.float32, device=device)
+        self.arena_bytes = top
+        lib = N_.lib()
+        self.calls = []
+        self._structs = []
+        for fn, cls, fields in self.ops:
+            st = cls()
+            for k, v in fields.items():
+                setattr(st, k, self.ptr(v) if isinstance(v, (Buf, tuple, th.Tensor)) or v is None else v)
+            self._structs.append(st)
+            self.calls.append((fn, getattr(lib, fn), C.byref(st)))
+
+    def ptr(self, v):
+        if v is None:
+            return None
+        if isinstance(v, th.Tensor):
+            return v.data_ptr()
+        off = 0
+        if isinstance(v, tuple):
+            v, off = v
+        base = self.arena if v.arena == "main" else self.stats_arena
+        return base.data_ptr() + v.offset + off
+
+    def set_t_source(self, table):
+        """Timestep embedding input: the float `t` buffer (table=None) or t_table[t_index] looked up on the device."""
+        st = self._structs[self.temb_op]
+        if table is None:
+            st.t, st.t_index, st.t_table = self.ptr(self.t), None, None
+        else:
+            st.t, st.t_index, st.t_table = None, self.ptr(self.t_index), table.data_ptr()
+            self.keep.append(table)
+
+    def view(self, b, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= s
+        esz = th.empty((), dtype=dtype).element_size()
+        return self.arena[b.offset:b.offset + n * esz].view(dtype).view(*shape)
+
+    def run(self, stream):
+        """Launch the whole schedule on `stream` (a raw cudaStream_t).  The caller has filled the input buffers."""
+        self.stats_arena.zero_()
+        s = C.c_void_p(stream)
+        for name, fn, ref in self.calls:
+            rc = fn(ref, s)
+            if rc != 0:
+                N_.check(rc, name)
+
+
+class DenoiserEngine:
+    def __init__(self, model, precision="bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        N_.verify_struct_sizes()
+        self.model, self.precision = model, precision
+        self.op_dtype = N_.BF16 if precision == "bf16" else N_.F32
+        self.op_torch = th.bfloat16 if precision == "bf16" else th.float32
+        self.op_size = 2 if precision == "bf16" else 4
+        self.use_tc = precision == "bf16"
+        self.plans = {}
+        self.packed = {}
+        self._versions = None
+        if not model.use_scale_shift_norm:
+            raise NotImplementedError("the fused GroupNorm+FiLM kernel implements use_scale_shift_norm=True "
+                                      "(the reference default, script_util.py:34)")
+
+    # ------------------------------------------------------------------ weights
+    def _param_versions(self):
+        return tuple(p._version for p in self.model.parameters()) + (next(self.model.parameters()).data_ptr(),)
+
+    def refresh_weights(self):
+        """(Re)pack weights if any parameter changed (optimizer step, load_state_dict, .to())."""
+        v = self._param_versions()
+        if v != self._versions:
+            self.packed.clear()
+            self.plans.clear()
+            self._versions = v
+
+    def _pack_simt(self, w):
+        """[co][ci][kh][kw] or [co][ci] -> fp32 [tap][ci][co]"""
+        key = ("simt", w.data_ptr())
+        if key not in self.packed:
+            w4 = w.detach().float()
+            if w4.dim() == 2:
+                w4 = w4[:, :, None, None]
+            co, ci, kh, kw = w4.shape
+            self.packed[key] = w4.permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous()
+        return self.packed[key]
+
+    def _pack_tc(self, w):
+        """[co][ci][kh][kw] or [co][ci] -> bf16 [tap][co_pad][ci_pad]  (K-major B operand, ci_pad % 64 == 0, co_pad % 16 == 0)"""
+        key = ("tc", w.data_ptr())
+        if key not in self.packed:
+            w4 = w.detach().float()
+            if w4.dim() == 2:
+                w4 = w4[:, :, None, None]
+            co, ci, kh, kw = w4.shape
+            cip, cop = (ci + 63) // 64 * 64, (co + 15) // 16 * 16
+            out = th.zeros(kh * kw, cop, cip, dtype=th.bfloat16, device=w.device)
+            out[:, :co, :ci] = w4.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(th.bfloat16)
+            self.packed[key] = out
+        return self.packed[key]
+
+    def _f32(self, p):
+        key = ("f32", p.data_ptr())
+        if key not in self.packed:
+            self.packed[key] = p.detach().float().contiguous()
+        return self.packed[key]
+
+    def _bias_sum(self, b0, b1):
+        key = ("bsum", b0.data_ptr(), b1.data_ptr())
+        if key not in self.packed:
+            self.packed[key] = (b0.detach().float() + b1.detach().float()).contiguous()
+        return self.packed[key]
+
+    # ------------------------------------------------------------------ plan compiler
+    def plan_for(self, B, T, H, W, device):
+        self.refresh_weights()
+        key = (B, T, H, W, str(device))
+        if key not in self.plans:
+            with th.cuda.device(device):
+                self.plans[key] = self._compile(B, T, H, W, device)
+        return self.plans[key]
+
+    def tc_ok(self, C0, C1, Cout, k, stride, upsample, Ho, Wo):
+        """Shapes the tcgen05 implicit-GEMM kernel takes (conv_tc.cu); everything else runs on the CUDA-core engine."""
+        if not self.use_tc:
+            return False
+        if stride != 1 or upsample:
+            return False
+        if C0 % 32 or (C1 and C1 % 32) or Cout % 16 or Cout < 16:
+            return False
+        # the 128-pixel M tile must be a whole number of image rows or a whole number of frames
+        hw = Ho * Wo
+        if Wo > 128 or (128 % Wo) or (hw > 128 and hw % 128) or (hw < 128 and 128 % hw):
+            return False
+        return True
+
+    def _compile(self, B, T, H, W, device):
+        m = self.model
+        from .unet import ResBlock, FactorizedAttentionBlock, Downsample, Upsample
+        P = Plan(self, B, T, H, W)
+        Nf = B * T
+        opd, osz = self.op_dtype, self.op_size
+        mc, ted = m.model_channels, m.model_channels * 4
+        Cin = m.in_channels  # includes indicator channel
+        f32 = self._f32
+
+        # ---------------- persistent inputs / outputs
+        P.x = P.buf("x", Nf * (Cin - 1) * H * W * 4, True)
+        P.x0 = P.buf("x0", Nf * (Cin - 1) * H * W * 4, True)
+        P.obs = P.buf("obs", Nf * 4, True)
+        P.mask = P.buf("mask", Nf * 4, True)
+        P.fi = P.buf("fi", Nf * 8, True)
+        P.t = P.buf("t", B * 4, True)
+        P.t_index = P.buf("t_index", B * 8, True)
+        P.eps = P.buf("eps", Nf * m.out_channels * H * W * 4, True)
+        P.use_t_index = False
+        P.t_table = None
+
+        # ---------------- conditioning path
+        res_blocks, attn_blocks = [], []
+        for blk in list(m.input_blocks) + [m.middle_block] + list(m.output_blocks):
+            for layer in blk:
+                if isinstance(layer, ResBlock):
+                    res_blocks.append(layer)
+                elif isinstance(layer, FactorizedAttentionBlock):
+                    attn_blocks.append(layer)
+        cols = 0
+        film_off, te_off = {}, {}
+        for rb in res_blocks:
+            film_off[id(rb)] = cols
+            cols += 2 * rb.out_channels
+        for ab in attn_blocks:
+            for which in ("rpe_q", "rpe_k", "rpe_v"):
+                te_off[(id(ab), which)] = cols
+                cols += ab.channels
+        cond_cols = cols
+        freqs = timestep_freqs(mc).to(device)
+        P.keep.append(freqs)
+        temb = P.buf("temb", B * mc * 4)
+        h1 = P.buf("time_h1", B * ted * 4)
+        emb = P.buf("emb", B * ted * 4)
+        cond = P.buf("cond", B * cond_cols * 4, True)  # live for the whole forward
+        P.temb_op = len(P.ops)
+        P.op("fdm_timestep_embedding", N_.TimestepEmbeddingArgs, t=P.t, t_index=None, t_table=None, freqs=freqs, out=temb,
+             B=B, dim=mc)
+
+        self._pending_groups = []
+
+        def emit_group(problems):
+            # device array is filled in after finalize() (needs resolved pointers); reserve its storage now
+            dev = th.zeros(len(problems) * C.sizeof(N_.LinearProblem), dtype=th.uint8, device=device)
+            P.keep.append(dev)
+            self._pending_groups.append((dev, problems))
+            touch = {}
+            for i, pr in enumerate(problems):
+                for k in ("x", "y"):
+                    b = pr[k][0] if isinstance(pr[k], tuple) else pr[k]
+                    if isinstance(b, Buf):
+                        touch[f"_{k}{i}"] = b
+            idx = len(P.ops)
+            P.op("fdm_grouped_linear", N_.GroupedLinearArgs, problems=dev, count=len(problems),
+                 max_M=max(p["M"] for p in problems), max_Nout=max(p["Nout"] for p in problems))
+            for b in touch.values():  # liveness of buffers referenced only through the device problem array
+                if b.arena == "main":
+                    b.first = idx if b.first is None else b.first
+                    b.last = idx
+
+        te0, te2 = m.time_embed[0], m.time_embed[2]
+        emit_group([dict(x=temb, w=f32(te0.weight), b=f32(te0.bias), y=h1, M=B, K=mc, Nout=ted, ldx=mc, ldy=ted, silu_in=0)])
+        emit_group([dict(x=h1, w=f32(te2.weight), b=f32(te2.bias), y=emb, M=B, K=ted, Nout=ted, ldx=ted, ldy=ted, silu_in=1)])
+        probs = []
+        for rb in res_blocks:
+            lin = rb.emb_layers[1]
+            probs.append(dict(x=emb, w=f32(lin.weight), b=f32(lin.bias), y=(cond, film_off[id(rb)] * 4), M=B, K=ted,
+                              Nout=2 * rb.out_channels, ldx=ted, ldy=cond_cols, silu_in=1))
+        for ab in attn_blocks:
+            for which in ("rpe_q", "rpe_k", "rpe_v"):
+                net = getattr(ab.temporal_attention, which).rpe_net
+                lin = net.embed_diffusion_time
+                probs.append(dict(x=emb, w=f32(lin.weight), b=f32(lin.bias), y=(cond, te_off[(id(ab), which)] * 4), M=B,
+                                  K=ted, Nout=ab.channels, ldx=ted, ldy=cond_cols, silu_in=0))
+        emit_group(probs)
+        # RPENet hidden + output tables for every temporal attention
+        R = {}
+        hid = {}
+        rh_probs, out_probs = [], []
+        for ab in attn_blocks:
+            Cc = ab.channels
+            for which in ("rpe_q", "rpe_k", "rpe_v"):
+                net = getattr(ab.temporal_attention, which).rpe_net
+                hb = P.buf(f"rpe_hidden", B * T * T * Cc * 4)
+                rb_ = P.buf(f"rpe_R", B * T * T * Cc * 4, True)
+                hid[(id(ab), which)], R[(id(ab), which)] = hb, rb_
+                rh_probs.append(dict(wd=f32(net.embed_distances.weight), bd=f32(net.embed_distances.bias), hidden=hb, C=Cc,
+                                     te_off=te_off[(id(ab), which)]))
+                out_probs.append(dict(x=hb, w=f32(net.out.weight), b=f32(net.out.bias), y=rb_, M=B * T * T, K=Cc, Nout=Cc,
+                                      ldx=Cc, ldy=Cc, silu_in=0))
+        if rh_probs:
+            dev = th.zeros(len(rh_probs) * C.sizeof(N_.RpeHiddenProblem), dtype=th.uint8, device=device)
+            P.keep.append(dev)
+            self._pending_rh = (dev, rh_probs)
+            idx = len(P.ops)
+            P.op("fdm_rpe_hidden", N_.RpeHiddenArgs, te=cond, frame_indices=P.fi, problems=dev, B=B, T=T,
+                 te_stride=cond_cols, count=len(rh_probs), max_C=max(p["C"] for p in rh_probs))
+            for p_ in rh_probs:
+                b = p_["hidden"]
+                b.first = idx if b.first is None else b.first
+                b.last = idx
+            emit_group(out_probs)
+        else:
+            self._pending_rh = None
+
+        # ---------------- conv helper
+        def conv(a0, C0, Hin, Win, w0, Cout, k, stride=1, upsample=0, a1=None, C1=0, w1=None, bias=None, resid=None,
+                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None):
+            a_dtype = opd if a_dtype is None else a_dtype
+            Hv, Wv = (Hin * 2, Win * 2) if upsample else (Hin, Win)
+            Ho, Wo = (Hv + 2 * (k // 2) - k) // stride + 1, (Wv + 2 * (k // 2) - k) // stride + 1
+            tc = a_dtype == N_.BF16 and self.tc_ok(C0, C1, Cout, k, stride, upsample, Ho, Wo)
+            pack = self._pack_tc if tc else self._pack_simt
+            P.op("fdm_conv", N_.ConvArgs, a0=a0, w0=pack(w0), a1=a1, w1=pack(w1) if w1 is not None else None, bias=bias,
+                 resid=resid, y_f32=y_f32, y_op=y_op, stats=stats, N=Nf, Hin=Hin, Win=Win, C0=C0, C1=C1, Cout=Cout,
+                 ksize=k, stride=stride, upsample=upsample, a_dtype=a_dtype, op_dtype=opd, out_nchw=out_nchw,
+                 engine=N_.CONV_TC if tc else N_.CONV_SIMT)
+            return Ho, Wo
+
+        # ---------------- network body
+        xin = P.buf("xin", Nf * H * W * Cin * 4)
+        P.op("fdm_input_prep", N_.InputPrepArgs, x=P.x, x0=P.x0, obs_mask=P.obs, xin=xin, N=Nf, C=Cin - 1, H=H, W=W)
+
+        class Act:  # residual-stream tensor: fp32 NHWC + its GroupNorm statistics
+            def __init__(s, buf, st, Cc, Hh, Ww):
+                s.buf, s.st, s.C, s.H, s.W = buf, st, Cc, Hh, Ww
+
+        def new_act(name, Cc, Hh, Ww):
+            return Act(P.buf(name, Nf * Hh * Ww * Cc * 4), P.stats(name, Nf, Cc), Cc, Hh, Ww)
+
+        def res_block(rb, xa, xb=None):
+            Hh, Ww = xa.H, xa.W
+            Ci = xa.C + (xb.C if xb else 0)
+            Co = rb.out_channels
+            hw = Hh * Ww
+            has_skip = not isinstance(rb.skip_connection, nn.Identity)
+            a1 = P.buf("res_a1", Nf * hw * Ci * osz)
+            raw = P.buf("res_raw", Nf * hw * Ci * osz) if has_skip else None
+            gn, c1 = rb.in_layers[0], rb.in_layers[2]
+            P.op("fdm_gn_apply", N_.GnApplyArgs, xa=xa.buf, xb=xb.buf if xb else None, stats_a=xa.st,
+                 stats_b=xb.st if xb else None, gamma=f32(gn.weight), beta=f32(gn.bias), film=None, out_op=a1, out_f32=None,
+                 raw_op=raw, N=Nf, HW=hw, Ca=xa.C, Cb=xb.C if xb else 0, T=T, film_stride=0, film_off=0, silu=1,
+                 op_dtype=opd, eps=gn.eps)
+            h1_ = new_act("res_h1", Co, Hh, Ww)
+            conv(a1, Ci, Hh, Ww, c1.weight, Co, 3, bias=f32(c1.bias), y_f32=h1_.buf, stats=h1_.st)
+            gn2, c2 = rb.out_layers[0], rb.out_layers[3]
+            a2 = P.buf("res_a2", Nf * hw * Co * osz)
+            P.op("fdm_gn_apply", N_.GnApplyArgs, xa=h1_.buf, xb=None, stats_a=h1_.st, stats_b=None, gamma=f32(gn2.weight),
+                 beta=f32(gn2.bias), film=cond, out_op=a2, out_f32=None, raw_op=None, N=Nf, HW=hw, Ca=Co, Cb=0, T=T,
+                 film_stride=cond_cols, film_off=film_off[id(rb)], silu=1, op_dtype=opd, eps=gn2.eps)
+            out = new_act("res_out", Co, Hh, Ww)
+            if has_skip:
+                sk = rb.skip_connection
+                if sk.kernel_size != (1, 1):
+                    raise NotImplementedError("ResBlock(use_conv=True) 3x3 skip is never built by create_model")
+                conv(a2, Co, Hh, Ww, c2.weight, Co, 3, a1=raw, C1=Ci, w1=sk.weight, bias=self._bias_sum(c2.bias, sk.bias),
+                     y_f32=out.buf, stats=out.st)
+            else:
+                conv(a2, Co, Hh, Ww, c2.weight, Co, 3, bias=f32(c2.bias), resid=xa.buf, y_f32=out.buf, stats=out.st)
+            return out
+
+        def attention(ab, x):
+            Cc, Hh, Ww, hw = x.C, x.H, x.W, x.H * x.W
+            ta, sa = ab.temporal_attention, ab.spatial_attention
+            # --- temporal: GN over (C/32 x T) per (b, pixel)
+            xn = P.buf("ta_xn", Nf * hw * Cc * 4)
+            xn_op = P.buf("ta_xn_op", Nf * hw * Cc * osz)
+            P.op("fdm_temporal_gn", N_.TemporalGnArgs, x=x.buf, gamma=f32(ta.norm.weight), beta=f32(ta.norm.bias),
+                 out_f32=xn, out_op=xn_op, B=B, T=T, HW=hw, C=Cc, op_dtype=opd, eps=ta.norm.eps)
+            qkv = P.buf("ta_qkv", Nf * hw * 3 * Cc * osz)
+            conv(xn_op, Cc, Hh, Ww, ta.qkv.weight, 3 * Cc, 1, bias=f32(ta.qkv.bias), y_op=qkv)
+            o = P.buf("ta_o", Nf * hw * Cc * osz)
+            P.op("fdm_attn_temporal", N_.AttnTemporalArgs, qkv=qkv, Rq=R[(id(ab), "rpe_q")], Rk=R[(id(ab), "rpe_k")],
+                 Rv=R[(id(ab), "rpe_v")], mask=P.mask, out=o, B=B, T=T, HW=hw, C=Cc, heads=ta.num_heads,
+                 qkv_dtype=opd, out_dtype=opd)
+            y = new_act("ta_y", Cc, Hh, Ww)
+            conv(o, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, bias=f32(ta.proj_out.bias), resid=xn, y_f32=y.buf, stats=y.st)
+            # --- spatial: plain per-frame GroupNorm, attention over the pixels of each frame
+            yn = P.buf("sa_yn", Nf * hw * Cc * 4)
+            yn_op = P.buf("sa_yn_op", Nf * hw * Cc * osz)
+            P.op("fdm_gn_apply", N_.GnApplyArgs, xa=y.buf, xb=None, stats_a=y.st, stats_b=None, gamma=f32(sa.norm.weight),
+                 beta=f32(sa.norm.bias), film=None, out_op=yn_op, out_f32=yn, raw_op=None, N=Nf, HW=hw, Ca=Cc, Cb=0, T=T,
+                 film_stride=0, film_off=0, silu=0, op_dtype=opd, eps=sa.norm.eps)
+            qkv2 = P.buf("sa_qkv", Nf * hw * 3 * Cc * osz)
+            conv(yn_op, Cc, Hh, Ww, sa.qkv.weight, 3 * Cc, 1, bias=f32(sa.qkv.bias), y_op=qkv2)
+            o2 = P.buf("sa_o", Nf * hw * Cc * osz)
+            P.op("fdm_attn_spatial", N_.AttnSpatialArgs, qkv=qkv2, out=o2, N=Nf, L=hw, C=Cc, heads=sa.num_heads,
+                 qkv_dtype=opd, out_dtype=opd)
+            z = new_act("sa_z", Cc, Hh, Ww)
+            conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf, stats=z.st)
+            return z
+
+        def resample(layer, x, down):
+            cv = layer.op if down else layer.conv
+            Ho, Wo = (x.H // 2, x.W // 2) if down else (x.H * 2, x.W * 2)
+            out = new_act("down" if down else "up", x.C, Ho, Wo)
+            # the CUDA-core engine gathers straight from the fp32 stream (stride 2 / folded nearest upsample)
+            conv(x.buf, x.C, x.H, x.W, cv.weight, x.C, 3, stride=2 if down else 1, upsample=0 if down else 1,
+                 bias=f32(cv.bias), y_f32=out.buf, stats=out.st, a_dtype=N_.F32)
+            return out
+
+        def run_stage(stage, h, skip=None):
+            for layer in stage:
+                if isinstance(layer, nn.Conv2d):  # stem
+                    out = new_act("stem", layer.out_channels, H, W)
+                    conv(xin, Cin, H, W, layer.weight, layer.out_channels, 3, bias=f32(layer.bias), y_f32=out.buf,
+                         stats=out.st, a_dtype=N_.F32)
+                    h = out
+                elif isinstance(layer, ResBlock):
+                    h = res_block(layer, h, skip)
+                    skip = None
+                elif isinstance(layer, FactorizedAttentionBlock):
+                    h = attention(layer, h)
+                elif isinstance(layer, Downsample):
+                    h = resample(layer, h, True)
+                elif isinstance(layer, Upsample):
+                    h = resample(layer, h, False)
+                else:
+                    raise NotImplementedError(type(layer))
+            return h
+
+        h, hs = None, []
+        for stage in m.input_blocks:
+            h = run_stage(stage, h)
+            hs.append(h)
+        h = run_stage(m.middle_block, h)
+        for stage in m.output_blocks:
+            h = run_stage(stage, h, hs.pop())
+        gn, cv = m.out[0], m.out[2]
+        a = P.buf("head_a", Nf * H * W * h.C * osz)
+        P.op("fdm_gn_apply", N_.GnApplyArgs, xa=h.buf, xb=None, stats_a=h.st, stats_b=None, gamma=f32(gn.weight),
+             beta=f32(gn.bias), film=None, out_op=a, out_f32=None, raw_op=None, N=Nf, HW=H * W, Ca=h.C, Cb=0, T=T,
+             film_stride=0, film_off=0, silu=1, op_dtype=opd, eps=gn.eps)
+        conv(a, h.C, H, W, cv.weight, m.out_channels, 3, bias=f32(cv.bias), y_f32=P.eps, out_nchw=1)
+
+        # skip-connection activations must stay alive until their consumer: handled by liveness (first/last use)
+        P.finalize(device)
+        # fill the device-side problem arrays now that pointers are known
+        for dev, problems in self._pending_groups:
+            arr = (N_.LinearProblem * len(problems))()
+            for i, pr in enumerate(problems):
+                for k in ("x", "w", "b", "y"):
+                    setattr(arr[i], k, P.ptr(pr[k]))
+                for k in ("M", "K", "Nout", "ldx", "ldy", "silu_in"):
+                    setattr(arr[i], k, pr[k])
+            dev.copy_(th.frombuffer(bytearray(bytes(arr)), dtype=th.uint8))
+        if self._pending_rh is not None:
+            dev, problems = self._pending_rh
+            arr = (N_.RpeHiddenProblem * len(problems))()
+            for i, pr in enumerate(problems):
+                arr[i].wd, arr[i].bd, arr[i].hidden = P.ptr(pr["wd"]), P.ptr(pr["bd"]), P.ptr(pr["hidden"])
+                arr[i].C, arr[i].te_off = pr["C"], pr["te_off"]
+            dev.copy_(th.frombuffer(bytearray(bytes(arr)), dtype=th.uint8))
+        self._pending_groups, self._pending_rh = [], None
+        # typed views of the I/O buffers
+        Cx = Cin - 1
+        P.x_view = P.view(P.x, (B, T, Cx, H, W), th.float32)
+        P.x0_view = P.view(P.x0, (B, T, Cx, H, W), th.float32)
+        P.obs_view = P.view(P.obs, (B, T), th.float32)
+        P.mask_view = P.view(P.mask, (B, T), th.float32)
+        P.fi_view = P.view(P.fi, (B, T), th.int64)
+        P.t_view = P.view(P.t, (B,), th.float32)
+        P.t_index_view = P.view(P.t_index, (B,), th.int64)
+        P.eps_view = P.view(P.eps, (B, T, m.out_channels, H, W), th.float32)
+        P.n_launches = len(P.calls) + 1  # + the statistics memset
+        return P
+
+    # ------------------------------------------------------------------ execution
+    def load_conditioning(self, P, x0, frame_indices, obs_mask, latent_mask):
+        """Copy the per-stage inputs (constant across diffusion steps) into the plan's static buffers."""
+        P.x0_view.copy_(x0)
+        P.fi_view.copy_(frame_indices)
+        P.obs_view.copy_(obs_mask.reshape(P.B, P.T))
+        th.clamp(obs_mask.reshape(P.B, P.T) + latent_mask.reshape(P.B, P.T), max=1, out=P.mask_view)
+
+    def forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask):
+        B, T, Cx, H, W = x.shape
+        P = self.plan_for(B, T, H, W, x.device)
+        if frame_indices is None:
+            raise ValueError("frame_indices is required (temporal RPE, rpe.py:146)")
+        self.load_conditioning(P, x0, frame_indices, obs_mask, latent_mask)
+        P.set_t_source(None)
+        P.x_view.copy_(x)
+        P.t_view.copy_(timesteps.reshape(B).float())
+        P.run(th.cuda.current_stream(x.device).cuda_stream)
+        return P.eps_view.clone()
