@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""
+bench.py — denoiser frame-steps/s (sampling) of the FDM hot path on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
+
+A "step" is one diffusion step of the sampler over one batch: UNetVideoModel forward (the whole kernel schedule)
++ the fused posterior update + the step's Gaussian noise draw, i.e. what `diffusion.p_sample` does.  One step
+processes B*K frame-steps per GPU.  Multi-GPU = the video batch sharded over ranks, no data-path collective
+(weak scaling: B videos per GPU fixed), launched by torchrun (one process per GPU).
+
+Lines printed (rank 0, ONE JSON line): see README/DESIGN.md §measurement for every key.
+  value     : whole-job frame-steps/s with inputs resident in HBM (CUDA events, L2 flushed between steps, max over ranks)
+  e2e       : same metric through diffusion.p_sample_loop with pinned HOST inputs, H2D + D2H inside the timed region
+  roofline  : the dominant kernel class (implicit-GEMM convs) timed alone with CUDA events: algorithmic FLOPs / time
+  cpu_baseline : the CPU oracle (port of the reference path) timed on this box's host cores on a bounded sample
+  --impl reference : times that CPU path only (rank 0), same workload/metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "latent-flexible-video-diffusion-modeling_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch as th  # noqa: E402
+
+PIXEL = dict(diffusion_space="pixel", pre_encoded=False, pre_encoded_stats_dict=None)
+
+# BASELINE.json configs.  `B` is videos PER GPU (weak scaling).
+WORKLOADS = {
+    # cfg4: hierarchy-2 sampling, 300-frame video, batch 64 sharded over 8 GPUs -> 8 videos/GPU, stage of K=20 frames,
+    # Carla-latent model of cfg2 (nc=64, nrb=1, 4x32x32 latents), 1000-step schedule.  The sampling headline.
+    "cfg4-sampling": dict(over=dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000),
+                          B=8, K=20, n_obs=10, video_len=300),
+    # cfg2 shape (batch 1, K=5): launch-latency bound by construction
+    "cfg2-sampling-b1": dict(over=dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000),
+                             B=1, K=5, n_obs=3, video_len=20),
+    # cfg1: the reference's own CPU-runnable case
+    "cfg1-sampling": dict(over=dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32),
+                          B=1, K=5, n_obs=3, video_len=20),
+    # cfg5: long-context temporal attention stress (nc=128, K=40, 4x64x64 latents)
+    "cfg5-sampling": dict(over=dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000),
+                          B=2, K=40, n_obs=20, video_len=300),
+}
+DEFAULT_WORKLOAD = "cfg4-sampling"
+
+
+def random_state_dict(model, seed=1):
+    """Random NON-ZERO weights (a freshly constructed model outputs eps == 0: zero_module, reference nn.py:68-74)."""
+    g = th.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        if v.dim() > 1:
+            sd[k] = th.randn(v.shape, generator=g) / (v[0].numel() ** 0.5)
+        elif k.endswith(".weight"):
+            sd[k] = 1.0 + 0.1 * th.randn(v.shape, generator=g)
+        else:
+            sd[k] = 0.1 * th.randn(v.shape, generator=g)
+    return sd
+
+
+def synthetic_batch(cfg_over, B, K, n_obs, video_len, seed):
+    g = th.Generator().manual_seed(seed)
+    C, S = cfg_over["in_channels"], cfg_over["image_size"]
+    x0 = th.randn(B, K, C, S, S, generator=g).clamp(-1, 1)
+    fi = th.stack([th.sort(th.randperm(video_len, generator=g)[:K]).values for _ in range(B)]).long()
+    obs = th.zeros(B, K, 1, 1, 1)
+    obs[:, :n_obs] = 1
+    return dict(x0=x0, frame_indices=fi, obs_mask=obs, latent_mask=1 - obs)
+
+
+def build_native(over, device):
+    from improved_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
+    d = model_and_diffusion_defaults()
+    d.update(over)
+    d["diffusion_space_kwargs"] = dict(PIXEL)
+    model, diffusion = create_model_and_diffusion(**d)
+    sd = random_state_dict(model)
+    model.load_state_dict(sd, strict=True)
+    model.to(device).eval()
+    return model, diffusion, sd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [s.strip() for s in line.split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    sm.append(float(c[0]))
+                    mx.append(float(c[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_port_steps(over, B, K, batch, sd, n_steps, warmup, threads):
+    """The reference path on host cores: the oracle port (oracle/fdm_oracle.py), fp32 torch CPU ops.  Checker/baseline only."""
+    from oracle import fdm_oracle as O
+    th.set_num_threads(threads)
+    cfg = O.make_cfg(**over)
+    tab = O.Tables(cfg)
+    g = th.Generator().manual_seed(123)
+    x = th.randn(batch["x0"].shape, generator=g)
+    times = []
+    n = tab.num_timesteps
+    with th.no_grad():
+        for s in range(warmup + n_steps):
+            t = th.full((B,), n - 1 - (s % n), dtype=th.int64)
+            noise = th.randn(x.shape, generator=g)
+            t0 = time.perf_counter()
+            out = O.p_sample(tab, sd, cfg, x, t, noise, batch)
+            dt = time.perf_counter() - t0
+            x = out["sample"]
+            if s >= warmup:
+                times.append(dt)
+    return times
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; /root/reference cannot travel to
+    the GPU box), all host threads, same workload / metric.  Rank 0 only."""
+    if rank != 0:
+        return
+    over, B, K = wl["over"], wl["B"], wl["K"]
+    from improved_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
+    d = model_and_diffusion_defaults()
+    d.update(over)
+    d["diffusion_space_kwargs"] = dict(PIXEL)
+    model, _ = create_model_and_diffusion(**d)
+    sd = random_state_dict(model)
+    batch = synthetic_batch(over, B, K, wl["n_obs"], wl["video_len"], seed=0)
+    threads = os.cpu_count() or 1
+    times = cpu_port_steps(over, B, K, batch, sd, args.steps, args.warmup, threads)
+    total = sum(times)
+    v = B * K * len(times) / total
+    line = {"impl": "reference", "metric": "denoiser frame-steps/sec (sampling)", "value": v, "unit": "frame-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, **{k: wl[k] for k in ("B", "K", "n_obs")}, **over},
+            "cpu_baseline": {"value": v, "unit": "frame-steps/s", "cores": threads, "kind": "port",
+                             "sample": f"{len(times)} diffusion steps of the same B={B},K={K} batch (oracle port, fp32, "
+                                       f"torch CPU ops, {threads} threads)"},
+            "e2e": {"value": v, "unit": "frame-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    if args.warmup < 3:
+        args.warmup = 3
+    import torch.distributed as dist
+    if not th.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    th.cuda.set_device(local)
+    dev = th.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from improved_diffusion import _native as N_
+    over, B, K = wl["over"], wl["B"], wl["K"]
+    model, diffusion, sd = build_native(over, dev)
+    model.precision = args.precision
+    batch = synthetic_batch(over, B, K, wl["n_obs"], wl["video_len"], seed=rank)  # each rank its own shard of videos
+    shape = tuple(batch["x0"].shape)
+    C, S = over["in_channels"], over["image_size"]
+
+    # ------------------------------------------------------------------ device-resident step (value)
+    eng = model.engine()
+    P = eng.plan_for(B, K, S, S, dev)
+    kw_dev = {k: v.to(dev) for k, v in batch.items()}
+    eng.load_conditioning(P, kw_dev["x0"], kw_dev["frame_indices"], kw_dev["obs_mask"], kw_dev["latent_mask"])
+    tb = diffusion._tables(dev)
+    P.set_t_source(tb["model_t"])
+    nbuf = th.empty(shape, device=dev)
+    step_args = N_.DdpmStepArgs(x=P.ptr(P.x), eps=P.ptr(P.eps), noise=nbuf.data_ptr(), coef=tb["step"].data_ptr(),
+                                t=P.ptr(P.t_index), sample=P.ptr(P.x), pred_xstart=None, per_video=K * C * S * S, B=B, clip=1)
+    stream = th.cuda.current_stream(dev)
+
+    def body():
+        s = th.cuda.current_stream(dev).cuda_stream
+        P.run(s)
+        N_.call("fdm_ddpm_step", step_args, s)
+
+    P.x_view.normal_()
+    P.t_index_view.fill_(diffusion.num_timesteps - 1)
+    nbuf.normal_()
+    body()
+    stream.synchronize()
+    graph = th.cuda.CUDAGraph()
+    with th.cuda.graph(graph):
+        body()
+    flush = th.empty(192 * 1024 * 1024, dtype=th.uint8, device=dev)  # > 126 MB L2
+
+    def one_step(i):
+        P.t_index_view.fill_(i)
+        nbuf.normal_()
+        graph.replay()
+
+    n_t = diffusion.num_timesteps
+    P.x_view.normal_()
+    for w in range(args.warmup):
+        one_step(n_t - 1 - (w % n_t))
+    th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    th.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    evs = [(th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        evs[k][0].record()
+        one_step(n_t - 1 - ((args.warmup + k) % n_t))
+        evs[k][1].record()
+    th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    th.cuda.synchronize()
+    clk = clocks.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = th.tensor([sum(step_ms)], device=dev, dtype=th.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B * K * args.steps / (total_ms * 1e-3)
+    assert bool(th.isfinite(P.x_view).all()), "non-finite sampler state"
+
+    # hot (no L2 flush, back-to-back) for information
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        one_step(n_t - 1 - (k % n_t))
+    e1.record()
+    th.cuda.synchronize()
+    hot_ms = e0.elapsed_time(e1) / args.steps
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel class (convs), timed alone
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf, peak_src = (peaks["bf16_tflops"], "measured") if "bf16_tflops" in peaks else (1590.0, "fallback")
+    conv_calls = [(fn, ref) for name, fn, ref in P.calls if name == "fdm_conv"]
+    import ctypes as C_
+    sp = C_.c_void_p(stream.cuda_stream)
+    reps = 20
+    for fn, ref in conv_calls:
+        fn(ref, sp)
+    th.cuda.synchronize()
+    c0, c1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(reps):
+        for fn, ref in conv_calls:
+            fn(ref, sp)
+    c1.record()
+    th.cuda.synchronize()
+    conv_ms = c0.elapsed_time(c1) / reps
+    conv_tf = P.conv_flops / (conv_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "fdm_conv (implicit-GEMM conv/linear launches of one step, timed alone back-to-back)",
+                "achieved": conv_tf, "peak": peak_tf, "peak_source": peak_src, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
+                "traffic": None, "launches_per_step": len(conv_calls), "ms_per_step": conv_ms,
+                "flops_per_step": P.conv_flops, "share_of_step": conv_ms / hot_ms}
+    step_tf = P.flops / (ms_per_step * 1e-3) / 1e12
+    step_roofline = {"bound": "tensor", "achieved": step_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": step_tf / peak_tf,
+                     "flops_per_frame_step": P.flops / (B * K)}
+
+    # ------------------------------------------------------------------ e2e through the public API (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        host = {k: v.pin_memory() for k, v in batch.items()}
+        out_host = th.empty(shape, dtype=th.float32).pin_memory()
+
+        def stage():
+            kw = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            final, _ = diffusion.p_sample_loop(model, shape, clip_denoised=True, model_kwargs=kw, latent_mask=kw["latent_mask"])
+            out_host.copy_(final, non_blocking=True)
+            th.cuda.synchronize()
+
+        stage()  # warm-up (captures the sampler graph)
+        th.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        stage()
+        if world > 1:
+            dist.barrier()
+        dt = th.tensor([time.perf_counter() - t0], device=dev, dtype=th.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = out_host.numel() * 4
+        e2e = {"value": world * B * K * n_t / dt, "unit": "frame-steps/s", "h2d_bytes_per_step": h2d / n_t,
+               "d2h_bytes_per_step": d2h / n_t, "what": f"diffusion.p_sample_loop, one stage of {n_t} steps, pinned host "
+               f"inputs -> device -> pinned host result, wall clock incl. copies", "seconds": dt}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        times = cpu_port_steps(over, B, K, batch, sd_cpu, n_steps=3, warmup=1, threads=threads)
+        cpu = {"value": B * K * len(times) / sum(times), "unit": "frame-steps/s", "cores": threads, "kind": "port",
+               "sample": f"{len(times)} diffusion steps (after 1 warm-up) of the same B={B},K={K} batch: oracle port of the "
+                         f"reference path, fp32 torch CPU ops, {threads} threads"}
+
+    if rank == 0:
+        line = {"metric": "denoiser frame-steps/sec (sampling)", "value": value, "unit": "frame-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_hot": hot_ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "videos_per_gpu": B, "frames_per_stage": K, "n_obs": wl["n_obs"],
+                           "latent": [C, S, S], **over, "sharding": f"video batch over {world} rank(s), no collective",
+                           "l2": "flushed between timed steps (192 MB memset outside the event pairs)",
+                           "weights": "random non-zero init (zero_module tensors re-randomised)"},
+                "clocks": clk, "e2e": e2e, "gpu_launches": args.steps * (len(P.calls) + 1),
+                "launches_per_step": len(P.calls) + 1, "roofline": roofline, "step_roofline": step_roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

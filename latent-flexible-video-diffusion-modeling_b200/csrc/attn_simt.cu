@@ -171,7 +171,9 @@ struct SAParams {
 
 template <int FQ, typename QT, typename OT>
 __global__ void __launch_bounds__(256) attn_spatial_kernel(SAParams p) {
-  constexpr int ROW = 4 * (FQ + 4);  // padded row: sub-vector `sub` starts at sub*(FQ+4)
+  constexpr int V = (FQ % 4 == 0) ? 4 : 2;   // vector width of shared-memory accesses (F = 24 -> FQ = 6 -> float2)
+  constexpr int SUB = FQ + V;                // padded sub-vector stride: lane `sub` starts at sub*SUB
+  constexpr int ROW = 4 * SUB;
   __shared__ __align__(16) float ks[SA_KC * ROW];
   __shared__ __align__(16) float vs[SA_KC * ROW];
   const int tid = threadIdx.x, sub = tid & 3, ql = tid >> 2;
@@ -184,38 +186,47 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(SAParams p) {
   {
     const QT* qp = base + (size_t)(q_ok ? qi : 0) * 3 * C + sub * FQ;
 #pragma unroll
-    for (int f = 0; f < FQ; f += 4) {
-      float4 v = OpType<QT>::load4(qp + f);
-      q[f] = v.x * p.scale; q[f + 1] = v.y * p.scale; q[f + 2] = v.z * p.scale; q[f + 3] = v.w * p.scale;
+    for (int f = 0; f < FQ; ++f) {
+      q[f] = OpType<QT>::load(qp + f) * p.scale;
+      o[f] = 0.f;
     }
-#pragma unroll
-    for (int f = 0; f < FQ; ++f) o[f] = 0.f;
   }
   float mrun = -INFINITY, lrun = 0.f;
   for (int j0 = 0; j0 < L; j0 += SA_KC) {
     __syncthreads();
-    for (int i = tid; i < SA_KC * (F / 4); i += 256) {
-      int j = i / (F / 4), fq = i - j * (F / 4);
-      int f = fq * 4;
+    for (int i = tid; i < SA_KC * (F / V); i += 256) {
+      int j = i / (F / V), f = (i - j * (F / V)) * V;
       int jj = min(j0 + j, L - 1);
       const QT* kp = base + (size_t)jj * 3 * C + C + f;
-      float4 kvv = OpType<QT>::load4(kp), vvv = OpType<QT>::load4(kp + C);
-      int off = j * ROW + (f / FQ) * (FQ + 4) + (f % FQ);
-      *reinterpret_cast<float4*>(&ks[off]) = kvv;
-      *reinterpret_cast<float4*>(&vs[off]) = vvv;
+      int off = j * ROW + (f / FQ) * SUB + (f % FQ);
+      if constexpr (V == 4) {
+        *reinterpret_cast<float4*>(&ks[off]) = OpType<QT>::load4(kp);
+        *reinterpret_cast<float4*>(&vs[off]) = OpType<QT>::load4(kp + C);
+      } else {
+        *reinterpret_cast<float2*>(&ks[off]) = make_float2(OpType<QT>::load(kp), OpType<QT>::load(kp + 1));
+        *reinterpret_cast<float2*>(&vs[off]) = make_float2(OpType<QT>::load(kp + C), OpType<QT>::load(kp + C + 1));
+      }
     }
     __syncthreads();
     float s[SA_KC];
     float cmax = -INFINITY;
 #pragma unroll
     for (int j = 0; j < SA_KC; ++j) {
-      const float* kr = &ks[j * ROW + sub * (FQ + 4)];
+      const float* kr = &ks[j * ROW + sub * SUB];
       float acc = 0.f;
+      if constexpr (V == 4) {
 #pragma unroll
-      for (int f = 0; f < FQ; f += 4) {
-        float4 kk = *reinterpret_cast<const float4*>(kr + f);
-        acc = fmaf(q[f], kk.x, acc); acc = fmaf(q[f + 1], kk.y, acc);
-        acc = fmaf(q[f + 2], kk.z, acc); acc = fmaf(q[f + 3], kk.w, acc);
+        for (int f = 0; f < FQ; f += 4) {
+          float4 kk = *reinterpret_cast<const float4*>(kr + f);
+          acc = fmaf(q[f], kk.x, acc); acc = fmaf(q[f + 1], kk.y, acc);
+          acc = fmaf(q[f + 2], kk.z, acc); acc = fmaf(q[f + 3], kk.w, acc);
+        }
+      } else {
+#pragma unroll
+        for (int f = 0; f < FQ; f += 2) {
+          float2 kk = *reinterpret_cast<const float2*>(kr + f);
+          acc = fmaf(q[f], kk.x, acc); acc = fmaf(q[f + 1], kk.y, acc);
+        }
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -231,12 +242,20 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(SAParams p) {
     for (int j = 0; j < SA_KC; ++j) {
       const float pj = expf(s[j] - mnew);
       lrun += pj;
-      const float* vr = &vs[j * ROW + sub * (FQ + 4)];
+      const float* vr = &vs[j * ROW + sub * SUB];
+      if constexpr (V == 4) {
 #pragma unroll
-      for (int f = 0; f < FQ; f += 4) {
-        float4 vv = *reinterpret_cast<const float4*>(vr + f);
-        o[f] = fmaf(pj, vv.x, o[f]); o[f + 1] = fmaf(pj, vv.y, o[f + 1]);
-        o[f + 2] = fmaf(pj, vv.z, o[f + 2]); o[f + 3] = fmaf(pj, vv.w, o[f + 3]);
+        for (int f = 0; f < FQ; f += 4) {
+          float4 vv = *reinterpret_cast<const float4*>(vr + f);
+          o[f] = fmaf(pj, vv.x, o[f]); o[f + 1] = fmaf(pj, vv.y, o[f + 1]);
+          o[f + 2] = fmaf(pj, vv.z, o[f + 2]); o[f + 3] = fmaf(pj, vv.w, o[f + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int f = 0; f < FQ; f += 2) {
+          float2 vv = *reinterpret_cast<const float2*>(vr + f);
+          o[f] = fmaf(pj, vv.x, o[f]); o[f + 1] = fmaf(pj, vv.y, o[f + 1]);
+        }
       }
     }
     mrun = mnew;
@@ -245,8 +264,7 @@ __global__ void __launch_bounds__(256) attn_spatial_kernel(SAParams p) {
     const float inv = 1.f / lrun;
     OT* op = reinterpret_cast<OT*>(p.out) + ((size_t)n * L + qi) * C + h * F + sub * FQ;
 #pragma unroll
-    for (int f = 0; f < FQ; f += 4)
-      OpType<OT>::store4(op + f, make_float4(o[f] * inv, o[f + 1] * inv, o[f + 2] * inv, o[f + 3] * inv));
+    for (int f = 0; f < FQ; ++f) OpType<OT>::store(op + f, o[f] * inv);
   }
 }
 
@@ -254,7 +272,9 @@ template <typename QT, typename OT>
 static int launch_spatial(const SAParams& p, cudaStream_t st) {
   dim3 grid((p.L + SA_QB - 1) / SA_QB, p.heads, p.N);
   switch (p.F) {
+    case 8: attn_spatial_kernel<2, QT, OT><<<grid, 256, 0, st>>>(p); break;
     case 16: attn_spatial_kernel<4, QT, OT><<<grid, 256, 0, st>>>(p); break;
+    case 24: attn_spatial_kernel<6, QT, OT><<<grid, 256, 0, st>>>(p); break;
     case 32: attn_spatial_kernel<8, QT, OT><<<grid, 256, 0, st>>>(p); break;
     case 48: attn_spatial_kernel<12, QT, OT><<<grid, 256, 0, st>>>(p); break;
     case 64: attn_spatial_kernel<16, QT, OT><<<grid, 256, 0, st>>>(p); break;

@@ -15,6 +15,7 @@ Design (B200-first, not a module walk):
   * the plan owns every intermediate buffer (liveness-packed arena), so a step is replayable as a CUDA graph.
 """
 import ctypes as C
+import os
 
 import torch as th
 import torch.nn as nn
@@ -41,6 +42,8 @@ class Plan:
         self.calls = None    # [(fn, byref(struct))] after finalize()
         self.stats_bytes = 0
         self.graphs = {}     # CUDA graphs captured over this plan (see gaussian_diffusion._graph_sampler)
+        self.flops = 0       # algorithmic 2*MAC of every conv / linear / attention matmul of one forward
+        self.conv_flops = 0
 
     # ---- buffers
     def buf(self, name, nbytes, persistent=False):
@@ -160,7 +163,8 @@ class DenoiserEngine:
         self.op_dtype = N_.BF16 if precision == "bf16" else N_.F32
         self.op_torch = th.bfloat16 if precision == "bf16" else th.float32
         self.op_size = 2 if precision == "bf16" else 4
-        self.use_tc = precision == "bf16"
+        # FDM_CONV_ENGINE=simt forces the CUDA-core implicit GEMM everywhere (debugging / A-B timing of the tcgen05 kernel)
+        self.use_tc = precision == "bf16" and os.environ.get("FDM_CONV_ENGINE", "tc") != "simt"
         self.plans = {}
         self.packed = {}
         self._versions = None
@@ -304,6 +308,7 @@ class DenoiserEngine:
                     if isinstance(b, Buf):
                         touch[f"_{k}{i}"] = b
             idx = len(P.ops)
+            P.flops += sum(2 * pr["M"] * pr["K"] * pr["Nout"] for pr in problems)
             P.op("fdm_grouped_linear", N_.GroupedLinearArgs, problems=dev, count=len(problems),
                  max_M=max(p["M"] for p in problems), max_Nout=max(p["Nout"] for p in problems))
             for b in touch.values():  # liveness of buffers referenced only through the device problem array
@@ -363,6 +368,9 @@ class DenoiserEngine:
             Hv, Wv = (Hin * 2, Win * 2) if upsample else (Hin, Win)
             Ho, Wo = (Hv + 2 * (k // 2) - k) // stride + 1, (Wv + 2 * (k // 2) - k) // stride + 1
             tc = a_dtype == N_.BF16 and self.tc_ok(C0, C1, Cout, k, stride, upsample, Ho, Wo)
+            fl = 2 * Nf * Ho * Wo * Cout * (k * k * C0 + C1)
+            P.flops += fl
+            P.conv_flops += fl
             pack = self._pack_tc if tc else self._pack_simt
             P.op("fdm_conv", N_.ConvArgs, a0=a0, w0=pack(w0), a1=a1, w1=pack(w1) if w1 is not None else None, bias=bias,
                  resid=resid, y_f32=y_f32, y_op=y_op, stats=stats, N=Nf, Hin=Hin, Win=Win, C0=C0, C1=C1, Cout=Cout,
@@ -423,6 +431,7 @@ class DenoiserEngine:
             qkv = P.buf("ta_qkv", Nf * hw * 3 * Cc * osz)
             conv(xn_op, Cc, Hh, Ww, ta.qkv.weight, 3 * Cc, 1, bias=f32(ta.qkv.bias), y_op=qkv)
             o = P.buf("ta_o", Nf * hw * Cc * osz)
+            P.flops += 10 * T * T * Cc * B * hw  # QK^T, PV and the three contextual RPE einsums (rpe.py:72-83,144,166)
             P.op("fdm_attn_temporal", N_.AttnTemporalArgs, qkv=qkv, Rq=R[(id(ab), "rpe_q")], Rk=R[(id(ab), "rpe_k")],
                  Rv=R[(id(ab), "rpe_v")], mask=P.mask, out=o, B=B, T=T, HW=hw, C=Cc, heads=ta.num_heads,
                  qkv_dtype=opd, out_dtype=opd)
@@ -437,6 +446,7 @@ class DenoiserEngine:
             qkv2 = P.buf("sa_qkv", Nf * hw * 3 * Cc * osz)
             conv(yn_op, Cc, Hh, Ww, sa.qkv.weight, 3 * Cc, 1, bias=f32(sa.qkv.bias), y_op=qkv2)
             o2 = P.buf("sa_o", Nf * hw * Cc * osz)
+            P.flops += 4 * hw * hw * Cc * Nf
             P.op("fdm_attn_spatial", N_.AttnSpatialArgs, qkv=qkv2, out=o2, N=Nf, L=hw, C=Cc, heads=sa.num_heads,
                  qkv_dtype=opd, out_dtype=opd)
             z = new_act("sa_z", Cc, Hh, Ww)

@@ -1,0 +1,124 @@
+"""
+GPU kernel-level parity (-m gpu): each C-ABI entry point of include/fdm_b200.h against the plain PyTorch op the
+reference calls at that site (torch fp32 on the same device).  bf16 tensor-core results are compared with a torch
+fp32 op fed the SAME bf16-rounded operands, so the tolerance only has to cover accumulation order (1e-3 rel-L2);
+fp32 CUDA-core results are held to 1e-5.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def pack_tc(w):
+    co, ci, kh, kw = w.shape
+    cip, cop = (ci + 63) // 64 * 64, (co + 15) // 16 * 16
+    out = torch.zeros(kh * kw, cop, cip, dtype=torch.bfloat16, device=w.device)
+    out[:, :co, :ci] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16)
+    return out
+
+
+def pack_simt(w):
+    co, ci, kh, kw = w.shape
+    return w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous().float()
+
+
+def run_conv(x_nhwc, w, bias, *, stride=1, engine, x1=None, w1=None, resid=None, want_op=False, want_stats=True):
+    """x_nhwc: [N,H,W,C] bf16 (TC) or fp32/bf16 (SIMT).  Returns (y_f32 [N,Ho,Wo,Co], y_op or None, stats or None)."""
+    from improved_diffusion import _native as N_
+    N, H, W, C0 = x_nhwc.shape
+    Co, _, k, _ = w.shape
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    dev = x_nhwc.device
+    y = torch.empty(N, Ho, Wo, Co, device=dev)
+    yop = torch.empty(N, Ho, Wo, Co, device=dev, dtype=torch.bfloat16) if want_op else None
+    stats = torch.zeros(N, Co, 2, device=dev) if want_stats else None
+    pk = pack_tc if engine == N_.CONV_TC else pack_simt
+    w0p = pk(w)
+    w1p = pk(w1) if w1 is not None else None
+    a = N_.ConvArgs(a0=x_nhwc.data_ptr(), w0=w0p.data_ptr(), a1=x1.data_ptr() if x1 is not None else None,
+                    w1=w1p.data_ptr() if w1p is not None else None, bias=bias.data_ptr() if bias is not None else None,
+                    resid=resid.data_ptr() if resid is not None else None, y_f32=y.data_ptr(),
+                    y_op=yop.data_ptr() if want_op else None, stats=stats.data_ptr() if want_stats else None,
+                    N=N, Hin=H, Win=W, C0=C0, C1=x1.shape[-1] if x1 is not None else 0, Cout=Co, ksize=k, stride=stride,
+                    upsample=0, a_dtype=N_.BF16 if x_nhwc.dtype == torch.bfloat16 else N_.F32, op_dtype=N_.BF16, out_nchw=0,
+                    engine=engine)
+    N_.call("fdm_conv", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return y, yop, stats
+
+
+CASES = [
+    # N, H, W, C0, Cout, k, stride, C1 (second K segment), resid
+    (5, 32, 32, 64, 64, 3, 1, 0, True),
+    (5, 32, 32, 64, 128, 3, 1, 64, False),   # ResBlock out-conv with 1x1 skip segment
+    (3, 16, 16, 128, 128, 3, 1, 0, True),
+    (5, 8, 8, 128, 128, 3, 1, 0, True),      # HW = 64 < 128: two frames per tile, ragged last tile
+    (7, 4, 4, 128, 128, 3, 1, 0, False),     # HW = 16: eight frames per tile, half-warp statistics segments
+    (2, 16, 16, 64, 192, 1, 1, 0, False),    # qkv linear (1x1), Cout = 3C
+    (2, 16, 16, 64, 64, 1, 1, 0, True),      # proj_out + residual
+    (2, 32, 32, 32, 32, 3, 1, 0, True),      # nc=32 model: C0 = 32 < the 64-wide K chunk (TMA zero-fill), BN = 32
+    (2, 16, 16, 96, 64, 3, 1, 0, False),     # C0 = 96: ragged second K chunk
+    (2, 16, 16, 192, 96, 3, 1, 96, False),   # Cout = 96: masked N tile
+    (1, 64, 64, 128, 128, 3, 1, 0, True),    # W = 64: two image rows per tile
+    (1, 128, 128, 64, 64, 3, 1, 0, False),   # W = 128: one row per tile
+    (3, 32, 32, 64, 64, 3, 2, 0, False),     # Downsample conv (stride 2) through TMA element strides
+    (5, 16, 16, 128, 128, 3, 2, 0, False),   # stride 2 -> 8x8 outputs, two frames per tile
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_tc_vs_torch(case):
+    from improved_diffusion import _native as N_
+    N, H, W, C0, Co, k, stride, C1, use_resid = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000)
+    x = torch.randn(N, H, W, C0, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Co, C0, k, k, device="cuda", generator=g) / (C0 * k * k) ** 0.5)
+    bias = 0.1 * torch.randn(Co, device="cuda", generator=g)
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    x1 = w1 = None
+    if C1:
+        x1 = torch.randn(N, Ho, Wo, C1, device="cuda", generator=g).to(torch.bfloat16)
+        w1 = torch.randn(Co, C1, 1, 1, device="cuda", generator=g) / C1 ** 0.5
+    resid = torch.randn(N, Ho, Wo, Co, device="cuda", generator=g) if use_resid else None
+    y, yop, stats = run_conv(x, w, bias, stride=stride, engine=N_.CONV_TC, x1=x1, w1=w1, resid=resid, want_op=True)
+    wq = w.to(torch.bfloat16).float()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wq, bias, stride=stride, padding=pad)
+    if C1:
+        ref = ref + F.conv2d(x1.float().permute(0, 3, 1, 2), w1.to(torch.bfloat16).float())
+    ref = ref.permute(0, 2, 3, 1)
+    if use_resid:
+        ref = ref + resid
+    assert rel(y, ref) <= 1e-3, rel(y, ref)
+    assert rel(yop.float(), ref) <= 6e-3
+    ref_stats = torch.stack([ref.sum(dim=(1, 2)), (ref * ref).sum(dim=(1, 2))], dim=-1)
+    assert rel(stats, ref_stats) <= 1e-3
+    # and against the CUDA-core engine on the same operands
+    y2, _, st2 = run_conv(x, w.to(torch.bfloat16).float(), bias, stride=stride, engine=N_.CONV_SIMT, x1=x1,
+                          w1=w1.to(torch.bfloat16).float() if C1 else None, resid=resid)
+    assert rel(y, y2) <= 1e-3
+
+
+def test_conv_simt_fp32_exact():
+    from improved_diffusion import _native as N_
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for (N, H, W, C0, Co, k, stride) in [(2, 32, 32, 5, 32, 3, 1), (2, 16, 16, 64, 4, 3, 1), (3, 32, 32, 64, 64, 3, 2)]:
+        x = torch.randn(N, H, W, C0, device="cuda", generator=g)
+        w = torch.randn(Co, C0, k, k, device="cuda", generator=g) / (C0 * k * k) ** 0.5
+        b = torch.randn(Co, device="cuda", generator=g)
+        y, _, stats = run_conv(x, w, b, stride=stride, engine=N_.CONV_SIMT)
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=stride, padding=k // 2).permute(0, 2, 3, 1)
+        torch.backends.cudnn.allow_tf32 = old
+        assert rel(y, ref) <= 1e-5
+        ref_stats = torch.stack([ref.sum(dim=(1, 2)), (ref * ref).sum(dim=(1, 2))], dim=-1)
+        assert rel(stats, ref_stats) <= 1e-4

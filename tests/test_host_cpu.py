@@ -1,0 +1,118 @@
+"""CPU: host-side logic of the drop-in package and the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fdm_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PIXEL = dict(diffusion_space="pixel", pre_encoded=False, pre_encoded_stats_dict=None)
+
+
+def build(over):
+    from improved_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
+    d = model_and_diffusion_defaults()
+    d.update(over)
+    d["diffusion_space_kwargs"] = dict(PIXEL)
+    return create_model_and_diffusion(**d)
+
+
+def test_library_exports_every_declared_symbol():
+    from improved_diffusion import _native
+    hdr = open(os.path.join(ROOT, "include", "fdm_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|const char\*)\s+(fdm_\w+)\s*\(", hdr, flags=re.M))
+    assert {"fdm_conv", "fdm_ddpm_step", "fdm_attn_temporal", "fdm_abi_version"} <= declared
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_native.ENTRY_POINTS) <= declared
+    assert _native.lib().fdm_abi_version() == 1
+    assert _native.verify_struct_sizes()
+    assert _native.lib().fdm_status_string(-2).decode().startswith("unsupported")
+
+
+def test_defaults_and_factory_contract():
+    from improved_diffusion.script_util import model_and_diffusion_defaults, create_model_and_diffusion
+    d = model_and_diffusion_defaults()
+    assert len(d) == 22 and d["num_heads"] == 4 and d["attention_resolutions"] == "16,8" and d["use_rpe_net"] is True
+    assert {k: v for k, v in d.items() if k != "diffusion_space_kwargs"} == \
+        {k: v for k, v in O.DEFAULTS.items() if k != "diffusion_space_kwargs"}
+    bad = dict(d, image_size=48, diffusion_space_kwargs=dict(PIXEL))
+    with pytest.raises(ValueError, match="unsupported image size"):
+        create_model_and_diffusion(**bad)
+    with pytest.raises(NotImplementedError):
+        create_model_and_diffusion(**dict(d, noise_schedule="nope", diffusion_space_kwargs=dict(PIXEL)))
+    with pytest.raises(AttributeError, match="beta"):  # rpe.py:50 — the reference's lookup-table branch is broken
+        create_model_and_diffusion(**dict(d, use_rpe_net=False, diffusion_space_kwargs=dict(PIXEL)))
+
+
+@pytest.mark.parametrize("over", [
+    dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1),
+    dict(image_size=64, in_channels=3, num_channels=32, num_res_blocks=2),
+    dict(image_size=128, in_channels=3, num_channels=32, num_res_blocks=1),
+])
+def test_state_dict_contract(over):
+    """Keys, order and shapes equal the reference's (oracle.param_shapes is pinned to the live reference by
+    tests/golden/make_golden.py through load_state_dict(strict=True) + key-order assert)."""
+    model, _ = build(over)
+    shapes = O.param_shapes(O.make_cfg(**over))
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(shapes.keys())
+    for k, s in shapes.items():
+        assert tuple(sd[k].shape) == tuple(s), k
+    # zero-initialised tensors of the reference (zero_module) are zero here too
+    zeros = [k for k in sd if k.endswith(("out_layers.3.weight", "proj_out.weight", "rpe_net.out.weight", "out.2.weight"))]
+    assert zeros and all(float(sd[k].abs().sum()) == 0 for k in zeros)
+    model.load_state_dict(O.init_state_dict(O.make_cfg(**over), seed=1), strict=True)
+
+
+@pytest.mark.parametrize("steps,respacing", [(32, ""), (1000, ""), (1000, "250"), (1000, "10,15,20"), (1000, "ddim50"), (32, "4")])
+def test_tables_match_oracle(steps, respacing):
+    _, diffusion = build(dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=steps,
+                              timestep_respacing=respacing))
+    tab = O.Tables(O.make_cfg(diffusion_steps=steps, timestep_respacing=respacing))
+    assert diffusion.num_timesteps == tab.num_timesteps
+    assert diffusion.timestep_map == tab.timestep_map
+    for name in ("betas", "alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                 "posterior_mean_coef1", "posterior_mean_coef2", "posterior_variance", "sqrt_alphas_cumprod",
+                 "sqrt_one_minus_alphas_cumprod"):
+        assert np.array_equal(getattr(diffusion, name), getattr(tab, name)), name
+    var, logvar = diffusion._fixed_variance()
+    assert np.array_equal(var, tab.model_variance) and np.array_equal(logvar, tab.model_log_variance)
+
+
+def test_space_timesteps_errors():
+    from improved_diffusion.respace import space_timesteps
+    assert space_timesteps(100, "ddim10") == O.space_timesteps(100, "ddim10")
+    with pytest.raises(ValueError):
+        space_timesteps(100, "ddim33")
+    with pytest.raises(ValueError):
+        space_timesteps(10, "20")
+    assert space_timesteps(300, [10, 15, 20]) == O.space_timesteps(300, [10, 15, 20])
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    model, diffusion = build(dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32))
+    inp = O.synthetic_inputs(O.make_cfg(image_size=32, in_channels=4), 1, 3, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(inp["x"], x0=inp["x0"], timesteps=torch.zeros(1), frame_indices=inp["frame_indices"],
+              obs_mask=inp["obs_mask"], latent_mask=inp["latent_mask"])
+
+
+def test_q_sample_and_losses_host_math_cpu():
+    """The torch (non-fused) branches of q_sample / p_mean_variance used for non-CUDA tensors follow the oracle."""
+    _, diffusion = build(dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32))
+    tab = O.Tables(O.make_cfg(diffusion_steps=32))
+    g = torch.Generator().manual_seed(0)
+    x0, noise = torch.randn(2, 3, 4, 8, 8, generator=g), torch.randn(2, 3, 4, 8, 8, generator=g)
+    t = torch.tensor([5, 31])
+    assert torch.equal(diffusion.q_sample(x0, t, noise), O.q_sample(tab, x0, t, noise))
+    eps = torch.randn(2, 3, 4, 8, 8, generator=g)
+    out = diffusion.p_mean_variance(lambda x, timesteps, **kw: (eps, None), x0, t)
+    ref = O.posterior_from_eps(tab, x0, t, eps)
+    for k in ("mean", "variance", "log_variance", "pred_xstart"):
+        assert torch.equal(out[k], ref[k]), k
