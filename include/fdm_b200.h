@@ -16,8 +16,10 @@
  *  - activations are channels-last: [N frames][H][W][C]; frame n = b*T + t.
  *  - dtype codes: FDM_F32 = 0, FDM_BF16 = 1 ("operand" tensors feeding tensor-core GEMMs are bf16 in
  *    bf16 mode and fp32 in the exact fp32 mode; residual stream, statistics, softmax are always fp32).
- *  - GroupNorm statistics buffers are [N][C] pairs (sum, sum of squares), fp32, accumulated with
- *    atomics by the producing kernel; the caller zeroes them (one memset per forward).
+ *  - GroupNorm statistics buffers are [N][C] pairs (sum, sum of squares) of DOUBLES: the producing kernel reduces
+ *    each warp's rows in a fixed order in fp32 and adds the partials with fp64 atomics, so the statistics are
+ *    reproducible to ~1e-16 run to run (fp32 atomics made the bf16 path chaotic at its rounding-noise level);
+ *    the caller zeroes them (one memset per forward).
  */
 #ifndef FDM_B200_H_
 #define FDM_B200_H_
@@ -84,7 +86,7 @@ typedef struct {
   const float* resid; /* [N][Ho][Wo][Cout] fp32 or NULL */
   float* y_f32;
   void* y_op;
-  float* stats;     /* [N][Cout][2] or NULL */
+  double* stats;    /* [N][Cout][2] or NULL */
   int32_t N, Hin, Win, C0, C1, Cout;
   int32_t ksize, stride, upsample;
   int32_t a_dtype, op_dtype, out_nchw, engine;
@@ -100,8 +102,8 @@ int fdm_conv(const fdm_conv_args* a, void* stream);
 typedef struct {
   const float* xa;      /* [N][HW][Ca] */
   const float* xb;      /* [N][HW][Cb] or NULL */
-  const float* stats_a; /* [N][Ca][2] */
-  const float* stats_b; /* [N][Cb][2] or NULL */
+  const double* stats_a; /* [N][Ca][2] */
+  const double* stats_b; /* [N][Cb][2] or NULL */
   const float* gamma;   /* [Ca+Cb] */
   const float* beta;
   const float* film;    /* [B][film_stride] rows: scale at [film_off + c], shift at [film_off + C + c]; or NULL */
@@ -179,7 +181,8 @@ int fdm_rpe_hidden(const fdm_rpe_hidden_args* a, void* stream);
  * A8  temporal attention core with in-kernel RPE and the two-group mask — rpe.py:139-170
  *   qkv: [B*T][HW][3C] (q|k|v, each [heads][F]);  Rq,Rk,Rv: [B][T][T][C] fp32 (R[b,t,s,h,f]);
  *   mask: [B][T] (1/0 group id);  out: [B*T][HW][C] op_dtype
- * A10 spatial attention core — same code path with no RPE / no mask; sequence = pixels of one frame
+ * A10 spatial attention core — no RPE / no mask; sequence = pixels of one frame.  bf16: S = QK^T and O = PV on tcgen05
+ *     (attn_tc.cu: whole score row in TMEM, softmax in fp32 from TMEM); fp32 mode: CUDA-core streaming softmax
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* qkv;
@@ -198,6 +201,7 @@ typedef struct {
   void* out;       /* [N][L][C] */
   int32_t N, L, C, heads;
   int32_t qkv_dtype, out_dtype;
+  int32_t engine; /* 0 = auto (tcgen05 kernel for bf16 when L in {16,32,64,128,256} and head dim % 16 == 0, else CUDA cores); 1 = force CUDA cores */
 } fdm_attn_spatial_args; /* which = 8 */
 int fdm_attn_spatial(const fdm_attn_spatial_args* a, void* stream);
 

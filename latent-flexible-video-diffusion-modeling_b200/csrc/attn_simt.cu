@@ -303,9 +303,17 @@ extern "C" int fdm_attn_temporal(const fdm_attn_temporal_args* a, void* stream) 
   return launch_temporal<__nv_bfloat16, __nv_bfloat16>(p, st);
 }
 
+namespace fdm {
+int attn_spatial_tc_launch(const fdm_attn_spatial_args* a, cudaStream_t st);  // attn_tc.cu
+}
+
 extern "C" int fdm_attn_spatial(const fdm_attn_spatial_args* a, void* stream) {
   FDM_REQUIRE(a && a->qkv && a->out, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->N > 0 && a->L > 0 && a->heads > 0 && a->C % a->heads == 0, FDM_ERR_BAD_ARG);
+  if (a->engine == 0 && a->qkv_dtype == FDM_BF16 && a->out_dtype == FDM_BF16) {
+    int rc = attn_spatial_tc_launch(a, (cudaStream_t)stream);
+    if (rc != FDM_ERR_UNSUPPORTED) return rc;
+  }
   const int F = a->C / a->heads;
   SAParams p{a->qkv, a->out, a->N, a->L, a->C, a->heads, F, 1.0f / sqrtf((float)F)};
   cudaStream_t st = (cudaStream_t)stream;

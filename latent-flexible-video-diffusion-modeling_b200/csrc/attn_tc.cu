@@ -1,0 +1,256 @@
+// Spatial self-attention core on tcgen05 (rpe.py:139-144,163-166 with no RPE / no mask): softmax(scale * Q K^T) V per
+// (frame, head), sequence = the L = H*W pixels of one frame.  In this U-Net attention only runs on 16x16, 8x8 (and the
+// 4x4 middle block of the 32-px model) feature maps, so L is 16, 64 or 256 and a whole score row fits in TMEM:
+// no streaming softmax is needed.
+//
+//   CTA = (128-query tile, head, frame), 128 threads (thread r <-> query row r <-> TMEM lane r).
+//   1. TMA: Q tile, all K and V rows of this (frame, head) from the packed [N][L][3C] bf16 qkv tensor, 64-channel
+//      boxes in the 128B-swizzled K-major layout (head dims 16/32/48 read only their first F/16 k-steps).
+//   2. S = Q K^T       tcgen05.mma  M=128, N=L, K=F       -> TMEM columns [0, L)
+//   3. softmax         each thread reads its row from TMEM twice (max, then exp2/sum), writes P (bf16, unnormalised)
+//                      into shared memory in the swizzled K-major layout (aliasing the dead Q/K tiles)
+//   4. O = P V         tcgen05.mma  M=128, N=F, K=L, V consumed as an MN-major operand straight from its [L][F] rows
+//                      -> TMEM columns [0, F) (aliasing S, which every thread has finished reading)
+//   5. O / rowsum -> bf16 -> out[N][L][C]
+#include "tc_common.cuh"
+#include <mutex>
+
+namespace fdm {
+
+struct SaTcParams {
+  __nv_bfloat16* out;
+  int L, C, F, heads;
+  int rows;     // TMA box rows = min(L, 128)
+  int cf;       // 64-wide channel chunks per head = ceil(F / 64)
+  int tmem_cols;
+  float scale_log2e;
+};
+
+// MN-major, 128-byte swizzle: rows (one per K index) of 128 bytes = 64 MN elements; 8-row groups 1024 bytes apart (SBO)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO: stride between 64-element MN blocks — a single block is used (N <= 64)
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: stride between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tq, const SaTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_load, bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
+  const int L = p.L, F = p.F, C = p.C;
+  const int kv_tile = L * 128;                 // bytes of one 64-channel chunk of K (or V)
+  uint8_t* v_s = smem;                         // [cf][L][128 B]
+  uint8_t* q_s = v_s + p.cf * kv_tile;         // [cf][128][128 B]
+  uint8_t* k_s = q_s + p.cf * 16384;           // [cf][L][128 B]
+  uint8_t* p_s = q_s;                          // [ceil(L/64)][128][128 B], aliases Q and K once S is complete
+
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tq) : "memory");
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (tid == 0) {
+    const int loads_kv = L / p.rows;
+    mbar_expect_tx(&bar_load, (uint32_t)(p.cf * (p.rows * 128 + 2 * kv_tile)));
+    for (int c = 0; c < p.cf; ++c) {
+      const int ch = h * F + c * 64;
+      tma_load_3d(q_s + c * 16384, &tq, &bar_load, ch, q0, n);
+      for (int j = 0; j < loads_kv; ++j) {
+        tma_load_3d(k_s + c * kv_tile + j * p.rows * 128, &tq, &bar_load, C + ch, j * p.rows, n);
+        tma_load_3d(v_s + c * kv_tile + j * p.rows * 128, &tq, &bar_load, 2 * C + ch, j * p.rows, n);
+      }
+    }
+    mbar_wait(&bar_load, 0);
+    tcgen05_fence_after();
+    // ---- S = Q K^T
+    const uint32_t idesc = make_idesc(L);
+    const int ksteps = F / 16;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int c = ks >> 2, kk = ks & 3;
+      const uint64_t ad = make_smem_desc(smem_u32(q_s + c * 16384)) + 2 * kk;
+      const uint64_t bd = make_smem_desc(smem_u32(k_s + c * kv_tile)) + 2 * kk;
+      umma_bf16(tmem, ad, bd, idesc, ks != 0);
+    }
+    umma_commit(&bar_s);
+  }
+  __syncwarp();
+  mbar_wait(&bar_s, 0);
+  tcgen05_fence_after();
+
+  // ---- softmax over this thread's row
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  float mx = -INFINITY;
+  if (L >= 32) {
+    for (int c = 0; c < L; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(trow + c, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+  } else {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(trow, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+  }
+  // every thread of the CTA must be done READING Q/K through the tensor core before P overwrites them: S is complete
+  // (bar_s), so the MMAs have retired; nothing else reads Q/K.
+  const float mneg = -mx * p.scale_log2e;
+  float sum = 0.f;
+  uint8_t* prow = p_s + tid * 128;
+  const int sw = tid & 7;
+  if (L >= 32) {
+    for (int c = 0; c < L; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(trow + c, v);
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        e[j] = exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, mneg));
+        sum += e[j];
+      }
+      uint8_t* chunk = prow + (c >> 6) * 16384;
+      const int piece0 = (c & 63) >> 3;  // 16-byte piece index inside the 128-byte row
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 w = make_uint4(pack_bf16(e[8 * q], e[8 * q + 1]), pack_bf16(e[8 * q + 2], e[8 * q + 3]),
+                             pack_bf16(e[8 * q + 4], e[8 * q + 5]), pack_bf16(e[8 * q + 6], e[8 * q + 7]));
+        *reinterpret_cast<uint4*>(chunk + (((piece0 + q) ^ sw) << 4)) = w;
+      }
+    }
+  } else {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(trow, v);
+    float e[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      e[j] = exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, mneg));
+      sum += e[j];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint4 w = make_uint4(pack_bf16(e[8 * q], e[8 * q + 1]), pack_bf16(e[8 * q + 2], e[8 * q + 3]),
+                           pack_bf16(e[8 * q + 4], e[8 * q + 5]), pack_bf16(e[8 * q + 6], e[8 * q + 7]));
+      *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = w;
+    }
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tcgen05_fence_after();
+    // ---- O = P V   (N chunks of <= 64 head dims; K = L keys in steps of 16)
+    for (int c = 0; c < p.cf; ++c) {
+      const int nf = min(64, F - c * 64);
+      const uint32_t idesc = make_idesc(nf, /*b_mn_major=*/1);
+      for (int ks = 0; ks < L / 16; ++ks) {
+        const uint64_t ad = make_smem_desc(smem_u32(p_s + (ks >> 2) * 16384)) + 2 * (ks & 3);
+        const uint64_t bd = make_smem_desc_mn(smem_u32(v_s + c * kv_tile + ks * 2048));
+        umma_bf16(tmem + c * 64, ad, bd, idesc, ks != 0);
+      }
+    }
+    umma_commit(&bar_o);
+  }
+  __syncwarp();
+  mbar_wait(&bar_o, 0);
+  tcgen05_fence_after();
+  const float inv = 1.f / sum;
+  const int q = q0 + tid;
+  __nv_bfloat16* orow = p.out + ((size_t)n * L + (q < L ? q : 0)) * C + h * F;
+  for (int f = 0; f < F; f += 16) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(trow + f, v);
+    if (q < L) {
+      uint4 w0 = make_uint4(pack_bf16(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv),
+                            pack_bf16(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv),
+                            pack_bf16(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv),
+                            pack_bf16(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv));
+      uint4 w1 = make_uint4(pack_bf16(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv),
+                            pack_bf16(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv),
+                            pack_bf16(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv),
+                            pack_bf16(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv));
+      *reinterpret_cast<uint4*>(orow + f) = w0;
+      *reinterpret_cast<uint4*>(orow + f + 8) = w1;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols));
+  }
+}
+
+static int pow2_at_least(int v, int lo) {
+  int r = lo;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+// returns FDM_ERR_UNSUPPORTED for shapes outside the kernel (the caller then uses the CUDA-core kernel)
+int attn_spatial_tc_launch(const fdm_attn_spatial_args* a, cudaStream_t st) {
+  const int F = a->C / a->heads, L = a->L;
+  FDM_REQUIRE(a->qkv_dtype == FDM_BF16 && a->out_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(F % 16 == 0 && F <= 128 && a->C % 8 == 0, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(L == 16 || L == 32 || L == 64 || L == 128 || L == 256, FDM_ERR_UNSUPPORTED);
+  SaTcParams p;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.L = L; p.C = a->C; p.F = F; p.heads = a->heads;
+  p.rows = L < 128 ? L : 128;
+  p.cf = (F + 63) / 64;
+  p.tmem_cols = pow2_at_least(L > F ? L : F, 32);
+  p.scale_log2e = 1.4426950408889634f / sqrtf((float)F);
+  EncodeTiledFn enc = get_tensormap_encoder();
+  FDM_REQUIRE(enc != nullptr, FDM_ERR_UNSUPPORTED);
+  CUtensorMap tq;
+  cuuint64_t dims[3] = {(cuuint64_t)3 * a->C, (cuuint64_t)L, (cuuint64_t)a->N};
+  cuuint64_t strides[2] = {(cuuint64_t)3 * a->C * 2, (cuuint64_t)L * 3 * a->C * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)p.rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  FDM_REQUIRE(enc(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->qkv), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, FDM_ERR_UNSUPPORTED);
+  const int kv_tile = L * 128;
+  const int pbytes = ((L + 63) / 64) * 16384;
+  const int qk = p.cf * (16384 + kv_tile);
+  const int smem = p.cf * kv_tile + (qk > pbytes ? qk : pbytes) + 1024;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_spatial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  if (attr_err != cudaSuccess) {
+    set_last_error(attr_err);
+    return FDM_ERR_CUDA;
+  }
+  FDM_REQUIRE(smem <= 200 * 1024, FDM_ERR_UNSUPPORTED);
+  dim3 grid((L + 127) / 128, a->heads, a->N);
+  attn_spatial_tc_kernel<<<grid, 128, smem, st>>>(tq, p);
+  return check_launch();
+}
+
+}  // namespace fdm

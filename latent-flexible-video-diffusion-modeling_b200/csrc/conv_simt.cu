@@ -21,7 +21,7 @@ struct ConvParams {
   const float* resid;
   float* y_f32;
   void* y_op;
-  float* stats;
+  double* stats;
   int N, Hin, Win, C0, C1, Cout, Ho, Wo;
   int ksize, stride, upsample, out_nchw;
   int M;  // N*Ho*Wo
@@ -203,9 +203,9 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
       int m = m0 + qq * 16;
       if (m < p.M && n0 + c < p.Cout) {
         int f = m / HWo;
-        float* dst = p.stats + ((size_t)f * p.Cout + n0 + c) * 2;
-        atomicAdd(dst, red[qq][c][0]);
-        atomicAdd(dst + 1, red[qq][c][1]);
+        double* dst = p.stats + ((size_t)f * p.Cout + n0 + c) * 2;
+        atomicAdd(dst, (double)red[qq][c][0]);
+        atomicAdd(dst + 1, (double)red[qq][c][1]);
       }
     }
   }
@@ -217,7 +217,7 @@ static int conv_simt_launch(const fdm_conv_args* a, cudaStream_t st) {
   ConvParams p;
   p.a0 = a->a0; p.w0 = reinterpret_cast<const float*>(a->w0);
   p.a1 = a->a1; p.w1 = reinterpret_cast<const float*>(a->w1);
-  p.bias = a->bias; p.resid = a->resid; p.y_f32 = a->y_f32; p.y_op = a->y_op; p.stats = a->stats;
+  p.bias = a->bias; p.resid = a->resid; p.y_f32 = a->y_f32; p.y_op = a->y_op; p.stats = reinterpret_cast<double*>(a->stats);
   p.N = a->N; p.Hin = a->Hin; p.Win = a->Win; p.C0 = a->C0; p.C1 = a->a1 ? a->C1 : 0; p.Cout = a->Cout;
   int Hv = a->upsample ? a->Hin * 2 : a->Hin, Wv = a->upsample ? a->Win * 2 : a->Win;
   int pad = a->ksize / 2;

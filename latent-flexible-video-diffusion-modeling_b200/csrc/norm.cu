@@ -7,7 +7,7 @@
 namespace fdm {
 
 struct GnParams {
-  const float* xa; const float* xb; const float* sa; const float* sb;
+  const float* xa; const float* xb; const double* sa; const double* sb;
   const float* gamma; const float* beta; const float* film;
   void* out_op; float* out_f32; void* raw_op;
   int N, HW, Ca, Cb, C, T, film_stride, film_off, silu, pix_per_block;
@@ -22,18 +22,18 @@ __global__ void gn_apply_kernel(GnParams p) {
   const int C = p.C, cpg = C / 32;
   if (threadIdx.x < 32) {
     const int g = threadIdx.x;
-    float s = 0.f, ss = 0.f;
+    double s = 0.0, ss = 0.0;
     for (int j = 0; j < cpg; ++j) {
       int c = g * cpg + j;
-      const float* st = c < p.Ca ? p.sa + ((size_t)n * p.Ca + c) * 2 : p.sb + ((size_t)n * p.Cb + (c - p.Ca)) * 2;
+      const double* st = c < p.Ca ? p.sa + ((size_t)n * p.Ca + c) * 2 : p.sb + ((size_t)n * p.Cb + (c - p.Ca)) * 2;
       s += st[0];
       ss += st[1];
     }
-    float cnt = (float)cpg * (float)p.HW;
-    float mean = s / cnt;
-    float var = fmaxf(ss / cnt - mean * mean, 0.f);
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + p.eps);
+    const double cnt = (double)cpg * (double)p.HW;
+    const double mean = s / cnt;
+    const double var = fmax(ss / cnt - mean * mean, 0.0);
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
   }
   __syncthreads();
   const int quads = C / 4;
@@ -92,18 +92,24 @@ __global__ void temporal_gn_kernel(TgnParams p) {
   const int cpg = p.C / 32, c0 = lane * cpg;
   const size_t fstride = (size_t)p.HW * p.C;
   const float* base = p.x + ((size_t)b * p.T * p.HW + px) * p.C + c0;
-  float s = 0.f, ss = 0.f;
+  // two-pass statistics (mean, then squared deviations): a group is only (C/32 x T) elements — as few as 2 — and
+  // E[x^2]-mean^2 cancels catastrophically when the group's spread is small against its mean
+  float s = 0.f;
   for (int t = 0; t < p.T; ++t) {
     const float* r = base + t * fstride;
-    for (int j = 0; j < cpg; ++j) {
-      float v = r[j];
-      s += v;
-      ss += v * v;
-    }
+    for (int j = 0; j < cpg; ++j) s += r[j];
   }
   const float cnt = (float)(cpg * p.T);
   const float mean = s / cnt;
-  const float rstd = rsqrtf(fmaxf(ss / cnt - mean * mean, 0.f) + p.eps);
+  float ss = 0.f;
+  for (int t = 0; t < p.T; ++t) {
+    const float* r = base + t * fstride;
+    for (int j = 0; j < cpg; ++j) {
+      float d = r[j] - mean;
+      ss = fmaf(d, d, ss);
+    }
+  }
+  const float rstd = rsqrtf(ss / cnt + p.eps);
   for (int t = 0; t < p.T; ++t) {
     const float* r = base + t * fstride;
     size_t o = ((size_t)(b * p.T + t) * p.HW + px) * p.C + c0;
@@ -122,7 +128,7 @@ extern "C" int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream) {
   FDM_REQUIRE(a && a->xa && a->stats_a && a->gamma && a->beta, FDM_ERR_BAD_ARG);
   FDM_REQUIRE((a->xb == nullptr) == (a->stats_b == nullptr), FDM_ERR_BAD_ARG);
   GnParams p;
-  p.xa = a->xa; p.xb = a->xb; p.sa = a->stats_a; p.sb = a->stats_b; p.gamma = a->gamma; p.beta = a->beta;
+  p.xa = a->xa; p.xb = a->xb; p.sa = reinterpret_cast<const double*>(a->stats_a); p.sb = reinterpret_cast<const double*>(a->stats_b); p.gamma = a->gamma; p.beta = a->beta;
   p.film = a->film; p.out_op = a->out_op; p.out_f32 = a->out_f32; p.raw_op = a->raw_op;
   p.N = a->N; p.HW = a->HW; p.Ca = a->Ca; p.Cb = a->xb ? a->Cb : 0; p.C = p.Ca + p.Cb; p.T = a->T > 0 ? a->T : 1;
   p.film_stride = a->film_stride; p.film_off = a->film_off; p.silu = a->silu; p.eps = a->eps;

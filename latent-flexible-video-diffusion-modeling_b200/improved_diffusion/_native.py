@@ -46,7 +46,7 @@ AttnTemporalArgs = _S("AttnTemporalArgs", [("qkv", vp), ("Rq", vp), ("Rk", vp), 
                                            ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("heads", i32),
                                            ("qkv_dtype", i32), ("out_dtype", i32)])
 AttnSpatialArgs = _S("AttnSpatialArgs", [("qkv", vp), ("out", vp), ("N", i32), ("L", i32), ("C", i32), ("heads", i32),
-                                         ("qkv_dtype", i32), ("out_dtype", i32)])
+                                         ("qkv_dtype", i32), ("out_dtype", i32), ("engine", i32)])
 CastArgs = _S("CastArgs", [("x", vp), ("out", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32),
                            ("upsample", i32), ("op_dtype", i32)])
 DdpmStepArgs = _S("DdpmStepArgs", [("x", vp), ("eps", vp), ("noise", vp), ("coef", vp), ("t", vp), ("sample", vp),

@@ -42,17 +42,20 @@ class Plan:
         self.calls = None    # [(fn, byref(struct))] after finalize()
         self.stats_bytes = 0
         self.graphs = {}     # CUDA graphs captured over this plan (see gaussian_diffusion._graph_sampler)
+        self.debug = os.environ.get("FDM_DEBUG_TAPS", "0") == "1"
+        self.taps = {}       # module name -> (Buf, C, H, W) of that layer's fp32 NHWC output (readable when debug)
         self.flops = 0       # algorithmic 2*MAC of every conv / linear / attention matmul of one forward
         self.conv_flops = 0
 
     # ---- buffers
     def buf(self, name, nbytes, persistent=False):
-        b = Buf(name, nbytes, persistent)
+        # FDM_DEBUG_TAPS=1: no buffer reuse, so every intermediate can be read back after a run (tests/debugging)
+        b = Buf(name, nbytes, persistent or self.debug)
         self.bufs.append(b)
         return b
 
     def stats(self, name, n, c):
-        b = Buf(name, n * c * 2 * 4, True, "stats")
+        b = Buf(name, n * c * 2 * 8, True, "stats")
         b.offset = self.stats_bytes
         self.stats_bytes += b.nbytes
         return b
@@ -136,6 +139,11 @@ class Plan:
         else:
             st.t, st.t_index, st.t_table = None, self.ptr(self.t_index), table.data_ptr()
             self.keep.append(table)
+
+    def tap(self, name):
+        """fp32 NCHW copy of a layer output (only meaningful with FDM_DEBUG_TAPS=1, after run())."""
+        b, Cc, Hh, Ww = self.taps[name]
+        return self.view(b, (self.B * self.T, Hh, Ww, Cc), th.float32).permute(0, 3, 1, 2).contiguous()
 
     def view(self, b, shape, dtype):
         n = 1
@@ -232,17 +240,17 @@ class DenoiserEngine:
 
     def tc_ok(self, C0, C1, Cout, k, stride, upsample, Ho, Wo):
         """Shapes the tcgen05 implicit-GEMM kernel takes (conv_tc.cu); everything else runs on the CUDA-core engine."""
-        if not self.use_tc:
+        if not self.use_tc or upsample:
             return False
-        if stride != 1 or upsample:
+        if C0 % 8 or (C1 and C1 % 8) or Cout % 4 or Cout < 16:
             return False
-        if C0 % 32 or (C1 and C1 % 32) or Cout % 16 or Cout < 16:
-            return False
-        # the 128-pixel M tile must be a whole number of image rows or a whole number of frames
+        # the 128-pixel M tile must be a box in (w, h, frame): whole rows of one frame, or whole frames
         hw = Ho * Wo
-        if Wo > 128 or (128 % Wo) or (hw > 128 and hw % 128) or (hw < 128 and 128 % hw):
-            return False
-        return True
+        if Wo >= 128:
+            return Wo % 128 == 0
+        if hw >= 128:
+            return 128 % Wo == 0 and hw % 128 == 0
+        return 128 % hw == 0 and (hw % 32 == 0 or 32 % hw == 0)
 
     def _compile(self, B, T, H, W, device):
         m = self.model
@@ -448,7 +456,7 @@ class DenoiserEngine:
             o2 = P.buf("sa_o", Nf * hw * Cc * osz)
             P.flops += 4 * hw * hw * Cc * Nf
             P.op("fdm_attn_spatial", N_.AttnSpatialArgs, qkv=qkv2, out=o2, N=Nf, L=hw, C=Cc, heads=sa.num_heads,
-                 qkv_dtype=opd, out_dtype=opd)
+                 qkv_dtype=opd, out_dtype=opd, engine=0 if self.use_tc else 1)
             z = new_act("sa_z", Cc, Hh, Ww)
             conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf, stats=z.st)
             return z
@@ -457,10 +465,21 @@ class DenoiserEngine:
             cv = layer.op if down else layer.conv
             Ho, Wo = (x.H // 2, x.W // 2) if down else (x.H * 2, x.W * 2)
             out = new_act("down" if down else "up", x.C, Ho, Wo)
-            # the CUDA-core engine gathers straight from the fp32 stream (stride 2 / folded nearest upsample)
-            conv(x.buf, x.C, x.H, x.W, cv.weight, x.C, 3, stride=2 if down else 1, upsample=0 if down else 1,
-                 bias=f32(cv.bias), y_f32=out.buf, stats=out.st, a_dtype=N_.F32)
+            Hc, Wc = (x.H, x.W) if down else (Ho, Wo)  # spatial size of the conv's input
+            if self.use_tc and self.tc_ok(x.C, 0, x.C, 3, 2 if down else 1, 0, Ho, Wo):
+                # bf16 operand copy of the fp32 stream (nearest x2 upsample folded into the cast, unet.py:85), then tcgen05
+                a = P.buf("resample_a", Nf * Hc * Wc * x.C * osz)
+                P.op("fdm_cast", N_.CastArgs, x=x.buf, out=a, N=Nf, H=x.H, W=x.W, C=x.C, upsample=0 if down else 1,
+                     op_dtype=opd)
+                conv(a, x.C, Hc, Wc, cv.weight, x.C, 3, stride=2 if down else 1, bias=f32(cv.bias), y_f32=out.buf,
+                     stats=out.st)
+            else:
+                # the CUDA-core engine gathers straight from the fp32 stream (stride 2 / folded nearest upsample)
+                conv(x.buf, x.C, x.H, x.W, cv.weight, x.C, 3, stride=2 if down else 1, upsample=0 if down else 1,
+                     bias=f32(cv.bias), y_f32=out.buf, stats=out.st, a_dtype=N_.F32)
             return out
+
+        names = {id(mod): name for name, mod in m.named_modules()}
 
         def run_stage(stage, h, skip=None):
             for layer in stage:
@@ -480,6 +499,7 @@ class DenoiserEngine:
                     h = resample(layer, h, False)
                 else:
                     raise NotImplementedError(type(layer))
+                P.taps[names[id(layer)]] = (h.buf, h.C, h.H, h.W)
             return h
 
         h, hs = None, []

@@ -39,7 +39,7 @@ def run_conv(x_nhwc, w, bias, *, stride=1, engine, x1=None, w1=None, resid=None,
     dev = x_nhwc.device
     y = torch.empty(N, Ho, Wo, Co, device=dev)
     yop = torch.empty(N, Ho, Wo, Co, device=dev, dtype=torch.bfloat16) if want_op else None
-    stats = torch.zeros(N, Co, 2, device=dev) if want_stats else None
+    stats = torch.zeros(N, Co, 2, device=dev, dtype=torch.float64) if want_stats else None
     pk = pack_tc if engine == N_.CONV_TC else pack_simt
     w0p = pk(w)
     w1p = pk(w1) if w1 is not None else None
@@ -122,3 +122,22 @@ def test_conv_simt_fp32_exact():
         assert rel(y, ref) <= 1e-5
         ref_stats = torch.stack([ref.sum(dim=(1, 2)), (ref * ref).sum(dim=(1, 2))], dim=-1)
         assert rel(stats, ref_stats) <= 1e-4
+
+
+@pytest.mark.parametrize("N,L,C,heads", [(5, 256, 128, 4), (3, 64, 128, 4), (7, 16, 128, 4), (2, 256, 64, 4), (2, 256, 192, 4),
+                                         (2, 256, 256, 4), (1, 64, 512, 4), (2, 256, 384, 4), (3, 64, 96, 4)])
+@pytest.mark.parametrize("engine", [0, 1])
+def test_attn_spatial_vs_torch(N, L, C, heads, engine):
+    """fdm_attn_spatial (engine 0: tcgen05 where the shape allows, 1: CUDA cores) vs softmax(q k^T / sqrt(F)) v in torch fp32."""
+    from improved_diffusion import _native as N_
+    g = torch.Generator(device="cuda").manual_seed(L + C)
+    qkv = torch.randn(N, L, 3 * C, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.empty(N, L, C, device="cuda", dtype=torch.bfloat16)
+    a = N_.AttnSpatialArgs(qkv=qkv.data_ptr(), out=out.data_ptr(), N=N, L=L, C=C, heads=heads, qkv_dtype=N_.BF16,
+                           out_dtype=N_.BF16, engine=engine)
+    N_.call("fdm_attn_spatial", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    F_ = C // heads
+    q, k, v = qkv.float().view(N, L, 3, heads, F_).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * F_ ** -0.5, dim=-1) @ v).permute(0, 2, 1, 3).reshape(N, L, C)
+    assert rel(out.float(), ref) <= 8e-3, rel(out.float(), ref)  # bf16 output rounding 2^-9 rms + bf16 P
