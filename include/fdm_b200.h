@@ -59,8 +59,9 @@ typedef struct {
   const float* x;
   const float* x0;
   const float* obs_mask; /* [N] */
-  float* xin;
-  int32_t N, C, H, W;
+  float* xin;      /* fp32 [N][H][W][C+1], or NULL */
+  void* xin_bf16;  /* bf16 [N][H][W][Cpad] (channels C+1..Cpad-1 zero: K padding for the tcgen05 stem conv), or NULL */
+  int32_t N, C, H, W, Cpad;
 } fdm_input_prep_args; /* which = 0 */
 int fdm_input_prep(const fdm_input_prep_args* a, void* stream);
 

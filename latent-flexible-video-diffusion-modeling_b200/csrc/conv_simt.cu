@@ -31,7 +31,6 @@ template <typename AT, typename OT>
 __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
-  __shared__ float red[4][BN][2];
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
@@ -188,24 +187,31 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
     }
   }
   if (p.stats != nullptr) {
-    // HW is a multiple of 16 for every feature map of the U-Net, so the 16-row sub-tile q = ty/4 lies in one frame
-    const int q = ty >> 2;
-    for (int i = tid; i < 4 * BN * 2; i += NT) (&red[0][0][0])[i] = 0.f;
-    __syncthreads();
+    // HW is a multiple of 16 for every feature map of the U-Net, so the 16-row sub-tile q = ty/4 lies in one frame.
+    // Fixed-order reduction (no shared-memory atomics): the statistics must not depend on scheduling.
+    __syncthreads();  // As/Bs are dead: reuse As as the [16 ty][64 cols] partial buffers
+    float* part1 = &As[0][0];            // 16*64 floats <= BK*(BM+4)
+    float* part2 = &Bs[0][0];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&red[q][tx * 4 + j][0], s1[j]);
-      atomicAdd(&red[q][tx * 4 + j][1], s2[j]);
+      part1[ty * BN + tx * 4 + j] = s1[j];
+      part2[ty * BN + tx * 4 + j] = s2[j];
     }
     __syncthreads();
     for (int i = tid; i < 4 * BN; i += NT) {
       int qq = i / BN, c = i - qq * BN;
       int m = m0 + qq * 16;
       if (m < p.M && n0 + c < p.Cout) {
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a1 += part1[(qq * 4 + k) * BN + c];
+          a2 += part2[(qq * 4 + k) * BN + c];
+        }
         int f = m / HWo;
         double* dst = p.stats + ((size_t)f * p.Cout + n0 + c) * 2;
-        atomicAdd(dst, (double)red[qq][c][0]);
-        atomicAdd(dst + 1, (double)red[qq][c][1]);
+        atomicAdd(dst, (double)a1);
+        atomicAdd(dst + 1, (double)a2);
       }
     }
   }

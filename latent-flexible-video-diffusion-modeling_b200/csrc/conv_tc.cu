@@ -35,6 +35,8 @@ struct TcParams {
   int wbox, hbox, nbox;  // output-pixel geometry of an M tile
   int taps, ksize, pad, stride;
   int kchunks0, kchunks1;
+  int klast0, klast1;  // 16-wide k-steps actually issued in the last 64-channel chunk of each K segment
+  int out_nchw;
 };
 
 template <int BN>
@@ -42,6 +44,7 @@ struct TcSmem {
   static constexpr int B_TILE_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = BN >= 128 ? 3 : 4;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int ROW = BN + 4;  // staging row stride (floats): 16-byte aligned, conflict-free float4 access
   static constexpr int STAGING_BYTES = TC_BM * ROW * 4;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(S::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tcgen05_fence_before();
@@ -136,8 +139,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
         const uint64_t adesc = make_smem_desc(a_addr);
         const uint64_t bdesc = make_smem_desc(a_addr + A_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
+        // channels beyond C0/C1 in the last chunk are TMA zero-fill: skip their k-steps
+        int nk = TC_BK / 16;
+        if (it < iters0) {
+          if ((it % p.kchunks0) == p.kchunks0 - 1) nk = p.klast0;
+        } else if (it == iters - 1) {
+          nk = p.klast1;
+        }
+        for (int k = 0; k < nk; ++k) {
           // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) start-address field
           umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
         }
@@ -152,16 +161,36 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     tcgen05_fence_after();
     float* stg = reinterpret_cast<float*>(smem);  // aliases the operand ring: every MMA (hence every smem read) has retired
     float* my_row = stg + (size_t)(g * 32 + lane) * S::ROW;
+    if constexpr (BN == 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(g * 32) << 16), v);
 #pragma unroll
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + c, v);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(my_row + c + j) =
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(my_row + j) =
             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + c, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(my_row + c + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
     }
     __syncwarp();
+    if (p.out_nchw) {
+      // narrow head conv (unet.py:402,462-464): eps written as [N][Cout][Ho][Wo] fp32; lane <-> pixel row, few channels
+      const int row = g * 32 + lane, m = m0 + row;
+      if (m < p.M) {
+        const int f = m / p.HWo, r = m - f * p.HWo;
+        for (int c = 0; c < BN && n_off + c < p.Cout; ++c) {
+          float v = stg[(size_t)row * S::ROW + c] + (p.bias ? p.bias[n_off + c] : 0.f);
+          p.y_f32[((size_t)f * p.Cout + n_off + c) * p.HWo + r] = v;
+        }
+      }
+    } else {
     // phase 2: this warp's 32 rows, lanes across channels (float4 each): coalesced global traffic
     constexpr int LPR = BN / 4;         // lanes per row
     constexpr int RPI = 32 / LPR > 0 ? 32 / LPR : 1;  // rows per iteration (BN <= 128)
@@ -211,12 +240,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
       }
     }
+    }  // !out_nchw
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS));
   }
 }
 
@@ -279,8 +309,13 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   FDM_REQUIRE(a->a_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
-  FDM_REQUIRE(!a->upsample && !a->out_nchw, FDM_ERR_UNSUPPORTED);
-  FDM_REQUIRE(a->C0 % 8 == 0 && (a->a1 == nullptr || a->C1 % 8 == 0) && a->Cout % 4 == 0, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(!a->upsample, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(a->C0 % 8 == 0 && (a->a1 == nullptr || a->C1 % 8 == 0), FDM_ERR_UNSUPPORTED);
+  if (a->out_nchw) {
+    FDM_REQUIRE(a->y_f32 != nullptr && a->y_op == nullptr && a->resid == nullptr && a->stats == nullptr, FDM_ERR_UNSUPPORTED);
+  } else {
+    FDM_REQUIRE(a->Cout % 4 == 0, FDM_ERR_UNSUPPORTED);
+  }
   FDM_REQUIRE(a->y_op == nullptr || a->op_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
   const int pad = a->ksize / 2;
   const int Ho = (a->Hin + 2 * pad - a->ksize) / a->stride + 1, Wo = (a->Win + 2 * pad - a->ksize) / a->stride + 1;
@@ -304,7 +339,10 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.taps = a->ksize * a->ksize; p.ksize = a->ksize; p.pad = pad; p.stride = a->stride;
   p.kchunks0 = (a->C0 + TC_BK - 1) / TC_BK;
   p.kchunks1 = a->a1 ? (a->C1 + TC_BK - 1) / TC_BK : 0;
-  const int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : 32);
+  p.klast0 = (a->C0 - (p.kchunks0 - 1) * TC_BK + 15) / 16;
+  p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * TC_BK + 15) / 16 : 0;
+  p.out_nchw = a->out_nchw;
+  const int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : (a->Cout > 16 ? 32 : 16));
   const int co_pad = round_up(a->Cout, 16);
   CUtensorMap ta0, tw0, ta1, tw1;
   bool ok = encode_act(&ta0, a->a0, a->N, a->Hin, a->Win, a->C0, p.wbox, p.hbox, p.nbox, a->stride) &&
@@ -319,7 +357,8 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   FDM_REQUIRE(ok, FDM_ERR_UNSUPPORTED);
   if (bn == 128) return launch_tc<128>(ta0, tw0, ta1, tw1, p, st);
   if (bn == 64) return launch_tc<64>(ta0, tw0, ta1, tw1, p, st);
-  return launch_tc<32>(ta0, tw0, ta1, tw1, p, st);
+  if (bn == 32) return launch_tc<32>(ta0, tw0, ta1, tw1, p, st);
+  return launch_tc<16>(ta0, tw0, ta1, tw1, p, st);
 }
 
 }  // namespace fdm

@@ -6,7 +6,8 @@ namespace fdm {
 
 // ---------------- A1 input prep (unet.py:439-449): NCHW frames -> NHWC (+indicator channel) ----------
 __global__ void input_prep_kernel(const float* __restrict__ x, const float* __restrict__ x0,
-                                  const float* __restrict__ obs, float* __restrict__ xin, int N, int C, int HW) {
+                                  const float* __restrict__ obs, float* __restrict__ xin,
+                                  __nv_bfloat16* __restrict__ xin_bf16, int N, int C, int HW, int Cpad) {
   // one thread per (n, pixel); reads are coalesced across pixels per channel plane
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * HW) return;
@@ -14,9 +15,18 @@ __global__ void input_prep_kernel(const float* __restrict__ x, const float* __re
   float m = obs[n];
   const float* xs = x + (size_t)n * C * HW + px;
   const float* x0s = x0 + (size_t)n * C * HW + px;
-  float* o = xin + (size_t)i * (C + 1);
-  for (int c = 0; c < C; ++c) o[c] = xs[(size_t)c * HW] * (1.f - m) + x0s[(size_t)c * HW] * m;
-  o[C] = m;
+  if (xin != nullptr) {
+    float* o = xin + (size_t)i * (C + 1);
+    for (int c = 0; c < C; ++c) o[c] = xs[(size_t)c * HW] * (1.f - m) + x0s[(size_t)c * HW] * m;
+    o[C] = m;
+  }
+  if (xin_bf16 != nullptr) {
+    __nv_bfloat16* o = xin_bf16 + (size_t)i * Cpad;
+    for (int c = 0; c < Cpad; ++c) {
+      float v = c < C ? xs[(size_t)c * HW] * (1.f - m) + x0s[(size_t)c * HW] * m : (c == C ? m : 0.f);
+      o[c] = __float2bfloat16_rn(v);
+    }
+  }
 }
 
 // ---------------- A6 nearest x2 upsample + cast (unet.py:85) ------------------------------------------
@@ -198,10 +208,11 @@ static inline int grid_for(long long total, int threads) {
 using namespace fdm;
 
 extern "C" int fdm_input_prep(const fdm_input_prep_args* a, void* stream) {
-  FDM_REQUIRE(a && a->x && a->x0 && a->obs_mask && a->xin, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a && a->x && a->x0 && a->obs_mask && (a->xin || a->xin_bf16), FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->N > 0 && a->C > 0 && a->H > 0 && a->W > 0, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->xin_bf16 == nullptr || a->Cpad > a->C, FDM_ERR_BAD_ARG);
   long long total = (long long)a->N * a->H * a->W;
-  input_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->x, a->x0, a->obs_mask, a->xin, a->N, a->C, a->H * a->W);
+  input_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->x, a->x0, a->obs_mask, a->xin, (__nv_bfloat16*)a->xin_bf16, a->N, a->C, a->H * a->W, a->Cpad);
   return check_launch();
 }
 

@@ -21,8 +21,8 @@ def _S(name, fields):
     return type(name, (C.Structure,), {"_fields_": fields})
 
 
-InputPrepArgs = _S("InputPrepArgs", [("x", vp), ("x0", vp), ("obs_mask", vp), ("xin", vp),
-                                     ("N", i32), ("C", i32), ("H", i32), ("W", i32)])
+InputPrepArgs = _S("InputPrepArgs", [("x", vp), ("x0", vp), ("obs_mask", vp), ("xin", vp), ("xin_bf16", vp),
+                                     ("N", i32), ("C", i32), ("H", i32), ("W", i32), ("Cpad", i32)])
 ConvArgs = _S("ConvArgs", [("a0", vp), ("w0", vp), ("a1", vp), ("w1", vp), ("bias", vp), ("resid", vp),
                            ("y_f32", vp), ("y_op", vp), ("stats", vp),
                            ("N", i32), ("Hin", i32), ("Win", i32), ("C0", i32), ("C1", i32), ("Cout", i32),

@@ -242,7 +242,7 @@ class DenoiserEngine:
         """Shapes the tcgen05 implicit-GEMM kernel takes (conv_tc.cu); everything else runs on the CUDA-core engine."""
         if not self.use_tc or upsample:
             return False
-        if C0 % 8 or (C1 and C1 % 8) or Cout % 4 or Cout < 16:
+        if C0 % 8 or (C1 and C1 % 8):
             return False
         # the 128-pixel M tile must be a box in (w, h, frame): whole rows of one frame, or whole frames
         hw = Ho * Wo
@@ -371,12 +371,12 @@ class DenoiserEngine:
 
         # ---------------- conv helper
         def conv(a0, C0, Hin, Win, w0, Cout, k, stride=1, upsample=0, a1=None, C1=0, w1=None, bias=None, resid=None,
-                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None):
+                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None, flop_c0=None):
             a_dtype = opd if a_dtype is None else a_dtype
             Hv, Wv = (Hin * 2, Win * 2) if upsample else (Hin, Win)
             Ho, Wo = (Hv + 2 * (k // 2) - k) // stride + 1, (Wv + 2 * (k // 2) - k) // stride + 1
-            tc = a_dtype == N_.BF16 and self.tc_ok(C0, C1, Cout, k, stride, upsample, Ho, Wo)
-            fl = 2 * Nf * Ho * Wo * Cout * (k * k * C0 + C1)
+            tc = a_dtype == N_.BF16 and self.tc_ok(C0, C1, Cout, k, stride, upsample, Ho, Wo) and (out_nchw or Cout % 4 == 0)
+            fl = 2 * Nf * Ho * Wo * Cout * (k * k * (flop_c0 or C0) + C1)  # algorithmic: padded channels do not count
             P.flops += fl
             P.conv_flops += fl
             pack = self._pack_tc if tc else self._pack_simt
@@ -387,8 +387,16 @@ class DenoiserEngine:
             return Ho, Wo
 
         # ---------------- network body
-        xin = P.buf("xin", Nf * H * W * Cin * 4)
-        P.op("fdm_input_prep", N_.InputPrepArgs, x=P.x, x0=P.x0, obs_mask=P.obs, xin=xin, N=Nf, C=Cin - 1, H=H, W=W)
+        # bf16 mode: the stem conv runs on tcgen05 over a bf16 copy of the network input, channels zero-padded to 8
+        stem_tc = self.use_tc and self.tc_ok(8, 0, m.model_channels, 3, 1, 0, H, W) and Cin <= 8
+        if stem_tc:
+            xin = P.buf("xin", Nf * H * W * 8 * 2)
+            P.op("fdm_input_prep", N_.InputPrepArgs, x=P.x, x0=P.x0, obs_mask=P.obs, xin=None, xin_bf16=xin, N=Nf, C=Cin - 1,
+                 H=H, W=W, Cpad=8)
+        else:
+            xin = P.buf("xin", Nf * H * W * Cin * 4)
+            P.op("fdm_input_prep", N_.InputPrepArgs, x=P.x, x0=P.x0, obs_mask=P.obs, xin=xin, xin_bf16=None, N=Nf, C=Cin - 1,
+                 H=H, W=W, Cpad=0)
 
         class Act:  # residual-stream tensor: fp32 NHWC + its GroupNorm statistics
             def __init__(s, buf, st, Cc, Hh, Ww):
@@ -485,8 +493,12 @@ class DenoiserEngine:
             for layer in stage:
                 if isinstance(layer, nn.Conv2d):  # stem
                     out = new_act("stem", layer.out_channels, H, W)
-                    conv(xin, Cin, H, W, layer.weight, layer.out_channels, 3, bias=f32(layer.bias), y_f32=out.buf,
-                         stats=out.st, a_dtype=N_.F32)
+                    if stem_tc:
+                        conv(xin, 8, H, W, layer.weight, layer.out_channels, 3, bias=f32(layer.bias), y_f32=out.buf,
+                             stats=out.st, a_dtype=N_.BF16, flop_c0=Cin)
+                    else:
+                        conv(xin, Cin, H, W, layer.weight, layer.out_channels, 3, bias=f32(layer.bias), y_f32=out.buf,
+                             stats=out.st, a_dtype=N_.F32)
                     h = out
                 elif isinstance(layer, ResBlock):
                     h = res_block(layer, h, skip)

@@ -141,3 +141,28 @@ def test_attn_spatial_vs_torch(N, L, C, heads, engine):
     q, k, v = qkv.float().view(N, L, 3, heads, F_).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax(q @ k.transpose(-1, -2) * F_ ** -0.5, dim=-1) @ v).permute(0, 2, 1, 3).reshape(N, L, C)
     assert rel(out.float(), ref) <= 8e-3, rel(out.float(), ref)  # bf16 output rounding 2^-9 rms + bf16 P
+
+
+@pytest.mark.parametrize("N,H,W,C0,Co", [(3, 32, 32, 64, 4), (2, 16, 16, 128, 3), (2, 32, 32, 8, 64)])
+def test_conv_tc_head_and_stem(N, H, W, C0, Co):
+    """Head conv (Cout 3/4, NCHW fp32 output, unet.py:402) and stem conv (5 input channels zero-padded to 8, unet.py:313)."""
+    from improved_diffusion import _native as N_
+    g = torch.Generator(device="cuda").manual_seed(C0 + Co)
+    x = torch.randn(N, H, W, C0, device="cuda", generator=g)
+    if C0 == 8:
+        x[..., 5:] = 0
+    x = x.to(torch.bfloat16)
+    w = torch.randn(Co, C0, 3, 3, device="cuda", generator=g) / (C0 * 9) ** 0.5
+    bias = 0.1 * torch.randn(Co, device="cuda", generator=g)
+    nchw = Co < 16
+    y = torch.empty((N, Co, H, W) if nchw else (N, H, W, Co), device="cuda")
+    wp = pack_tc(w)
+    a = N_.ConvArgs(a0=x.data_ptr(), w0=wp.data_ptr(), a1=None, w1=None, bias=bias.data_ptr(), resid=None, y_f32=y.data_ptr(),
+                    y_op=None, stats=None, N=N, Hin=H, Win=W, C0=C0, C1=0, Cout=Co, ksize=3, stride=1, upsample=0,
+                    a_dtype=N_.BF16, op_dtype=N_.BF16, out_nchw=int(nchw), engine=N_.CONV_TC)
+    N_.call("fdm_conv", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1)
+    if not nchw:
+        ref = ref.permute(0, 2, 3, 1)
+    assert rel(y, ref) <= 1e-3, rel(y, ref)
