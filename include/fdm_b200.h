@@ -77,7 +77,9 @@ int fdm_input_prep(const fdm_input_prep_args* a, void* stream);
  *   Outputs (any subset): y_f32 [.,Cout] fp32; y_op [.,Cout] in op_dtype; stats (sum,sumsq per frame,
  *   channel); out_nchw: y_f32 is written as [N][Cout][Ho][Wo] (the head conv producing eps).
  * ---------------------------------------------------------------------------------------------- */
-enum { FDM_CONV_SIMT = 0, FDM_CONV_TC = 1 };
+/* FDM_CONV_TC: tcgen05; picks the row-halo persistent kernel (conv_halo.cu) for 3x3 stride-1 convs on 16/32/64-wide maps,
+ * else the per-tap kernel (conv_tc.cu).  FDM_CONV_TC_TAP forces the per-tap kernel (tests / A-B timing). */
+enum { FDM_CONV_SIMT = 0, FDM_CONV_TC = 1, FDM_CONV_TC_TAP = 2 };
 typedef struct {
   const void* a0;   /* segment-0 input  [N][Hin][Win][C0], a_dtype */
   const void* w0;   /* segment-0 weights */

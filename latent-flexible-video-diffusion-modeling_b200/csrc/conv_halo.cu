@@ -1,0 +1,355 @@
+// 3x3 stride-1 convolution as implicit GEMM on tcgen05 — the "halo" kernel for the feature maps that carry the FLOPs
+// (W in {16,32,64}: whole image rows per M tile).  Same math / epilogue contract as conv_tc.cu, different data movement.
+//
+// Why: conv_tc.cu re-loads the A operand once per filter tap (9 x 16 KB per 128-pixel tile) and its B tile once per
+// CTA; measured with in-kernel timestamps the main loop runs at the SM's L2->shared-memory ingest rate (~64 B/clk),
+// 4-5x slower than the MMAs need.  Here one persistent CTA per SM computes TWO vertically adjacent 128-pixel M tiles:
+//   * per (64-channel chunk, filter column s) ONE TMA box of (2*hbox + 2) full image rows is loaded, shifted by s-1
+//     in w (hardware zero-fill = padding).  Because the rows are full width, the three filter rows r = 0,1,2 of both
+//     M tiles are just 1024-byte-aligned offsets into that box ((j*hbox + r) * W pixels), addressed by the UMMA
+//     shared-memory descriptor: 6 A operands from one load (A traffic / 2.4-3.6).
+//   * the three weight tiles (r = 0,1,2 for this s) are shared by both M tiles (B traffic / 2).
+//   * accumulators: 2 tiles x BN columns, double-buffered in TMEM (up to 512 columns), so the epilogue of work item i
+//     overlaps the main loop of item i+1 inside the same CTA (warp-specialised: TMA / MMA / 4 epilogue warps).
+//   * GroupNorm statistics: per-warp column sums are combined across the 4 epilogue warps and both tiles in shared
+//     memory before the fp64 atomics (8x fewer atomics than one per warp).
+#include "tc_common.cuh"
+#include <mutex>
+
+namespace fdm {
+
+constexpr int HALO_THREADS = 192;
+constexpr int HALO_MAX_STAGES = 4;
+constexpr int HALO_STG_ROW = 36;  // floats per staged row (32 columns + 4 pad): conflict-free float4 access
+
+struct HaloParams {
+  const float* bias;
+  const float* resid;
+  float* y_f32;
+  __nv_bfloat16* y_op;
+  double* stats;
+  int Cout, W, HW, hbox;
+  int pairs_per_frame, n_items, ntiles;
+  int kchunks0, kchunks1, klast0, klast1;
+  int stages, a_bytes, stage_bytes;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap ta0,
+                                                                   const __grid_constant__ CUtensorMap tw0,
+                                                                   const __grid_constant__ CUtensorMap ta1,
+                                                                   const __grid_constant__ CUtensorMap tw1,
+                                                                   const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[HALO_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[HALO_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  constexpr int TMEM_COLS = 4 * BN;  // 2 accumulator buffers x 2 M tiles
+  constexpr int B_TAP_BYTES = BN * 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);  // [4 warps][32][HALO_STG_ROW]
+  float* statbuf = staging + 4 * 32 * HALO_STG_ROW;                                    // [2 tiles][4 warps][BN][2]
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&ta0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tw0) : "memory");
+    if (p.kchunks1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&ta1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tw1) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
+        const int n = pair / p.pairs_per_frame, h0 = (pair - n * p.pairs_per_frame) * 2 * p.hbox;
+        for (int kc = 0; kc < p.kchunks0; ++kc) {
+          for (int s = 0; s < 3; ++s, ++it) {
+            const int stage = it % p.stages;
+            mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
+            uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
+            uint8_t* b_dst = a_dst + p.a_bytes;
+            mbar_expect_tx(&full_bar[stage], p.a_bytes + 3 * B_TAP_BYTES);
+            tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - 1, h0 - 1, n);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) tma_load_3d(b_dst + r * B_TAP_BYTES, &tw0, &full_bar[stage], kc * 64, n_off, r * 3 + s);
+          }
+        }
+        for (int kc = 0; kc < p.kchunks1; ++kc, ++it) {
+          const int stage = it % p.stages;
+          mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
+          uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
+          mbar_expect_tx(&full_bar[stage], 256 * 128 + B_TAP_BYTES);
+          tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * 64, 0, h0, n);
+          tma_load_3d(a_dst + p.a_bytes, &tw1, &full_bar[stage], kc * 64, n_off, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      const uint32_t row_bytes = (uint32_t)p.W * 128;  // one image row of the A box
+      uint32_t it = 0, local = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+        const uint32_t buf = local & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t acc0 = tmem_base + buf * 2 * BN;
+        for (int kc = 0; kc < p.kchunks0; ++kc) {
+          const int nk = (kc == p.kchunks0 - 1) ? p.klast0 : 4;
+          for (int s = 0; s < 3; ++s, ++it) {
+            const int stage = it % p.stages;
+            mbar_wait(&full_bar[stage], (it / p.stages) & 1);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+            const uint32_t b_addr = a_addr + p.a_bytes;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const uint64_t bdesc = make_smem_desc(b_addr + r * B_TAP_BYTES);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(j * p.hbox + r) * row_bytes);
+                for (int k = 0; k < nk; ++k)
+                  umma_bf16(acc0 + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | s | r | k) != 0);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+          }
+        }
+        for (int kc = 0; kc < p.kchunks1; ++kc, ++it) {
+          const int nk = (kc == p.kchunks1 - 1) ? p.klast1 : 4;
+          const int stage = it % p.stages;
+          mbar_wait(&full_bar[stage], (it / p.stages) & 1);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(j * p.hbox) * row_bytes);
+            for (int k = 0; k < nk; ++k) umma_bf16(acc0 + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int g = warp & 3;            // TMEM lane group [32g, 32g+32)
+    float* stg = staging + g * 32 * HALO_STG_ROW;
+    const int sub = lane >> 3, cq = (lane & 7) * 4;
+    const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
+    uint32_t local = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
+      const uint32_t buf = local & 1;
+      const size_t m_pair = (size_t)pair * 256;
+      mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + buf * 2 * BN + j * BN + c, v);
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            *reinterpret_cast<float4*>(stg + lane * HALO_STG_ROW + q) =
+                make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+          __syncwarp();
+          const int col = n_off + c + cq;
+          const bool col_ok = col < p.Cout;
+          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          const size_t m_w = m_pair + j * 128 + g * 32;  // first row of this warp's 32 rows
+          float4 res[8];
+          if (p.resid != nullptr && col_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              res[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (m_w + i * 4 + sub) * p.Cout + col));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + sub;
+            const float4 a = *reinterpret_cast<const float4*>(stg + row * HALO_STG_ROW + cq);
+            const float o[4] = {a.x + bias.x + res[i].x, a.y + bias.y + res[i].y, a.z + bias.z + res[i].z, a.w + bias.w + res[i].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s1[q] += o[q]; s2[q] = fmaf(o[q], o[q], s2[q]); }
+            if (col_ok) {
+              const size_t off = (m_w + row) * p.Cout + col;
+              if (p.y_f32 != nullptr) *reinterpret_cast<float4*>(p.y_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.y_op != nullptr) OpType<__nv_bfloat16>::store4(p.y_op + off, make_float4(o[0], o[1], o[2], o[3]));
+            }
+          }
+          if (p.stats != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 8);
+              s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 8);
+              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 16);
+              s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 16);
+            }
+            if (sub == 0) {
+              float* d = statbuf + ((size_t)(j * 4 + g) * BN + c + cq) * 2;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { d[2 * q] = s1[q]; d[2 * q + 1] = s2[q]; }
+            }
+          }
+          __syncwarp();  // staging is overwritten by the next chunk
+        }
+      }
+      // all TMEM reads of this accumulator buffer are complete (tcgen05.wait::ld inside the load helper)
+      tcgen05_fence_before();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (p.stats != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // both tiles lie in one frame (a pair never straddles frames): 8 partials per (column, moment), fixed order
+        const int frame = (int)(m_pair / p.HW);
+        for (int i = et; i < BN * 2; i += 128) {
+          const int cc = i >> 1;
+          if (n_off + cc < p.Cout) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc += statbuf[(size_t)k * BN * 2 + i];
+            atomicAdd(p.stats + ((size_t)frame * p.Cout + n_off + cc) * 2 + (i & 1), (double)acc);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static bool encode4(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int rows) {
+  EncodeTiledFn enc = get_tensormap_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool encode3w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int ci_pad, int bn) {
+  EncodeTiledFn enc = get_tensormap_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)ci_pad, (cuuint64_t)co_pad, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)ci_pad * 2, (cuuint64_t)co_pad * ci_pad * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_num_sms = 0;
+
+template <int BN>
+static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
+                       HaloParams& p, cudaStream_t st) {
+  constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers
+  const int extra = 1024 + 4 * 32 * HALO_STG_ROW * 4 + 2 * 4 * BN * 2 * 4;  // alignment slack + staging + statbuf
+  p.a_bytes = (2 * p.hbox + 2) * p.W * 128;
+  p.stage_bytes = p.a_bytes + 3 * BN * 128;
+  p.stages = (SMEM_MAX - extra) / p.stage_bytes;
+  if (p.stages > HALO_MAX_STAGES) p.stages = HALO_MAX_STAGES;
+  if (p.stages < 2) return FDM_ERR_UNSUPPORTED;
+  const int smem = p.stages * p.stage_bytes + extra;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+  });
+  if (attr_err != cudaSuccess) {
+    set_last_error(attr_err);
+    return FDM_ERR_CUDA;
+  }
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  const int grid = p.n_items < sms ? p.n_items : sms;
+  conv_halo_kernel<BN><<<grid, HALO_THREADS, smem, st>>>(ta0, tw0, ta1, tw1, p);
+  return check_launch();
+}
+
+// FDM_ERR_UNSUPPORTED => the caller falls back to the per-tap kernel of conv_tc.cu
+int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
+  FDM_REQUIRE(a->a_dtype == FDM_BF16 && a->ksize == 3 && a->stride == 1 && !a->upsample && !a->out_nchw, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(a->C0 % 8 == 0 && (a->a1 == nullptr || a->C1 % 8 == 0) && a->Cout % 4 == 0 && a->Cout >= 32, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(a->y_op == nullptr || a->op_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
+  const int W = a->Win, H = a->Hin;
+  FDM_REQUIRE(W == 16 || W == 32 || W == 64, FDM_ERR_UNSUPPORTED);
+  const int hbox = 128 / W;
+  FDM_REQUIRE(H % (2 * hbox) == 0, FDM_ERR_UNSUPPORTED);
+  HaloParams p;
+  p.bias = a->bias; p.resid = a->resid; p.y_f32 = a->y_f32; p.y_op = reinterpret_cast<__nv_bfloat16*>(a->y_op);
+  p.stats = reinterpret_cast<double*>(a->stats);
+  p.Cout = a->Cout; p.W = W; p.HW = H * W; p.hbox = hbox;
+  p.pairs_per_frame = H / (2 * hbox);
+  const int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : 32);
+  p.ntiles = (a->Cout + bn - 1) / bn;
+  p.n_items = a->N * p.pairs_per_frame * p.ntiles;
+  p.kchunks0 = (a->C0 + 63) / 64;
+  p.kchunks1 = a->a1 ? (a->C1 + 63) / 64 : 0;
+  p.klast0 = (a->C0 - (p.kchunks0 - 1) * 64 + 15) / 16;
+  p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * 64 + 15) / 16 : 0;
+  const int co_pad = (a->Cout + 15) / 16 * 16;
+  CUtensorMap ta0, tw0, ta1, tw1;
+  bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, 2 * hbox + 2) && encode3w(&tw0, a->w0, 9, co_pad, p.kchunks0 * 64, bn);
+  if (ok && a->a1) {
+    ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, 2 * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, bn);
+  } else {
+    ta1 = ta0;
+    tw1 = tw0;
+  }
+  FDM_REQUIRE(ok, FDM_ERR_UNSUPPORTED);
+  if (bn == 128) return launch_halo<128>(ta0, tw0, ta1, tw1, p, st);
+  if (bn == 64) return launch_halo<64>(ta0, tw0, ta1, tw1, p, st);
+  return launch_halo<32>(ta0, tw0, ta1, tw1, p, st);
+}
+
+}  // namespace fdm

@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
   }
 }
 
-int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st);  // conv_tc.cu
+int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st);    // conv_tc.cu (one TMA box per filter tap)
+int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st);  // conv_halo.cu (3x3 s1, row-halo reuse, persistent)
 
 static int conv_simt_launch(const fdm_conv_args* a, cudaStream_t st) {
   ConvParams p;
@@ -254,7 +255,11 @@ extern "C" int fdm_conv(const fdm_conv_args* a, void* stream) {
   FDM_REQUIRE(a->y_f32 != nullptr || a->y_op != nullptr, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(!(a->out_nchw && a->y_f32 == nullptr), FDM_ERR_BAD_ARG);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->engine == FDM_CONV_TC) return conv_tc_launch(a, st);
+  if (a->engine == FDM_CONV_TC) {
+    int rc = conv_halo_launch(a, st);
+    return rc == FDM_ERR_UNSUPPORTED ? conv_tc_launch(a, st) : rc;
+  }
+  if (a->engine == FDM_CONV_TC_TAP) return conv_tc_launch(a, st);
   FDM_REQUIRE(a->engine == FDM_CONV_SIMT, FDM_ERR_BAD_ARG);
   return conv_simt_launch(a, st);
 }

@@ -37,6 +37,7 @@ struct TcParams {
   int kchunks0, kchunks1;
   int klast0, klast1;  // 16-wide k-steps actually issued in the last 64-channel chunk of each K segment
   int out_nchw;
+  unsigned long long* trace;  // debug: per-CTA phase timestamps (fdm_debug_set_trace), NULL in production
 };
 
 template <int BN>
@@ -66,6 +67,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, n_off = blockIdx.y * BN;
+  unsigned long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+#define FDM_TRACE(slot) do { if (tr != nullptr) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tr[slot] = t_; } } while (0)
+  if (threadIdx.x == 0) FDM_TRACE(0);
   const int m0 = mt * TC_BM;
   const int iters0 = p.taps * p.kchunks0;
   const int iters = iters0 + p.kchunks1;
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) FDM_TRACE(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -135,6 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         const int stage = it % S::STAGES;
         const uint32_t phase = (it / S::STAGES) & 1;
         mbar_wait(&full_bar[stage], phase);
+        if (it == 0) FDM_TRACE(2);
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
         const uint64_t adesc = make_smem_desc(a_addr);
@@ -153,11 +159,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
       }
       umma_commit(&tmem_full_bar);       // accumulator complete
+      FDM_TRACE(3);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int g = warp & 3;  // TMEM lane group this warp may access: lanes [32g, 32g+32)
     mbar_wait(&tmem_full_bar, 0);
+    if (warp == 2 && lane == 0) FDM_TRACE(4);
     tcgen05_fence_after();
     float* stg = reinterpret_cast<float*>(smem);  // aliases the operand ring: every MMA (hence every smem read) has retired
     float* my_row = stg + (size_t)(g * 32 + lane) * S::ROW;
@@ -180,6 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       }
     }
     __syncwarp();
+    if (warp == 2 && lane == 0) FDM_TRACE(5);
     if (p.out_nchw) {
       // narrow head conv (unet.py:402,462-464): eps written as [N][Cout][Ho][Wo] fp32; lane <-> pixel row, few channels
       const int row = g * 32 + lane, m = m0 + row;
@@ -244,6 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FDM_TRACE(6);
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS));
@@ -251,6 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------- host side
+static unsigned long long* g_trace = nullptr;
 EncodeTiledFn get_tensormap_encoder() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
@@ -342,6 +353,7 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.klast0 = (a->C0 - (p.kchunks0 - 1) * TC_BK + 15) / 16;
   p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * TC_BK + 15) / 16 : 0;
   p.out_nchw = a->out_nchw;
+  p.trace = g_trace;
   const int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : (a->Cout > 16 ? 32 : 16));
   const int co_pad = round_up(a->Cout, 16);
   CUtensorMap ta0, tw0, ta1, tw1;
@@ -362,3 +374,7 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
 }
 
 }  // namespace fdm
+
+// debug hook (not part of the product ABI): per-CTA globaltimer stamps of the next conv_tc launches are written to
+// trace[cta][8] = {start, prologue done, first operands landed, last MMA issued, accumulator ready, staged, done}
+extern "C" void fdm_debug_set_trace(unsigned long long* trace) { fdm::g_trace = trace; }

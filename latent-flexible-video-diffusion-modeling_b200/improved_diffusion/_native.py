@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfdm_sm100.so")
 
 F32, BF16 = 0, 1
-CONV_SIMT, CONV_TC = 0, 1
+CONV_SIMT, CONV_TC, CONV_TC_TAP = 0, 1, 2
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

@@ -40,7 +40,7 @@ def run_conv(x_nhwc, w, bias, *, stride=1, engine, x1=None, w1=None, resid=None,
     y = torch.empty(N, Ho, Wo, Co, device=dev)
     yop = torch.empty(N, Ho, Wo, Co, device=dev, dtype=torch.bfloat16) if want_op else None
     stats = torch.zeros(N, Co, 2, device=dev, dtype=torch.float64) if want_stats else None
-    pk = pack_tc if engine == N_.CONV_TC else pack_simt
+    pk = pack_simt if engine == N_.CONV_SIMT else pack_tc
     w0p = pk(w)
     w1p = pk(w1) if w1 is not None else None
     a = N_.ConvArgs(a0=x_nhwc.data_ptr(), w0=w0p.data_ptr(), a1=x1.data_ptr() if x1 is not None else None,
@@ -71,11 +71,16 @@ CASES = [
     (1, 128, 128, 64, 64, 3, 1, 0, False),   # W = 128: one row per tile
     (3, 32, 32, 64, 64, 3, 2, 0, False),     # Downsample conv (stride 2) through TMA element strides
     (5, 16, 16, 128, 128, 3, 2, 0, False),   # stride 2 -> 8x8 outputs, two frames per tile
+    (40, 32, 32, 64, 64, 3, 1, 0, True),     # > 148 work items: persistent halo CTAs loop, TMEM double buffering wraps
+    (24, 16, 16, 256, 128, 3, 1, 128, True), # halo kernel: 4 K chunks + skip segment, BN = 128
+    (3, 64, 64, 192, 192, 3, 1, 0, False),   # W = 64 halo (hbox = 2), Cout = 192 -> masked second N tile
+    (6, 32, 32, 32, 32, 3, 1, 0, True),      # BN = 32
 ]
 
 
+@pytest.mark.parametrize("engine", [1, 2], ids=["auto", "tap"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
-def test_conv_tc_vs_torch(case):
+def test_conv_tc_vs_torch(case, engine):
     from improved_diffusion import _native as N_
     N, H, W, C0, Co, k, stride, C1, use_resid = case
     g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000)
@@ -89,7 +94,7 @@ def test_conv_tc_vs_torch(case):
         x1 = torch.randn(N, Ho, Wo, C1, device="cuda", generator=g).to(torch.bfloat16)
         w1 = torch.randn(Co, C1, 1, 1, device="cuda", generator=g) / C1 ** 0.5
     resid = torch.randn(N, Ho, Wo, Co, device="cuda", generator=g) if use_resid else None
-    y, yop, stats = run_conv(x, w, bias, stride=stride, engine=N_.CONV_TC, x1=x1, w1=w1, resid=resid, want_op=True)
+    y, yop, stats = run_conv(x, w, bias, stride=stride, engine=engine, x1=x1, w1=w1, resid=resid, want_op=True)
     wq = w.to(torch.bfloat16).float()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wq, bias, stride=stride, padding=pad)
     if C1:
