@@ -72,8 +72,9 @@ int fdm_input_prep(const fdm_input_prep_args* a, void* stream);
  *   segment 0: ksize in {1,3}, stride in {1,2}, optional nearest x2 upsample folded into the gather
  *              (F.interpolate + conv, unet.py:85-87); segment 1 (optional): a 1x1 conv over a second
  *              input with the same spatial size as the output (the ResBlock skip_connection, :180).
- *   Weight layouts:  engine FDM_CONV_SIMT: fp32 [tap][ci][co];  engine FDM_CONV_TC: bf16 [tap][co][ci_pad]
- *   (ci_pad = ci rounded up to 64), both produced by the host from PyTorch's [co][ci][kh][kw].
+ *   Weight layouts:  engine FDM_CONV_SIMT: fp32 [tap = kh*k + kw][ci][co];  engine FDM_CONV_TC: bf16 [tap = kw*k + kh][co_pad][ci_pad]
+ *   (filter-column major so one TMA box covers a filter column; ci_pad = ci rounded up to 64, co_pad to 16), both produced by
+ *   the host from PyTorch's [co][ci][kh][kw].
  *   Outputs (any subset): y_f32 [.,Cout] fp32; y_op [.,Cout] in op_dtype; stats (sum,sumsq per frame,
  *   channel); out_nchw: y_f32 is written as [N][Cout][Ho][Wo] (the head conv producing eps).
  * ---------------------------------------------------------------------------------------------- */
@@ -169,7 +170,7 @@ int fdm_grouped_linear(const fdm_grouped_linear_args* a, void* stream);
 typedef struct {
   const float* wd;  /* [C][3] embed_distances.weight */
   const float* bd;  /* [C] */
-  float* hidden;    /* [B][T][T][C] */
+  void* hidden;     /* [B][T][T][C], fp32 or bf16 (hidden_dtype of the launch) */
   int32_t C, te_off; /* this net's W_t·temb + b_t lives at te[b][te_off .. te_off+C) */
 } fdm_rpe_hidden_problem; /* which = 14 */
 typedef struct {
@@ -177,6 +178,7 @@ typedef struct {
   const int64_t* frame_indices; /* [B][T] */
   const fdm_rpe_hidden_problem* problems; /* DEVICE array, one per RPENet */
   int32_t B, T, te_stride, count, max_C;
+  int32_t hidden_dtype; /* FDM_F32 (then W_o via fdm_grouped_linear) or FDM_BF16 (then W_o via fdm_conv on tcgen05, 1x1 over B*T*T rows) */
 } fdm_rpe_hidden_args; /* which = 6 */
 int fdm_rpe_hidden(const fdm_rpe_hidden_args* a, void* stream);
 

@@ -32,6 +32,7 @@ struct HaloParams {
   int pairs_per_frame, n_items, ntiles;
   int kchunks0, kchunks1, klast0, klast1;
   int stages, a_bytes, stage_bytes;
+  long long* trace;  // debug (fdm_debug_set_trace): per-CTA cycle counters, NULL in production
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
+    {
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
@@ -99,52 +100,79 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
             uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
             uint8_t* b_dst = a_dst + p.a_bytes;
-            mbar_expect_tx(&full_bar[stage], p.a_bytes + 3 * B_TAP_BYTES);
-            tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - 1, h0 - 1, n);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) tma_load_3d(b_dst + r * B_TAP_BYTES, &tw0, &full_bar[stage], kc * 64, n_off, r * 3 + s);
+            if (elect_one_sync()) {
+              mbar_expect_tx(&full_bar[stage], p.a_bytes + 3 * B_TAP_BYTES);
+              tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - 1, h0 - 1, n);
+              // weights are packed filter-column major ([s][r][co][ci]): the three filter rows of column s are ONE box
+              // (a TMA instruction costs ~450 clk + 0.4 clk/row on this part, measured: tools/tma_bench.cu)
+              tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * 64, n_off, s * 3);
+            }
+            __syncwarp();
           }
         }
         for (int kc = 0; kc < p.kchunks1; ++kc, ++it) {
           const int stage = it % p.stages;
           mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
           uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
-          mbar_expect_tx(&full_bar[stage], 256 * 128 + B_TAP_BYTES);
-          tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * 64, 0, h0, n);
-          tma_load_3d(a_dst + p.a_bytes, &tw1, &full_bar[stage], kc * 64, n_off, 0);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&full_bar[stage], 256 * 128 + B_TAP_BYTES);
+            tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * 64, 0, h0, n);
+            tma_load_3d(a_dst + p.a_bytes, &tw1, &full_bar[stage], kc * 64, n_off, 0);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc(BN);
-      const uint32_t row_bytes = (uint32_t)p.W * 128;  // one image row of the A box
+      const uint32_t row16 = ((uint32_t)p.W * 128) >> 4;         // one image row of the A box, in descriptor units (16 B)
+      const uint32_t tile_rows16 = (uint32_t)p.hbox * row16;     // second M tile starts hbox rows further down
       uint32_t it = 0, local = 0;
+      long long t_wait_tmem = 0, t_wait_full = 0, t_begin = clock64();
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
         const uint32_t buf = local & 1;
+        long long c0 = clock64();
         mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);
+        t_wait_tmem += clock64() - c0;
         tcgen05_fence_after();
         const uint32_t acc0 = tmem_base + buf * 2 * BN;
         for (int kc = 0; kc < p.kchunks0; ++kc) {
           const int nk = (kc == p.kchunks0 - 1) ? p.klast0 : 4;
           for (int s = 0; s < 3; ++s, ++it) {
             const int stage = it % p.stages;
+            long long c1 = clock64();
             mbar_wait(&full_bar[stage], (it / p.stages) & 1);
+            t_wait_full += clock64() - c1;
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
-            const uint32_t b_addr = a_addr + p.a_bytes;
+            const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + (size_t)stage * p.stage_bytes));
+            const uint32_t b_lo0 = a_lo0 + (p.a_bytes >> 4);
+            const uint32_t first = (kc | s) != 0;  // 0 only for the very first stage of the item
+            if (elect_one_sync()) {
+            if (nk == 4) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const uint64_t bdesc = make_smem_desc(b_addr + r * B_TAP_BYTES);
+              for (int r = 0; r < 3; ++r) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(j * p.hbox + r) * row_bytes);
-                for (int k = 0; k < nk; ++k)
-                  umma_bf16(acc0 + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | s | r | k) != 0);
+                for (int j = 0; j < 2; ++j) {
+                  const uint32_t a_lo = a_lo0 + (j ? tile_rows16 : 0u) + r * row16;
+                  const uint32_t b_lo = b_lo0 + r * (B_TAP_BYTES >> 4);
+                  umma_bf16_lo(acc0 + j * BN, a_lo, b_lo, idesc, r == 0 ? first : 1u);
+                  umma_bf16_lo(acc0 + j * BN, a_lo + 2, b_lo + 2, idesc, 1u);
+                  umma_bf16_lo(acc0 + j * BN, a_lo + 4, b_lo + 4, idesc, 1u);
+                  umma_bf16_lo(acc0 + j * BN, a_lo + 6, b_lo + 6, idesc, 1u);
+                }
               }
+            } else {
+              for (int r = 0; r < 3; ++r)
+                for (int j = 0; j < 2; ++j)
+                  for (int k = 0; k < nk; ++k)
+                    umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + r * row16 + 2 * k,
+                                 b_lo0 + r * (B_TAP_BYTES >> 4) + 2 * k, idesc, (r | k) == 0 ? first : 1u);
             }
             umma_commit(&empty_bar[stage]);
+            }
+            __syncwarp();
           }
         }
         for (int kc = 0; kc < p.kchunks1; ++kc, ++it) {
@@ -152,16 +180,24 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           const int stage = it % p.stages;
           mbar_wait(&full_bar[stage], (it / p.stages) & 1);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes);
+          const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + (size_t)stage * p.stage_bytes));
+          const uint32_t b_lo0 = a_lo0 + (p.a_bytes >> 4);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(j * p.hbox) * row_bytes);
-            for (int k = 0; k < nk; ++k) umma_bf16(acc0 + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+            for (int j = 0; j < 2; ++j)
+              for (int k = 0; k < nk; ++k)
+                umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + 2 * k, b_lo0 + 2 * k, idesc, 1u);
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
         }
-        umma_commit(&tmem_full_bar[buf]);
+        if (elect_one_sync()) umma_commit(&tmem_full_bar[buf]);
+        __syncwarp();
+      }
+      if (p.trace != nullptr && lane == 0) {
+        p.trace[blockIdx.x * 8 + 0] = clock64() - t_begin;
+        p.trace[blockIdx.x * 8 + 1] = t_wait_tmem;
+        p.trace[blockIdx.x * 8 + 2] = t_wait_full;
       }
     }
   } else {
@@ -171,15 +207,25 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     const int sub = lane >> 3, cq = (lane & 7) * 4;
     const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
     uint32_t local = 0;
+    long long e_wait = 0, e_begin = clock64(), e_stats = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
       const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
       const uint32_t buf = local & 1;
       const size_t m_pair = (size_t)pair * 256;
+      // bias for this lane's 4 columns of every 32-column chunk: loaded before the accumulator wait (latency hidden)
+      float4 biasv[BN / 32];
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        const int col = n_off + cc * 32 + cq;
+        biasv[cc] = (p.bias != nullptr && col < p.Cout) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      long long c2 = clock64();
       mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
+      e_wait += clock64() - c2;
       tcgen05_fence_after();
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + buf * 2 * BN + j * BN + c, v);
@@ -190,8 +236,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           __syncwarp();
           const int col = n_off + c + cq;
           const bool col_ok = col < p.Cout;
-          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col_ok && p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          const float4 bias = biasv[c / 32];
           const size_t m_w = m_pair + j * 128 + g * 32;  // first row of this warp's 32 rows
           float4 res[8];
           if (p.resid != nullptr && col_ok) {
@@ -236,6 +281,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       // all TMEM reads of this accumulator buffer are complete (tcgen05.wait::ld inside the load helper)
       tcgen05_fence_before();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      long long c3 = clock64();
       if (p.stats != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         // both tiles lie in one frame (a pair never straddles frames): 8 partials per (column, moment), fixed order
@@ -251,6 +297,13 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      e_stats += clock64() - c3;
+    }
+    if (p.trace != nullptr && warp == 2 && lane == 0) {
+      p.trace[blockIdx.x * 8 + 3] = clock64() - e_begin;
+      p.trace[blockIdx.x * 8 + 4] = e_wait;
+      p.trace[blockIdx.x * 8 + 5] = e_stats;
+      p.trace[blockIdx.x * 8 + 6] = local;
     }
   }
   tcgen05_fence_before();
@@ -272,18 +325,19 @@ static bool encode4(CUtensorMap* m, const void* ptr, int N, int H, int W, int C,
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-static bool encode3w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int ci_pad, int bn) {
+static bool encode3w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int ci_pad, int bn, int box_taps) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) return false;
   cuuint64_t dims[3] = {(cuuint64_t)ci_pad, (cuuint64_t)co_pad, (cuuint64_t)taps};
   cuuint64_t strides[2] = {(cuuint64_t)ci_pad * 2, (cuuint64_t)co_pad * ci_pad * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)bn, (cuuint32_t)box_taps};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int g_num_sms = 0;
+static long long* g_trace = nullptr;
 
 template <int BN>
 static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
@@ -333,15 +387,16 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   const int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : 32);
   p.ntiles = (a->Cout + bn - 1) / bn;
   p.n_items = a->N * p.pairs_per_frame * p.ntiles;
+  p.trace = g_trace;
   p.kchunks0 = (a->C0 + 63) / 64;
   p.kchunks1 = a->a1 ? (a->C1 + 63) / 64 : 0;
   p.klast0 = (a->C0 - (p.kchunks0 - 1) * 64 + 15) / 16;
   p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * 64 + 15) / 16 : 0;
   const int co_pad = (a->Cout + 15) / 16 * 16;
   CUtensorMap ta0, tw0, ta1, tw1;
-  bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, 2 * hbox + 2) && encode3w(&tw0, a->w0, 9, co_pad, p.kchunks0 * 64, bn);
+  bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, 2 * hbox + 2) && encode3w(&tw0, a->w0, 9, co_pad, p.kchunks0 * 64, bn, 3);
   if (ok && a->a1) {
-    ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, 2 * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, bn);
+    ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, 2 * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, bn, 1);
   } else {
     ta1 = ta0;
     tw1 = tw0;
@@ -353,3 +408,8 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
 }
 
 }  // namespace fdm
+
+// debug hook (not part of the product ABI): the next conv_halo launches write per-CTA cycle counters to trace[cta][8] =
+// {MMA warp total, MMA waiting for a free accumulator, MMA waiting for operands, epilogue total, epilogue waiting for
+//  the accumulator, epilogue statistics phase, items}
+extern "C" void fdm_debug_set_trace(long long* trace) { fdm::g_trace = trace; }

@@ -37,19 +37,19 @@ struct TcParams {
   int kchunks0, kchunks1;
   int klast0, klast1;  // 16-wide k-steps actually issued in the last 64-channel chunk of each K segment
   int out_nchw;
-  unsigned long long* trace;  // debug: per-CTA phase timestamps (fdm_debug_set_trace), NULL in production
+  int stages;
 };
+
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_STG_ROW = 36;  // floats per staged row (32 columns + 4 pad): conflict-free float4 access
 
 template <int BN>
 struct TcSmem {
   static constexpr int B_TILE_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = BN >= 128 ? 3 : 4;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int ROW = BN + 4;  // staging row stride (floats): 16-byte aligned, conflict-free float4 access
-  static constexpr int STAGING_BYTES = TC_BM * ROW * 4;
-  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int BYTES = (RING_BYTES > STAGING_BYTES ? RING_BYTES : STAGING_BYTES) + 1024;  // + alignment slack
+  static constexpr int EXTRA_BYTES = 1024;  // alignment slack (the epilogue staging aliases the dead operand ring)
+  static_assert(STAGE_BYTES >= 4 * 32 * TC_STG_ROW * 4, "one stage must hold the epilogue staging");
 };
 
 template <int BN>
@@ -60,19 +60,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   using S = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[S::STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[S::STAGES];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, n_off = blockIdx.y * BN;
-  unsigned long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
-#define FDM_TRACE(slot) do { if (tr != nullptr) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tr[slot] = t_; } } while (0)
-  if (threadIdx.x == 0) FDM_TRACE(0);
   const int m0 = mt * TC_BM;
   const int iters0 = p.taps * p.kchunks0;
   const int iters = iters0 + p.kchunks1;
+  const int stages = p.stages;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&ta0) : "memory");
@@ -83,7 +81,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < S::STAGES; ++i) {
+    for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -98,11 +96,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  if (threadIdx.x == 0) FDM_TRACE(1);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
+    {
       // first output pixel of the tile -> box origin in (w, h, n)
       int w0, h0, n0;
       if (p.nbox > 1) {
@@ -114,146 +111,167 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         w0 = r - h0 * p.Wo;
       }
       for (int it = 0; it < iters; ++it) {
-        const int stage = it % S::STAGES;
-        const uint32_t phase = (it / S::STAGES) & 1;
+        const int stage = it % stages;
+        const uint32_t phase = (it / stages) & 1;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* a_dst = smem + stage * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + A_TILE_BYTES;
-        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-        if (it < iters0) {
-          const int tap = it / p.kchunks0, kc = it - tap * p.kchunks0;
-          const int r = tap / p.ksize, s = tap - r * p.ksize;
-          tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * TC_BK, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
-          tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * TC_BK, n_off, tap);
-        } else {
-          const int kc = it - iters0;
-          tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * TC_BK, w0, h0, n0);
-          tma_load_3d(b_dst, &tw1, &full_bar[stage], kc * TC_BK, n_off, 0);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          if (it < iters0) {
+            const int tap = it / p.kchunks0, kc = it - tap * p.kchunks0;
+            const int s = tap / p.ksize, r = tap - s * p.ksize;  // weights are packed filter-column major: tap = s*k + r
+            tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * TC_BK, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
+            tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * TC_BK, n_off, tap);
+          } else {
+            const int kc = it - iters0;
+            tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * TC_BK, w0, h0, n0);
+            tma_load_3d(b_dst, &tw1, &full_bar[stage], kc * TC_BK, n_off, 0);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc(BN);
+      int kc_cnt = 0, stage = 0;
+      uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
-        const int stage = it % S::STAGES;
-        const uint32_t phase = (it / S::STAGES) & 1;
         mbar_wait(&full_bar[stage], phase);
-        if (it == 0) FDM_TRACE(2);
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(a_addr);
-        const uint64_t bdesc = make_smem_desc(a_addr + A_TILE_BYTES);
+        const uint32_t a_lo = smem_desc_lo(smem_u32(smem + stage * S::STAGE_BYTES));
+        const uint32_t b_lo = a_lo + (A_TILE_BYTES >> 4);
         // channels beyond C0/C1 in the last chunk are TMA zero-fill: skip their k-steps
         int nk = TC_BK / 16;
         if (it < iters0) {
-          if ((it % p.kchunks0) == p.kchunks0 - 1) nk = p.klast0;
+          if (kc_cnt == p.kchunks0 - 1) nk = p.klast0;
+          if (++kc_cnt == p.kchunks0) kc_cnt = 0;
         } else if (it == iters - 1) {
           nk = p.klast1;
         }
-        for (int k = 0; k < nk; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) start-address field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) start-address field
+        if (elect_one_sync()) {
+        if (nk == 4) {
+          umma_bf16_lo(tmem_base, a_lo, b_lo, idesc, it != 0);
+          umma_bf16_lo(tmem_base, a_lo + 2, b_lo + 2, idesc, 1u);
+          umma_bf16_lo(tmem_base, a_lo + 4, b_lo + 4, idesc, 1u);
+          umma_bf16_lo(tmem_base, a_lo + 6, b_lo + 6, idesc, 1u);
+        } else {
+          for (int k = 0; k < nk; ++k) umma_bf16_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, idesc, (it | k) != 0);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tmem_full_bar);       // accumulator complete
-      FDM_TRACE(3);
+      if (elect_one_sync()) umma_commit(&tmem_full_bar);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // 32-column chunks: TMEM -> registers -> this warp's padded staging slice -> lanes across channels (float4), 4 rows per
+    // instruction; the 8 residual loads of a chunk are issued before any is used (memory-level parallelism).
     const int g = warp & 3;  // TMEM lane group this warp may access: lanes [32g, 32g+32)
+    // staging aliases the operand ring: every MMA (hence every shared-memory read) has retired once tmem_full fires
+    float* stg = reinterpret_cast<float*>(smem) + g * 32 * TC_STG_ROW;
+    const int sub = lane >> 3, cq = (lane & 7) * 4;
+    const int m_w = m0 + g * 32;  // first row of this warp
     mbar_wait(&tmem_full_bar, 0);
-    if (warp == 2 && lane == 0) FDM_TRACE(4);
     tcgen05_fence_after();
-    float* stg = reinterpret_cast<float*>(smem);  // aliases the operand ring: every MMA (hence every smem read) has retired
-    float* my_row = stg + (size_t)(g * 32 + lane) * S::ROW;
-    if constexpr (BN == 16) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(g * 32) << 16), v);
+    const bool two_frames = p.HWo < 32;  // HWo == 16: rows [0,16) and [16,32) of the warp belong to different frames
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + c, v);
 #pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(my_row + j) =
-            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-    } else {
+      for (int q = 0; q < 32; q += 4)
+        *reinterpret_cast<float4*>(stg + lane * TC_STG_ROW + q) =
+            make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+      __syncwarp();
+      if (p.out_nchw) {
+        // narrow head conv (unet.py:402,462-464): eps written as [N][Cout][Ho][Wo] fp32; lane <-> pixel row, few channels
+        const int m = m_w + lane;
+        if (m < p.M) {
+          const int f = m / p.HWo, r = m - f * p.HWo;
+          for (int cc = 0; cc < 32 && n_off + c + cc < p.Cout; ++cc) {
+            float o = stg[lane * TC_STG_ROW + cc] + (p.bias ? p.bias[n_off + c + cc] : 0.f);
+            p.y_f32[((size_t)f * p.Cout + n_off + c + cc) * p.HWo + r] = o;
+          }
+        }
+      } else {
+        const int col = n_off + c + cq;
+        const bool col_ok = col < p.Cout;  // Cout % 4 == 0
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        float4 res[8];
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + c, v);
+        for (int i = 0; i < 8; ++i) {
+          const int m = m_w + i * 4 + sub;
+          res[i] = (p.resid != nullptr && col_ok && m < p.M) ? __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)m * p.Cout + col))
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float s1[2][4], s2[2][4];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(my_row + c + j) =
-              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s1[hh][q] = s2[hh][q] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + sub;
+          const int m = m_w + row;
+          const float4 a = *reinterpret_cast<const float4*>(stg + row * TC_STG_ROW + cq);
+          const float o[4] = {a.x + bias.x + res[i].x, a.y + bias.y + res[i].y, a.z + bias.z + res[i].z, a.w + bias.w + res[i].w};
+          if (m < p.M && col_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s1[i >> 2][q] += o[q]; s2[i >> 2][q] = fmaf(o[q], o[q], s2[i >> 2][q]); }
+            const size_t off = (size_t)m * p.Cout + col;
+            if (p.y_f32 != nullptr) *reinterpret_cast<float4*>(p.y_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.y_op != nullptr) OpType<__nv_bfloat16>::store4(p.y_op + off, make_float4(o[0], o[1], o[2], o[3]));
+          }
+        }
+        if (p.stats != nullptr) {
+          // combine the 4 row-subgroups (lanes with equal lane%8); one fp64 atomic per (frame, channel, moment) per warp
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              s1[hh][q] += __shfl_xor_sync(0xffffffffu, s1[hh][q], 8);
+              s2[hh][q] += __shfl_xor_sync(0xffffffffu, s2[hh][q], 8);
+              s1[hh][q] += __shfl_xor_sync(0xffffffffu, s1[hh][q], 16);
+              s2[hh][q] += __shfl_xor_sync(0xffffffffu, s2[hh][q], 16);
+            }
+          if (sub == 0 && col_ok) {
+            if (two_frames) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int mseg = m_w + hh * 16;
+                if (mseg < p.M) {
+                  double* dst = p.stats + ((size_t)(mseg / p.HWo) * p.Cout + col) * 2;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    atomicAdd(dst + 2 * q, (double)s1[hh][q]);
+                    atomicAdd(dst + 2 * q + 1, (double)s2[hh][q]);
+                  }
+                }
+              }
+            } else if (m_w < p.M) {
+              double* dst = p.stats + ((size_t)(m_w / p.HWo) * p.Cout + col) * 2;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                atomicAdd(dst + 2 * q, (double)(s1[0][q] + s1[1][q]));
+                atomicAdd(dst + 2 * q + 1, (double)(s2[0][q] + s2[1][q]));
+              }
+            }
+          }
+        }
       }
+      __syncwarp();  // staging slice is overwritten by the next chunk
     }
-    __syncwarp();
-    if (warp == 2 && lane == 0) FDM_TRACE(5);
-    if (p.out_nchw) {
-      // narrow head conv (unet.py:402,462-464): eps written as [N][Cout][Ho][Wo] fp32; lane <-> pixel row, few channels
-      const int row = g * 32 + lane, m = m0 + row;
-      if (m < p.M) {
-        const int f = m / p.HWo, r = m - f * p.HWo;
-        for (int c = 0; c < BN && n_off + c < p.Cout; ++c) {
-          float v = stg[(size_t)row * S::ROW + c] + (p.bias ? p.bias[n_off + c] : 0.f);
-          p.y_f32[((size_t)f * p.Cout + n_off + c) * p.HWo + r] = v;
-        }
-      }
-    } else {
-    // phase 2: this warp's 32 rows, lanes across channels (float4 each): coalesced global traffic
-    constexpr int LPR = BN / 4;         // lanes per row
-    constexpr int RPI = 32 / LPR > 0 ? 32 / LPR : 1;  // rows per iteration (BN <= 128)
-    const int cl = (lane % LPR) * 4, rsub = lane / LPR;
-    const int cg = n_off + cl;
-    const bool col_ok = cg < p.Cout;    // Cout % 4 == 0
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col_ok && p.bias != nullptr) bias = *reinterpret_cast<const float4*>(p.bias + cg);
-    const int seg_rows = p.HWo < 32 ? p.HWo : 32;  // rows of one frame inside this warp's 32 rows
-    for (int seg0 = 0; seg0 < 32; seg0 += seg_rows) {
-      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-      const int mseg = m0 + g * 32 + seg0;
-      for (int rr = rsub; rr < seg_rows; rr += RPI) {
-        const int row = g * 32 + seg0 + rr;
-        const int m = m0 + row;
-        if (m < p.M && col_ok) {
-          float4 a = *reinterpret_cast<const float4*>(stg + (size_t)row * S::ROW + cl);
-          float v[4] = {a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w};
-          const size_t o = (size_t)m * p.Cout + cg;
-          if (p.resid != nullptr) {
-            float4 r4 = *reinterpret_cast<const float4*>(p.resid + o);
-            v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { s1[j] += v[j]; s2[j] += v[j] * v[j]; }
-          if (p.y_f32 != nullptr) *reinterpret_cast<float4*>(p.y_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
-          if (p.y_op != nullptr) OpType<__nv_bfloat16>::store4(p.y_op + o, make_float4(v[0], v[1], v[2], v[3]));
-        }
-      }
-      if (p.stats != nullptr) {
-        // combine the RPI row-subgroups of the warp, then one atomic per (frame, channel) per warp segment
-#pragma unroll
-        for (int off = 16; off >= LPR; off >>= 1) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
-          }
-        }
-        if (rsub == 0 && col_ok && mseg < p.M) {
-          double* dst = p.stats + ((size_t)(mseg / p.HWo) * p.Cout + cg) * 2;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            atomicAdd(dst + 2 * j, (double)s1[j]);
-            atomicAdd(dst + 2 * j + 1, (double)s2[j]);
-          }
-        }
-      }
-    }
-    }  // !out_nchw
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) FDM_TRACE(6);
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS));
@@ -261,7 +279,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------- host side
-static unsigned long long* g_trace = nullptr;
 EncodeTiledFn get_tensormap_encoder() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
@@ -301,18 +318,30 @@ static bool encode_w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int 
 
 template <int BN>
 static int launch_tc(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
-                     const TcParams& p, cudaStream_t st) {
+                     TcParams& p, cudaStream_t st) {
+  using S = TcSmem<BN>;
+  constexpr int SMEM_MAX = 226 * 1024;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::BYTES);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
   });
   if (attr_err != cudaSuccess) {
     set_last_error(attr_err);
     return FDM_ERR_CUDA;
   }
   dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.Cout + BN - 1) / BN);
-  conv_tc_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::BYTES, st>>>(ta0, tw0, ta1, tw1, p);
+  // pipeline depth: a grid that cannot even fill the SMs once is latency-bound -> one CTA per SM with as many operand
+  // stages in flight as the K loop has iterations (up to 8); otherwise two CTAs per SM share the shared memory.
+  const long ctas = (long)grid.x * grid.y;
+  const int budget = ctas <= 148 ? SMEM_MAX : SMEM_MAX / 2;
+  int stages = (budget - S::EXTRA_BYTES) / S::STAGE_BYTES;
+  const int iters = p.taps * p.kchunks0 + p.kchunks1;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages > iters) stages = iters;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  conv_tc_kernel<BN><<<grid, TC_THREADS, stages * S::STAGE_BYTES + S::EXTRA_BYTES, st>>>(ta0, tw0, ta1, tw1, p);
   return check_launch();
 }
 
@@ -353,8 +382,10 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.klast0 = (a->C0 - (p.kchunks0 - 1) * TC_BK + 15) / 16;
   p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * TC_BK + 15) / 16 : 0;
   p.out_nchw = a->out_nchw;
-  p.trace = g_trace;
-  const int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : (a->Cout > 16 ? 32 : 16));
+  // N tile: as wide as Cout allows, but narrowed while the grid would leave most SMs idle (small feature maps)
+  int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : (a->Cout > 16 ? 32 : 16));
+  const int mtiles = (p.M + TC_BM - 1) / TC_BM;
+  while (bn > 32 && mtiles * ((a->Cout + bn - 1) / bn) < 120) bn >>= 1;
   const int co_pad = round_up(a->Cout, 16);
   CUtensorMap ta0, tw0, ta1, tw1;
   bool ok = encode_act(&ta0, a->a0, a->N, a->Hin, a->Win, a->C0, p.wbox, p.hbox, p.nbox, a->stride) &&
@@ -375,6 +406,3 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
 
 }  // namespace fdm
 
-// debug hook (not part of the product ABI): per-CTA globaltimer stamps of the next conv_tc launches are written to
-// trace[cta][8] = {start, prologue done, first operands landed, last MMA issued, accumulator ready, staged, done}
-extern "C" void fdm_debug_set_trace(unsigned long long* trace) { fdm::g_trace = trace; }

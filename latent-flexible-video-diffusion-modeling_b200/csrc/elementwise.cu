@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256) grouped_linear_kernel(const fdm_linear_pr
 }
 
 // ---------------- A9 RPENet hidden layer (rpe.py:21-30) -----------------------------------------------
+template <typename OT>
 __global__ void rpe_hidden_kernel(const float* __restrict__ te, const int64_t* __restrict__ fi,
                                   const fdm_rpe_hidden_problem* __restrict__ probs, int B, int T, int te_stride) {
   const fdm_rpe_hidden_problem pr = probs[blockIdx.y];
@@ -193,7 +194,7 @@ __global__ void rpe_hidden_kernel(const float* __restrict__ te, const int64_t* _
     // embed_distances(feats) = f0*w0 + f1*w1 + f2*w2 + bd, then + (W_t temb + b_t)
     float e = fmaf(f2, pr.wd[c * 3 + 2], fmaf(f1, pr.wd[c * 3 + 1], f0 * pr.wd[c * 3])) + pr.bd[c];
     e += te[(size_t)b * te_stride + pr.te_off + c];
-    pr.hidden[i] = silu_precise(e);
+    OpType<OT>::store(reinterpret_cast<OT*>(pr.hidden) + i, silu_precise(e));
   }
 }
 
@@ -279,6 +280,9 @@ extern "C" int fdm_rpe_hidden(const fdm_rpe_hidden_args* a, void* stream) {
   int gx = grid_for(total, 256);
   if (gx > 592) gx = 592;
   dim3 grid(gx, a->count);
-  rpe_hidden_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a->te, a->frame_indices, a->problems, a->B, a->T, a->te_stride);
+  if (a->hidden_dtype == FDM_BF16)
+    rpe_hidden_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a->te, a->frame_indices, a->problems, a->B, a->T, a->te_stride);
+  else
+    rpe_hidden_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a->te, a->frame_indices, a->problems, a->B, a->T, a->te_stride);
   return check_launch();
 }

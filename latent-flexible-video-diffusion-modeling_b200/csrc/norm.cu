@@ -20,12 +20,27 @@ __global__ void gn_apply_kernel(GnParams p) {
   __shared__ float s_mean[32], s_rstd[32];
   const int n = blockIdx.y;
   const int C = p.C, cpg = C / 32;
+  const int quads = C / 4;
+  const int q = threadIdx.x % quads, pl = threadIdx.x / quads, ppi = blockDim.x / quads;
+  const int c = q * 4;
+  const bool from_a = c < p.Ca;  // Ca, Cb are multiples of 4: a quad never straddles the concat boundary
+  const float* src = from_a ? p.xa + (size_t)n * p.HW * p.Ca + c : p.xb + (size_t)n * p.HW * p.Cb + (c - p.Ca);
+  const int sstride = from_a ? p.Ca : p.Cb;
+  const int p0 = blockIdx.x * p.pix_per_block;
+  const int p1 = min(p0 + p.pix_per_block, p.HW);
+  // the first trip's activation loads are in flight while the (latency-bound) statistics prologue runs
+  float4 xs[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int pp = p0 + pl + u * ppi;
+    if (pp < p1) xs[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)pp * sstride));
+  }
   if (threadIdx.x < 32) {
     const int g = threadIdx.x;
     double s = 0.0, ss = 0.0;
     for (int j = 0; j < cpg; ++j) {
-      int c = g * cpg + j;
-      const double* st = c < p.Ca ? p.sa + ((size_t)n * p.Ca + c) * 2 : p.sb + ((size_t)n * p.Cb + (c - p.Ca)) * 2;
+      int cc = g * cpg + j;
+      const double* st = cc < p.Ca ? p.sa + ((size_t)n * p.Ca + cc) * 2 : p.sb + ((size_t)n * p.Cb + (cc - p.Ca)) * 2;
       s += st[0];
       ss += st[1];
     }
@@ -36,9 +51,6 @@ __global__ void gn_apply_kernel(GnParams p) {
     s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
   }
   __syncthreads();
-  const int quads = C / 4;
-  const int q = threadIdx.x % quads, pl = threadIdx.x / quads, ppi = blockDim.x / quads;
-  const int c = q * 4;
   float mul[4], add[4];  // v = x*mul + add, folding mean/rstd/gamma/beta/FiLM
   {
     const int b = n / p.T;
@@ -57,23 +69,31 @@ __global__ void gn_apply_kernel(GnParams p) {
       add[j] = be;
     }
   }
-  const bool from_a = c < p.Ca;  // Ca, Cb are multiples of 4: a quad never straddles the concat boundary
-  const float* src = from_a ? p.xa + (size_t)n * p.HW * p.Ca + c : p.xb + (size_t)n * p.HW * p.Cb + (c - p.Ca);
-  const int sstride = from_a ? p.Ca : p.Cb;
-  const int p0 = blockIdx.x * p.pix_per_block;
-  const int p1 = min(p0 + p.pix_per_block, p.HW);
-  for (int px = p0 + pl; px < p1; px += ppi) {
-    float4 x = *reinterpret_cast<const float4*>(src + (size_t)px * sstride);
-    float v[4] = {x.x * mul[0] + add[0], x.y * mul[1] + add[1], x.z * mul[2] + add[2], x.w * mul[3] + add[3]};
-    if (p.silu) {
+  // 4 pixels per thread per trip, all loads issued before the first use (memory-level parallelism)
+  for (int px = p0 + pl; px < p1; px += 4 * ppi) {
+    if (px != p0 + pl) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = silu_precise(v[j]);
+      for (int u = 0; u < 4; ++u) {
+        const int pp = px + u * ppi;
+        if (pp < p1) xs[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)pp * sstride));
+      }
     }
-    size_t o = ((size_t)n * p.HW + px) * C + c;
-    float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
-    if (p.out_op != nullptr) OpType<OT>::store4(reinterpret_cast<OT*>(p.out_op) + o, v4);
-    if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = v4;
-    if (p.raw_op != nullptr) OpType<OT>::store4(reinterpret_cast<OT*>(p.raw_op) + o, x);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = px + u * ppi;
+      if (pp >= p1) break;
+      const float4 x = xs[u];
+      float v[4] = {x.x * mul[0] + add[0], x.y * mul[1] + add[1], x.z * mul[2] + add[2], x.w * mul[3] + add[3]};
+      if (p.silu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = silu_precise(v[j]);
+      }
+      size_t o = ((size_t)n * p.HW + pp) * C + c;
+      float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
+      if (p.out_op != nullptr) OpType<OT>::store4(reinterpret_cast<OT*>(p.out_op) + o, v4);
+      if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = v4;
+      if (p.raw_op != nullptr) OpType<OT>::store4(reinterpret_cast<OT*>(p.raw_op) + o, x);
+    }
   }
 }
 
@@ -83,40 +103,61 @@ struct TgnParams {
   float eps;
 };
 
-// one warp per (b, pixel); lane g owns group g (cpg consecutive channels) across all T frames
-template <typename OT>
-__global__ void temporal_gn_kernel(TgnParams p) {
+// one warp per (b, pixel); lane g owns group g (cpg consecutive channels) across all T frames.
+// Statistics in ONE pass around a pivot (the group's first value): var = E[(x-p)^2] - (E[x-p])^2 is well conditioned even
+// for the tiny groups of this norm (as few as C/32 * T = 2 values), where E[x^2]-mean^2 cancels catastrophically.
+// Second pass re-reads the (L1/L2-resident) values, normalises and writes.  V = vector width of the channel accesses.
+template <typename OT, int V>
+__global__ void __launch_bounds__(256) temporal_gn_kernel(TgnParams p) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= p.B * p.HW) return;
   const int b = warp / p.HW, px = warp - b * p.HW;
   const int cpg = p.C / 32, c0 = lane * cpg;
   const size_t fstride = (size_t)p.HW * p.C;
   const float* base = p.x + ((size_t)b * p.T * p.HW + px) * p.C + c0;
-  // two-pass statistics (mean, then squared deviations): a group is only (C/32 x T) elements — as few as 2 — and
-  // E[x^2]-mean^2 cancels catastrophically when the group's spread is small against its mean
-  float s = 0.f;
+  const float pivot = __ldg(base);
+  float s = 0.f, ss = 0.f;
+#pragma unroll 4
   for (int t = 0; t < p.T; ++t) {
     const float* r = base + t * fstride;
-    for (int j = 0; j < cpg; ++j) s += r[j];
-  }
-  const float cnt = (float)(cpg * p.T);
-  const float mean = s / cnt;
-  float ss = 0.f;
-  for (int t = 0; t < p.T; ++t) {
-    const float* r = base + t * fstride;
-    for (int j = 0; j < cpg; ++j) {
-      float d = r[j] - mean;
-      ss = fmaf(d, d, ss);
+    for (int j = 0; j < cpg; j += V) {
+      float v[V];
+      if constexpr (V == 4) { float4 q = __ldg(reinterpret_cast<const float4*>(r + j)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+      else if constexpr (V == 2) { float2 q = __ldg(reinterpret_cast<const float2*>(r + j)); v[0] = q.x; v[1] = q.y; }
+      else v[0] = __ldg(r + j);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float d = v[k] - pivot;
+        s += d;
+        ss = fmaf(d, d, ss);
+      }
     }
   }
-  const float rstd = rsqrtf(ss / cnt + p.eps);
+  const float cnt = (float)(cpg * p.T);
+  const float md = s / cnt;
+  const float mean = pivot + md;
+  const float rstd = rsqrtf(fmaxf(ss / cnt - md * md, 0.f) + p.eps);
+#pragma unroll 4
   for (int t = 0; t < p.T; ++t) {
     const float* r = base + t * fstride;
-    size_t o = ((size_t)(b * p.T + t) * p.HW + px) * p.C + c0;
-    for (int j = 0; j < cpg; ++j) {
-      float v = (r[j] - mean) * rstd * p.gamma[c0 + j] + p.beta[c0 + j];
-      if (p.out_f32 != nullptr) p.out_f32[o + j] = v;
-      if (p.out_op != nullptr) OpType<OT>::store(reinterpret_cast<OT*>(p.out_op) + o + j, v);
+    const size_t o = ((size_t)(b * p.T + t) * p.HW + px) * p.C + c0;
+    for (int j = 0; j < cpg; j += V) {
+      float v[V];
+      if constexpr (V == 4) { float4 q = __ldg(reinterpret_cast<const float4*>(r + j)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+      else if constexpr (V == 2) { float2 q = __ldg(reinterpret_cast<const float2*>(r + j)); v[0] = q.x; v[1] = q.y; }
+      else v[0] = __ldg(r + j);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = (v[k] - mean) * rstd * __ldg(p.gamma + c0 + j + k) + __ldg(p.beta + c0 + j + k);
+      if constexpr (V == 4) {
+        if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(v[0], v[1], v[2], v[3]);
+        if (p.out_op != nullptr) OpType<OT>::store4(reinterpret_cast<OT*>(p.out_op) + o + j, make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          if (p.out_f32 != nullptr) p.out_f32[o + j + k] = v[k];
+          if (p.out_op != nullptr) OpType<OT>::store(reinterpret_cast<OT*>(p.out_op) + o + j + k, v[k]);
+        }
+      }
     }
   }
 }
@@ -159,7 +200,14 @@ extern "C" int fdm_temporal_gn(const fdm_temporal_gn_args* a, void* stream) {
   const int threads = 256;
   const int blocks = (int)((warps * 32 + threads - 1) / threads);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->op_dtype == FDM_BF16) temporal_gn_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(p);
-  else temporal_gn_kernel<float><<<blocks, threads, 0, st>>>(p);
+  const int cpg = a->C / 32;
+#define FDM_TGN(OT)                                                                    \
+  do {                                                                                 \
+    if (cpg % 4 == 0) temporal_gn_kernel<OT, 4><<<blocks, threads, 0, st>>>(p);         \
+    else if (cpg % 2 == 0) temporal_gn_kernel<OT, 2><<<blocks, threads, 0, st>>>(p);    \
+    else temporal_gn_kernel<OT, 1><<<blocks, threads, 0, st>>>(p);                      \
+  } while (0)
+  if (a->op_dtype == FDM_BF16) FDM_TGN(__nv_bfloat16);
+  else FDM_TGN(float);
   return check_launch();
 }

@@ -72,6 +72,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
   return d;
 }
+// The MMA issuer is ONE thread: its scalar instruction stream paces the tensor pipe (measured: ~110 clk per tcgen05.mma with
+// 64-bit descriptor arithmetic in the loop vs 32-64 clk of tensor work).  So descriptors are kept as a constant high word
+// and a 32-bit low word (start address >> 4 | LBO) that is advanced with plain 32-bit adds.
+constexpr uint32_t SMEM_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+// D[tmem] (+)= A * B with descriptors given as (lo, constant hi); `accumulate` is a compile-time-foldable flag
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SMEM_DESC_HI_SW128) : "memory");
+}
+
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
 __host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -86,6 +104,21 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One lane of a CONVERGED warp.  tcgen05.mma / TMA take their operands from the uniform datapath; issued under a plain
+// `if (lane == 0)` the compiler cannot prove uniformity and wraps every instruction in an ELECT/branch "waterfall" loop
+// (seen in SASS: ~9 extra instructions per UTCHMMA).  Keeping the issuing warp converged and predicating on elect.sync
+// gives straight-line UTCHMMA / UTMALDG sequences.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
 }
 
 // generic-proxy writes to shared memory (st.shared) must be fenced before the async proxy (tcgen05.mma / TMA) reads them

@@ -41,7 +41,8 @@ LinearProblem = _S("LinearProblem", [("x", vp), ("w", vp), ("b", vp), ("y", vp),
 GroupedLinearArgs = _S("GroupedLinearArgs", [("problems", vp), ("count", i32), ("max_M", i32), ("max_Nout", i32)])
 RpeHiddenProblem = _S("RpeHiddenProblem", [("wd", vp), ("bd", vp), ("hidden", vp), ("C", i32), ("te_off", i32)])
 RpeHiddenArgs = _S("RpeHiddenArgs", [("te", vp), ("frame_indices", vp), ("problems", vp),
-                                     ("B", i32), ("T", i32), ("te_stride", i32), ("count", i32), ("max_C", i32)])
+                                     ("B", i32), ("T", i32), ("te_stride", i32), ("count", i32), ("max_C", i32),
+                                     ("hidden_dtype", i32)])
 AttnTemporalArgs = _S("AttnTemporalArgs", [("qkv", vp), ("Rq", vp), ("Rk", vp), ("Rv", vp), ("mask", vp), ("out", vp),
                                            ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("heads", i32),
                                            ("qkv_dtype", i32), ("out_dtype", i32)])

@@ -204,7 +204,8 @@ class DenoiserEngine:
         return self.packed[key]
 
     def _pack_tc(self, w):
-        """[co][ci][kh][kw] or [co][ci] -> bf16 [tap][co_pad][ci_pad]  (K-major B operand, ci_pad % 64 == 0, co_pad % 16 == 0)"""
+        """[co][ci][kh][kw] or [co][ci] -> bf16 [tap = kw*k + kh][co_pad][ci_pad]  (K-major B operand, filter-column major taps,
+        ci_pad % 64 == 0, co_pad % 16 == 0)"""
         key = ("tc", w.data_ptr())
         if key not in self.packed:
             w4 = w.detach().float()
@@ -213,7 +214,7 @@ class DenoiserEngine:
             co, ci, kh, kw = w4.shape
             cip, cop = (ci + 63) // 64 * 64, (co + 15) // 16 * 16
             out = th.zeros(kh * kw, cop, cip, dtype=th.bfloat16, device=w.device)
-            out[:, :co, :ci] = w4.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(th.bfloat16)
+            out[:, :co, :ci] = w4.permute(3, 2, 0, 1).reshape(kh * kw, co, ci).to(th.bfloat16)
             self.packed[key] = out
         return self.packed[key]
 
@@ -339,52 +340,65 @@ class DenoiserEngine:
                 probs.append(dict(x=emb, w=f32(lin.weight), b=f32(lin.bias), y=(cond, te_off[(id(ab), which)] * 4), M=B,
                                   K=ted, Nout=ab.channels, ldx=ted, ldy=cond_cols, silu_in=0))
         emit_group(probs)
-        # RPENet hidden + output tables for every temporal attention
+        # RPENet hidden + output tables for every temporal attention.  bf16 mode: the C x C output linear of each net runs on
+        # tcgen05 (fdm_conv, 1x1 over the B*T*T rows, bf16 hidden); fp32 mode: one grouped CUDA-core launch.
         R = {}
         hid = {}
-        rh_probs, out_probs = [], []
+        rh_probs, out_probs, rpe_tc = [], [], []
+        hsz = self.op_size if self.use_tc else 4
         for ab in attn_blocks:
             Cc = ab.channels
             for which in ("rpe_q", "rpe_k", "rpe_v"):
                 net = getattr(ab.temporal_attention, which).rpe_net
-                hb = P.buf(f"rpe_hidden", B * T * T * Cc * 4)
+                hb = P.buf(f"rpe_hidden", B * T * T * Cc * hsz)
                 rb_ = P.buf(f"rpe_R", B * T * T * Cc * 4, True)
                 hid[(id(ab), which)], R[(id(ab), which)] = hb, rb_
                 rh_probs.append(dict(wd=f32(net.embed_distances.weight), bd=f32(net.embed_distances.bias), hidden=hb, C=Cc,
                                      te_off=te_off[(id(ab), which)]))
                 out_probs.append(dict(x=hb, w=f32(net.out.weight), b=f32(net.out.bias), y=rb_, M=B * T * T, K=Cc, Nout=Cc,
                                       ldx=Cc, ldy=Cc, silu_in=0))
+                rpe_tc.append((hb, Cc, net, rb_))
+        self._pending_rpe_tc = []
         if rh_probs:
             dev = th.zeros(len(rh_probs) * C.sizeof(N_.RpeHiddenProblem), dtype=th.uint8, device=device)
             P.keep.append(dev)
             self._pending_rh = (dev, rh_probs)
             idx = len(P.ops)
             P.op("fdm_rpe_hidden", N_.RpeHiddenArgs, te=cond, frame_indices=P.fi, problems=dev, B=B, T=T,
-                 te_stride=cond_cols, count=len(rh_probs), max_C=max(p["C"] for p in rh_probs))
+                 te_stride=cond_cols, count=len(rh_probs), max_C=max(p["C"] for p in rh_probs),
+                 hidden_dtype=self.op_dtype if self.use_tc else N_.F32)
             for p_ in rh_probs:
                 b = p_["hidden"]
                 b.first = idx if b.first is None else b.first
                 b.last = idx
-            emit_group(out_probs)
+            if self.use_tc:
+                self._pending_rpe_tc = rpe_tc  # emitted right after the conv helper is defined
+            else:
+                emit_group(out_probs)
         else:
             self._pending_rh = None
 
         # ---------------- conv helper
         def conv(a0, C0, Hin, Win, w0, Cout, k, stride=1, upsample=0, a1=None, C1=0, w1=None, bias=None, resid=None,
-                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None, flop_c0=None):
+                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None, flop_c0=None, n_frames=None):
             a_dtype = opd if a_dtype is None else a_dtype
+            Nf_ = Nf if n_frames is None else n_frames
             Hv, Wv = (Hin * 2, Win * 2) if upsample else (Hin, Win)
             Ho, Wo = (Hv + 2 * (k // 2) - k) // stride + 1, (Wv + 2 * (k // 2) - k) // stride + 1
             tc = a_dtype == N_.BF16 and self.tc_ok(C0, C1, Cout, k, stride, upsample, Ho, Wo) and (out_nchw or Cout % 4 == 0)
-            fl = 2 * Nf * Ho * Wo * Cout * (k * k * (flop_c0 or C0) + C1)  # algorithmic: padded channels do not count
+            fl = 2 * Nf_ * Ho * Wo * Cout * (k * k * (flop_c0 or C0) + C1)  # algorithmic: padded channels do not count
             P.flops += fl
             P.conv_flops += fl
             pack = self._pack_tc if tc else self._pack_simt
             P.op("fdm_conv", N_.ConvArgs, a0=a0, w0=pack(w0), a1=a1, w1=pack(w1) if w1 is not None else None, bias=bias,
-                 resid=resid, y_f32=y_f32, y_op=y_op, stats=stats, N=Nf, Hin=Hin, Win=Win, C0=C0, C1=C1, Cout=Cout,
+                 resid=resid, y_f32=y_f32, y_op=y_op, stats=stats, N=Nf_, Hin=Hin, Win=Win, C0=C0, C1=C1, Cout=Cout,
                  ksize=k, stride=stride, upsample=upsample, a_dtype=a_dtype, op_dtype=opd, out_nchw=out_nchw,
                  engine=N_.CONV_TC if tc else N_.CONV_SIMT)
             return Ho, Wo
+
+        for hb, Cc, net, rb_ in self._pending_rpe_tc:
+            conv(hb, Cc, 1, 1, net.out.weight, Cc, 1, bias=f32(net.out.bias), y_f32=rb_, n_frames=B * T * T)
+        self._pending_rpe_tc = []
 
         # ---------------- network body
         # bf16 mode: the stem conv runs on tcgen05 over a bf16 copy of the network input, channels zero-padded to 8

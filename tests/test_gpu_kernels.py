@@ -20,7 +20,7 @@ def pack_tc(w):
     co, ci, kh, kw = w.shape
     cip, cop = (ci + 63) // 64 * 64, (co + 15) // 16 * 16
     out = torch.zeros(kh * kw, cop, cip, dtype=torch.bfloat16, device=w.device)
-    out[:, :co, :ci] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16)
+    out[:, :co, :ci] = w.permute(3, 2, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16)  # tap = kw*k + kh
     return out
 
 
