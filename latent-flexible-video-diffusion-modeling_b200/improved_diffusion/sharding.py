@@ -1,0 +1,64 @@
+"""
+Multi-GPU data parallelism for the hot path, one process per GPU under torchrun:
+
+  * sampling: the videos of a batch are independent through the whole sampler (GroupNorm is per frame / per pixel,
+    attention is per (video, pixel) / (video, frame)), so the batch dimension is split across ranks with NO collective
+    inside the loop — the reference does the same with SLURM array tasks (scripts/video_sample.py:192-201).  An optional
+    one-shot all_gather returns the full batch on every rank.
+  * training: torch DistributedDataParallel around the model exactly as train_util.py:118-125 (NCCL gradient allreduce
+    over NVLink/NVSwitch, 128 MB buckets, broadcast_buffers=False); `wrap_ddp` is that call with the reference's arguments.
+"""
+import torch as th
+import torch.distributed as dist
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous, balanced [lo, hi) of `n` batch rows for `rank`: the first n % world ranks get one extra row."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _rank_world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def sample_sharded(diffusion, model, shape, model_kwargs, *, noise=None, gather=True, group=None, **kwargs):
+    """diffusion.p_sample_loop over this rank's rows of the batch.  Returns the full [B,...] tensor when `gather`
+    (ragged shards are padded for the all_gather and trimmed after), else this rank's rows and their (lo, hi)."""
+    rank, world = _rank_world(group)
+    B = shape[0]
+    lo, hi = shard_bounds(B, rank, world)
+    cut = lambda v: v[lo:hi] if isinstance(v, th.Tensor) and v.dim() > 0 and v.shape[0] == B else v
+    local_kw = {k: cut(v) for k, v in (model_kwargs or {}).items()}
+    for k in ("latent_mask",):
+        if k in kwargs:
+            kwargs[k] = cut(kwargs[k])
+    if hi > lo:
+        local, _ = diffusion.p_sample_loop(model, (hi - lo,) + tuple(shape[1:]), noise=cut(noise), model_kwargs=local_kw, **kwargs)
+    else:
+        dev = next(model.parameters()).device
+        local = th.empty((0,) + tuple(shape[1:]), device=dev)
+    if not gather or world == 1:
+        return (local, (lo, hi)) if not gather else local
+    width = (B + world - 1) // world
+    pad = th.zeros((width,) + tuple(shape[1:]), device=local.device, dtype=local.dtype)
+    pad[: hi - lo] = local
+    parts = [th.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = []
+    for r, part in enumerate(parts):
+        a, b = shard_bounds(B, r, world)
+        out.append(part[: b - a])
+    return th.cat(out, dim=0)
+
+
+def wrap_ddp(model, device=None):
+    """The DDP wrap of train_util.py:118-125 (CPU / gloo processes wrap without device_ids)."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    kw = dict(broadcast_buffers=False, bucket_cap_mb=128, find_unused_parameters=False)
+    if device is not None and th.device(device).type == "cuda":
+        return DDP(model, device_ids=[device], output_device=device, **kw)
+    return DDP(model, **kw)

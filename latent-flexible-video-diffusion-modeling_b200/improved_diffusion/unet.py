@@ -147,15 +147,16 @@ class UNetVideoModel(nn.Module):
     def forward(self, x, *, x0, timesteps, frame_indices=None, obs_mask=None, latent_mask=None,
                 return_attn_weights=False):
         """(eps [B,T,C_out,H,W] fp32, attns) — same contract as unet.py:428-464."""
-        if not x.is_cuda:
-            raise RuntimeError("UNetVideoModel runs on sm_100a kernels only: move the model and inputs to a CUDA "
-                               "device (there is no CPU fallback)")
         if return_attn_weights:
             raise NotImplementedError("return_attn_weights=True (attention-map logging, train_util.py:461) is "
                                       "outside the hot path (SURVEY §8f-4)")
         needs_grad = th.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
+            # training: interim PyTorch-autograd expression of the same network (see autograd_path.py / DESIGN.md)
             from .autograd_path import differentiable_forward
             return differentiable_forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask), None
+        if not x.is_cuda:
+            raise RuntimeError("UNetVideoModel inference runs on sm_100a kernels only: move the model and inputs to a CUDA "
+                               "device (there is no CPU fallback)")
         eps = self.engine().forward(x, x0, timesteps, frame_indices, obs_mask, latent_mask)
         return eps, None

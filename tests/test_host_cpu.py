@@ -98,7 +98,7 @@ def test_space_timesteps_errors():
 def test_cpu_tensor_is_rejected_loudly():
     model, diffusion = build(dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32))
     inp = O.synthetic_inputs(O.make_cfg(image_size=32, in_channels=4), 1, 3, 1)
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
         model(inp["x"], x0=inp["x0"], timesteps=torch.zeros(1), frame_indices=inp["frame_indices"],
               obs_mask=inp["obs_mask"], latent_mask=inp["latent_mask"])
 
@@ -116,3 +116,26 @@ def test_q_sample_and_losses_host_math_cpu():
     ref = O.posterior_from_eps(tab, x0, t, eps)
     for k in ("mean", "variance", "log_variance", "pred_xstart"):
         assert torch.equal(out[k], ref[k]), k
+
+
+def test_training_losses_and_grads_match_reference(golden):
+    """training_losses through the public API (autograd path) against the committed reference run: loss terms, parameter
+    gradients, and every parameter receiving a gradient (DDP find_unused_parameters=False, train_util.py:124)."""
+    g = golden("train_cfg1")
+    model, diffusion = build(g["over"])
+    model.load_state_dict(O.init_state_dict(O.make_cfg(**g["over"]), seed=1), strict=True)
+    model.precision = "fp32"
+    model.train()
+    inp = g["inputs"]
+    kw = dict(frame_indices=inp["frame_indices"], obs_mask=inp["obs_mask"], latent_mask=inp["latent_mask"], x0=inp["x0"])
+    terms = diffusion.training_losses(model, inp["x0"], g["t"], model_kwargs=kw, noise=g["noise"],
+                                      latent_mask=1 - inp["obs_mask"], eval_mask=inp["latent_mask"])
+    terms["loss"].mean().backward()
+    for k in ("loss", "mse", "eval-mse"):
+        assert O.rel_l2(terms[k].detach(), g["terms"][k]) <= 1e-5, k
+    grads = dict(model.named_parameters())
+    for k, ref in g["grads"].items():
+        assert O.rel_l2(grads[k].grad, ref) <= 1e-4, k
+    for k, nrm in g["grad_norms"].items():
+        assert grads[k].grad is not None, k
+        assert abs(float(grads[k].grad.norm()) - nrm) <= 1e-3 * max(nrm, 1e-6), k
