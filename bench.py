@@ -192,6 +192,53 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bench_train(dev, world, precision, steps=10, warmup=3):
+    """train samples/s on BASELINE cfg2 (Carla-latent: nc=64, nrb=1, K=5, batch 1 per GPU, 1000-step schedule): one
+    training_losses forward + backward (+ DDP gradient allreduce when world > 1) + AdamW step per iteration.
+    The backward still runs on the interim PyTorch-autograd path — reported so the number exists, not as
+    a B200-native result."""
+    import torch.distributed as dist
+    over = dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000)
+    model, diffusion, _ = build_native(over, dev)
+    model.precision = precision
+    model.train()
+    net = model
+    if world > 1:
+        from improved_diffusion.sharding import wrap_ddp
+        net = wrap_ddp(model, dev)
+    opt = th.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0)
+    B, K = 1, 5
+    batch = {k: v.to(dev) for k, v in synthetic_batch(over, B, K, 3, 20, seed=1).items()}
+    g = th.Generator(device=dev).manual_seed(0)
+
+    def step():
+        t = th.randint(0, diffusion.num_timesteps, (B,), device=dev, generator=g)
+        terms = diffusion.training_losses(net, batch["x0"], t, model_kwargs=batch, latent_mask=1 - batch["obs_mask"],
+                                          eval_mask=batch["latent_mask"])
+        opt.zero_grad(set_to_none=True)
+        terms["loss"].mean().backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    th.cuda.synchronize()
+    ms = th.tensor([e0.elapsed_time(e1)], device=dev, dtype=th.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"metric": "train samples/sec", "value": world * B * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps,
+            "config": {"workload": "cfg2-train", "batch_per_gpu": B, "frames": K, **over, "optimizer": "AdamW"},
+            "path": "interim: forward/backward through PyTorch autograd (cuDNN/cuBLAS), fused q_sample kernel; DDP when n_gpus > 1"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -202,6 +249,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -373,6 +421,11 @@ def main():
                "sample": f"{len(times)} diffusion steps (after 1 warm-up) of the same B={B},K={K} batch: oracle port of the "
                          f"reference path, fp32 torch CPU ops, {threads} threads"}
 
+    # ------------------------------------------------------------------ secondary metric: train samples/s (BASELINE cfg2)
+    train = None
+    if not args.no_train:
+        train = bench_train(dev, world, args.precision)
+
     if rank == 0:
         line = {"metric": "denoiser frame-steps/sec (sampling)", "value": value, "unit": "frame-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_hot": hot_ms,
@@ -384,7 +437,7 @@ def main():
                            "weights": "random non-zero init (zero_module tensors re-randomised)"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": args.steps * (len(P.calls) + 1),
                 "launches_per_step": len(P.calls) + 1, "roofline": roofline, "step_roofline": step_roofline,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
