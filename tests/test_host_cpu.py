@@ -139,3 +139,24 @@ def test_training_losses_and_grads_match_reference(golden):
     for k, nrm in g["grad_norms"].items():
         assert grads[k].grad is not None, k
         assert abs(float(grads[k].grad.norm()) - nrm) <= 1e-3 * max(nrm, 1e-6), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/improved_diffusion"), reason="reference checkout only exists in the build container")
+def test_drop_in_package_path_resolution():
+    """FDM_REFERENCE_PATH: hot-path modules come from this repo, every other improved_diffusion module from the reference
+    (INTEGRATION.md §2).  Runs the reference's own hierarchy-2 sampling-scheme iterator through the mixed package."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, improved_diffusion\n"
+        "from improved_diffusion import sampling_schemes, unet, gaussian_diffusion\n"
+        "assert sampling_schemes.__file__.startswith('/root/reference'), sampling_schemes.__file__\n"
+        "assert '_b200' in unet.__file__ and '_b200' in gaussian_diffusion.__file__\n"
+        "it = sampling_schemes.sampling_schemes['hierarchy-2'](video_length=300, num_obs=36, max_frames=20, step_size=10)\n"
+        "stages = [(len(o), len(l)) for o, l in it]\n"
+        "assert len(stages) == 27 and sum(o + l for o, l in stages) == 534, (len(stages), sum(o + l for o, l in stages))\n"
+    )
+    env = dict(os.environ, FDM_REFERENCE_PATH="/root/reference",
+               PYTHONPATH=os.path.join(ROOT, "latent-flexible-video-diffusion-modeling_b200"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
