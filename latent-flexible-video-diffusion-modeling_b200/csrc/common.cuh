@@ -23,7 +23,7 @@ inline int check_launch() {
     if (!(cond)) return (code); \
   } while (0)
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // exact-ish sigmoid for the fp32 parity mode (expf, not __expf): used where 1e-4 end-to-end matters
 __device__ __forceinline__ float silu_precise(float v) { return v / (1.0f + expf(-v)); }

@@ -32,6 +32,8 @@ struct HaloParams {
   int pairs_per_frame, n_items, ntiles;
   int kchunks0, kchunks1, klast0, klast1;
   int stages, a_bytes, stage_bytes;
+  int a_bytes0;  // bytes of the segment-0 A box ((2*hbox + ks - 1) rows); a_bytes is the slot size
+  int ks;  // filter size 3 (row halo of 2) or 1 (pointwise: no halo, one 'column', one 'row')
   long long* trace;  // debug (fdm_debug_set_trace): per-CTA cycle counters, NULL in production
 };
 
@@ -94,18 +96,19 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
         const int n = pair / p.pairs_per_frame, h0 = (pair - n * p.pairs_per_frame) * 2 * p.hbox;
+        const int pad = p.ks >> 1;
         for (int kc = 0; kc < p.kchunks0; ++kc) {
-          for (int s = 0; s < 3; ++s, ++it) {
+          for (int s = 0; s < p.ks; ++s, ++it) {
             const int stage = it % p.stages;
             mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
             uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
             uint8_t* b_dst = a_dst + p.a_bytes;
             if (elect_one_sync()) {
-              mbar_expect_tx(&full_bar[stage], p.a_bytes + 3 * B_TAP_BYTES);
-              tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - 1, h0 - 1, n);
+              mbar_expect_tx(&full_bar[stage], p.a_bytes0 + p.ks * B_TAP_BYTES);
+              tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - pad, h0 - pad, n);
               // weights are packed filter-column major ([s][r][co][ci]): the three filter rows of column s are ONE box
               // (a TMA instruction costs ~450 clk + 0.4 clk/row on this part, measured: tools/tma_bench.cu)
-              tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * 64, n_off, s * 3);
+              tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * 64, n_off, s * p.ks);
             }
             __syncwarp();
           }
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
         const uint32_t acc0 = tmem_base + buf * 2 * BN;
         for (int kc = 0; kc < p.kchunks0; ++kc) {
           const int nk = (kc == p.kchunks0 - 1) ? p.klast0 : 4;
-          for (int s = 0; s < 3; ++s, ++it) {
+          for (int s = 0; s < p.ks; ++s, ++it) {
             const int stage = it % p.stages;
             long long c1 = clock64();
             mbar_wait(&full_bar[stage], (it / p.stages) & 1);
@@ -151,8 +154,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             const uint32_t first = (kc | s) != 0;  // 0 only for the very first stage of the item
             if (elect_one_sync()) {
             if (nk == 4) {
-#pragma unroll
-              for (int r = 0; r < 3; ++r) {
+              for (int r = 0; r < p.ks; ++r) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                   const uint32_t a_lo = a_lo0 + (j ? tile_rows16 : 0u) + r * row16;
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                 }
               }
             } else {
-              for (int r = 0; r < 3; ++r)
+              for (int r = 0; r < p.ks; ++r)
                 for (int j = 0; j < 2; ++j)
                   for (int k = 0; k < nk; ++k)
                     umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + r * row16 + 2 * k,
@@ -344,8 +346,9 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
                        HaloParams& p, cudaStream_t st) {
   constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers
   const int extra = 1024 + 4 * 32 * HALO_STG_ROW * 4 + 2 * 4 * BN * 2 * 4;  // alignment slack + staging + statbuf
-  p.a_bytes = (2 * p.hbox + 2) * p.W * 128;
-  p.stage_bytes = p.a_bytes + 3 * BN * 128;
+  p.a_bytes0 = (2 * p.hbox + p.ks - 1) * p.W * 128;
+  p.a_bytes = p.a_bytes0 > 256 * 128 ? p.a_bytes0 : 256 * 128;  // the skip segment's box is 256 pixels
+  p.stage_bytes = p.a_bytes + p.ks * BN * 128;
   p.stages = (SMEM_MAX - extra) / p.stage_bytes;
   if (p.stages > HALO_MAX_STAGES) p.stages = HALO_MAX_STAGES;
   if (p.stages < 2) return FDM_ERR_UNSUPPORTED;
@@ -372,7 +375,8 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
 
 // FDM_ERR_UNSUPPORTED => the caller falls back to the per-tap kernel of conv_tc.cu
 int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
-  FDM_REQUIRE(a->a_dtype == FDM_BF16 && a->ksize == 3 && a->stride == 1 && !a->upsample && !a->out_nchw, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(a->a_dtype == FDM_BF16 && (a->ksize == 3 || a->ksize == 1) && a->stride == 1 && !a->upsample && !a->out_nchw,
+              FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->C0 % 8 == 0 && (a->a1 == nullptr || a->C1 % 8 == 0) && a->Cout % 4 == 0 && a->Cout >= 32, FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->y_op == nullptr || a->op_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
   const int W = a->Win, H = a->Hin;
@@ -388,13 +392,15 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.ntiles = (a->Cout + bn - 1) / bn;
   p.n_items = a->N * p.pairs_per_frame * p.ntiles;
   p.trace = g_trace;
+  p.ks = a->ksize;
   p.kchunks0 = (a->C0 + 63) / 64;
   p.kchunks1 = a->a1 ? (a->C1 + 63) / 64 : 0;
   p.klast0 = (a->C0 - (p.kchunks0 - 1) * 64 + 15) / 16;
   p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * 64 + 15) / 16 : 0;
   const int co_pad = (a->Cout + 15) / 16 * 16;
   CUtensorMap ta0, tw0, ta1, tw1;
-  bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, 2 * hbox + 2) && encode3w(&tw0, a->w0, 9, co_pad, p.kchunks0 * 64, bn, 3);
+  bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, 2 * hbox + a->ksize - 1) &&
+            encode3w(&tw0, a->w0, a->ksize * a->ksize, co_pad, p.kchunks0 * 64, bn, a->ksize);
   if (ok && a->a1) {
     ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, 2 * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, bn, 1);
   } else {

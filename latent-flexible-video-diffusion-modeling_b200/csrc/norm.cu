@@ -85,8 +85,15 @@ __global__ void gn_apply_kernel(GnParams p) {
       const float4 x = xs[u];
       float v[4] = {x.x * mul[0] + add[0], x.y * mul[1] + add[1], x.z * mul[2] + add[2], x.w * mul[3] + add[3]};
       if (p.silu) {
+        // bf16-only outputs: __expf-based SiLU (rel. error ~1e-6, far below the bf16 rounding of the store);
+        // whenever an fp32 copy is written (fp32 parity mode) the precise expf version is used
+        if (sizeof(OT) == 2 && p.out_f32 == nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = silu_precise(v[j]);
+          for (int j = 0; j < 4; ++j) v[j] = silu_f(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = silu_precise(v[j]);
+        }
       }
       size_t o = ((size_t)n * p.HW + pp) * C + c;
       float4 v4 = make_float4(v[0], v[1], v[2], v[3]);

@@ -75,6 +75,8 @@ CASES = [
     (24, 16, 16, 256, 128, 3, 1, 128, True), # halo kernel: 4 K chunks + skip segment, BN = 128
     (3, 64, 64, 192, 192, 3, 1, 0, False),   # W = 64 halo (hbox = 2), Cout = 192 -> masked second N tile
     (6, 32, 32, 32, 32, 3, 1, 0, True),      # BN = 32
+    (40, 16, 16, 128, 384, 1, 1, 0, False),  # qkv linear through the halo kernel's pointwise mode, 3 N tiles, > 148 items
+    (40, 16, 16, 128, 128, 1, 1, 0, True),   # proj_out + residual, pointwise mode
 ]
 
 
