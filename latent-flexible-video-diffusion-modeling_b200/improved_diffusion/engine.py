@@ -44,6 +44,8 @@ class Plan:
         self.graphs = {}     # CUDA graphs captured over this plan (see gaussian_diffusion._graph_sampler)
         self.debug = os.environ.get("FDM_DEBUG_TAPS", "0") == "1"
         self.taps = {}       # module name -> (Buf, C, H, W) of that layer's fp32 NHWC output (readable when debug)
+        self.side_begin = self.side_end = self.join_at = 0  # op index range of the RPE-table branch / its first consumer
+        self.side_stream = self.ev_fork = self.ev_join = None
         self.flops = 0       # algorithmic 2*MAC of every conv / linear / attention matmul of one forward
         self.conv_flops = 0
 
@@ -153,13 +155,31 @@ class Plan:
         return self.arena[b.offset:b.offset + n * esz].view(dtype).view(*shape)
 
     def run(self, stream):
-        """Launch the whole schedule on `stream` (a raw cudaStream_t).  The caller has filled the input buffers."""
+        """Launch the whole schedule on `stream` (the raw cudaStream_t of torch's CURRENT stream).  The caller has filled the
+        input buffers.  The RPE-table branch (rpe_hidden + the 21 RPENet output GEMMs: small grids that depend only on
+        (t, frame_indices)) is forked onto a side stream and joined before the first temporal attention, so it overlaps the
+        stem / first ResBlocks instead of running in front of them; inside a CUDA-graph capture the fork/join become graph
+        edges."""
         self.stats_arena.zero_()
         s = C.c_void_p(stream)
-        for name, fn, ref in self.calls:
-            rc = fn(ref, s)
+        lo, hi, join = self.side_begin, self.side_end, self.join_at
+        use_side = hi > lo and self.side_stream is not None
+        if use_side:
+            main = th.cuda.current_stream(self.arena.device)
+            assert main.cuda_stream == stream, "Plan.run expects torch's current stream"
+            ss = C.c_void_p(self.side_stream.cuda_stream)
+        for i, (name, fn, ref) in enumerate(self.calls):
+            if use_side:
+                if i == lo:
+                    self.ev_fork.record(main)
+                    self.side_stream.wait_event(self.ev_fork)
+                if i == join:
+                    main.wait_event(self.ev_join)
+            rc = fn(ref, ss if (use_side and lo <= i < hi) else s)
             if rc != 0:
                 N_.check(rc, name)
+            if use_side and i == hi - 1:
+                self.ev_join.record(self.side_stream)
 
 
 class DenoiserEngine:
@@ -350,7 +370,7 @@ class DenoiserEngine:
             Cc = ab.channels
             for which in ("rpe_q", "rpe_k", "rpe_v"):
                 net = getattr(ab.temporal_attention, which).rpe_net
-                hb = P.buf(f"rpe_hidden", B * T * T * Cc * hsz)
+                hb = P.buf(f"rpe_hidden", B * T * T * Cc * hsz, True)  # side-stream lifetime: never aliased with main-branch buffers
                 rb_ = P.buf(f"rpe_R", B * T * T * Cc * 4, True)
                 hid[(id(ab), which)], R[(id(ab), which)] = hb, rb_
                 rh_probs.append(dict(wd=f32(net.embed_distances.weight), bd=f32(net.embed_distances.bias), hidden=hb, C=Cc,
@@ -364,6 +384,7 @@ class DenoiserEngine:
             P.keep.append(dev)
             self._pending_rh = (dev, rh_probs)
             idx = len(P.ops)
+            P.side_begin = idx
             P.op("fdm_rpe_hidden", N_.RpeHiddenArgs, te=cond, frame_indices=P.fi, problems=dev, B=B, T=T,
                  te_stride=cond_cols, count=len(rh_probs), max_C=max(p["C"] for p in rh_probs),
                  hidden_dtype=self.op_dtype if self.use_tc else N_.F32)
@@ -375,6 +396,7 @@ class DenoiserEngine:
                 self._pending_rpe_tc = rpe_tc  # emitted right after the conv helper is defined
             else:
                 emit_group(out_probs)
+            P.side_end = len(P.ops)
         else:
             self._pending_rh = None
 
@@ -398,6 +420,7 @@ class DenoiserEngine:
 
         for hb, Cc, net, rb_ in self._pending_rpe_tc:
             conv(hb, Cc, 1, 1, net.out.weight, Cc, 1, bias=f32(net.out.bias), y_f32=rb_, n_frames=B * T * T)
+            P.side_end = len(P.ops)
         self._pending_rpe_tc = []
 
         # ---------------- network body
@@ -542,6 +565,11 @@ class DenoiserEngine:
              film_stride=0, film_off=0, silu=1, op_dtype=opd, eps=gn.eps)
         conv(a, h.C, H, W, cv.weight, m.out_channels, 3, bias=f32(cv.bias), y_f32=P.eps, out_nchw=1)
 
+        P.join_at = next((i for i, (fn, _, _) in enumerate(P.ops) if fn == "fdm_attn_temporal"), len(P.ops))
+        if (th.device(device).type == "cuda" and P.side_end > P.side_begin and P.join_at >= P.side_end
+                and os.environ.get("FDM_SIDE_STREAM", "1") != "0"):
+            P.side_stream = th.cuda.Stream(device)
+            P.ev_fork, P.ev_join = th.cuda.Event(), th.cuda.Event()
         # skip-connection activations must stay alive until their consumer: handled by liveness (first/last use)
         P.finalize(device)
         # fill the device-side problem arrays now that pointers are known

@@ -188,3 +188,19 @@ def test_training_losses_on_gpu_match_reference(golden, precision):
         e = O.rel_l2(grads[k].grad.cpu(), ref)
         # fp32: cuDNN/cuBLAS on the GPU vs the reference's CPU run; bf16: autocast gradient noise through ~45 layers
         assert e <= (3e-3 if precision == "fp32" else 2e-1), (k, e)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_wide_model_64px_vs_oracle(precision):
+    """cfg5's model family (64-px 4-channel latents, nc = 128 -> C up to 512, head dims 96/128, 64-wide halo convs) on a short
+    clip against the CPU oracle computed in the test."""
+    over = dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000)
+    model, diffusion, cfg, sd = build(over, precision)
+    inp = O.synthetic_inputs(cfg, 1, 3, 1, seed=21, video_len=300, pad_rows=(0,))
+    ts = torch.tensor([613.0])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, cfg, inp["x"], inp["x0"], ts, inp["frame_indices"], inp["obs_mask"], inp["latent_mask"])
+        eps, _ = model(inp["x"].cuda(), timesteps=ts.cuda(), **cuda_kw(inp))
+    e = O.rel_l2(eps.cpu(), ref)
+    print(f"wide 64px [{precision}] eps rel-L2 = {e:.3e}")
+    assert e <= TOL[precision]
