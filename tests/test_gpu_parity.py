@@ -129,7 +129,9 @@ def test_ragged_and_odd_shapes():
     """T not a multiple of anything, B > 1 with distinct frame indices per row, all-latent and all-observed rows."""
     over = dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=1000)
     model, diffusion, cfg, sd = build(over, "fp32")
-    for (B, T, n_obs, pads) in [(3, 7, 2, (0, 2)), (1, 2, 0, ()), (2, 3, 3, ()), (1, 11, 4, (0,))]:
+    # T = 17 / 25 / 33 / 40 exercise every unrolled key-count variant of the temporal attention kernel (<= 24, 32, 40)
+    for (B, T, n_obs, pads) in [(3, 7, 2, (0, 2)), (1, 2, 0, ()), (2, 3, 3, ()), (1, 11, 4, (0,)), (1, 17, 8, ()), (1, 25, 3, (0,)),
+                                (1, 33, 30, ()), (1, 40, 20, (0,))]:
         inp = O.synthetic_inputs(cfg, B, T, n_obs, seed=B * 10 + T, video_len=300, pad_rows=pads)
         t = torch.tensor([(37 * (b + 1)) % 1000 for b in range(B)])
         ts = O.model_timesteps(O.Tables(cfg), t)
@@ -204,3 +206,19 @@ def test_wide_model_64px_vs_oracle(precision):
     e = O.rel_l2(eps.cpu(), ref)
     print(f"wide 64px [{precision}] eps rel-L2 = {e:.3e}")
     assert e <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pixel_space_128px_vs_oracle(precision):
+    """cfg3's model family (128-px RGB frames: 5 resolution levels, channel_mult (1,1,2,3,4), 128-wide per-tap convs at the top,
+    64/32/16-wide halo convs below) at reduced width on a 2-frame clip against the CPU oracle."""
+    over = dict(image_size=128, in_channels=3, num_channels=32, num_res_blocks=1, diffusion_steps=1000)
+    model, diffusion, cfg, sd = build(over, precision)
+    inp = O.synthetic_inputs(cfg, 1, 2, 1, seed=31, video_len=40)
+    ts = torch.tensor([250.0])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, cfg, inp["x"], inp["x0"], ts, inp["frame_indices"], inp["obs_mask"], inp["latent_mask"])
+        eps, _ = model(inp["x"].cuda(), timesteps=ts.cuda(), **cuda_kw(inp))
+    e = O.rel_l2(eps.cpu(), ref)
+    print(f"128px [{precision}] eps rel-L2 = {e:.3e}")
+    assert eps.shape == (1, 2, 3, 128, 128) and e <= TOL[precision]
