@@ -1,6 +1,7 @@
 // C-ABI housekeeping: version, status strings, struct sizes (so the ctypes mirror can be verified on CPU).
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace fdm {
 static thread_local char g_last_err[256] = "";
@@ -8,6 +9,13 @@ void set_last_error(cudaError_t e) {
   const char* s = cudaGetErrorString(e);
   strncpy(g_last_err, s ? s : "unknown", sizeof(g_last_err) - 1);
   g_last_err[sizeof(g_last_err) - 1] = 0;
+}
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FDM_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 }  // namespace fdm
 

@@ -64,6 +64,8 @@ struct KvTile<__nv_bfloat16> {
 // (then Rv[t,:,chunk]) into a private slice with lane-parallel loads and reads them back as float4 broadcasts.
 template <int TP, int TPW, typename QT, typename OT>
 __global__ void __launch_bounds__(TA_MAX_WARPS * 32) attn_temporal_kernel(TAParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float ta_smem[];
   using KV = KvTile<QT>;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nthreads = blockDim.x;
@@ -231,7 +233,7 @@ static int launch_temporal_cfg(TAParams& p, cudaStream_t st) {
   const size_t smem = ((size_t)p.T * KvTile<QT>::WORDS_PER_S + (size_t)p.nw * 2 * TPW * p.T * TA_FC) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(attn_temporal_kernel<TP, TPW, QT, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  attn_temporal_kernel<TP, TPW, QT, OT><<<grid, p.nw * 32, smem, st>>>(p);
+  fdm::launch(attn_temporal_kernel<TP, TPW, QT, OT>, dim3(grid), dim3(p.nw * 32), smem, st, p);
   return check_launch();
 }
 
@@ -261,6 +263,8 @@ struct SAParams {
 
 template <int FQ, typename QT, typename OT>
 __global__ void __launch_bounds__(256) attn_spatial_kernel(SAParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int V = (FQ % 4 == 0) ? 4 : 2;   // vector width of shared-memory accesses (F = 24 -> FQ = 6 -> float2)
   constexpr int SUB = FQ + V;                // padded sub-vector stride: lane `sub` starts at sub*SUB
   constexpr int ROW = 4 * SUB;
@@ -362,14 +366,14 @@ template <typename QT, typename OT>
 static int launch_spatial(const SAParams& p, cudaStream_t st) {
   dim3 grid((p.L + SA_QB - 1) / SA_QB, p.heads, p.N);
   switch (p.F) {
-    case 8: attn_spatial_kernel<2, QT, OT><<<grid, 256, 0, st>>>(p); break;
-    case 16: attn_spatial_kernel<4, QT, OT><<<grid, 256, 0, st>>>(p); break;
-    case 24: attn_spatial_kernel<6, QT, OT><<<grid, 256, 0, st>>>(p); break;
-    case 32: attn_spatial_kernel<8, QT, OT><<<grid, 256, 0, st>>>(p); break;
-    case 48: attn_spatial_kernel<12, QT, OT><<<grid, 256, 0, st>>>(p); break;
-    case 64: attn_spatial_kernel<16, QT, OT><<<grid, 256, 0, st>>>(p); break;
-    case 96: attn_spatial_kernel<24, QT, OT><<<grid, 256, 0, st>>>(p); break;
-    case 128: attn_spatial_kernel<32, QT, OT><<<grid, 256, 0, st>>>(p); break;
+    case 8: fdm::launch(attn_spatial_kernel<2, QT, OT>, dim3(grid), dim3(256), 0, st, p); break;
+    case 16: fdm::launch(attn_spatial_kernel<4, QT, OT>, dim3(grid), dim3(256), 0, st, p); break;
+    case 24: fdm::launch(attn_spatial_kernel<6, QT, OT>, dim3(grid), dim3(256), 0, st, p); break;
+    case 32: fdm::launch(attn_spatial_kernel<8, QT, OT>, dim3(grid), dim3(256), 0, st, p); break;
+    case 48: fdm::launch(attn_spatial_kernel<12, QT, OT>, dim3(grid), dim3(256), 0, st, p); break;
+    case 64: fdm::launch(attn_spatial_kernel<16, QT, OT>, dim3(grid), dim3(256), 0, st, p); break;
+    case 96: fdm::launch(attn_spatial_kernel<24, QT, OT>, dim3(grid), dim3(256), 0, st, p); break;
+    case 128: fdm::launch(attn_spatial_kernel<32, QT, OT>, dim3(grid), dim3(256), 0, st, p); break;
     default: return FDM_ERR_UNSUPPORTED;
   }
   return check_launch();

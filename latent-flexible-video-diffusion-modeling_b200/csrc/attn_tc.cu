@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
   __shared__ __align__(8) uint64_t bar_load, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
 
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
   const int L = p.L, F = p.F, C = p.C;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();
 
   if (tid == 0) {
     const int loads_kv = L / p.rows;
@@ -249,7 +251,7 @@ int attn_spatial_tc_launch(const fdm_attn_spatial_args* a, cudaStream_t st) {
   }
   FDM_REQUIRE(smem <= 200 * 1024, FDM_ERR_UNSUPPORTED);
   dim3 grid((L + 127) / 128, a->heads, a->N);
-  attn_spatial_tc_kernel<<<grid, 128, smem, st>>>(tq, p);
+  fdm::launch(attn_spatial_tc_kernel, dim3(grid), dim3(128), smem, st, tq, p);
   return check_launch();
 }
 

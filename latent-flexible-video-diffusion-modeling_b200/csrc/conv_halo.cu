@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
   constexpr int TMEM_COLS = 4 * BN;  // 2 accumulator buffers x 2 M tiles
   constexpr int B_TAP_BYTES = BN * 128;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);  // [4 warps][32][HALO_STG_ROW]
   float* statbuf = staging + 4 * 32 * HALO_STG_ROW;                                    // [2 tiles][4 warps][BN][2]
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
@@ -369,7 +371,7 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
   }
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   const int grid = p.n_items < sms ? p.n_items : sms;
-  conv_halo_kernel<BN><<<grid, HALO_THREADS, smem, st>>>(ta0, tw0, ta1, tw1, p);
+  fdm::launch(conv_halo_kernel<BN>, dim3(grid), dim3(HALO_THREADS), smem, st, ta0, tw0, ta1, tw1, p);
   return check_launch();
 }
 

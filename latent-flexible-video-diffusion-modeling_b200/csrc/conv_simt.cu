@@ -29,6 +29,8 @@ struct ConvParams {
 
 template <typename AT, typename OT>
 __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
 
@@ -235,10 +237,10 @@ static int conv_simt_launch(const fdm_conv_args* a, cudaStream_t st) {
   if (a->stats != nullptr) FDM_REQUIRE((p.Ho * p.Wo) % 16 == 0, FDM_ERR_UNSUPPORTED);
   dim3 grid((p.M + BM - 1) / BM, (p.Cout + BN - 1) / BN);
   bool abf = a->a_dtype == FDM_BF16, obf = a->op_dtype == FDM_BF16;
-  if (!abf && !obf) conv_simt_kernel<float, float><<<grid, NT, 0, st>>>(p);
-  else if (!abf && obf) conv_simt_kernel<float, __nv_bfloat16><<<grid, NT, 0, st>>>(p);
-  else if (abf && !obf) conv_simt_kernel<__nv_bfloat16, float><<<grid, NT, 0, st>>>(p);
-  else conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, NT, 0, st>>>(p);
+  if (!abf && !obf) fdm::launch(conv_simt_kernel<float, float>, dim3(grid), dim3(NT), 0, st, p);
+  else if (!abf && obf) fdm::launch(conv_simt_kernel<float, __nv_bfloat16>, dim3(grid), dim3(NT), 0, st, p);
+  else if (abf && !obf) fdm::launch(conv_simt_kernel<__nv_bfloat16, float>, dim3(grid), dim3(NT), 0, st, p);
+  else fdm::launch(conv_simt_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(NT), 0, st, p);
   return check_launch();
 }
 

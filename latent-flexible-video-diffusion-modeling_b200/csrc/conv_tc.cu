@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, n_off = blockIdx.y * BN;
   const int m0 = mt * TC_BM;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
@@ -341,7 +343,7 @@ static int launch_tc(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUten
   if (stages > iters) stages = iters;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  conv_tc_kernel<BN><<<grid, TC_THREADS, stages * S::STAGE_BYTES + S::EXTRA_BYTES, st>>>(ta0, tw0, ta1, tw1, p);
+  fdm::launch(conv_tc_kernel<BN>, dim3(grid), dim3(TC_THREADS), stages * S::STAGE_BYTES + S::EXTRA_BYTES, st, ta0, tw0, ta1, tw1, p);
   return check_launch();
 }
 

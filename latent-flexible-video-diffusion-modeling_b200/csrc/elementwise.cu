@@ -8,6 +8,8 @@ namespace fdm {
 __global__ void input_prep_kernel(const float* __restrict__ x, const float* __restrict__ x0,
                                   const float* __restrict__ obs, float* __restrict__ xin,
                                   __nv_bfloat16* __restrict__ xin_bf16, int N, int C, int HW, int Cpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one thread per (n, pixel); reads are coalesced across pixels per channel plane
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * HW) return;
@@ -32,6 +34,8 @@ __global__ void input_prep_kernel(const float* __restrict__ x, const float* __re
 // ---------------- A6 nearest x2 upsample + cast (unet.py:85) ------------------------------------------
 template <typename OT>
 __global__ void cast_kernel(const float* __restrict__ x, OT* __restrict__ out, int N, int H, int W, int C, int up) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
   const int quads = C / 4;
   long long total = (long long)N * Ho * Wo * quads;
@@ -52,6 +56,8 @@ __global__ void ddpm_step_kernel(const float4* __restrict__ x, const float4* __r
                                  const float4* __restrict__ noise, const float* __restrict__ coef,
                                  const int64_t* __restrict__ t, float4* __restrict__ sample,
                                  float4* __restrict__ pred, long long per_video4, int B, int clip) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long total = per_video4 * B;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / per_video4);
@@ -78,6 +84,8 @@ __global__ void ddpm_step_kernel(const float4* __restrict__ x, const float4* __r
 __global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise,
                                 const float* __restrict__ coef2, const int64_t* __restrict__ t,
                                 float4* __restrict__ xt, long long per_video4, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long total = per_video4 * B;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / per_video4);
@@ -92,6 +100,8 @@ __global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __r
 __global__ void masked_mse_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
                                   const float* __restrict__ m1, const float* __restrict__ m2,
                                   float* __restrict__ mse, float* __restrict__ evl, long long per_frame, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = blockIdx.y, b = f / T;
   const float* e = eps + (size_t)f * per_frame;
   const float* n = noise + (size_t)f * per_frame;
@@ -119,6 +129,8 @@ __global__ void masked_mse_kernel(const float* __restrict__ eps, const float* __
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, const int64_t* __restrict__ t_index,
                                           const float* __restrict__ t_table, const float* __restrict__ freqs,
                                           float* __restrict__ out, int B, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -135,6 +147,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, const int
 // tile 16 rows x 64 cols per block, K streamed through shared memory in chunks of 32.
 constexpr int GL_TM = 16, GL_TN = 64, GL_TK = 32;
 __global__ void __launch_bounds__(256) grouped_linear_kernel(const fdm_linear_problem* __restrict__ probs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const fdm_linear_problem pr = probs[blockIdx.z];
   const int m0 = blockIdx.y * GL_TM, n0 = blockIdx.x * GL_TN;
   if (m0 >= pr.M || n0 >= pr.Nout) return;
@@ -180,6 +194,8 @@ __global__ void __launch_bounds__(256) grouped_linear_kernel(const fdm_linear_pr
 template <typename OT>
 __global__ void rpe_hidden_kernel(const float* __restrict__ te, const int64_t* __restrict__ fi,
                                   const fdm_rpe_hidden_problem* __restrict__ probs, int B, int T, int te_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const fdm_rpe_hidden_problem pr = probs[blockIdx.y];
   const int C = pr.C;
   long long total = (long long)B * T * T * C;
@@ -213,7 +229,7 @@ extern "C" int fdm_input_prep(const fdm_input_prep_args* a, void* stream) {
   FDM_REQUIRE(a->N > 0 && a->C > 0 && a->H > 0 && a->W > 0, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->xin_bf16 == nullptr || a->Cpad > a->C, FDM_ERR_BAD_ARG);
   long long total = (long long)a->N * a->H * a->W;
-  input_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a->x, a->x0, a->obs_mask, a->xin, (__nv_bfloat16*)a->xin_bf16, a->N, a->C, a->H * a->W, a->Cpad);
+  fdm::launch(input_prep_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, a->x, a->x0, a->obs_mask, a->xin, (__nv_bfloat16*)a->xin_bf16, a->N, a->C, a->H * a->W, a->Cpad);
   return check_launch();
 }
 
@@ -223,9 +239,9 @@ extern "C" int fdm_cast(const fdm_cast_args* a, void* stream) {
   long long total = (long long)a->N * a->H * a->W * (a->upsample ? 4 : 1) * (a->C / 4);
   int g = grid_for(total, 256);
   if (a->op_dtype == FDM_BF16)
-    cast_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(a->x, (__nv_bfloat16*)a->out, a->N, a->H, a->W, a->C, a->upsample);
+    fdm::launch(cast_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, (cudaStream_t)stream, a->x, (__nv_bfloat16*)a->out, a->N, a->H, a->W, a->C, a->upsample);
   else
-    cast_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(a->x, (float*)a->out, a->N, a->H, a->W, a->C, a->upsample);
+    fdm::launch(cast_kernel<float>, dim3(g), dim3(256), 0, (cudaStream_t)stream, a->x, (float*)a->out, a->N, a->H, a->W, a->C, a->upsample);
   return check_launch();
 }
 
@@ -233,8 +249,7 @@ extern "C" int fdm_ddpm_step(const fdm_ddpm_step_args* a, void* stream) {
   FDM_REQUIRE(a && a->x && a->eps && a->noise && a->coef && a->t && a->sample, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->per_video % 4 == 0 && a->B > 0, FDM_ERR_UNSUPPORTED);
   long long pv4 = a->per_video / 4;
-  ddpm_step_kernel<<<grid_for(pv4 * a->B, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)a->x, (const float4*)a->eps, (const float4*)a->noise, a->coef, a->t, (float4*)a->sample,
+  fdm::launch(ddpm_step_kernel, dim3(grid_for(pv4 * a->B, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)a->x, (const float4*)a->eps, (const float4*)a->noise, a->coef, a->t, (float4*)a->sample,
       (float4*)a->pred_xstart, pv4, a->B, a->clip);
   return check_launch();
 }
@@ -243,8 +258,7 @@ extern "C" int fdm_q_sample(const fdm_q_sample_args* a, void* stream) {
   FDM_REQUIRE(a && a->x0 && a->noise && a->coef2 && a->t && a->x_t, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->per_video % 4 == 0 && a->B > 0, FDM_ERR_UNSUPPORTED);
   long long pv4 = a->per_video / 4;
-  q_sample_kernel<<<grid_for(pv4 * a->B, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)a->x0, (const float4*)a->noise, a->coef2, a->t, (float4*)a->x_t, pv4, a->B);
+  fdm::launch(q_sample_kernel, dim3(grid_for(pv4 * a->B, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)a->x0, (const float4*)a->noise, a->coef2, a->t, (float4*)a->x_t, pv4, a->B);
   return check_launch();
 }
 
@@ -254,7 +268,7 @@ extern "C" int fdm_masked_mse(const fdm_masked_mse_args* a, void* stream) {
   int chunks = (int)((a->per_frame + 256 * 8 - 1) / (256 * 8));
   if (chunks > 64) chunks = 64;
   dim3 grid(chunks, a->B * a->T);
-  masked_mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a->eps, a->noise, a->m1, a->m2, a->mse, a->eval, a->per_frame, a->T);
+  fdm::launch(masked_mse_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a->eps, a->noise, a->m1, a->m2, a->mse, a->eval, a->per_frame, a->T);
   return check_launch();
 }
 
@@ -262,7 +276,7 @@ extern "C" int fdm_timestep_embedding(const fdm_timestep_embedding_args* a, void
   FDM_REQUIRE(a && a->freqs && a->out && a->B > 0 && a->dim >= 2, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->t != nullptr || (a->t_index != nullptr && a->t_table != nullptr), FDM_ERR_BAD_ARG);
   int total = a->B * (a->dim / 2);
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a->t, a->t_index, a->t_table, a->freqs, a->out, a->B, a->dim);
+  fdm::launch(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, (cudaStream_t)stream, a->t, a->t_index, a->t_table, a->freqs, a->out, a->B, a->dim);
   return check_launch();
 }
 
@@ -270,7 +284,7 @@ extern "C" int fdm_grouped_linear(const fdm_grouped_linear_args* a, void* stream
   FDM_REQUIRE(a && a->problems && a->count > 0 && a->max_M > 0 && a->max_Nout > 0, FDM_ERR_BAD_ARG);
   dim3 grid((a->max_Nout + GL_TN - 1) / GL_TN, (a->max_M + GL_TM - 1) / GL_TM, a->count);
   FDM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, FDM_ERR_UNSUPPORTED);
-  grouped_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a->problems);
+  fdm::launch(grouped_linear_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a->problems);
   return check_launch();
 }
 
@@ -281,8 +295,8 @@ extern "C" int fdm_rpe_hidden(const fdm_rpe_hidden_args* a, void* stream) {
   if (gx > 592) gx = 592;
   dim3 grid(gx, a->count);
   if (a->hidden_dtype == FDM_BF16)
-    rpe_hidden_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a->te, a->frame_indices, a->problems, a->B, a->T, a->te_stride);
+    fdm::launch(rpe_hidden_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a->te, a->frame_indices, a->problems, a->B, a->T, a->te_stride);
   else
-    rpe_hidden_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a->te, a->frame_indices, a->problems, a->B, a->T, a->te_stride);
+    fdm::launch(rpe_hidden_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a->te, a->frame_indices, a->problems, a->B, a->T, a->te_stride);
   return check_launch();
 }

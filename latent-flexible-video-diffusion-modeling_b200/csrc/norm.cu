@@ -17,6 +17,8 @@ struct GnParams {
 // grid: (ceil(HW / pix_per_block), N); block: (C/4) * ppi threads  (ppi pixels per iteration)
 template <typename OT>
 __global__ void gn_apply_kernel(GnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_mean[32], s_rstd[32];
   const int n = blockIdx.y;
   const int C = p.C, cpg = C / 32;
@@ -116,6 +118,8 @@ struct TgnParams {
 // Second pass re-reads the (L1/L2-resident) values, normalises and writes.  V = vector width of the channel accesses.
 template <typename OT, int V>
 __global__ void __launch_bounds__(256) temporal_gn_kernel(TgnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= p.B * p.HW) return;
   const int b = warp / p.HW, px = warp - b * p.HW;
@@ -193,8 +197,8 @@ extern "C" int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream) {
   p.pix_per_block = ppb;
   dim3 grid((a->HW + ppb - 1) / ppb, a->N);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->op_dtype == FDM_BF16) gn_apply_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(p);
-  else gn_apply_kernel<float><<<grid, threads, 0, st>>>(p);
+  if (a->op_dtype == FDM_BF16) fdm::launch(gn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(threads), 0, st, p);
+  else fdm::launch(gn_apply_kernel<float>, dim3(grid), dim3(threads), 0, st, p);
   return check_launch();
 }
 
@@ -210,9 +214,9 @@ extern "C" int fdm_temporal_gn(const fdm_temporal_gn_args* a, void* stream) {
   const int cpg = a->C / 32;
 #define FDM_TGN(OT)                                                                    \
   do {                                                                                 \
-    if (cpg % 4 == 0) temporal_gn_kernel<OT, 4><<<blocks, threads, 0, st>>>(p);         \
-    else if (cpg % 2 == 0) temporal_gn_kernel<OT, 2><<<blocks, threads, 0, st>>>(p);    \
-    else temporal_gn_kernel<OT, 1><<<blocks, threads, 0, st>>>(p);                      \
+    if (cpg % 4 == 0) fdm::launch(temporal_gn_kernel<OT, 4>, dim3(blocks), dim3(threads), 0, st, p);         \
+    else if (cpg % 2 == 0) fdm::launch(temporal_gn_kernel<OT, 2>, dim3(blocks), dim3(threads), 0, st, p);    \
+    else fdm::launch(temporal_gn_kernel<OT, 1>, dim3(blocks), dim3(threads), 0, st, p);                      \
   } while (0)
   if (a->op_dtype == FDM_BF16) FDM_TGN(__nv_bfloat16);
   else FDM_TGN(float);
