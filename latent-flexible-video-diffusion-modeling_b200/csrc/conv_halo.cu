@@ -18,9 +18,8 @@
 
 namespace fdm {
 
-constexpr int HALO_THREADS = 192;
+constexpr int HALO_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int HALO_MAX_STAGES = 4;
-constexpr int HALO_STG_ROW = 36;  // floats per staged row (32 columns + 4 pad): conflict-free float4 access
 
 struct HaloParams {
   const float* bias;
@@ -59,8 +58,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);  // [4 warps][32][HALO_STG_ROW]
-  float* statbuf = staging + 4 * 32 * HALO_STG_ROW;                                    // [2 tiles][4 warps][BN][2]
+  float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);  // [8 warps][32][16], XOR-swizzled
+  float* statbuf = staging + 8 * 32 * 16;                                              // [2 tiles][4 lane groups][BN][2]
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&ta0) : "memory");
@@ -77,7 +76,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[i], 8);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -205,92 +204,95 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int g = warp & 3;            // TMEM lane group [32g, 32g+32)
-    float* stg = staging + g * 32 * HALO_STG_ROW;
-    const int sub = lane >> 3, cq = (lane & 7) * 4;
-    const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane group: warps 2-5 drain M tile 0, warps 6-9 M tile 1 of the item.  16-column chunks:
+    // TMEM -> registers -> XOR-swizzled [32][16] staging slice (conflict-free without padding) -> 4 lanes per row (float4),
+    // 8 rows per instruction; the residual loads of a chunk are issued before any is used.
+    const int e = warp - 2;
+    const int g = warp & 3;            // TMEM lane group [32g, 32g+32) this warp may access
+    const int j = e >> 2;              // M tile of the pair
+    float* stg = staging + e * 32 * 16;
+    const int sub = lane >> 2, cq4 = lane & 3;
+    const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
     uint32_t local = 0;
     long long e_wait = 0, e_begin = clock64(), e_stats = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
       const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
       const uint32_t buf = local & 1;
       const size_t m_pair = (size_t)pair * 256;
-      // bias for this lane's 4 columns of every 32-column chunk: loaded before the accumulator wait (latency hidden)
-      float4 biasv[BN / 32];
+      const size_t m_w = m_pair + j * 128 + g * 32;  // first row of this warp's 32 rows
+      // bias for this lane's 4 columns of every 16-column chunk: loaded before the accumulator wait (latency hidden)
+      float4 biasv[BN / 16];
 #pragma unroll
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        const int col = n_off + cc * 32 + cq;
+      for (int cc = 0; cc < BN / 16; ++cc) {
+        const int col = n_off + cc * 16 + cq4 * 4;
         biasv[cc] = (p.bias != nullptr && col < p.Cout) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       long long c2 = clock64();
       mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
       e_wait += clock64() - c2;
       tcgen05_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + buf * 2 * BN + j * BN + c, v);
+      for (int c = 0; c < BN; c += 16) {
+        const int col = n_off + c + cq4 * 4;
+        const bool col_ok = col < p.Cout;
+        float4 res[4];
+        if (p.resid != nullptr && col_ok) {
 #pragma unroll
-          for (int q = 0; q < 32; q += 4)
-            *reinterpret_cast<float4*>(stg + lane * HALO_STG_ROW + q) =
-                make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
-          __syncwarp();
-          const int col = n_off + c + cq;
-          const bool col_ok = col < p.Cout;
-          const float4 bias = biasv[c / 32];
-          const size_t m_w = m_pair + j * 128 + g * 32;  // first row of this warp's 32 rows
-          float4 res[8];
-          if (p.resid != nullptr && col_ok) {
+          for (int i = 0; i < 4; ++i)
+            res[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (m_w + i * 8 + sub) * p.Cout + col));
+        } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              res[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (m_w + i * 4 + sub) * p.Cout + col));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = i * 4 + sub;
-            const float4 a = *reinterpret_cast<const float4*>(stg + row * HALO_STG_ROW + cq);
-            const float o[4] = {a.x + bias.x + res[i].x, a.y + bias.y + res[i].y, a.z + bias.z + res[i].z, a.w + bias.w + res[i].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { s1[q] += o[q]; s2[q] = fmaf(o[q], o[q], s2[q]); }
-            if (col_ok) {
-              const size_t off = (m_w + row) * p.Cout + col;
-              if (p.y_f32 != nullptr) *reinterpret_cast<float4*>(p.y_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.y_op != nullptr) OpType<__nv_bfloat16>::store4(p.y_op + off, make_float4(o[0], o[1], o[2], o[3]));
-            }
-          }
-          if (p.stats != nullptr) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 8);
-              s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 8);
-              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 16);
-              s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 16);
-            }
-            if (sub == 0) {
-              float* d = statbuf + ((size_t)(j * 4 + g) * BN + c + cq) * 2;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { d[2 * q] = s1[q]; d[2 * q + 1] = s2[q]; }
-            }
-          }
-          __syncwarp();  // staging is overwritten by the next chunk
+          for (int i = 0; i < 4; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(g * 32) << 16) + buf * 2 * BN + j * BN + c, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(stg + lane * 16 + ((q ^ ((lane >> 1) & 3)) << 2)) =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        __syncwarp();
+        const float4 bias = biasv[c / 16];
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 8 + sub;
+          const float4 a = *reinterpret_cast<const float4*>(stg + row * 16 + ((cq4 ^ ((row >> 1) & 3)) << 2));
+          const float o[4] = {a.x + bias.x + res[i].x, a.y + bias.y + res[i].y, a.z + bias.z + res[i].z, a.w + bias.w + res[i].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { s1[q] += o[q]; s2[q] = fmaf(o[q], o[q], s2[q]); }
+          if (col_ok) {
+            const size_t off = (m_w + row) * p.Cout + col;
+            if (p.y_f32 != nullptr) *reinterpret_cast<float4*>(p.y_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.y_op != nullptr) OpType<__nv_bfloat16>::store4(p.y_op + off, make_float4(o[0], o[1], o[2], o[3]));
+          }
+        }
+        if (p.stats != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int off = 4; off <= 16; off <<= 1) {
+              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], off);
+              s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], off);
+            }
+          }
+          if (sub == 0) {
+            float* d = statbuf + ((size_t)(j * 4 + g) * BN + c + cq4 * 4) * 2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { d[2 * q] = s1[q]; d[2 * q + 1] = s2[q]; }
+          }
+        }
+        __syncwarp();  // staging is overwritten by the next chunk
       }
-      // all TMEM reads of this accumulator buffer are complete (tcgen05.wait::ld inside the load helper)
+      // all TMEM reads of this warp's part of the accumulator buffer are complete (tcgen05.wait::ld inside the load helper)
       tcgen05_fence_before();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
       long long c3 = clock64();
       if (p.stats != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         // both tiles lie in one frame (a pair never straddles frames): 8 partials per (column, moment), fixed order
         const int frame = (int)(m_pair / p.HW);
-        for (int i = et; i < BN * 2; i += 128) {
+        for (int i = et; i < BN * 2; i += 256) {
           const int cc = i >> 1;
           if (n_off + cc < p.Cout) {
             float acc = 0.f;
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             atomicAdd(p.stats + ((size_t)frame * p.Cout + n_off + cc) * 2 + (i & 1), (double)acc);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       e_stats += clock64() - c3;
     }
@@ -347,7 +349,7 @@ template <int BN>
 static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
                        HaloParams& p, cudaStream_t st) {
   constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers
-  const int extra = 1024 + 4 * 32 * HALO_STG_ROW * 4 + 2 * 4 * BN * 2 * 4;  // alignment slack + staging + statbuf
+  const int extra = 1024 + 8 * 32 * 16 * 4 + 2 * 4 * BN * 2 * 4;  // alignment slack + staging + statbuf
   p.a_bytes0 = (2 * p.hbox + p.ks - 1) * p.W * 128;
   p.a_bytes = p.a_bytes0 > 256 * 128 ? p.a_bytes0 : 256 * 128;  // the skip segment's box is 256 pixels
   p.stage_bytes = p.a_bytes + p.ks * BN * 128;

@@ -29,7 +29,7 @@ def pack_simt(w):
     return w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous().float()
 
 
-def run_conv(x_nhwc, w, bias, *, stride=1, engine, x1=None, w1=None, resid=None, want_op=False, want_stats=True):
+def run_conv(x_nhwc, w, bias, *, stride=1, engine, x1=None, w1=None, resid=None, want_op=False, want_stats=True, want_f32=True):
     """x_nhwc: [N,H,W,C] bf16 (TC) or fp32/bf16 (SIMT).  Returns (y_f32 [N,Ho,Wo,Co], y_op or None, stats or None)."""
     from improved_diffusion import _native as N_
     N, H, W, C0 = x_nhwc.shape
@@ -45,7 +45,7 @@ def run_conv(x_nhwc, w, bias, *, stride=1, engine, x1=None, w1=None, resid=None,
     w1p = pk(w1) if w1 is not None else None
     a = N_.ConvArgs(a0=x_nhwc.data_ptr(), w0=w0p.data_ptr(), a1=x1.data_ptr() if x1 is not None else None,
                     w1=w1p.data_ptr() if w1p is not None else None, bias=bias.data_ptr() if bias is not None else None,
-                    resid=resid.data_ptr() if resid is not None else None, y_f32=y.data_ptr(),
+                    resid=resid.data_ptr() if resid is not None else None, y_f32=y.data_ptr() if want_f32 else None,
                     y_op=yop.data_ptr() if want_op else None, stats=stats.data_ptr() if want_stats else None,
                     N=N, Hin=H, Win=W, C0=C0, C1=x1.shape[-1] if x1 is not None else 0, Cout=Co, ksize=k, stride=stride,
                     upsample=0, a_dtype=N_.BF16 if x_nhwc.dtype == torch.bfloat16 else N_.F32, op_dtype=N_.BF16, out_nchw=0,

@@ -7,7 +7,8 @@ from improved_diffusion import _native as N_
 from test_gpu_kernels import run_conv
 
 N, H, W, C0, Co = map(int, sys.argv[1:6])
-use_resid = len(sys.argv) > 6
+use_resid = "resid" in sys.argv[6:]
+kw = dict(want_stats="nostats" not in sys.argv[6:], want_op="op" in sys.argv[6:], want_f32="nof32" not in sys.argv[6:])
 x = torch.randn(N, H, W, C0, device="cuda").to(torch.bfloat16)
 w = torch.randn(Co, C0, 3, 3, device="cuda") / (C0 * 9) ** 0.5
 b = torch.randn(Co, device="cuda")
@@ -16,7 +17,7 @@ lib = N_.lib()
 for rep in range(3):
     tr = torch.zeros(148, 8, dtype=torch.int64, device="cuda")
     lib.fdm_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
-    run_conv(x, w, b, engine=N_.CONV_TC, resid=resid)
+    run_conv(x, w, b, engine=N_.CONV_TC, resid=resid, **kw)
 lib.fdm_debug_set_trace(ctypes.c_void_p(0))
 t = tr.cpu().float()
 t = t[t[:, 6] > 0]
