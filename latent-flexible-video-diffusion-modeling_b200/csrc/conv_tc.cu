@@ -183,10 +183,37 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     mbar_wait(&tmem_full_bar, 0);
     tcgen05_fence_after();
     const bool two_frames = p.HWo < 32;  // HWo == 16: rows [0,16) and [16,32) of the warp belong to different frames
+    // bf16-only outputs without residual / statistics (the qkv linears): each lane owns 32 consecutive channels of its row =
+    // 64 contiguous bytes -> packed 16-byte stores straight from the TMEM registers, no shared-memory transpose
+    const bool direct = BN >= 32 && p.y_f32 == nullptr && p.y_op != nullptr && p.resid == nullptr && p.stats == nullptr &&
+                        !p.out_nchw && (p.Cout & 31) == 0;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + c, v);
+      if (direct) {
+        const int m = m_w + lane;
+        if (m < p.M && n_off + c < p.Cout) {
+          __nv_bfloat16* dst = p.y_op + (size_t)m * p.Cout + n_off + c;
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (p.bias != nullptr) {
+              b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n_off + c + q));
+              b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n_off + c + q + 4));
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[q]) + b0.x, __uint_as_float(v[q + 1]) + b0.y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[q + 2]) + b0.z, __uint_as_float(v[q + 3]) + b0.w);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[q + 4]) + b1.x, __uint_as_float(v[q + 5]) + b1.y);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[q + 6]) + b1.z, __uint_as_float(v[q + 7]) + b1.w);
+            uint4 w;
+            w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+            w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(dst + q) = w;
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int q = 0; q < 32; q += 4)
         *reinterpret_cast<float4*>(stg + lane * TC_STG_ROW + q) =

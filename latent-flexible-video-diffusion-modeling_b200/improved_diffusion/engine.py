@@ -435,14 +435,19 @@ class DenoiserEngine:
             P.op("fdm_input_prep", N_.InputPrepArgs, x=P.x, x0=P.x0, obs_mask=P.obs, xin=xin, xin_bf16=None, N=Nf, C=Cin - 1,
                  H=H, W=W, Cpad=0)
 
-        class Act:  # residual-stream tensor: fp32 NHWC + its GroupNorm statistics
+        class Act:  # residual-stream tensor: fp32 NHWC + its GroupNorm statistics (+ optional bf16 operand copy)
             def __init__(s, buf, st, Cc, Hh, Ww):
-                s.buf, s.st, s.C, s.H, s.W = buf, st, Cc, Hh, Ww
+                s.buf, s.st, s.C, s.H, s.W, s.op = buf, st, Cc, Hh, Ww, None
+
+        def with_op_copy(act):
+            """Ask the producing conv to also store a bf16 copy (a stride-2 Downsample conv reads it directly: no cast pass)."""
+            act.op = P.buf("act_op", Nf * act.H * act.W * act.C * osz)
+            return act.op
 
         def new_act(name, Cc, Hh, Ww):
             return Act(P.buf(name, Nf * Hh * Ww * Cc * 4), P.stats(name, Nf, Cc), Cc, Hh, Ww)
 
-        def res_block(rb, xa, xb=None):
+        def res_block(rb, xa, xb=None, want_op=False):
             Hh, Ww = xa.H, xa.W
             Ci = xa.C + (xb.C if xb else 0)
             Co = rb.out_channels
@@ -463,17 +468,18 @@ class DenoiserEngine:
                  beta=f32(gn2.bias), film=cond, out_op=a2, out_f32=None, raw_op=None, N=Nf, HW=hw, Ca=Co, Cb=0, T=T,
                  film_stride=cond_cols, film_off=film_off[id(rb)], silu=1, op_dtype=opd, eps=gn2.eps)
             out = new_act("res_out", Co, Hh, Ww)
+            yop = with_op_copy(out) if want_op else None
             if has_skip:
                 sk = rb.skip_connection
                 if sk.kernel_size != (1, 1):
                     raise NotImplementedError("ResBlock(use_conv=True) 3x3 skip is never built by create_model")
                 conv(a2, Co, Hh, Ww, c2.weight, Co, 3, a1=raw, C1=Ci, w1=sk.weight, bias=self._bias_sum(c2.bias, sk.bias),
-                     y_f32=out.buf, stats=out.st)
+                     y_f32=out.buf, y_op=yop, stats=out.st)
             else:
-                conv(a2, Co, Hh, Ww, c2.weight, Co, 3, bias=f32(c2.bias), resid=xa.buf, y_f32=out.buf, stats=out.st)
+                conv(a2, Co, Hh, Ww, c2.weight, Co, 3, bias=f32(c2.bias), resid=xa.buf, y_f32=out.buf, y_op=yop, stats=out.st)
             return out
 
-        def attention(ab, x):
+        def attention(ab, x, want_op=False):
             Cc, Hh, Ww, hw = x.C, x.H, x.W, x.H * x.W
             ta, sa = ab.temporal_attention, ab.spatial_attention
             # --- temporal: GN over (C/32 x T) per (b, pixel)
@@ -503,7 +509,8 @@ class DenoiserEngine:
             P.op("fdm_attn_spatial", N_.AttnSpatialArgs, qkv=qkv2, out=o2, N=Nf, L=hw, C=Cc, heads=sa.num_heads,
                  qkv_dtype=opd, out_dtype=opd, engine=0 if self.use_tc else 1)
             z = new_act("sa_z", Cc, Hh, Ww)
-            conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf, stats=z.st)
+            conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf,
+                 y_op=with_op_copy(z) if want_op else None, stats=z.st)
             return z
 
         def resample(layer, x, down):
@@ -512,10 +519,13 @@ class DenoiserEngine:
             out = new_act("down" if down else "up", x.C, Ho, Wo)
             Hc, Wc = (x.H, x.W) if down else (Ho, Wo)  # spatial size of the conv's input
             if self.use_tc and self.tc_ok(x.C, 0, x.C, 3, 2 if down else 1, 0, Ho, Wo):
-                # bf16 operand copy of the fp32 stream (nearest x2 upsample folded into the cast, unet.py:85), then tcgen05
-                a = P.buf("resample_a", Nf * Hc * Wc * x.C * osz)
-                P.op("fdm_cast", N_.CastArgs, x=x.buf, out=a, N=Nf, H=x.H, W=x.W, C=x.C, upsample=0 if down else 1,
-                     op_dtype=opd)
+                if down and x.op is not None:
+                    a = x.op  # the producing conv already stored the bf16 operand copy
+                else:
+                    # bf16 operand copy of the fp32 stream (nearest x2 upsample folded into the cast, unet.py:85), then tcgen05
+                    a = P.buf("resample_a", Nf * Hc * Wc * x.C * osz)
+                    P.op("fdm_cast", N_.CastArgs, x=x.buf, out=a, N=Nf, H=x.H, W=x.W, C=x.C, upsample=0 if down else 1,
+                         op_dtype=opd)
                 conv(a, x.C, Hc, Wc, cv.weight, x.C, 3, stride=2 if down else 1, bias=f32(cv.bias), y_f32=out.buf,
                      stats=out.st)
             else:
@@ -526,8 +536,10 @@ class DenoiserEngine:
 
         names = {id(mod): name for name, mod in m.named_modules()}
 
-        def run_stage(stage, h, skip=None):
-            for layer in stage:
+        def run_stage(stage, h, skip=None, feeds_downsample=False):
+            layers = list(stage)
+            for li, layer in enumerate(layers):
+                want_op = feeds_downsample and li == len(layers) - 1 and self.use_tc
                 if isinstance(layer, nn.Conv2d):  # stem
                     out = new_act("stem", layer.out_channels, H, W)
                     if stem_tc:
@@ -538,10 +550,10 @@ class DenoiserEngine:
                              stats=out.st, a_dtype=N_.F32)
                     h = out
                 elif isinstance(layer, ResBlock):
-                    h = res_block(layer, h, skip)
+                    h = res_block(layer, h, skip, want_op=want_op)
                     skip = None
                 elif isinstance(layer, FactorizedAttentionBlock):
-                    h = attention(layer, h)
+                    h = attention(layer, h, want_op=want_op)
                 elif isinstance(layer, Downsample):
                     h = resample(layer, h, True)
                 elif isinstance(layer, Upsample):
@@ -552,8 +564,11 @@ class DenoiserEngine:
             return h
 
         h, hs = None, []
-        for stage in m.input_blocks:
-            h = run_stage(stage, h)
+        in_stages = list(m.input_blocks)
+        for si, stage in enumerate(in_stages):
+            nxt = in_stages[si + 1] if si + 1 < len(in_stages) else None
+            feeds = nxt is not None and len(nxt) == 1 and isinstance(nxt[0], Downsample)
+            h = run_stage(stage, h, feeds_downsample=feeds)
             hs.append(h)
         h = run_stage(m.middle_block, h)
         for stage in m.output_blocks:
