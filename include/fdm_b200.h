@@ -164,6 +164,7 @@ typedef struct {
   const fdm_linear_problem* problems; /* DEVICE array */
   int32_t count;
   int32_t max_M, max_Nout; /* grid sizing */
+  int32_t max_K;           /* largest K of the group (shared-memory sizing of the small-M kernel); 0 = unknown -> tiled kernel */
 } fdm_grouped_linear_args; /* which = 5 */
 int fdm_grouped_linear(const fdm_grouped_linear_args* a, void* stream);
 

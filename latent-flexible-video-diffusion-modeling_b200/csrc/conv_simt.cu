@@ -7,6 +7,7 @@
 // GEMM view:  Y[M = N*Ho*Wo, Cout] = sum over (segment, tap, ci) A[pixel(m, tap), ci] * W[tap][ci][co]
 // Tile 64 pixels x 64 channels x 16 k, 256 threads, 4x4 outputs per thread.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fdm {
 
@@ -260,7 +261,8 @@ extern "C" int fdm_conv(const fdm_conv_args* a, void* stream) {
   if (a->engine == FDM_CONV_TC) {
     // the halo kernel also has a pointwise mode, but measured slower than the per-tap kernel for the 1x1 qkv / proj_out
     // linears on B200 (35 vs 28 us, 30 vs 17 us: two short K stages cannot amortise the persistent pipeline) -> 3x3 only
-    int rc = a->ksize == 3 ? conv_halo_launch(a, st) : FDM_ERR_UNSUPPORTED;
+    static const bool pw = getenv("FDM_HALO_POINTWISE") != nullptr;
+    int rc = (a->ksize == 3 || pw) ? conv_halo_launch(a, st) : FDM_ERR_UNSUPPORTED;
     return rc == FDM_ERR_UNSUPPORTED ? conv_tc_launch(a, st) : rc;
   }
   if (a->engine == FDM_CONV_TC_TAP) return conv_tc_launch(a, st);

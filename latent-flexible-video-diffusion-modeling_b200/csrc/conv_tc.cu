@@ -38,6 +38,9 @@ struct TcParams {
   int klast0, klast1;  // 16-wide k-steps actually issued in the last 64-channel chunk of each K segment
   int out_nchw;
   int stages;
+  int nr;           // filter rows grouped into one pipeline stage: 1, or 3 (one TMA box of weights per filter column)
+  int a_slot;       // bytes of the A region of a stage = nr * 16 KB
+  int stage_bytes;  // nr * (16 KB + BN * 128)
 };
 
 constexpr int TC_MAX_STAGES = 8;
@@ -69,9 +72,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, n_off = blockIdx.y * BN;
   const int m0 = mt * TC_BM;
-  const int iters0 = p.taps * p.kchunks0;
+  const int iters0 = (p.taps / p.nr) * p.kchunks0;
   const int iters = iters0 + p.kchunks1;
   const int stages = p.stages;
+  constexpr int B_TAP_BYTES = BN * 128;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&ta0) : "memory");
@@ -116,17 +120,29 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         const int stage = it % stages;
         const uint32_t phase = (it / stages) & 1;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* a_dst = smem + stage * S::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_TILE_BYTES;
+        uint8_t* a_dst = smem + stage * p.stage_bytes;
+        uint8_t* b_dst = a_dst + p.a_slot;
         if (elect_one_sync()) {
-          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           if (it < iters0) {
-            const int tap = it / p.kchunks0, kc = it - tap * p.kchunks0;
-            const int s = tap / p.ksize, r = tap - s * p.ksize;  // weights are packed filter-column major: tap = s*k + r
-            tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * TC_BK, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
-            tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * TC_BK, n_off, tap);
+            const int grp = it / p.kchunks0, kc = it - grp * p.kchunks0;
+            mbar_expect_tx(&full_bar[stage], p.nr * (A_TILE_BYTES + B_TAP_BYTES));
+            if (p.nr == 1) {
+              const int s = grp / p.ksize, r = grp - s * p.ksize;  // weights are packed filter-column major: tap = s*k + r
+              tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * TC_BK, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
+              tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * TC_BK, n_off, grp);
+            } else {
+              // grouped stage = one filter column s: three shifted A boxes, ONE weight box covering its three filter rows
+              // (a TMA instruction costs ~450 clk + 0.4 clk/row here: 4 instructions per 3 taps instead of 6)
+              const int s = grp;
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+                tma_load_4d(a_dst + r * A_TILE_BYTES, &ta0, &full_bar[stage], kc * TC_BK, w0 * p.stride + s - p.pad,
+                            h0 * p.stride + r - p.pad, n0);
+              tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * TC_BK, n_off, s * 3);
+            }
           } else {
             const int kc = it - iters0;
+            mbar_expect_tx(&full_bar[stage], A_TILE_BYTES + B_TAP_BYTES);
             tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * TC_BK, w0, h0, n0);
             tma_load_3d(b_dst, &tw1, &full_bar[stage], kc * TC_BK, n_off, 0);
           }
@@ -143,11 +159,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       for (int it = 0; it < iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t a_lo = smem_desc_lo(smem_u32(smem + stage * S::STAGE_BYTES));
-        const uint32_t b_lo = a_lo + (A_TILE_BYTES >> 4);
+        const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + stage * p.stage_bytes));
+        const uint32_t b_lo0 = a_lo0 + (p.a_slot >> 4);
         // channels beyond C0/C1 in the last chunk are TMA zero-fill: skip their k-steps
         int nk = TC_BK / 16;
+        int rows = 1;
         if (it < iters0) {
+          rows = p.nr;
           if (kc_cnt == p.kchunks0 - 1) nk = p.klast0;
           if (++kc_cnt == p.kchunks0) kc_cnt = 0;
         } else if (it == iters - 1) {
@@ -155,13 +173,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
         // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) start-address field
         if (elect_one_sync()) {
-        if (nk == 4) {
-          umma_bf16_lo(tmem_base, a_lo, b_lo, idesc, it != 0);
-          umma_bf16_lo(tmem_base, a_lo + 2, b_lo + 2, idesc, 1u);
-          umma_bf16_lo(tmem_base, a_lo + 4, b_lo + 4, idesc, 1u);
-          umma_bf16_lo(tmem_base, a_lo + 6, b_lo + 6, idesc, 1u);
-        } else {
-          for (int k = 0; k < nk; ++k) umma_bf16_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, idesc, (it | k) != 0);
+        for (int r = 0; r < rows; ++r) {
+          const uint32_t a_lo = a_lo0 + r * (A_TILE_BYTES >> 4), b_lo = b_lo0 + r * (B_TAP_BYTES >> 4);
+          if (nk == 4) {
+            umma_bf16_lo(tmem_base, a_lo, b_lo, idesc, (it | r) != 0);
+            umma_bf16_lo(tmem_base, a_lo + 2, b_lo + 2, idesc, 1u);
+            umma_bf16_lo(tmem_base, a_lo + 4, b_lo + 4, idesc, 1u);
+            umma_bf16_lo(tmem_base, a_lo + 6, b_lo + 6, idesc, 1u);
+          } else {
+            for (int k = 0; k < nk; ++k) umma_bf16_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, idesc, (it | r | k) != 0);
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         }
@@ -334,12 +355,12 @@ static bool encode_act(CUtensorMap* m, const void* ptr, int N, int H, int W, int
 }
 
 // weights [taps][co_pad][ci_pad] bf16 as a (ci_pad, co_pad, taps) tensor; box (64, BN, 1)
-static bool encode_w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int ci_pad, int bn) {
+static bool encode_w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int ci_pad, int bn, int box_taps) {
   EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) return false;
   cuuint64_t dims[3] = {(cuuint64_t)ci_pad, (cuuint64_t)co_pad, (cuuint64_t)taps};
   cuuint64_t strides[2] = {(cuuint64_t)ci_pad * 2, (cuuint64_t)co_pad * ci_pad * 2};
-  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)bn, 1};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)bn, (cuuint32_t)box_taps};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -362,15 +383,16 @@ static int launch_tc(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUten
   dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.Cout + BN - 1) / BN);
   // pipeline depth: a grid that cannot even fill the SMs once is latency-bound -> one CTA per SM with as many operand
   // stages in flight as the K loop has iterations (up to 8); otherwise two CTAs per SM share the shared memory.
-  const long ctas = (long)grid.x * grid.y;
-  const int budget = ctas <= 148 ? SMEM_MAX : SMEM_MAX / 2;
-  int stages = (budget - S::EXTRA_BYTES) / S::STAGE_BYTES;
-  const int iters = p.taps * p.kchunks0 + p.kchunks1;
+  const int budget = (long)grid.x * grid.y <= 148 ? SMEM_MAX : SMEM_MAX / 2;
+  p.a_slot = p.nr * A_TILE_BYTES;
+  p.stage_bytes = p.nr * S::STAGE_BYTES;
+  int stages = (budget - S::EXTRA_BYTES) / p.stage_bytes;
+  const int iters = (p.taps / p.nr) * p.kchunks0 + p.kchunks1;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > iters) stages = iters;
-  if (stages < 1) stages = 1;
+  if (stages < 1) return FDM_ERR_UNSUPPORTED;
   p.stages = stages;
-  fdm::launch(conv_tc_kernel<BN>, dim3(grid), dim3(TC_THREADS), stages * S::STAGE_BYTES + S::EXTRA_BYTES, st, ta0, tw0, ta1, tw1, p);
+  fdm::launch(conv_tc_kernel<BN>, dim3(grid), dim3(TC_THREADS), stages * p.stage_bytes + S::EXTRA_BYTES, st, ta0, tw0, ta1, tw1, p);
   return check_launch();
 }
 
@@ -414,14 +436,19 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   // N tile: as wide as Cout allows, but narrowed while the grid would leave most SMs idle (small feature maps)
   int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : (a->Cout > 16 ? 32 : 16));
   const int mtiles = (p.M + TC_BM - 1) / TC_BM;
-  while (bn > 32 && mtiles * ((a->Cout + bn - 1) / bn) < 120) bn >>= 1;
+  // (small grids run at the per-SM TMA instruction rate, so more CTAs only help while they land on idle SMs: never exceed 148)
+  while (bn > 32 && mtiles * ((a->Cout + bn / 2 - 1) / (bn / 2)) <= 148) bn >>= 1;
   const int co_pad = round_up(a->Cout, 16);
+  // small grids (one CTA per SM, whole shared memory for the operand ring) run at the TMA INSTRUCTION rate: group the three
+  // filter rows of a filter column into one stage so a single weight box serves three taps
+  const long ctas = (long)mtiles * ((a->Cout + bn - 1) / bn);
+  p.nr = (a->ksize == 3 && ctas <= 148) ? 3 : 1;
   CUtensorMap ta0, tw0, ta1, tw1;
   bool ok = encode_act(&ta0, a->a0, a->N, a->Hin, a->Win, a->C0, p.wbox, p.hbox, p.nbox, a->stride) &&
-            encode_w(&tw0, a->w0, p.taps, co_pad, round_up(a->C0, TC_BK), bn);
+            encode_w(&tw0, a->w0, p.taps, co_pad, round_up(a->C0, TC_BK), bn, p.nr);
   if (ok && a->a1) {
     ok = encode_act(&ta1, a->a1, a->N, Ho, Wo, a->C1, p.wbox, p.hbox, p.nbox, 1) &&
-         encode_w(&tw1, a->w1, 1, co_pad, round_up(a->C1, TC_BK), bn);
+         encode_w(&tw1, a->w1, 1, co_pad, round_up(a->C1, TC_BK), bn, 1);
   } else {
     ta1 = ta0;
     tw1 = tw0;

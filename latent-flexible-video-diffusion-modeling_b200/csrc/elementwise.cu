@@ -142,9 +142,47 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, const int
   if ((dim & 1) && k == 0) out[(size_t)b * dim + dim - 1] = 0.f;
 }
 
-// ---------------- grouped small linear: y = act(x) W^T + b,  M small (<= a few thousand) ---------------
-// block (32 x 8): each warp computes 1 output column for up to 32... simple mapping: thread = (row m, col n)
-// tile 16 rows x 64 cols per block, K streamed through shared memory in chunks of 32.
+// ---------------- grouped small linear: y = act(x) W^T + b -------------------------------------------------------------
+// Two kernels.  (1) M <= 8 (the per-step conditioning path: time MLP, FiLM and RPE time projections all have M = B rows):
+// one WARP per output column, lanes split K with coalesced reads of the weight row, shuffle reduction — hundreds of
+// independent warps instead of a handful of 16x64 tiles walking K serially (these launches sit on the step's critical path).
+// (2) general tiled kernel (fp32 mode's RPENet output linear, M = B*T*T rows).
+constexpr int GL_SMALL_M = 8;
+__global__ void __launch_bounds__(256) grouped_linear_small_kernel(const fdm_linear_problem* __restrict__ probs) {
+  extern __shared__ float gl_xs[];  // [M][K]: the (activated) input rows, computed once per block
+  pdl_launch_dependents();
+  pdl_wait();
+  const fdm_linear_problem pr = probs[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (blockIdx.x * 8 >= pr.Nout) return;  // whole block out of range for this (narrower) problem
+  for (int i = threadIdx.x; i < pr.M * pr.K; i += 256) {
+    const int m = i / pr.K, k = i - m * pr.K;
+    float xv = __ldg(pr.x + (size_t)m * pr.ldx + k);
+    gl_xs[i] = pr.silu_in ? silu_precise(xv) : xv;
+  }
+  __syncthreads();
+  if (n >= pr.Nout) return;
+  float acc[GL_SMALL_M];
+#pragma unroll
+  for (int m = 0; m < GL_SMALL_M; ++m) acc[m] = 0.f;
+  const float* wrow = pr.w + (size_t)n * pr.K;
+  for (int k = lane; k < pr.K; k += 32) {
+    const float w = __ldg(wrow + k);
+#pragma unroll
+    for (int m = 0; m < GL_SMALL_M; ++m)
+      if (m < pr.M) acc[m] = fmaf(gl_xs[m * pr.K + k], w, acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < GL_SMALL_M; ++m) acc[m] = warp_sum(acc[m]);
+  if (lane == 0) {
+    const float bias = pr.b ? pr.b[n] : 0.f;
+#pragma unroll
+    for (int m = 0; m < GL_SMALL_M; ++m)
+      if (m < pr.M) pr.y[(size_t)m * pr.ldy + n] = acc[m] + bias;
+  }
+}
+
 constexpr int GL_TM = 16, GL_TN = 64, GL_TK = 32;
 __global__ void __launch_bounds__(256) grouped_linear_kernel(const fdm_linear_problem* __restrict__ probs) {
   pdl_launch_dependents();
@@ -282,6 +320,13 @@ extern "C" int fdm_timestep_embedding(const fdm_timestep_embedding_args* a, void
 
 extern "C" int fdm_grouped_linear(const fdm_grouped_linear_args* a, void* stream) {
   FDM_REQUIRE(a && a->problems && a->count > 0 && a->max_M > 0 && a->max_Nout > 0, FDM_ERR_BAD_ARG);
+  if (a->max_M <= GL_SMALL_M && a->max_K > 0 && (size_t)a->max_M * a->max_K * sizeof(float) <= 48 * 1024) {
+    dim3 grid((a->max_Nout + 7) / 8, a->count);
+    FDM_REQUIRE(grid.y <= 65535, FDM_ERR_UNSUPPORTED);
+    fdm::launch(grouped_linear_small_kernel, grid, dim3(256), (size_t)a->max_M * a->max_K * sizeof(float), (cudaStream_t)stream,
+                a->problems);
+    return check_launch();
+  }
   dim3 grid((a->max_Nout + GL_TN - 1) / GL_TN, (a->max_M + GL_TM - 1) / GL_TM, a->count);
   FDM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, FDM_ERR_UNSUPPORTED);
   fdm::launch(grouped_linear_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a->problems);

@@ -38,7 +38,7 @@ TimestepEmbeddingArgs = _S("TimestepEmbeddingArgs", [("t", vp), ("t_index", vp),
                                                      ("B", i32), ("dim", i32)])
 LinearProblem = _S("LinearProblem", [("x", vp), ("w", vp), ("b", vp), ("y", vp),
                                      ("M", i32), ("K", i32), ("Nout", i32), ("ldx", i32), ("ldy", i32), ("silu_in", i32)])
-GroupedLinearArgs = _S("GroupedLinearArgs", [("problems", vp), ("count", i32), ("max_M", i32), ("max_Nout", i32)])
+GroupedLinearArgs = _S("GroupedLinearArgs", [("problems", vp), ("count", i32), ("max_M", i32), ("max_Nout", i32), ("max_K", i32)])
 RpeHiddenProblem = _S("RpeHiddenProblem", [("wd", vp), ("bd", vp), ("hidden", vp), ("C", i32), ("te_off", i32)])
 RpeHiddenArgs = _S("RpeHiddenArgs", [("te", vp), ("frame_indices", vp), ("problems", vp),
                                      ("B", i32), ("T", i32), ("te_stride", i32), ("count", i32), ("max_C", i32),

@@ -339,7 +339,8 @@ class DenoiserEngine:
             idx = len(P.ops)
             P.flops += sum(2 * pr["M"] * pr["K"] * pr["Nout"] for pr in problems)
             P.op("fdm_grouped_linear", N_.GroupedLinearArgs, problems=dev, count=len(problems),
-                 max_M=max(p["M"] for p in problems), max_Nout=max(p["Nout"] for p in problems))
+                 max_M=max(p["M"] for p in problems), max_Nout=max(p["Nout"] for p in problems),
+                 max_K=max(p["K"] for p in problems))
             for b in touch.values():  # liveness of buffers referenced only through the device problem array
                 if b.arena == "main":
                     b.first = idx if b.first is None else b.first
