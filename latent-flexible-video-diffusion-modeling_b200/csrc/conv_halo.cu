@@ -31,6 +31,7 @@ struct HaloParams {
   int pairs_per_frame, n_items, ntiles;
   int kchunks0, kchunks1, klast0, klast1;
   int stages, a_bytes, stage_bytes;
+  int tpi;       // M tiles per work item: 2 (B shared by two tiles) or 1 (finer items when 2-tile items quantise badly on 148 SMs)
   int a_bytes0;  // bytes of the segment-0 A box ((2*hbox + ks - 1) rows); a_bytes is the slot size
   int ks;  // filter size 3 (row halo of 2) or 1 (pointwise: no halo, one 'column', one 'row')
   long long* trace;  // debug (fdm_debug_set_trace): per-CTA cycle counters, NULL in production
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
-        const int n = pair / p.pairs_per_frame, h0 = (pair - n * p.pairs_per_frame) * 2 * p.hbox;
+        const int n = pair / p.pairs_per_frame, h0 = (pair - n * p.pairs_per_frame) * p.tpi * p.hbox;
         const int pad = p.ks >> 1;
         for (int kc = 0; kc < p.kchunks0; ++kc) {
           for (int s = 0; s < p.ks; ++s, ++it) {
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
           uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
           if (elect_one_sync()) {
-            mbar_expect_tx(&full_bar[stage], 256 * 128 + B_TAP_BYTES);
+            mbar_expect_tx(&full_bar[stage], p.tpi * 128 * 128 + B_TAP_BYTES);
             tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * 64, 0, h0, n);
             tma_load_3d(a_dst + p.a_bytes, &tw1, &full_bar[stage], kc * 64, n_off, 0);
           }
@@ -156,8 +157,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             if (elect_one_sync()) {
             if (nk == 4) {
               for (int r = 0; r < p.ks; ++r) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < p.tpi; ++j) {
                   const uint32_t a_lo = a_lo0 + (j ? tile_rows16 : 0u) + r * row16;
                   const uint32_t b_lo = b_lo0 + r * (B_TAP_BYTES >> 4);
                   umma_bf16_lo(acc0 + j * BN, a_lo, b_lo, idesc, r == 0 ? first : 1u);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
               }
             } else {
               for (int r = 0; r < p.ks; ++r)
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < p.tpi; ++j)
                   for (int k = 0; k < nk; ++k)
                     umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + r * row16 + 2 * k,
                                  b_lo0 + r * (B_TAP_BYTES >> 4) + 2 * k, idesc, (r | k) == 0 ? first : 1u);
@@ -186,8 +186,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + (size_t)stage * p.stage_bytes));
           const uint32_t b_lo0 = a_lo0 + (p.a_bytes >> 4);
           if (elect_one_sync()) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < p.tpi; ++j)
               for (int k = 0; k < nk; ++k)
                 umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + 2 * k, b_lo0 + 2 * k, idesc, 1u);
             umma_commit(&empty_bar[stage]);
@@ -210,7 +209,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     // 8 rows per instruction; the residual loads of a chunk are issued before any is used.
     const int e = warp - 2;
     const int g = warp & 3;            // TMEM lane group [32g, 32g+32) this warp may access
-    const int j = e >> 2;              // M tile of the pair
+    const int hslot = e >> 2;          // second set of four warps: M tile 1 (two-tile items) or the upper half of the columns
+    const int j = p.tpi == 2 ? hslot : 0;
+    const int c_begin = p.tpi == 2 ? 0 : hslot * (BN / 2), c_end = p.tpi == 2 ? BN : c_begin + BN / 2;
     float* stg = staging + e * 32 * 16;
     const int sub = lane >> 2, cq4 = lane & 3;
     const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
       const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
       const uint32_t buf = local & 1;
-      const size_t m_pair = (size_t)pair * 256;
+      const size_t m_pair = (size_t)pair * p.tpi * 128;
       const size_t m_w = m_pair + j * 128 + g * 32;  // first row of this warp's 32 rows
       // bias for this lane's 4 columns of every 16-column chunk: loaded before the accumulator wait (latency hidden)
       float4 biasv[BN / 16];
@@ -232,8 +233,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
       e_wait += clock64() - c2;
       tcgen05_fence_after();
-#pragma unroll
-      for (int c = 0; c < BN; c += 16) {
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 16) {
         const int col = n_off + c + cq4 * 4;
         const bool col_ok = col < p.Cout;
         float4 res[4];
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             }
           }
           if (sub == 0) {
-            float* d = statbuf + ((size_t)(j * 4 + g) * BN + c + cq4 * 4) * 2;
+            float* d = statbuf + ((size_t)(hslot * 4 + g) * BN + c + cq4 * 4) * 2;
 #pragma unroll
             for (int q = 0; q < 4; ++q) { d[2 * q] = s1[q]; d[2 * q + 1] = s2[q]; }
           }
@@ -295,9 +296,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
         for (int i = et; i < BN * 2; i += 256) {
           const int cc = i >> 1;
           if (n_off + cc < p.Cout) {
+            // two-tile items: 8 partials per column (2 tiles x 4 lane groups); one-tile items: the 4 lane groups of the warp set
+            // that drained this half of the columns
+            const int k0 = p.tpi == 2 ? 0 : (cc < BN / 2 ? 0 : 4), k1 = p.tpi == 2 ? 8 : k0 + 4;
             float acc = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc += statbuf[(size_t)k * BN * 2 + i];
+            for (int k = k0; k < k1; ++k) acc += statbuf[(size_t)k * BN * 2 + i];
             atomicAdd(p.stats + ((size_t)frame * p.Cout + n_off + cc) * 2 + (i & 1), (double)acc);
           }
         }
@@ -350,8 +353,8 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
                        HaloParams& p, cudaStream_t st) {
   constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers
   const int extra = 1024 + 8 * 32 * 16 * 4 + 2 * 4 * BN * 2 * 4;  // alignment slack + staging + statbuf
-  p.a_bytes0 = (2 * p.hbox + p.ks - 1) * p.W * 128;
-  p.a_bytes = p.a_bytes0 > 256 * 128 ? p.a_bytes0 : 256 * 128;  // the skip segment's box is 256 pixels
+  p.a_bytes0 = (p.tpi * p.hbox + p.ks - 1) * p.W * 128;
+  p.a_bytes = p.a_bytes0 > p.tpi * 128 * 128 ? p.a_bytes0 : p.tpi * 128 * 128;  // the skip segment's box has no halo
   p.stage_bytes = p.a_bytes + p.ks * BN * 128;
   p.stages = (SMEM_MAX - extra) / p.stage_bytes;
   if (p.stages > HALO_MAX_STAGES) p.stages = HALO_MAX_STAGES;
@@ -386,14 +389,23 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   const int W = a->Win, H = a->Hin;
   FDM_REQUIRE(W == 16 || W == 32 || W == 64, FDM_ERR_UNSUPPORTED);
   const int hbox = 128 / W;
-  FDM_REQUIRE(H % (2 * hbox) == 0, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(H % hbox == 0, FDM_ERR_UNSUPPORTED);
   HaloParams p;
   p.bias = a->bias; p.resid = a->resid; p.y_f32 = a->y_f32; p.y_op = reinterpret_cast<__nv_bfloat16*>(a->y_op);
   p.stats = reinterpret_cast<double*>(a->stats);
   p.Cout = a->Cout; p.W = W; p.HW = H * W; p.hbox = hbox;
-  p.pairs_per_frame = H / (2 * hbox);
   const int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : 32);
   p.ntiles = (a->Cout + bn - 1) / bn;
+  // items of two M tiles share the weight tiles, but a grid of persistent CTAs finishes with its slowest CTA: pick the item
+  // size whose rounds-on-148-SMs x per-item cost is smaller (measured on B200: one-tile items cost ~30 % more per tile —
+  // no B sharing, relatively larger halo — so they only pay when two-tile items waste a whole round)
+  {
+    const long tiles = (long)a->N * (H / hbox) * p.ntiles;
+    const long rounds1 = (tiles + 147) / 148, rounds2 = (tiles / 2 + 147) / 148;
+    const bool two_ok = H % (2 * hbox) == 0;
+    p.tpi = (two_ok && 20 * rounds2 <= 13 * rounds1) ? 2 : 1;
+  }
+  p.pairs_per_frame = H / (p.tpi * hbox);
   p.n_items = a->N * p.pairs_per_frame * p.ntiles;
   p.trace = g_trace;
   p.ks = a->ksize;
@@ -403,10 +415,10 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * 64 + 15) / 16 : 0;
   const int co_pad = (a->Cout + 15) / 16 * 16;
   CUtensorMap ta0, tw0, ta1, tw1;
-  bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, 2 * hbox + a->ksize - 1) &&
+  bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, p.tpi * hbox + a->ksize - 1) &&
             encode3w(&tw0, a->w0, a->ksize * a->ksize, co_pad, p.kchunks0 * 64, bn, a->ksize);
   if (ok && a->a1) {
-    ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, 2 * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, bn, 1);
+    ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, p.tpi * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, bn, 1);
   } else {
     ta1 = ta0;
     tw1 = tw0;
