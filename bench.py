@@ -357,26 +357,58 @@ def main():
     except Exception:
         pass
     peak_tf, peak_src = (peaks["bf16_tflops"], "measured") if "bf16_tflops" in peaks else (1590.0, "fallback")
-    conv_calls = [(fn, ref) for name, fn, ref in P.calls if name == "fdm_conv"]
     import ctypes as C_
     sp = C_.c_void_p(stream.cuda_stream)
-    reps = 20
-    for fn, ref in conv_calls:
-        fn(ref, sp)
-    th.cuda.synchronize()
-    c0, c1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-    c0.record()
-    for _ in range(reps):
-        for fn, ref in conv_calls:
+
+    def is_halo(st):
+        """launches served by conv_halo_kernel (conv_halo.cu): 3x3 stride-1 tcgen05 convs on 16/32/64-wide maps"""
+        if not (st.engine == N_.CONV_TC and st.ksize == 3 and st.stride == 1 and not st.upsample and not st.out_nchw):
+            return False
+        return st.Win in (16, 32, 64) and st.Hin % (128 // st.Win) == 0 and st.Cout >= 32 and st.Cout % 4 == 0 and st.C0 % 8 == 0
+
+    def conv_flops(st):
+        pad = st.ksize // 2
+        ho = (st.Hin + 2 * pad - st.ksize) // st.stride + 1
+        wo = (st.Win + 2 * pad - st.ksize) // st.stride + 1
+        return 2 * st.N * ho * wo * st.Cout * (st.ksize * st.ksize * st.C0 + st.C1)
+
+    def time_calls(calls, reps=20):
+        for fn, ref in calls:
             fn(ref, sp)
-    c1.record()
-    th.cuda.synchronize()
-    conv_ms = c0.elapsed_time(c1) / reps
+        th.cuda.synchronize()
+        c0, c1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(reps):
+            for fn, ref in calls:
+                fn(ref, sp)
+        c1.record()
+        th.cuda.synchronize()
+        return c0.elapsed_time(c1) / reps
+
+    convs = [(fn, ref, st) for (name, fn, ref), st in zip(P.calls, P._structs) if name == "fdm_conv"]
+    halo = [(fn, ref, st) for fn, ref, st in convs if is_halo(st)]
+    conv_ms = time_calls([(fn, ref) for fn, ref, _ in convs])
     conv_tf = P.conv_flops / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "fdm_conv (implicit-GEMM conv/linear launches of one step, timed alone back-to-back)",
-                "achieved": conv_tf, "peak": peak_tf, "peak_source": peak_src, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
-                "traffic": None, "launches_per_step": len(conv_calls), "ms_per_step": conv_ms,
-                "flops_per_step": P.conv_flops, "share_of_step": conv_ms / hot_ms}
+    roofline = None
+    if halo:
+        # the dominant kernel: conv_halo_kernel.  achieved = algorithmic FLOPs per launch / average launch duration, measured
+        # live with CUDA events over its launches of one step run back-to-back on the stream they are launched on
+        halo_ms = time_calls([(fn, ref) for fn, ref, _ in halo])
+        halo_fl = sum(conv_flops(st) for _, _, st in halo)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_halo_traffic.json")))
+            if tj.get("workload") == args.workload:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        achieved = halo_fl / (halo_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "conv_halo_kernel (3x3 stride-1 implicit-GEMM convs, tcgen05)", "achieved": achieved,
+                    "peak": peak_tf, "peak_source": peak_src, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                    "launches_per_step": len(halo), "flops_per_launch": halo_fl / len(halo), "us_per_launch": 1e3 * halo_ms / len(halo),
+                    "share_of_step": halo_ms / hot_ms, "share_of_step_flops": halo_fl / P.flops}
+    all_convs = {"achieved": conv_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf, "launches_per_step": len(convs),
+                 "ms_per_step": conv_ms, "share_of_step": conv_ms / hot_ms, "flops_per_step": P.conv_flops}
     step_tf = P.flops / (ms_per_step * 1e-3) / 1e12
     step_roofline = {"bound": "tensor", "achieved": step_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": step_tf / peak_tf,
                      "flops_per_frame_step": P.flops / (B * K)}
@@ -436,7 +468,8 @@ def main():
                            "l2": "flushed between timed steps (192 MB memset outside the event pairs)",
                            "weights": "random non-zero init (zero_module tensors re-randomised)"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": args.steps * (len(P.calls) + 1),
-                "launches_per_step": len(P.calls) + 1, "roofline": roofline, "step_roofline": step_roofline,
+                "launches_per_step": len(P.calls) + 1, "roofline": roofline, "roofline_all_convs": all_convs,
+                "step_roofline": step_roofline,
                 "cpu_baseline": cpu, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:

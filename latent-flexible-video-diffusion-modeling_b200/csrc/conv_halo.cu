@@ -41,7 +41,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN>
+template <int BN, int TPI>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap ta0,
                                                                    const __grid_constant__ CUtensorMap tw0,
                                                                    const __grid_constant__ CUtensorMap ta1,
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
-        const int n = pair / p.pairs_per_frame, h0 = (pair - n * p.pairs_per_frame) * p.tpi * p.hbox;
+        const int n = pair / p.pairs_per_frame, h0 = (pair - n * p.pairs_per_frame) * TPI * p.hbox;
         const int pad = p.ks >> 1;
         for (int kc = 0; kc < p.kchunks0; ++kc) {
           for (int s = 0; s < p.ks; ++s, ++it) {
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
           uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
           if (elect_one_sync()) {
-            mbar_expect_tx(&full_bar[stage], p.tpi * 128 * 128 + B_TAP_BYTES);
+            mbar_expect_tx(&full_bar[stage], TPI * 128 * 128 + B_TAP_BYTES);
             tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * 64, 0, h0, n);
             tma_load_3d(a_dst + p.a_bytes, &tw1, &full_bar[stage], kc * 64, n_off, 0);
           }
@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             if (elect_one_sync()) {
             if (nk == 4) {
               for (int r = 0; r < p.ks; ++r) {
-                for (int j = 0; j < p.tpi; ++j) {
+#pragma unroll
+                for (int j = 0; j < TPI; ++j) {
                   const uint32_t a_lo = a_lo0 + (j ? tile_rows16 : 0u) + r * row16;
                   const uint32_t b_lo = b_lo0 + r * (B_TAP_BYTES >> 4);
                   umma_bf16_lo(acc0 + j * BN, a_lo, b_lo, idesc, r == 0 ? first : 1u);
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
               }
             } else {
               for (int r = 0; r < p.ks; ++r)
-                for (int j = 0; j < p.tpi; ++j)
+                for (int j = 0; j < TPI; ++j)
                   for (int k = 0; k < nk; ++k)
                     umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + r * row16 + 2 * k,
                                  b_lo0 + r * (B_TAP_BYTES >> 4) + 2 * k, idesc, (r | k) == 0 ? first : 1u);
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + (size_t)stage * p.stage_bytes));
           const uint32_t b_lo0 = a_lo0 + (p.a_bytes >> 4);
           if (elect_one_sync()) {
-            for (int j = 0; j < p.tpi; ++j)
+#pragma unroll
+            for (int j = 0; j < TPI; ++j)
               for (int k = 0; k < nk; ++k)
                 umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + 2 * k, b_lo0 + 2 * k, idesc, 1u);
             umma_commit(&empty_bar[stage]);
@@ -210,8 +212,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     const int e = warp - 2;
     const int g = warp & 3;            // TMEM lane group [32g, 32g+32) this warp may access
     const int hslot = e >> 2;          // second set of four warps: M tile 1 (two-tile items) or the upper half of the columns
-    const int j = p.tpi == 2 ? hslot : 0;
-    const int c_begin = p.tpi == 2 ? 0 : hslot * (BN / 2), c_end = p.tpi == 2 ? BN : c_begin + BN / 2;
+    const int j = TPI == 2 ? hslot : 0;
+    constexpr int CW = TPI == 2 ? BN : BN / 2;  // columns drained by this warp
+    const int c_begin = TPI == 2 ? 0 : hslot * CW;
     float* stg = staging + e * 32 * 16;
     const int sub = lane >> 2, cq4 = lane & 3;
     const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
@@ -220,21 +223,22 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
       const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
       const uint32_t buf = local & 1;
-      const size_t m_pair = (size_t)pair * p.tpi * 128;
+      const size_t m_pair = (size_t)pair * TPI * 128;
       const size_t m_w = m_pair + j * 128 + g * 32;  // first row of this warp's 32 rows
       // bias for this lane's 4 columns of every 16-column chunk: loaded before the accumulator wait (latency hidden)
-      float4 biasv[BN / 16];
+      float4 biasv[CW / 16];
 #pragma unroll
-      for (int cc = 0; cc < BN / 16; ++cc) {
-        const int col = n_off + cc * 16 + cq4 * 4;
+      for (int cc = 0; cc < CW / 16; ++cc) {
+        const int col = n_off + c_begin + cc * 16 + cq4 * 4;
         biasv[cc] = (p.bias != nullptr && col < p.Cout) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       long long c2 = clock64();
       mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
       e_wait += clock64() - c2;
       tcgen05_fence_after();
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; c += 16) {
+#pragma unroll
+      for (int ci = 0; ci < CW; ci += 16) {
+        const int c = c_begin + ci;
         const int col = n_off + c + cq4 * 4;
         const bool col_ok = col < p.Cout;
         float4 res[4];
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           *reinterpret_cast<float4*>(stg + lane * 16 + ((q ^ ((lane >> 1) & 3)) << 2)) =
               make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
         __syncwarp();
-        const float4 bias = biasv[c / 16];
+        const float4 bias = biasv[ci / 16];
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           if (n_off + cc < p.Cout) {
             // two-tile items: 8 partials per column (2 tiles x 4 lane groups); one-tile items: the 4 lane groups of the warp set
             // that drained this half of the columns
-            const int k0 = p.tpi == 2 ? 0 : (cc < BN / 2 ? 0 : 4), k1 = p.tpi == 2 ? 8 : k0 + 4;
+            const int k0 = TPI == 2 ? 0 : (cc < BN / 2 ? 0 : 4), k1 = TPI == 2 ? 8 : k0 + 4;
             float acc = 0.f;
             for (int k = k0; k < k1; ++k) acc += statbuf[(size_t)k * BN * 2 + i];
             atomicAdd(p.stats + ((size_t)frame * p.Cout + n_off + cc) * 2 + (i & 1), (double)acc);
@@ -348,7 +352,7 @@ static bool encode3w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int 
 static int g_num_sms = 0;
 static long long* g_trace = nullptr;
 
-template <int BN>
+template <int BN, int TPI>
 static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
                        HaloParams& p, cudaStream_t st) {
   constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers
@@ -363,7 +367,7 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN, TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (g_num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);
@@ -376,7 +380,7 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
   }
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   const int grid = p.n_items < sms ? p.n_items : sms;
-  fdm::launch(conv_halo_kernel<BN>, dim3(grid), dim3(HALO_THREADS), smem, st, ta0, tw0, ta1, tw1, p);
+  fdm::launch(conv_halo_kernel<BN, TPI>, dim3(grid), dim3(HALO_THREADS), smem, st, ta0, tw0, ta1, tw1, p);
   return check_launch();
 }
 
@@ -424,9 +428,14 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
     tw1 = tw0;
   }
   FDM_REQUIRE(ok, FDM_ERR_UNSUPPORTED);
-  if (bn == 128) return launch_halo<128>(ta0, tw0, ta1, tw1, p, st);
-  if (bn == 64) return launch_halo<64>(ta0, tw0, ta1, tw1, p, st);
-  return launch_halo<32>(ta0, tw0, ta1, tw1, p, st);
+  if (p.tpi == 2) {
+    if (bn == 128) return launch_halo<128, 2>(ta0, tw0, ta1, tw1, p, st);
+    if (bn == 64) return launch_halo<64, 2>(ta0, tw0, ta1, tw1, p, st);
+    return launch_halo<32, 2>(ta0, tw0, ta1, tw1, p, st);
+  }
+  if (bn == 128) return launch_halo<128, 1>(ta0, tw0, ta1, tw1, p, st);
+  if (bn == 64) return launch_halo<64, 1>(ta0, tw0, ta1, tw1, p, st);
+  return launch_halo<32, 1>(ta0, tw0, ta1, tw1, p, st);
 }
 
 }  // namespace fdm
