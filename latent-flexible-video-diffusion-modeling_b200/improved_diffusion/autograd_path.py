@@ -48,7 +48,7 @@ def _rpe_table(net, temb, dist, heads):
     return net.out(F.silu(e)).view(B, T, T, heads, C // heads)
 
 
-def _attention(att, x, temb, frame_indices, attn_mask):
+def _attention(att, x, temb, frame_indices, attn_mask, collect=None):
     """RPEAttention._forward over the last axis of x [B, D, C, T] (rpe.py:133-174), quirks included: the residual is
     added to the GroupNorm-ed input; GroupNorm statistics span (C/32 x T); the mask is two-group block-diagonal."""
     B, D, C, T = x.shape
@@ -70,27 +70,29 @@ def _attention(att, x, temb, frame_indices, attn_mask):
     out = p @ v
     if att.has_rpe:
         out = out + th.einsum("bdhts,btshf->bdhtf", p, _rpe_table(att.rpe_v.rpe_net, temb, dist, H).type(p.dtype))
+    if collect is not None:  # attention-map logging (rpe.py:128-130): mean over heads, absolute value
+        collect.append(p.detach().reshape(B * D, -1, T, T).mean(dim=1).abs())
     out = att.proj_out(out.permute(0, 1, 3, 2, 4).reshape(B, D, T, C))
     return (xn + out).permute(0, 1, 3, 2)
 
 
-def _factorized_attention(fab, x, temb, attn_mask, T, frame_indices):
+def _factorized_attention(fab, x, temb, attn_mask, T, frame_indices, attns=None):
     BT, C, H, W = x.shape
     B = BT // T
     x = x.view(B, T, C, H, W).permute(0, 3, 4, 2, 1).reshape(B, H * W, C, T)
-    x = _attention(fab.temporal_attention, x, temb, frame_indices, attn_mask)
+    x = _attention(fab.temporal_attention, x, temb, frame_indices, attn_mask, None if attns is None else attns["temporal"])
     x = x.reshape(B, H, W, C, T).permute(0, 4, 3, 1, 2).reshape(B, T, C, H * W)
-    x = _attention(fab.spatial_attention, x, temb, None, None)
+    x = _attention(fab.spatial_attention, x, temb, None, None, None if attns is None else attns["spatial"])
     return x.reshape(BT, C, H, W)
 
 
-def _run(stage, h, emb, attn_mask, T, frame_indices):
+def _run(stage, h, emb, attn_mask, T, frame_indices, attns=None):
     from .unet import Downsample, FactorizedAttentionBlock, ResBlock, Upsample
     for layer in stage:
         if isinstance(layer, ResBlock):
             h = _res_block(layer, h, emb)
         elif isinstance(layer, FactorizedAttentionBlock):
-            h = _factorized_attention(layer, h, emb, attn_mask, T, frame_indices)
+            h = _factorized_attention(layer, h, emb, attn_mask, T, frame_indices, attns)
         elif isinstance(layer, Downsample):
             h = layer.op(h)
         elif isinstance(layer, Upsample):
@@ -100,7 +102,11 @@ def _run(stage, h, emb, attn_mask, T, frame_indices):
     return h
 
 
-def differentiable_forward(model, x, x0, timesteps, frame_indices, obs_mask, latent_mask):
+def differentiable_forward(model, x, x0, timesteps, frame_indices, obs_mask, latent_mask, attns=None):
+    """`attns`: optional {"spatial": [], "temporal": [], "mixed": []} filled with the per-block attention maps exactly as
+    UNetVideoModel.forward(return_attn_weights=True) does upstream (unet.py:451-463) — the logging path of
+    TrainLoop.log_samples (train_util.py:451-463); it needs materialised attention matrices, so it runs here, not on the
+    fused kernels."""
     B, T, C, H, W = x.shape
     bf16 = model.precision == "bf16" and x.is_cuda
     ctx = th.autocast("cuda", dtype=th.bfloat16) if bf16 else contextlib.nullcontext()
@@ -117,11 +123,11 @@ def differentiable_forward(model, x, x0, timesteps, frame_indices, obs_mask, lat
             emb = model.time_embed(timestep_embedding(t, model.model_channels))
             hs = []
             for stage in model.input_blocks:
-                h = _run(stage, h, emb, attn_mask, T, frame_indices)
+                h = _run(stage, h, emb, attn_mask, T, frame_indices, attns)
                 hs.append(h)
-            h = _run(model.middle_block, h, emb, attn_mask, T, frame_indices)
+            h = _run(model.middle_block, h, emb, attn_mask, T, frame_indices, attns)
             for stage in model.output_blocks:
-                h = _run(stage, th.cat([h, hs.pop()], dim=1), emb, attn_mask, T, frame_indices)
+                h = _run(stage, th.cat([h, hs.pop()], dim=1), emb, attn_mask, T, frame_indices, attns)
             out = model.out[2](_silu(_gn(model.out[0], h)))
         return out.float().view(B, T, -1, H, W)
     finally:

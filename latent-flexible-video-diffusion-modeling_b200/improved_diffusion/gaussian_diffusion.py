@@ -267,14 +267,34 @@ class GaussianDiffusion:
         if fused is not None:
             final = fused(noise, clip_denoised, progress)
             return (self.decode(final) if return_decoded else final), {}
-        if return_attn_weights:
-            raise NotImplementedError("attention-map logging is outside the hot path (SURVEY §8f-4)")
-        final = None
-        for out in self.p_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
-                                                  denoised_fn=denoised_fn, model_kwargs=model_kwargs, device=device,
-                                                  progress=progress, latent_mask=latent_mask):
+        final, attns = None, {}
+        for k, out in enumerate(self.p_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
+                                                               denoised_fn=denoised_fn, model_kwargs=model_kwargs,
+                                                               device=device, progress=progress, latent_mask=latent_mask,
+                                                               return_attn_weights=return_attn_weights)):
             final = out
-        return (self.decode(final["sample"]) if return_decoded else final["sample"]), {}
+            if return_attn_weights:
+                self._accumulate_attention(attns, out["attn"], k, shape[0])
+        return (self.decode(final["sample"]) if return_decoded else final["sample"]), attns
+
+    def _accumulate_attention(self, attns, step_attn, k, batch):
+        """Per-quartile running mean of the attention maps over the reverse process (gaussian_diffusion.py:448-469): iteration k
+        of the loop is diffusion index t = N-1-k; maps are averaged over the batch, spatial maps are resized (nearest) to the
+        largest map of the U-Net and renormalised to keep their mean."""
+        quartile = (4 * (self.num_timesteps - k - 1)) // self.num_timesteps
+        for key, layers in step_attn.items():
+            if not layers:
+                continue
+            tag = f"attn/q{quartile}-{key}"
+            acc = attns.get(tag, 0)
+            target = layers[0][0].shape
+            for a in layers:
+                a = a.view(batch, a.shape[0] // batch, *a.shape[1:]).mean(dim=1)
+                if "temporal" not in key:
+                    r = th.nn.functional.interpolate(a.unsqueeze(0), size=target, mode="nearest").squeeze(0)
+                    a = r / r.mean() * a.mean()
+                acc = acc + a / (self.num_timesteps / 4)
+            attns[tag] = acc
 
     # ---- CUDA-graph sampler: {denoiser schedule + fused posterior update} replayed once per diffusion step
     def _graph_sampler(self, model, shape, denoised_fn, model_kwargs, device, return_attn_weights):

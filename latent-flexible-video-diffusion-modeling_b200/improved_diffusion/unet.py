@@ -148,8 +148,12 @@ class UNetVideoModel(nn.Module):
                 return_attn_weights=False):
         """(eps [B,T,C_out,H,W] fp32, attns) — same contract as unet.py:428-464."""
         if return_attn_weights:
-            raise NotImplementedError("return_attn_weights=True (attention-map logging, train_util.py:461) is "
-                                      "outside the hot path (SURVEY §8f-4)")
+            # attention-map logging of TrainLoop.log_samples (train_util.py:451-463): needs the materialised T x T / HW x HW
+            # attention matrices, which the fused kernels never form -> PyTorch expression of the same network (slow path)
+            from .autograd_path import differentiable_forward
+            attns = {"spatial": [], "temporal": [], "mixed": []}
+            out = differentiable_forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, attns=attns)
+            return out, attns
         needs_grad = th.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
             # training: interim PyTorch-autograd expression of the same network (see autograd_path.py / DESIGN.md)

@@ -131,6 +131,24 @@ def train_case(name, over, B, T, n_obs, pad_rows=(), seed=0):
                     grads={k: grads[k] for k in keep}), os.path.join(HERE, name + ".pt"))
 
 
+def attn_case(name, over, B, T, n_obs, seed=0):
+    """p_sample_loop(return_attn_weights=True): the per-quartile attention-map averages that TrainLoop.log_samples logs."""
+    print(name)
+    model, diffusion, cfg, sd = build_ref(over)
+    model.eval()
+    inp = O.synthetic_inputs(cfg, B, T, n_obs, seed=seed)
+    shape = tuple(inp["x0"].shape)
+    n = diffusion.num_timesteps
+    torch.manual_seed(4321)
+    noises = [torch.randn(*shape) for _ in range(n + 1)]
+    torch.manual_seed(4321)
+    final, attns = diffusion.p_sample_loop(model, shape, clip_denoised=True, model_kwargs=kw_of(inp), latent_mask=inp["latent_mask"],
+                                           return_attn_weights=True)
+    assert attns, "reference returned no attention maps"
+    torch.save(dict(over=over, B=B, T=T, n_obs=n_obs, seed=seed, noises=noises, final=final.clone(), inputs=inp,
+                    attns={k: v.clone() for k, v in attns.items()}), os.path.join(HERE, name + ".pt"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     small = dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32)
@@ -142,4 +160,5 @@ if __name__ == "__main__":
              B=1, T=5, n_obs=3, seed=7)
     sample_case("sample_cfg1", dict(small, timestep_respacing="4"), B=1, T=5, n_obs=3)
     train_case("train_cfg1", small, B=2, T=4, n_obs=2, pad_rows=(1,), seed=11)
+    attn_case("attn_cfg1", dict(small, timestep_respacing="4"), B=2, T=3, n_obs=1, seed=13)
     print("golden fixtures written to", HERE)

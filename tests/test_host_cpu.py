@@ -160,3 +160,24 @@ def test_drop_in_package_path_resolution():
                PYTHONPATH=os.path.join(ROOT, "latent-flexible-video-diffusion-modeling_b200"))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_attention_map_logging_matches_reference(golden):
+    """p_sample_loop(return_attn_weights=True) — the path TrainLoop.log_samples takes (train_util.py:451-463): same samples and
+    the same per-quartile attention-map averages as the reference (tests/golden/attn_cfg1.pt)."""
+    g = golden("attn_cfg1")
+    model, diffusion = build(g["over"])
+    model.load_state_dict(O.init_state_dict(O.make_cfg(**g["over"]), seed=1), strict=True)
+    model.precision = "fp32"
+    model.eval()
+    inp = g["inputs"]
+    kw = dict(frame_indices=inp["frame_indices"], obs_mask=inp["obs_mask"], latent_mask=inp["latent_mask"], x0=inp["x0"])
+    it = iter(g["noises"][1:])
+    diffusion._noise_fn = lambda x: next(it)
+    with torch.no_grad():
+        final, attns = diffusion.p_sample_loop(model, tuple(inp["x0"].shape), noise=g["noises"][0], model_kwargs=kw,
+                                               latent_mask=inp["latent_mask"], return_attn_weights=True)
+    assert O.rel_l2(final, g["final"]) <= 1e-5
+    assert set(attns) == set(g["attns"])
+    for k, ref in g["attns"].items():
+        assert attns[k].shape == ref.shape and O.rel_l2(attns[k], ref) <= 1e-5, k
