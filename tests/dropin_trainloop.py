@@ -1,0 +1,60 @@
+"""Helper run as a SUBPROCESS by tests/test_host_cpu.py (needs /root/reference): the reference's own TrainLoop
+(improved_diffusion/train_util.py, unmodified) driving THIS repo's model + diffusion for two optimizer steps on CPU.
+mpi4py / blobfile / wandb are absent or unwanted here and are stubbed; everything else is the reference's code."""
+import os
+import sys
+import types
+
+import torch as th
+import torch.distributed as dist
+
+# ---- stubs for the process/logging plumbing (out of scope)
+comm = types.SimpleNamespace(rank=0, size=1, Get_rank=lambda: 0, Get_size=lambda: 1, bcast=lambda x, root=0: x,
+                             gather=lambda x, root=0: [x])
+sys.modules["mpi4py"] = types.SimpleNamespace(MPI=types.SimpleNamespace(COMM_WORLD=comm))
+sys.modules["mpi4py.MPI"] = sys.modules["mpi4py"].MPI
+sys.modules["blobfile"] = types.SimpleNamespace(BlobFile=open, join=os.path.join, dirname=os.path.dirname, exists=os.path.exists)
+logged = []
+sys.modules["wandb"] = types.SimpleNamespace(log=lambda d, **k: logged.append(dict(d)), Video=lambda *a, **k: None,
+                                             run=types.SimpleNamespace(id="test"), init=lambda **k: None)
+
+import improved_diffusion  # noqa: E402  (this repo's package; FDM_REFERENCE_PATH appends the reference's modules)
+from improved_diffusion import train_util, unet  # noqa: E402
+from improved_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults  # noqa: E402
+
+assert train_util.__file__.startswith("/root/reference"), train_util.__file__
+assert "_b200" in unet.__file__
+
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[1], DIFFUSION_TRAINING_TEST="1")
+dist.init_process_group("gloo", rank=0, world_size=1)
+th.manual_seed(0)
+d = model_and_diffusion_defaults()
+d.update(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32,
+         diffusion_space_kwargs=dict(diffusion_space="pixel", pre_encoded=False, pre_encoded_stats_dict=None))
+model, diffusion = create_model_and_diffusion(**d)
+model.precision = "fp32"
+
+
+def data():
+    g = th.Generator().manual_seed(1)
+    while True:
+        yield th.randn(2, 12, 4, 32, 32, generator=g).clamp(-1, 1), {}
+
+
+train_util.TrainLoop.save = lambda self: None  # checkpoint I/O is out of scope here
+args = types.SimpleNamespace(resume_id="", T=12)
+before = [p.detach().clone() for p in model.parameters()]
+loop = train_util.TrainLoop(model=model, diffusion=diffusion, data=data(), batch_size=2, microbatch=-1, lr=1e-3, ema_rate="0.9999",
+                            log_interval=1, save_interval=10 ** 9, resume_checkpoint="", use_fp16=False,
+                            diffusion_space_kwargs=d["diffusion_space_kwargs"], fp16_scale_growth=1e-3, schedule_sampler=None,
+                            weight_decay=0.0, lr_anneal_steps=0, sample_interval=None, pad_with_random_frames=True, max_frames=5,
+                            enc_dec_chunk_size=10, args=args)
+loop.run_loop()
+changed = sum(int(not th.equal(a, p.detach())) for a, p in zip(before, model.parameters()))
+keys = set().union(*[set(x) for x in logged])
+# a freshly built model is mostly zero-initialised (zero_module): only part of the tensors get a non-zero gradient in 2 steps
+assert loop.step >= 1 and changed > 50, (loop.step, changed)
+assert {"loss", "mse", "grad_norm", "step"} <= keys, keys
+assert all(th.isfinite(p).all() for p in model.parameters())
+print("DROPIN_OK steps", loop.step + 1, "params changed", changed, "logged", sorted(keys)[:6])
+dist.destroy_process_group()

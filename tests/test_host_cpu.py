@@ -181,3 +181,21 @@ def test_attention_map_logging_matches_reference(golden):
     assert set(attns) == set(g["attns"])
     for k, ref in g["attns"].items():
         assert attns[k].shape == ref.shape and O.rel_l2(attns[k], ref) <= 1e-5, k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/improved_diffusion"), reason="reference checkout only exists in the build container")
+def test_drop_in_under_reference_trainloop():
+    """The reference's unmodified TrainLoop (train_util.py) runs two optimizer steps over this repo's model + diffusion
+    (mask sampling, training_losses, backward, AdamW, EMA, loss logging): tests/dropin_trainloop.py in a subprocess."""
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, FDM_REFERENCE_PATH="/root/reference",
+               PYTHONPATH=os.path.join(ROOT, "latent-flexible-video-diffusion-modeling_b200"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_trainloop.py"), str(port)], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DROPIN_OK" in r.stdout, (r.stdout[-1000:], r.stderr[-2000:])
