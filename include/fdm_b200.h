@@ -199,6 +199,8 @@ typedef struct {
   void* out;
   int32_t B, T, HW, C, heads;
   int32_t qkv_dtype, out_dtype;
+  const void* Rq_op; /* optional bf16 copies of Rq / Rk: with bf16 qkv the two relative-position SCORE terms then run as */
+  const void* Rk_op; /* mma.sync GEMMs over pixels (attn_temporal_mma.cu); NULL -> everything on CUDA cores            */
 } fdm_attn_temporal_args; /* which = 7 */
 int fdm_attn_temporal(const fdm_attn_temporal_args* a, void* stream);
 

@@ -45,7 +45,7 @@ RpeHiddenArgs = _S("RpeHiddenArgs", [("te", vp), ("frame_indices", vp), ("proble
                                      ("hidden_dtype", i32)])
 AttnTemporalArgs = _S("AttnTemporalArgs", [("qkv", vp), ("Rq", vp), ("Rk", vp), ("Rv", vp), ("mask", vp), ("out", vp),
                                            ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("heads", i32),
-                                           ("qkv_dtype", i32), ("out_dtype", i32)])
+                                           ("qkv_dtype", i32), ("out_dtype", i32), ("Rq_op", vp), ("Rk_op", vp)])
 AttnSpatialArgs = _S("AttnSpatialArgs", [("qkv", vp), ("out", vp), ("N", i32), ("L", i32), ("C", i32), ("heads", i32),
                                          ("qkv_dtype", i32), ("out_dtype", i32), ("engine", i32)])
 CastArgs = _S("CastArgs", [("x", vp), ("out", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32),

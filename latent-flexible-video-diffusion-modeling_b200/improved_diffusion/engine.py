@@ -193,6 +193,7 @@ class DenoiserEngine:
         self.op_size = 2 if precision == "bf16" else 4
         # FDM_CONV_ENGINE=simt forces the CUDA-core implicit GEMM everywhere (debugging / A-B timing of the tcgen05 kernel)
         self.use_tc = precision == "bf16" and os.environ.get("FDM_CONV_ENGINE", "tc") != "simt"
+        self.temporal_mma = os.environ.get("FDM_TEMPORAL_MMA", "0") == "1"
         self.plans = {}
         self.packed = {}
         self._versions = None
@@ -363,7 +364,7 @@ class DenoiserEngine:
         emit_group(probs)
         # RPENet hidden + output tables for every temporal attention.  bf16 mode: the C x C output linear of each net runs on
         # tcgen05 (fdm_conv, 1x1 over the B*T*T rows, bf16 hidden); fp32 mode: one grouped CUDA-core launch.
-        R = {}
+        R, R_op = {}, {}
         hid = {}
         rh_probs, out_probs, rpe_tc = [], [], []
         hsz = self.op_size if self.use_tc else 4
@@ -374,11 +375,16 @@ class DenoiserEngine:
                 hb = P.buf(f"rpe_hidden", B * T * T * Cc * hsz, True)  # side-stream lifetime: never aliased with main-branch buffers
                 rb_ = P.buf(f"rpe_R", B * T * T * Cc * 4, True)
                 hid[(id(ab), which)], R[(id(ab), which)] = hb, rb_
+                # bf16 copies of the score tables feed the mma.sync R-term GEMMs of the experimental temporal attention kernel
+                # (attn_temporal_mma.cu).  Measured on B200 it is NOT faster than the CUDA-core kernel (cfg4 step 2.37 vs
+                # 2.27 ms, cfg5 8.7 vs 8.0 ms), so it is off unless FDM_TEMPORAL_MMA=1.
+                rop = P.buf(f"rpe_R_op", B * T * T * Cc * 2, True) if (self.use_tc and self.temporal_mma and which != "rpe_v") else None
+                R_op[(id(ab), which)] = rop
                 rh_probs.append(dict(wd=f32(net.embed_distances.weight), bd=f32(net.embed_distances.bias), hidden=hb, C=Cc,
                                      te_off=te_off[(id(ab), which)]))
                 out_probs.append(dict(x=hb, w=f32(net.out.weight), b=f32(net.out.bias), y=rb_, M=B * T * T, K=Cc, Nout=Cc,
                                       ldx=Cc, ldy=Cc, silu_in=0))
-                rpe_tc.append((hb, Cc, net, rb_))
+                rpe_tc.append((hb, Cc, net, rb_, rop))
         self._pending_rpe_tc = []
         if rh_probs:
             dev = th.zeros(len(rh_probs) * C.sizeof(N_.RpeHiddenProblem), dtype=th.uint8, device=device)
@@ -419,8 +425,8 @@ class DenoiserEngine:
                  engine=N_.CONV_TC if tc else N_.CONV_SIMT)
             return Ho, Wo
 
-        for hb, Cc, net, rb_ in self._pending_rpe_tc:
-            conv(hb, Cc, 1, 1, net.out.weight, Cc, 1, bias=f32(net.out.bias), y_f32=rb_, n_frames=B * T * T)
+        for hb, Cc, net, rb_, rop in self._pending_rpe_tc:
+            conv(hb, Cc, 1, 1, net.out.weight, Cc, 1, bias=f32(net.out.bias), y_f32=rb_, y_op=rop, n_frames=B * T * T)
             P.side_end = len(P.ops)
         self._pending_rpe_tc = []
 
@@ -494,7 +500,7 @@ class DenoiserEngine:
             P.flops += 10 * T * T * Cc * B * hw  # QK^T, PV and the three contextual RPE einsums (rpe.py:72-83,144,166)
             P.op("fdm_attn_temporal", N_.AttnTemporalArgs, qkv=qkv, Rq=R[(id(ab), "rpe_q")], Rk=R[(id(ab), "rpe_k")],
                  Rv=R[(id(ab), "rpe_v")], mask=P.mask, out=o, B=B, T=T, HW=hw, C=Cc, heads=ta.num_heads,
-                 qkv_dtype=opd, out_dtype=opd)
+                 qkv_dtype=opd, out_dtype=opd, Rq_op=R_op.get((id(ab), "rpe_q")), Rk_op=R_op.get((id(ab), "rpe_k")))
             y = new_act("ta_y", Cc, Hh, Ww)
             conv(o, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, bias=f32(ta.proj_out.bias), resid=xn, y_f32=y.buf, stats=y.st)
             # --- spatial: plain per-frame GroupNorm, attention over the pixels of each frame

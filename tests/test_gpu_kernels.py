@@ -173,3 +173,40 @@ def test_conv_tc_head_and_stem(N, H, W, C0, Co):
     if not nchw:
         ref = ref.permute(0, 2, 3, 1)
     assert rel(y, ref) <= 1e-3, rel(y, ref)
+
+
+@pytest.mark.parametrize("B,T,HW,C,heads", [(2, 5, 256, 64, 4), (1, 20, 64, 128, 4), (2, 7, 16, 128, 4), (1, 40, 256, 384, 4),
+                                            (1, 33, 64, 96, 4), (3, 12, 40, 128, 4)])
+@pytest.mark.parametrize("use_mma", [False, True])
+def test_attn_temporal_vs_torch(B, T, HW, C, heads, use_mma):
+    """fdm_attn_temporal (CUDA-core kernel, and the variant with the two R score terms on mma.sync) against
+    softmax(scale (q k^T + q.Rk + k.Rq) + two-group mask) (v + Rv) in torch fp32 (rpe.py:139-170)."""
+    from improved_diffusion import _native as N_
+    F_ = C // heads
+    if use_mma and F_ % 16:
+        pytest.skip("the mma variant needs head dim % 16 == 0 (engine falls back to the CUDA-core kernel)")
+    g = torch.Generator(device="cuda").manual_seed(T * 7 + C)
+    qkv = torch.randn(B * T, HW, 3 * C, device="cuda", generator=g).to(torch.bfloat16)
+    Rq, Rk, Rv = (0.5 * torch.randn(B, T, T, C, device="cuda", generator=g) for _ in range(3))
+    mask = (torch.rand(B, T, device="cuda", generator=g) > 0.3).float()
+    out = torch.empty(B * T, HW, C, device="cuda", dtype=torch.bfloat16)
+    Rq_op, Rk_op = Rq.to(torch.bfloat16), Rk.to(torch.bfloat16)
+    a = N_.AttnTemporalArgs(qkv=qkv.data_ptr(), Rq=Rq.data_ptr(), Rk=Rk.data_ptr(), Rv=Rv.data_ptr(), mask=mask.data_ptr(),
+                            out=out.data_ptr(), B=B, T=T, HW=HW, C=C, heads=heads, qkv_dtype=N_.BF16, out_dtype=N_.BF16,
+                            Rq_op=Rq_op.data_ptr() if use_mma else None, Rk_op=Rk_op.data_ptr() if use_mma else None)
+    N_.call("fdm_attn_temporal", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    x = qkv.float().view(B, T, HW, 3, heads, F_).permute(3, 0, 2, 4, 1, 5)  # 3 B HW H T F
+    q, k, v = x[0], x[1], x[2]
+    rq = (Rq_op.float() if use_mma else Rq).view(B, T, T, heads, F_)
+    rk = (Rk_op.float() if use_mma else Rk).view(B, T, T, heads, F_)
+    rv = Rv.view(B, T, T, heads, F_)
+    w = q @ k.transpose(-1, -2)
+    w = w + torch.einsum("bdhtf,btshf->bdhts", q, rk) + torch.einsum("bdhtf,btshf->bdhts", k, rq).transpose(-1, -2)
+    w = w * F_ ** -0.5
+    allowed = mask.view(B, 1, T) * mask.view(B, T, 1) + (1 - mask.view(B, 1, T)) * (1 - mask.view(B, T, 1))
+    w = w.masked_fill((allowed == 0).view(B, 1, 1, T, T), float("-inf"))
+    p = torch.softmax(w, dim=-1)
+    o = p @ v + torch.einsum("bdhts,btshf->bdhtf", p, rv)
+    ref = o.permute(0, 3, 1, 2, 4).reshape(B * T, HW, C)  # B T HW H F
+    assert rel(out.float(), ref) <= 6e-3, rel(out.float(), ref)
