@@ -218,7 +218,8 @@ int fdm_attn_spatial(const fdm_attn_spatial_args* a, void* stream);
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* x; /* [N][H][W][C] */
-  void* out;      /* [N][H*f][W*f][C], f = upsample ? 2 : 1 */
+  void* out;      /* [N][H*f][W*f][C], f = upsample ? 2 : 1;  upsample = 2: ZERO-INSERTION (value at even (h,w), zeros
+                     elsewhere): the gradient of a stride-2 conv's output prepared for its dgrad/wgrad as stride-1 convs */
   int32_t N, H, W, C, upsample, op_dtype;
 } fdm_cast_args; /* which = 9 */
 int fdm_cast(const fdm_cast_args* a, void* stream);
@@ -268,6 +269,159 @@ typedef struct {
   int32_t B, T;
 } fdm_masked_mse_args; /* which = 12 */
 int fdm_masked_mse(const fdm_masked_mse_args* a, void* stream);
+
+
+/* ================================================================================================
+ * BACKWARD (training) — replaces what torch.autograd runs for the reference's training step
+ * (gaussian_diffusion.py:754-796 -> loss.backward() in train_util.py:318-344): cuDNN conv dgrad/wgrad,
+ * native_group_norm_backward, softmax/bmm/einsum backward, addmm backward.
+ *
+ * Gradient conventions: gradients of the fp32 residual stream are fp32 [N][H][W][C]; gradients of GEMM
+ * operands (outputs of GroupNorm-apply, qkv, attention outputs) are in the operand dtype.  conv DGRAD is
+ * fdm_conv itself over weights packed with mode FDM_PACK_*_DGRAD (a 3x3 pad-1 conv with the filter
+ * rotated by 180 degrees and channels swapped; stride-2 dgrad runs over a zero-inserted gradient, see
+ * fdm_cast upsample = 2).  Parameter gradients are written in PyTorch's parameter layout, fp32.
+ * ============================================================================================== */
+
+/* B0  weight packing: ONE launch re-packs every parameter after an optimizer step (device problem array) */
+enum {
+  FDM_PACK_TC_FWD = 0,     /* bf16 [tap = kw*k + kh][co_pad16][ci_pad64] = W[co][ci][kh][kw] */
+  FDM_PACK_TC_DGRAD = 1,   /* bf16 [tap = s*k + r][ci_pad16][co_pad64]   = W[co][ci][k-1-r][k-1-s] */
+  FDM_PACK_SIMT_FWD = 2,   /* fp32 [tap = kh*k + kw][ci][co] */
+  FDM_PACK_SIMT_DGRAD = 3, /* fp32 [tap = r*k + s][co][ci]               = W[co][ci][k-1-r][k-1-s] */
+  FDM_PACK_SUM2 = 4        /* fp32 [co] = src[co] + src2[co] (bias of a conv fused with its 1x1 skip conv) */
+};
+typedef struct {
+  const float* src;  /* PyTorch parameter: [co][ci][k][k] (Linear: k = 1) */
+  const float* src2; /* FDM_PACK_SUM2 only */
+  void* dst;         /* padding regions are never written: allocate zeroed */
+  int32_t co, ci, k, mode;
+} fdm_pack_problem; /* which = 15 */
+typedef struct {
+  const fdm_pack_problem* problems; /* DEVICE array */
+  int32_t count;
+  int32_t max_elems; /* largest co*ci*k*k of the group (grid sizing) */
+} fdm_pack_weights_args; /* which = 16 */
+int fdm_pack_weights(const fdm_pack_weights_args* a, void* stream);
+
+/* B1  conv / linear WGRAD (+ bias gradient) — cudnn_convolution_backward_weight / addmm backward at the nn.Conv2d / nn.Linear
+ *     sites listed at fdm_conv.   dw[co][ci][kh][kw] = sum_{n,oh,ow} dy[n,oh,ow,co] * a[n, oh*stride+kh-pad, ow*stride+kw-pad, ci]
+ *     split over pixel ranges into fp32 partials (workspace), then reduced in a fixed order (deterministic). */
+typedef struct {
+  const void* a;    /* forward input operand [N][Hin][Win][C], a_dtype */
+  const void* dy;   /* [N][Ho][Wo][Cout], dy_dtype */
+  float* dw;        /* [Cout][Cw][k][k] fp32, Cw <= C true input channels (padded operand channels are skipped) */
+  float* dbias;     /* [Cout] or NULL: column sums of dy */
+  float* dbias2;    /* [Cout] or NULL: a second copy (the 1x1 skip conv's bias sees the same gradient) */
+  void* workspace;  /* >= fdm_conv_wgrad_workspace(...) bytes */
+  size_t workspace_bytes;
+  int32_t N, Hin, Win, C, Cw, Cout, ksize, stride;
+  int32_t a_dtype, dy_dtype, engine; /* engine: FDM_CONV_SIMT | FDM_CONV_TC */
+} fdm_conv_wgrad_args; /* which = 17 */
+int fdm_conv_wgrad(const fdm_conv_wgrad_args* a, void* stream);
+size_t fdm_conv_wgrad_workspace(const fdm_conv_wgrad_args* a);
+
+/* B2  GroupNorm(+FiLM)(+SiLU) backward — native_group_norm_backward + silu_backward + the FiLM chain (unet.py:199-203)
+ *     du = (dy_op + dy_f32) * silu'(u);  per (n,c): A = sum_hw du*xhat, B = sum_hw du  (scratch `ab`, fp64 atomics)
+ *     dx = rstd * (du*k_c - mean_g(k_c*B) - xhat * mean_g(k_c*A)),  k_c = gamma_c * (1 + scale_c);   gx (+)= dx (+ draw_op)
+ *     dgamma_c = sum_n (1+scale) A;  dbeta_c = sum_n (1+scale) B;  dscale[b,c] = sum_{n in b} (gamma A + beta B);  dshift[b,c] = sum B */
+typedef struct {
+  const float* xa; const float* xb; const double* stats_a; const double* stats_b;
+  const float* gamma; const float* beta; const float* film;
+  const void* dy_op;    /* gradient wrt out_op (op_dtype) or NULL */
+  const float* dy_f32;  /* gradient wrt out_f32 or NULL */
+  const void* draw_op;  /* gradient wrt raw_op (op_dtype) or NULL */
+  float* gxa; float* gxb; /* gradients wrt xa / xb */
+  double* ab;           /* scratch [N][Ca+Cb][2], zeroed by the caller */
+  float* dgamma; float* dbeta; /* [Ca+Cb], overwritten */
+  float* dfilm;         /* [B][film_stride] rows (scale grads at film_off + c, shift grads at film_off + C + c), overwritten; or NULL */
+  int32_t N, HW, Ca, Cb, T, film_stride, film_off, silu, op_dtype;
+  int32_t acc_a, acc_b; /* 1: gx += dx, 0: gx = dx */
+  float eps;
+} fdm_gn_bwd_args; /* which = 18 */
+int fdm_gn_bwd(const fdm_gn_bwd_args* a, void* stream);
+
+/* B3  temporal GroupNorm backward (rpe.py:135-137) */
+typedef struct {
+  const float* x; const float* gamma;
+  const void* dy_op; const float* dy_f32;
+  float* gx;
+  float* dgamma; float* dbeta; /* [C], zeroed by the caller (atomic accumulation) */
+  int32_t B, T, HW, C, op_dtype, accumulate;
+  float eps;
+} fdm_temporal_gn_bwd_args; /* which = 19 */
+int fdm_temporal_gn_bwd(const fdm_temporal_gn_bwd_args* a, void* stream);
+
+/* B4  attention backward (rpe.py:139-170): recomputes the scores (flash-style), no stored attention matrix.
+ *     lse / dsum: scratch [rows] fp32 (log-sum-exp of each score row, and sum_j P_ij dP_ij)
+ *     spatial:  rows = N*heads*L;   temporal: rows = B*heads*T*HW;  dRq/dRk/dRv fp32 [B][T][T][C], zeroed by the caller */
+typedef struct {
+  const void* qkv; const void* out; /* the forward output (D_i = dO_i . O_i) */
+  const void* dout; void* dqkv;
+  float* lse; float* dsum;
+  int32_t N, L, C, heads, dtype;
+} fdm_attn_spatial_bwd_args; /* which = 20 */
+int fdm_attn_spatial_bwd(const fdm_attn_spatial_bwd_args* a, void* stream);
+
+typedef struct {
+  const void* qkv; const void* out; const float* Rq; const float* Rk; const float* Rv; const float* mask; const void* dout;
+  void* dqkv; float* dRq; float* dRk; float* dRv;
+  float* lse; float* dsum;
+  int32_t B, T, HW, C, heads, dtype;
+} fdm_attn_temporal_bwd_args; /* which = 21 */
+int fdm_attn_temporal_bwd(const fdm_attn_temporal_bwd_args* a, void* stream);
+
+/* B5  conditioning path backward: RPENet hidden layer (rpe.py:21-30) and the grouped small linears */
+typedef struct {
+  const float* wd; const float* bd;
+  const void* dhidden; /* [B][T][T][C] gradient wrt SiLU(e), dhidden_dtype */
+  float* dwd;          /* [C][3], zeroed by the caller */
+  float* dbd;          /* [C],    zeroed by the caller */
+  int32_t C, te_off;
+} fdm_rpe_hidden_bwd_problem; /* which = 22 */
+typedef struct {
+  const float* te; const int64_t* frame_indices;
+  const fdm_rpe_hidden_bwd_problem* problems; /* DEVICE array */
+  float* dte; /* [B][te_stride]: d(W_t temb + b_t) written at te_off + c */
+  int32_t B, T, te_stride, count, max_C, dhidden_dtype;
+} fdm_rpe_hidden_bwd_args; /* which = 23 */
+int fdm_rpe_hidden_bwd(const fdm_rpe_hidden_bwd_args* a, void* stream);
+
+typedef struct {
+  const float* x; const float* w; const float* dy;
+  float* dw;      /* [Nout][K] overwritten */
+  float* db;      /* [Nout] overwritten, or NULL */
+  float* dx_part; /* [M][K] this problem's contribution to dx (silu' applied when silu_in), or NULL */
+  int32_t M, K, Nout, ldx, ldy, silu_in;
+} fdm_linear_bwd_problem; /* which = 24 */
+typedef struct {
+  const fdm_linear_bwd_problem* problems; /* DEVICE array */
+  int32_t count, max_M, max_Nout, max_K;
+} fdm_grouped_linear_bwd_args; /* which = 25 */
+int fdm_grouped_linear_bwd(const fdm_grouped_linear_bwd_args* a, void* stream);
+
+/* out[i] (+)= sum_p parts[p*part_stride + i]  (fixed order) */
+typedef struct {
+  const float* parts; float* out;
+  int64_t part_stride, n;
+  int32_t count, accumulate;
+} fdm_sum_parts_args; /* which = 26 */
+int fdm_sum_parts(const fdm_sum_parts_args* a, void* stream);
+
+/* B6  gradient plumbing: dst (+)= src, optionally summing 2x2 blocks of a twice-larger src (backward of the nearest x2
+ *     upsample, unet.py:85);  NCHW fp32 -> NHWC operand with zero channel padding (gradient of eps entering the head conv) */
+typedef struct {
+  const void* src; float* dst;
+  int32_t N, H, W, C; /* dst dims */
+  int32_t pool, src_dtype, accumulate;
+} fdm_accum_args; /* which = 27 */
+int fdm_accum(const fdm_accum_args* a, void* stream);
+
+typedef struct {
+  const float* src; void* dst;
+  int32_t N, C, H, W, Cpad, op_dtype;
+} fdm_nchw_to_nhwc_args; /* which = 28 */
+int fdm_nchw_to_nhwc(const fdm_nchw_to_nhwc_args* a, void* stream);
 
 #ifdef __cplusplus
 }

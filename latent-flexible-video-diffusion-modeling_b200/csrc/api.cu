@@ -51,6 +51,20 @@ extern "C" size_t fdm_struct_size(int which) {
     case 12: return sizeof(fdm_masked_mse_args);
     case 13: return sizeof(fdm_linear_problem);
     case 14: return sizeof(fdm_rpe_hidden_problem);
+    case 15: return sizeof(fdm_pack_problem);
+    case 16: return sizeof(fdm_pack_weights_args);
+    case 17: return sizeof(fdm_conv_wgrad_args);
+    case 18: return sizeof(fdm_gn_bwd_args);
+    case 19: return sizeof(fdm_temporal_gn_bwd_args);
+    case 20: return sizeof(fdm_attn_spatial_bwd_args);
+    case 21: return sizeof(fdm_attn_temporal_bwd_args);
+    case 22: return sizeof(fdm_rpe_hidden_bwd_problem);
+    case 23: return sizeof(fdm_rpe_hidden_bwd_args);
+    case 24: return sizeof(fdm_linear_bwd_problem);
+    case 25: return sizeof(fdm_grouped_linear_bwd_args);
+    case 26: return sizeof(fdm_sum_parts_args);
+    case 27: return sizeof(fdm_accum_args);
+    case 28: return sizeof(fdm_nchw_to_nhwc_args);
     default: return 0;
   }
 }

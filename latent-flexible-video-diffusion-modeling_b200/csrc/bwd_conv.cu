@@ -1,0 +1,234 @@
+// Convolution / linear WEIGHT gradient and bias gradient (cudnn_convolution_backward_weight / addmm backward at the
+// nn.Conv2d sites unet.py:76,108,155,169,176-180,313,402 and nn.Linear sites rpe.py:14,111-112).
+//
+// GEMM view per filter tap:  dW_tap[ci][co] = sum over output pixels m of  A[pixel(m, tap)][ci] * dY[m][co]
+// i.e. M = Cin, N = Cout, K = N*Ho*Wo pixels.  K is split over CTAs into fp32 partials, reduced in a fixed order by a second
+// kernel that also writes PyTorch's [co][ci][kh][kw] layout (deterministic; no atomics).
+// Engine FDM_CONV_SIMT (this file): CUDA cores, fp32 accumulate, any dtype / shape.  Engine FDM_CONV_TC: wgrad_tc.cu.
+#include "common.cuh"
+
+namespace fdm {
+
+constexpr int WG_BM = 64, WG_BN = 64, WG_BK = 16, WG_NT = 256;
+
+struct WgradParams {
+  const void* a; const void* dy; float* part;
+  int N, Hin, Win, C, Cout, Ho, Wo, ksize, stride;
+  long long M;        // output pixels
+  long long chunk;    // pixels per split
+  int ci_tiles;
+};
+
+template <typename AT, typename DT>
+__global__ void __launch_bounds__(WG_NT) wgrad_simt_kernel(WgradParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ __align__(16) float As[WG_BK][WG_BM + 4];
+  __shared__ __align__(16) float Bs[WG_BK][WG_BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int ci0 = (blockIdx.x % p.ci_tiles) * WG_BM, co0 = (blockIdx.x / p.ci_tiles) * WG_BN;
+  const int tap = blockIdx.y, taps = p.ksize * p.ksize;
+  const int r = tap / p.ksize, s = tap - r * p.ksize, pad = p.ksize >> 1;
+  const long long m_begin = (long long)blockIdx.z * p.chunk;
+  const long long m_end = m_begin + p.chunk < p.M ? m_begin + p.chunk : p.M;
+  const int HWo = p.Ho * p.Wo;
+  const AT* A = reinterpret_cast<const AT*>(p.a);
+  const DT* DY = reinterpret_cast<const DT*>(p.dy);
+  // load mapping: pixel row lp = tid / 16 (0..15), 4 consecutive channels at (tid % 16) * 4
+  const int lp = tid >> 4, lc = (tid & 15) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long m0 = m_begin; m0 < m_end; m0 += WG_BK) {
+    const long long m = m0 + lp;
+    float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < m_end) {
+      const int fn = (int)(m / HWo);
+      const int rem = (int)(m - (long long)fn * HWo);
+      const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+      const int ih = oh * p.stride + r - pad, iw = ow * p.stride + s - pad;
+      if (ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win) {
+        const AT* arow = A + ((size_t)(fn * p.Hin + ih) * p.Win + iw) * p.C;
+        const int c = ci0 + lc;
+        if ((p.C & 3) == 0 && c + 3 < p.C) {
+          const float4 v = OpType<AT>::load4(arow + c);
+          av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < p.C) av[j] = OpType<AT>::load(arow + c + j);
+        }
+      }
+      const DT* drow = DY + (size_t)m * p.Cout;
+      const int c = co0 + lc;
+      if ((p.Cout & 3) == 0 && c + 3 < p.Cout) {
+        const float4 v = OpType<DT>::load4(drow + c);
+        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < p.Cout) bv[j] = OpType<DT>::load(drow + c + j);
+      }
+    }
+    *reinterpret_cast<float4*>(&As[lp][lc]) = make_float4(av[0], av[1], av[2], av[3]);
+    *reinterpret_cast<float4*>(&Bs[lp][lc]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WG_BK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // partial [split][tap][ci][co]
+  float* out = p.part + ((size_t)blockIdx.z * taps + tap) * p.C * p.Cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + ty * 4 + i;
+    if (ci >= p.C) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co < p.Cout) out[(size_t)ci * p.Cout + co] = acc[i][j];
+    }
+  }
+}
+
+// dw[co][ci < Cw][kh][kw] = sum_split part[split][tap = kh*k+kw][ci][co]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splits, int taps, int C, int Cw,
+                                    int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)taps * Cw * Cout;
+  const size_t sstride = (size_t)taps * C * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long long r = i / Cout;
+    const int ci = (int)(r % Cw), tap = (int)(r / Cw);
+    const float* src = part + ((size_t)tap * C + ci) * Cout + co;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += src[k * sstride];
+    dw[((size_t)co * Cw + ci) * taps + tap] = s;
+  }
+}
+
+// column sums of dy [rows][C]: stage 1 -> part[block][C], stage 2 -> out (and out2)
+template <typename DT>
+__global__ void __launch_bounds__(256) colsum_kernel(const DT* __restrict__ x, float* __restrict__ part, long long rows, int C,
+                                                     long long rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += OpType<DT>::load(x + (size_t)r * C + c);
+    part[(size_t)blockIdx.x * C + c] = s;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, float* __restrict__ out2, int blocks,
+                                    int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += part[(size_t)b * C + c];
+  if (out != nullptr) out[c] = s;
+  if (out2 != nullptr) out2[c] = s;
+}
+
+struct WgradGeom {
+  int Ho, Wo, taps, splits, ci_tiles, co_tiles, cs_blocks;
+  long long M, chunk, cs_rows;
+  size_t part_bytes, cs_bytes;
+};
+
+static inline WgradGeom wgrad_geom(const fdm_conv_wgrad_args* a) {
+  WgradGeom g;
+  const int pad = a->ksize / 2;
+  g.Ho = (a->Hin + 2 * pad - a->ksize) / a->stride + 1;
+  g.Wo = (a->Win + 2 * pad - a->ksize) / a->stride + 1;
+  g.taps = a->ksize * a->ksize;
+  g.M = (long long)a->N * g.Ho * g.Wo;
+  g.ci_tiles = (a->C + WG_BM - 1) / WG_BM;
+  g.co_tiles = (a->Cout + WG_BN - 1) / WG_BN;
+  const long long base = (long long)g.ci_tiles * g.co_tiles * g.taps;
+  long long want = (148LL * 4 + base - 1) / base;  // ~4 CTAs per SM in total
+  const long long max_splits = (g.M + 4 * WG_BK - 1) / (4 * WG_BK);  // at least 64 pixels per split
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  g.chunk = ((g.M + want - 1) / want + WG_BK - 1) / WG_BK * WG_BK;
+  g.splits = (int)((g.M + g.chunk - 1) / g.chunk);
+  g.part_bytes = (size_t)g.splits * g.taps * a->C * a->Cout * sizeof(float);
+  g.cs_blocks = (int)(g.M / 64 > 592 ? 592 : (g.M / 64 > 0 ? g.M / 64 : 1));
+  g.cs_rows = (g.M + g.cs_blocks - 1) / g.cs_blocks;
+  g.cs_blocks = (int)((g.M + g.cs_rows - 1) / g.cs_rows);
+  g.cs_bytes = (size_t)g.cs_blocks * a->Cout * sizeof(float);
+  return g;
+}
+
+int conv_wgrad_tc(const fdm_conv_wgrad_args* a, cudaStream_t st);  // wgrad_tc.cu (returns FDM_ERR_UNSUPPORTED for shapes it does not take)
+
+}  // namespace fdm
+
+using namespace fdm;
+
+extern "C" size_t fdm_conv_wgrad_workspace(const fdm_conv_wgrad_args* a) {
+  if (a == nullptr || a->ksize < 1 || a->stride < 1) return 0;
+  const WgradGeom g = wgrad_geom(a);
+  return ((g.part_bytes + 255) / 256 * 256) + g.cs_bytes + 256;
+}
+
+extern "C" int fdm_conv_wgrad(const fdm_conv_wgrad_args* a, void* stream) {
+  FDM_REQUIRE(a && a->a && a->dy && a->dw && a->workspace, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->N > 0 && a->C > 0 && a->Cout > 0 && a->Cw > 0 && a->Cw <= a->C, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE((a->ksize == 1 || a->ksize == 3) && (a->stride == 1 || a->stride == 2), FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(a->workspace_bytes >= fdm_conv_wgrad_workspace(a), FDM_ERR_BAD_ARG);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const WgradGeom g = wgrad_geom(a);
+  float* part = reinterpret_cast<float*>(a->workspace);
+  float* cs_part = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + (g.part_bytes + 255) / 256 * 256);
+  bool done = false;
+  if (a->engine == FDM_CONV_TC) {
+    const int rc = conv_wgrad_tc(a, st);
+    if (rc == FDM_OK) done = true;
+    else if (rc != FDM_ERR_UNSUPPORTED) return rc;
+  }
+  if (!done) {
+    WgradParams p;
+    p.a = a->a; p.dy = a->dy; p.part = part;
+    p.N = a->N; p.Hin = a->Hin; p.Win = a->Win; p.C = a->C; p.Cout = a->Cout; p.Ho = g.Ho; p.Wo = g.Wo;
+    p.ksize = a->ksize; p.stride = a->stride; p.M = g.M; p.chunk = g.chunk; p.ci_tiles = g.ci_tiles;
+    dim3 grid(g.ci_tiles * g.co_tiles, g.taps, g.splits);
+    FDM_REQUIRE(grid.z <= 65535, FDM_ERR_UNSUPPORTED);
+    const bool ab = a->a_dtype == FDM_BF16, db = a->dy_dtype == FDM_BF16;
+    if (ab && db) fdm::launch(wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16>, grid, dim3(WG_NT), 0, st, p);
+    else if (ab) fdm::launch(wgrad_simt_kernel<__nv_bfloat16, float>, grid, dim3(WG_NT), 0, st, p);
+    else if (db) fdm::launch(wgrad_simt_kernel<float, __nv_bfloat16>, grid, dim3(WG_NT), 0, st, p);
+    else fdm::launch(wgrad_simt_kernel<float, float>, grid, dim3(WG_NT), 0, st, p);
+    const long long total = (long long)g.taps * a->Cw * a->Cout;
+    long long gr = (total + 255) / 256;
+    if (gr > 148 * 8) gr = 148 * 8;
+    fdm::launch(wgrad_reduce_kernel, dim3((unsigned)gr), dim3(256), 0, st, (const float*)part, a->dw, g.splits, g.taps, a->C, a->Cw, a->Cout);
+  }
+  if (a->dbias != nullptr || a->dbias2 != nullptr) {
+    if (a->dy_dtype == FDM_BF16)
+      fdm::launch(colsum_kernel<__nv_bfloat16>, dim3(g.cs_blocks), dim3(256), 0, st, (const __nv_bfloat16*)a->dy, cs_part, g.M, a->Cout, g.cs_rows);
+    else
+      fdm::launch(colsum_kernel<float>, dim3(g.cs_blocks), dim3(256), 0, st, (const float*)a->dy, cs_part, g.M, a->Cout, g.cs_rows);
+    fdm::launch(colsum_final_kernel, dim3((a->Cout + 127) / 128), dim3(128), 0, st, (const float*)cs_part, a->dbias, a->dbias2, g.cs_blocks, a->Cout);
+  }
+  return check_launch();
+}

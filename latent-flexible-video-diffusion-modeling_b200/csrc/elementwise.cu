@@ -46,7 +46,9 @@ __global__ void cast_kernel(const float* __restrict__ x, OT* __restrict__ out, i
     long long r = pix / Wo;
     int oh = (int)(r % Ho), n = (int)(r / Ho);
     int ih = up ? oh >> 1 : oh, iw = up ? ow >> 1 : ow;
-    float4 v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W + iw) * C + q * 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    // up == 2: zero insertion (gradient of a stride-2 conv output, laid out for a stride-1 dgrad / wgrad)
+    if (up != 2 || ((oh | ow) & 1) == 0) v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W + iw) * C + q * 4);
     OpType<OT>::store4(out + (size_t)pix * C + q * 4, v);
   }
 }

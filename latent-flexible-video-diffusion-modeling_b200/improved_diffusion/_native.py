@@ -57,14 +57,60 @@ QSampleArgs = _S("QSampleArgs", [("x0", vp), ("noise", vp), ("coef2", vp), ("t",
 MaskedMseArgs = _S("MaskedMseArgs", [("eps", vp), ("noise", vp), ("m1", vp), ("m2", vp), ("mse", vp), ("eval", vp),
                                      ("per_frame", i64), ("B", i32), ("T", i32)])
 
+# ---- backward (training) structures
+sz = C.c_size_t
+PackProblem = _S("PackProblem", [("src", vp), ("src2", vp), ("dst", vp), ("co", i32), ("ci", i32), ("k", i32), ("mode", i32)])
+PackWeightsArgs = _S("PackWeightsArgs", [("problems", vp), ("count", i32), ("max_elems", i32)])
+ConvWgradArgs = _S("ConvWgradArgs", [("a", vp), ("dy", vp), ("dw", vp), ("dbias", vp), ("dbias2", vp), ("workspace", vp),
+                                     ("workspace_bytes", sz),
+                                     ("N", i32), ("Hin", i32), ("Win", i32), ("C", i32), ("Cw", i32), ("Cout", i32),
+                                     ("ksize", i32), ("stride", i32), ("a_dtype", i32), ("dy_dtype", i32), ("engine", i32)])
+GnBwdArgs = _S("GnBwdArgs", [("xa", vp), ("xb", vp), ("stats_a", vp), ("stats_b", vp), ("gamma", vp), ("beta", vp), ("film", vp),
+                             ("dy_op", vp), ("dy_f32", vp), ("draw_op", vp), ("gxa", vp), ("gxb", vp), ("ab", vp),
+                             ("dgamma", vp), ("dbeta", vp), ("dfilm", vp),
+                             ("N", i32), ("HW", i32), ("Ca", i32), ("Cb", i32), ("T", i32), ("film_stride", i32),
+                             ("film_off", i32), ("silu", i32), ("op_dtype", i32), ("acc_a", i32), ("acc_b", i32), ("eps", f32)])
+TemporalGnBwdArgs = _S("TemporalGnBwdArgs", [("x", vp), ("gamma", vp), ("dy_op", vp), ("dy_f32", vp), ("gx", vp),
+                                             ("dgamma", vp), ("dbeta", vp),
+                                             ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("op_dtype", i32),
+                                             ("accumulate", i32), ("eps", f32)])
+AttnSpatialBwdArgs = _S("AttnSpatialBwdArgs", [("qkv", vp), ("out", vp), ("dout", vp), ("dqkv", vp), ("lse", vp), ("dsum", vp),
+                                               ("N", i32), ("L", i32), ("C", i32), ("heads", i32), ("dtype", i32)])
+AttnTemporalBwdArgs = _S("AttnTemporalBwdArgs", [("qkv", vp), ("out", vp), ("Rq", vp), ("Rk", vp), ("Rv", vp), ("mask", vp),
+                                                 ("dout", vp), ("dqkv", vp), ("dRq", vp), ("dRk", vp), ("dRv", vp),
+                                                 ("lse", vp), ("dsum", vp),
+                                                 ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("heads", i32), ("dtype", i32)])
+RpeHiddenBwdProblem = _S("RpeHiddenBwdProblem", [("wd", vp), ("bd", vp), ("dhidden", vp), ("dwd", vp), ("dbd", vp),
+                                                 ("C", i32), ("te_off", i32)])
+RpeHiddenBwdArgs = _S("RpeHiddenBwdArgs", [("te", vp), ("frame_indices", vp), ("problems", vp), ("dte", vp),
+                                           ("B", i32), ("T", i32), ("te_stride", i32), ("count", i32), ("max_C", i32),
+                                           ("dhidden_dtype", i32)])
+LinearBwdProblem = _S("LinearBwdProblem", [("x", vp), ("w", vp), ("dy", vp), ("dw", vp), ("db", vp), ("dx_part", vp),
+                                           ("M", i32), ("K", i32), ("Nout", i32), ("ldx", i32), ("ldy", i32), ("silu_in", i32)])
+GroupedLinearBwdArgs = _S("GroupedLinearBwdArgs", [("problems", vp), ("count", i32), ("max_M", i32), ("max_Nout", i32),
+                                                   ("max_K", i32)])
+SumPartsArgs = _S("SumPartsArgs", [("parts", vp), ("out", vp), ("part_stride", i64), ("n", i64), ("count", i32),
+                                   ("accumulate", i32)])
+AccumArgs = _S("AccumArgs", [("src", vp), ("dst", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32), ("pool", i32),
+                             ("src_dtype", i32), ("accumulate", i32)])
+NchwToNhwcArgs = _S("NchwToNhwcArgs", [("src", vp), ("dst", vp), ("N", i32), ("C", i32), ("H", i32), ("W", i32), ("Cpad", i32),
+                                       ("op_dtype", i32)])
+PACK_TC_FWD, PACK_TC_DGRAD, PACK_SIMT_FWD, PACK_SIMT_DGRAD, PACK_SUM2 = 0, 1, 2, 3, 4
+
 # index = `which` of fdm_struct_size (include/fdm_b200.h)
 STRUCTS = [InputPrepArgs, ConvArgs, GnApplyArgs, TemporalGnArgs, TimestepEmbeddingArgs, GroupedLinearArgs,
            RpeHiddenArgs, AttnTemporalArgs, AttnSpatialArgs, CastArgs, DdpmStepArgs, QSampleArgs, MaskedMseArgs,
-           LinearProblem, RpeHiddenProblem]
+           LinearProblem, RpeHiddenProblem,
+           PackProblem, PackWeightsArgs, ConvWgradArgs, GnBwdArgs, TemporalGnBwdArgs, AttnSpatialBwdArgs, AttnTemporalBwdArgs,
+           RpeHiddenBwdProblem, RpeHiddenBwdArgs, LinearBwdProblem, GroupedLinearBwdArgs, SumPartsArgs, AccumArgs,
+           NchwToNhwcArgs]
 
 ENTRY_POINTS = ["fdm_input_prep", "fdm_conv", "fdm_gn_apply", "fdm_temporal_gn", "fdm_timestep_embedding",
                 "fdm_grouped_linear", "fdm_rpe_hidden", "fdm_attn_temporal", "fdm_attn_spatial", "fdm_cast",
-                "fdm_ddpm_step", "fdm_q_sample", "fdm_masked_mse"]
+                "fdm_ddpm_step", "fdm_q_sample", "fdm_masked_mse",
+                "fdm_pack_weights", "fdm_conv_wgrad", "fdm_gn_bwd", "fdm_temporal_gn_bwd", "fdm_attn_spatial_bwd",
+                "fdm_attn_temporal_bwd", "fdm_rpe_hidden_bwd", "fdm_grouped_linear_bwd", "fdm_sum_parts", "fdm_accum",
+                "fdm_nchw_to_nhwc"]
 
 _lib = None
 
@@ -91,6 +137,8 @@ def lib():
             fn = getattr(L, name)
             fn.restype = C.c_int
             fn.argtypes = [vp, vp]
+        L.fdm_conv_wgrad_workspace.restype = C.c_size_t
+        L.fdm_conv_wgrad_workspace.argtypes = [vp]
         if L.fdm_abi_version() != 1:
             raise NativeError(f"libfdm_sm100.so ABI {L.fdm_abi_version()} != 1")
         _lib = L

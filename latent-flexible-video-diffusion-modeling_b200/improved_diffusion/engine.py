@@ -37,6 +37,12 @@ class Plan:
     def __init__(self, engine, B, T, H, W):
         self.engine, self.B, self.T, self.H, self.W = engine, B, T, H, W
         self.ops = []        # (entry point name, struct class, {field: python value | Buf | tensor | (Buf, byte offset)})
+        self.bops = []       # backward schedule (training plans only), same format
+        self.cur = self.ops  # list that op() appends to
+        self.train = False
+        self.tape = []       # backward emitters, one per forward block, run in reverse after the forward schedule is built
+        self.bzero_bytes = 0  # arena zeroed at the start of every backward (atomic accumulators, GroupNorm-backward sums)
+        self.pack_problems = []  # (src param, src2, dst tensor, co, ci, k, mode): re-packed by ONE launch per forward
         self.bufs = []
         self.keep = []       # tensors that must outlive the plan (weights views, problem arrays)
         self.calls = None    # [(fn, byref(struct))] after finalize()
@@ -52,8 +58,14 @@ class Plan:
     # ---- buffers
     def buf(self, name, nbytes, persistent=False):
         # FDM_DEBUG_TAPS=1: no buffer reuse, so every intermediate can be read back after a run (tests/debugging)
-        b = Buf(name, nbytes, persistent or self.debug)
+        b = Buf(name, nbytes, persistent or self.debug or self.train)
         self.bufs.append(b)
+        return b
+
+    def bzero(self, name, nbytes):
+        b = Buf(name, nbytes, True, "bzero")
+        b.offset = self.bzero_bytes
+        self.bzero_bytes += b.nbytes
         return b
 
     def stats(self, name, n, c):
@@ -63,6 +75,9 @@ class Plan:
         return b
 
     def op(self, fn, cls, **fields):
+        if self.cur is not self.ops:
+            self.cur.append((fn, cls, fields))
+            return
         idx = len(self.ops)
         for v in fields.values():
             b = v[0] if isinstance(v, tuple) else v
@@ -111,16 +126,18 @@ class Plan:
                 free = merged
         self.arena = th.empty(max(top, 256), dtype=th.uint8, device=device)
         self.stats_arena = th.zeros(max(self.stats_bytes, 256) // 4, dtype=th.float32, device=device)
+        self.bzero_arena = th.zeros(max(self.bzero_bytes, 256) // 4, dtype=th.float32, device=device)
         self.arena_bytes = top
         lib = N_.lib()
-        self.calls = []
+        self.calls, self.bcalls = [], []
         self._structs = []
-        for fn, cls, fields in self.ops:
-            st = cls()
-            for k, v in fields.items():
-                setattr(st, k, self.ptr(v) if isinstance(v, (Buf, tuple, th.Tensor)) or v is None else v)
-            self._structs.append(st)
-            self.calls.append((fn, getattr(lib, fn), C.byref(st)))
+        for ops, calls in ((self.ops, self.calls), (self.bops, self.bcalls)):
+            for fn, cls, fields in ops:
+                st = cls()
+                for k, v in fields.items():
+                    setattr(st, k, self.ptr(v) if isinstance(v, (Buf, tuple, th.Tensor)) or v is None else v)
+                self._structs.append(st)
+                calls.append((fn, getattr(lib, fn), C.byref(st)))
 
     def ptr(self, v):
         if v is None:
@@ -130,7 +147,7 @@ class Plan:
         off = 0
         if isinstance(v, tuple):
             v, off = v
-        base = self.arena if v.arena == "main" else self.stats_arena
+        base = {"main": self.arena, "stats": self.stats_arena, "bzero": self.bzero_arena}[v.arena]
         return base.data_ptr() + v.offset + off
 
     def set_t_source(self, table):
@@ -153,6 +170,17 @@ class Plan:
             n *= s
         esz = th.empty((), dtype=dtype).element_size()
         return self.arena[b.offset:b.offset + n * esz].view(dtype).view(*shape)
+
+    def run_backward(self, stream):
+        """Launch the backward schedule (training plans): zero the accumulator arena and the flat parameter-gradient buffer,
+        then every backward kernel in order on `stream`.  The caller has copied d(loss)/d(eps) into `geps_view`."""
+        self.bzero_arena.zero_()
+        self.pgrad.zero_()
+        s = C.c_void_p(stream)
+        for name, fn, ref in self.bcalls:
+            rc = fn(ref, s)
+            if rc != 0:
+                N_.check(rc, name)
 
     def run(self, stream):
         """Launch the whole schedule on `stream` (the raw cudaStream_t of torch's CURRENT stream).  The caller has filled the
