@@ -210,6 +210,38 @@ class Plan:
                 self.ev_join.record(self.side_stream)
 
 
+class _DenoiserFn(th.autograd.Function):
+    """UNetVideoModel.forward as ONE autograd node: forward = the plan's kernel schedule, backward = its backward schedule
+    (conv dgrad/wgrad, GroupNorm / attention / conditioning-path backward kernels of libfdm_sm100.so); parameter gradients come
+    back as views of one flat buffer.  Replaces the ~1500-node autograd graph torch builds for the reference model."""
+
+    @staticmethod
+    def forward(ctx, engine, x, x0, timesteps, frame_indices, obs_mask, latent_mask, *params):
+        B, T, Cx, H, W = x.shape
+        P = engine.plan_for(B, T, H, W, x.device, train=True)
+        engine.load_conditioning(P, x0, frame_indices, obs_mask, latent_mask)
+        P.set_t_source(None)
+        P.x_view.copy_(x)
+        P.t_view.copy_(timesteps.reshape(B).float())
+        P.run(th.cuda.current_stream(x.device).cuda_stream)
+        P.generation = getattr(P, "generation", 0) + 1
+        ctx.plan, ctx.generation = P, P.generation
+        return P.eps_view.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        P = ctx.plan
+        if P.generation != ctx.generation:
+            raise RuntimeError("the activations of this forward were overwritten by a later forward of the same shape "
+                               "(the training plan keeps ONE set of saved activations): call backward before the next forward")
+        P.geps_view.copy_(g)
+        P.run_backward(th.cuda.current_stream(g.device).cuda_stream)
+        flat = P.pgrad.clone()  # the plan's buffer is reused by the next backward; autograd owns this copy
+        base = P.pgrad.data_ptr()
+        grads = tuple(flat[(v.data_ptr() - base) // 4:(v.data_ptr() - base) // 4 + v.numel()].view(v.shape) for v in P.pgrad_views)
+        return (None,) * 7 + grads
+
+
 class DenoiserEngine:
     def __init__(self, model, precision="bf16"):
         if precision not in ("bf16", "fp32"):
@@ -223,6 +255,7 @@ class DenoiserEngine:
         self.use_tc = precision == "bf16" and os.environ.get("FDM_CONV_ENGINE", "tc") != "simt"
         self.temporal_mma = os.environ.get("FDM_TEMPORAL_MMA", "0") == "1"
         self.plans = {}
+        self.train_plans = {}
         self.packed = {}
         self._versions = None
         if not model.use_scale_shift_norm:
@@ -280,7 +313,16 @@ class DenoiserEngine:
         return self.packed[key]
 
     # ------------------------------------------------------------------ plan compiler
-    def plan_for(self, B, T, H, W, device):
+    def plan_for(self, B, T, H, W, device, train=False):
+        if train:
+            # training plans survive optimizer steps: their packed weights are refreshed by ONE fdm_pack_weights launch at the
+            # head of every forward; they are rebuilt only when a parameter's storage moves (.to(), re-materialisation)
+            key = (B, T, H, W, str(device), tuple(p.data_ptr() for p in self.model.parameters()))
+            if key not in self.train_plans:
+                self.train_plans.clear()
+                with th.cuda.device(device):
+                    self.train_plans[key] = self._compile(B, T, H, W, device, train=True)
+            return self.train_plans[key]
         self.refresh_weights()
         key = (B, T, H, W, str(device))
         if key not in self.plans:
@@ -302,15 +344,62 @@ class DenoiserEngine:
             return 128 % Wo == 0 and hw % 128 == 0
         return 128 % hw == 0 and (hw % 32 == 0 or 32 % hw == 0)
 
-    def _compile(self, B, T, H, W, device):
+    def _compile(self, B, T, H, W, device, train=False):
         m = self.model
         from .unet import ResBlock, FactorizedAttentionBlock, Downsample, Upsample
         P = Plan(self, B, T, H, W)
+        P.train = train
         Nf = B * T
         opd, osz = self.op_dtype, self.op_size
         mc, ted = m.model_channels, m.model_channels * 4
         Cin = m.in_channels  # includes indicator channel
         f32 = self._f32
+        bias_sum = self._bias_sum
+        pack_fwd = lambda w, tc: (self._pack_tc if tc else self._pack_simt)(w)
+        if train:
+            # ---- training plan: parameters are read in place (fp32) and packed operands live in persistent tensors that ONE
+            #      fdm_pack_weights launch refreshes at the head of every forward; parameter gradients go to one flat buffer
+            params = list(m.parameters())
+            for p_ in params:
+                assert p_.dtype == th.float32 and p_.is_contiguous(), "training plans expect contiguous fp32 master weights"
+            sizes = [(p_.numel() + 63) // 64 * 64 for p_ in params]
+            P.pgrad = th.zeros(sum(sizes), dtype=th.float32, device=device)
+            offs, o = {}, 0
+            for p_, n_ in zip(params, sizes):
+                offs[id(p_)] = o
+                o += n_
+            P.pgrad_views = [P.pgrad[offs[id(p_)]:offs[id(p_)] + p_.numel()].view(p_.shape) for p_ in params]
+            pg = lambda p_: P.pgrad[offs[id(p_)]:offs[id(p_)] + p_.numel()]  # gradient slot of a parameter
+            f32 = lambda p_: p_.detach()
+            packed = {}
+            r16, r64 = (lambda v: (v + 15) // 16 * 16), (lambda v: (v + 63) // 64 * 64)
+
+            def pack_w(w, mode):
+                key = (mode, id(w))
+                if key not in packed:
+                    co, ci = w.shape[0], w.shape[1]
+                    k = w.shape[2] if w.dim() == 4 else 1
+                    shape, dty = {N_.PACK_TC_FWD: ((k * k, r16(co), r64(ci)), th.bfloat16),
+                                  N_.PACK_TC_DGRAD: ((k * k, r16(ci), r64(co)), th.bfloat16),
+                                  N_.PACK_SIMT_FWD: ((k * k, ci, co), th.float32),
+                                  N_.PACK_SIMT_DGRAD: ((k * k, co, ci), th.float32)}[mode]
+                    packed[key] = th.zeros(shape, dtype=dty, device=device)
+                    P.pack_problems.append((w, None, packed[key], co, ci, k, mode))
+                return packed[key]
+
+            def bias_sum(b0, b1):
+                key = ("sum2", id(b0))
+                if key not in packed:
+                    packed[key] = th.zeros(b0.numel(), dtype=th.float32, device=device)
+                    P.pack_problems.append((b0, b1, packed[key], b0.numel(), 1, 1, N_.PACK_SUM2))
+                return packed[key]
+
+            pack_fwd = lambda w, tc: pack_w(w, N_.PACK_TC_FWD if tc else N_.PACK_SIMT_FWD)
+            pack_dgrad = lambda w, tc: pack_w(w, N_.PACK_TC_DGRAD if tc else N_.PACK_SIMT_DGRAD)
+            P.keep.append(packed)
+            pack_fields = dict(problems=None, count=0, max_elems=0)
+            P.op("fdm_pack_weights", N_.PackWeightsArgs, **pack_fields)
+            pack_fields = P.ops[-1][2]
 
         # ---------------- persistent inputs / outputs
         P.x = P.buf("x", Nf * (Cin - 1) * H * W * 4, True)
@@ -382,14 +471,17 @@ class DenoiserEngine:
         for rb in res_blocks:
             lin = rb.emb_layers[1]
             probs.append(dict(x=emb, w=f32(lin.weight), b=f32(lin.bias), y=(cond, film_off[id(rb)] * 4), M=B, K=ted,
-                              Nout=2 * rb.out_channels, ldx=ted, ldy=cond_cols, silu_in=1))
+                              Nout=2 * rb.out_channels, ldx=ted, ldy=cond_cols, silu_in=1, lin=lin,
+                              off=film_off[id(rb)]))
         for ab in attn_blocks:
             for which in ("rpe_q", "rpe_k", "rpe_v"):
                 net = getattr(ab.temporal_attention, which).rpe_net
                 lin = net.embed_diffusion_time
                 probs.append(dict(x=emb, w=f32(lin.weight), b=f32(lin.bias), y=(cond, te_off[(id(ab), which)] * 4), M=B,
-                                  K=ted, Nout=ab.channels, ldx=ted, ldy=cond_cols, silu_in=0))
+                                  K=ted, Nout=ab.channels, ldx=ted, ldy=cond_cols, silu_in=0, lin=lin,
+                                  off=te_off[(id(ab), which)]))
         emit_group(probs)
+        film_probs = probs
         # RPENet hidden + output tables for every temporal attention.  bf16 mode: the C x C output linear of each net runs on
         # tcgen05 (fdm_conv, 1x1 over the B*T*T rows, bf16 hidden); fp32 mode: one grouped CUDA-core launch.
         R, R_op = {}, {}
@@ -446,7 +538,7 @@ class DenoiserEngine:
             fl = 2 * Nf_ * Ho * Wo * Cout * (k * k * (flop_c0 or C0) + C1)  # algorithmic: padded channels do not count
             P.flops += fl
             P.conv_flops += fl
-            pack = self._pack_tc if tc else self._pack_simt
+            pack = lambda w_: pack_fwd(w_, tc)
             P.op("fdm_conv", N_.ConvArgs, a0=a0, w0=pack(w0), a1=a1, w1=pack(w1) if w1 is not None else None, bias=bias,
                  resid=resid, y_f32=y_f32, y_op=y_op, stats=stats, N=Nf_, Hin=Hin, Win=Win, C0=C0, C1=C1, Cout=Cout,
                  ksize=k, stride=stride, upsample=upsample, a_dtype=a_dtype, op_dtype=opd, out_nchw=out_nchw,
@@ -457,6 +549,114 @@ class DenoiserEngine:
             conv(hb, Cc, 1, 1, net.out.weight, Cc, 1, bias=f32(net.out.bias), y_f32=rb_, y_op=rop, n_frames=B * T * T)
             P.side_end = len(P.ops)
         self._pending_rpe_tc = []
+
+        # ---------------- backward helpers (training plans): every forward block below registers ONE emitter on P.tape;
+        # the emitters run in reverse once the forward schedule is complete and append to P.bops
+        P.pending = []   # (device byte tensor, struct class, [field dicts]) filled in after finalize()
+        gbufs, ginit = {}, set()
+        lib = N_.lib()
+        F32_, hdt = N_.F32, (opd if self.use_tc else N_.F32)
+
+        def gact(a):
+            """fp32 gradient buffer of a residual-stream tensor"""
+            if id(a.buf) not in gbufs:
+                gbufs[id(a.buf)] = P.buf("g_act", Nf * a.H * a.W * a.C * 4)
+            return gbufs[id(a.buf)]
+
+        def acc(a):
+            """1 once the gradient buffer of `a` holds a contribution (later writers accumulate, the first one overwrites)"""
+            k_, r_ = id(a.buf), 0
+            if k_ in ginit:
+                r_ = 1
+            ginit.add(k_)
+            return r_
+
+        def to_op(g, Cc, Hh, Ww, n=None, up=0):
+            """fp32 gradient -> operand-dtype copy feeding dgrad / wgrad (up = 2: zero insertion for a stride-2 conv)"""
+            f_ = 2 if up else 1
+            o_ = P.buf("g_op", (n or Nf) * Hh * f_ * Ww * f_ * Cc * osz)
+            P.op("fdm_cast", N_.CastArgs, x=g, out=o_, N=n or Nf, H=Hh, W=Ww, C=Cc, upsample=up, op_dtype=opd)
+            return o_
+
+        def dgrad(gy, Cg, Hg, Wg, w, Co, k, out_op=None, out_f32=None, resid=None, n=None):
+            """gradient wrt a stride-1 conv's input: fdm_conv over the rotated / channel-swapped weights"""
+            tc = self.use_tc and opd == N_.BF16 and self.tc_ok(Cg, 0, Co, k, 1, 0, Hg, Wg) and Co % 4 == 0
+            fl = 2 * (n or Nf) * Hg * Wg * Co * k * k * Cg
+            P.bflops += fl
+            P.op("fdm_conv", N_.ConvArgs, a0=gy, w0=pack_dgrad(w, tc), a1=None, w1=None, bias=None, resid=resid,
+                 y_f32=out_f32, y_op=out_op, stats=None, N=n or Nf, Hin=Hg, Win=Wg, C0=Cg, C1=0, Cout=Co, ksize=k, stride=1,
+                 upsample=0, a_dtype=opd, op_dtype=opd, out_nchw=0, engine=N_.CONV_TC if tc else N_.CONV_SIMT)
+
+        def wgrad(a, a_dtype, Cs, Cw, Hin, Win, gy, Co, k, stride, w, biases=(), n=None):
+            """dW (PyTorch layout, into the flat parameter-gradient buffer) and the bias gradient(s)"""
+            fields = dict(N=n or Nf, Hin=Hin, Win=Win, C=Cs, Cw=Cw, Cout=Co, ksize=k, stride=stride, a_dtype=a_dtype,
+                          dy_dtype=opd, engine=N_.CONV_TC if self.use_tc else N_.CONV_SIMT)
+            need = int(lib.fdm_conv_wgrad_workspace(C.byref(N_.ConvWgradArgs(**fields))))
+            P.wg_ws.nbytes = max(P.wg_ws.nbytes, (need + 255) // 256 * 256)
+            pad_ = k // 2
+            P.bflops += 2 * (n or Nf) * ((Hin + 2 * pad_ - k) // stride + 1) * ((Win + 2 * pad_ - k) // stride + 1) * Co * k * k * Cw
+            P.op("fdm_conv_wgrad", N_.ConvWgradArgs, a=a, dy=gy, dw=pg(w), dbias=pg(biases[0]) if biases else None,
+                 dbias2=pg(biases[1]) if len(biases) > 1 else None, workspace=P.wg_ws, workspace_bytes=need, **fields)
+
+        def gn_bwd(xa, xb, gn, foff, dy_op, dy_f32, draw, silu):
+            Cc = xa.C + (xb.C if xb else 0)
+            ab_ = P.bzero("gn_ab", Nf * Cc * 16)
+            P.op("fdm_gn_bwd", N_.GnBwdArgs, xa=xa.buf, xb=xb.buf if xb else None, stats_a=xa.st,
+                 stats_b=xb.st if xb else None, gamma=f32(gn.weight), beta=f32(gn.bias), film=cond if foff is not None else None,
+                 dy_op=dy_op, dy_f32=dy_f32, draw_op=draw, gxa=gact(xa), gxb=gact(xb) if xb else None, ab=ab_,
+                 dgamma=pg(gn.weight), dbeta=pg(gn.bias), dfilm=dcond if foff is not None else None, N=Nf, HW=xa.H * xa.W,
+                 Ca=xa.C, Cb=xb.C if xb else 0, T=T, film_stride=cond_cols if foff is not None else 0,
+                 film_off=foff if foff is not None else 0, silu=silu, op_dtype=opd, acc_a=acc(xa),
+                 acc_b=acc(xb) if xb else 0, eps=gn.eps)
+
+        if train:
+            P.bflops = 0
+            P.wg_ws = P.buf("wgrad_ws", 256)
+            dcond = P.buf("dcond", B * cond_cols * 4)
+            dRb = {}
+            for ab in attn_blocks:
+                for which in ("rpe_q", "rpe_k", "rpe_v"):
+                    dRb[(id(ab), which)] = P.bzero("dR", B * T * T * ab.channels * 4)
+
+            def cond_bwd():
+                BTT = B * T * T
+                rp = []
+                for ab in attn_blocks:
+                    Cc = ab.channels
+                    for which in ("rpe_q", "rpe_k", "rpe_v"):
+                        net, key = getattr(ab.temporal_attention, which).rpe_net, (id(ab), which)
+                        g_ = to_op(dRb[key], Cc, 1, 1, n=BTT)
+                        dh = P.buf("rpe_dhid", BTT * Cc * osz)
+                        dgrad(g_, Cc, 1, 1, net.out.weight, Cc, 1, out_op=dh, n=BTT)
+                        wgrad(hid[key], hdt, Cc, Cc, 1, 1, g_, Cc, 1, 1, net.out.weight, (net.out.bias,), n=BTT)
+                        rp.append(dict(wd=f32(net.embed_distances.weight), bd=f32(net.embed_distances.bias), dhidden=dh,
+                                       dwd=pg(net.embed_distances.weight), dbd=pg(net.embed_distances.bias), C=Cc,
+                                       te_off=te_off[key]))
+                if rp:
+                    dev_ = th.zeros(len(rp) * C.sizeof(N_.RpeHiddenBwdProblem), dtype=th.uint8, device=device)
+                    P.pending.append((dev_, N_.RpeHiddenBwdProblem, rp))
+                    P.op("fdm_rpe_hidden_bwd", N_.RpeHiddenBwdArgs, te=cond, frame_indices=P.fi, problems=dev_, dte=dcond,
+                         B=B, T=T, te_stride=cond_cols, count=len(rp), max_C=max(r_["C"] for r_ in rp), dhidden_dtype=opd)
+
+                def lin_bwd(problems):
+                    dev_ = th.zeros(len(problems) * C.sizeof(N_.LinearBwdProblem), dtype=th.uint8, device=device)
+                    P.pending.append((dev_, N_.LinearBwdProblem, problems))
+                    P.op("fdm_grouped_linear_bwd", N_.GroupedLinearBwdArgs, problems=dev_, count=len(problems),
+                         max_M=max(q_["M"] for q_ in problems), max_Nout=max(q_["Nout"] for q_ in problems),
+                         max_K=max(q_["K"] for q_ in problems))
+                parts = P.buf("demb_parts", len(film_probs) * B * ted * 4)
+                lin_bwd([dict(x=emb, w=f32(q_["lin"].weight), dy=(dcond, q_["off"] * 4), dw=pg(q_["lin"].weight),
+                              db=pg(q_["lin"].bias), dx_part=(parts, i_ * B * ted * 4), M=B, K=ted, Nout=q_["Nout"], ldx=ted,
+                              ldy=cond_cols, silu_in=q_["silu_in"]) for i_, q_ in enumerate(film_probs)])
+                demb = P.buf("demb", B * ted * 4)
+                P.op("fdm_sum_parts", N_.SumPartsArgs, parts=parts, out=demb, part_stride=B * ted, n=B * ted,
+                     count=len(film_probs), accumulate=0)
+                dh1 = P.buf("dtime_h1", B * ted * 4)
+                lin_bwd([dict(x=h1, w=f32(te2.weight), dy=demb, dw=pg(te2.weight), db=pg(te2.bias), dx_part=dh1, M=B, K=ted,
+                              Nout=ted, ldx=ted, ldy=ted, silu_in=1)])
+                lin_bwd([dict(x=temb, w=f32(te0.weight), dy=dh1, dw=pg(te0.weight), db=pg(te0.bias), dx_part=None, M=B, K=mc,
+                              Nout=ted, ldx=mc, ldy=ted, silu_in=0)])
+            P.tape.append(cond_bwd)
 
         # ---------------- network body
         # bf16 mode: the stem conv runs on tcgen05 over a bf16 copy of the network input, channels zero-padded to 8
@@ -504,14 +704,38 @@ class DenoiserEngine:
                  film_stride=cond_cols, film_off=film_off[id(rb)], silu=1, op_dtype=opd, eps=gn2.eps)
             out = new_act("res_out", Co, Hh, Ww)
             yop = with_op_copy(out) if want_op else None
+            sk = rb.skip_connection
             if has_skip:
-                sk = rb.skip_connection
                 if sk.kernel_size != (1, 1):
                     raise NotImplementedError("ResBlock(use_conv=True) 3x3 skip is never built by create_model")
-                conv(a2, Co, Hh, Ww, c2.weight, Co, 3, a1=raw, C1=Ci, w1=sk.weight, bias=self._bias_sum(c2.bias, sk.bias),
+                conv(a2, Co, Hh, Ww, c2.weight, Co, 3, a1=raw, C1=Ci, w1=sk.weight, bias=bias_sum(c2.bias, sk.bias),
                      y_f32=out.buf, y_op=yop, stats=out.st)
             else:
                 conv(a2, Co, Hh, Ww, c2.weight, Co, 3, bias=f32(c2.bias), resid=xa.buf, y_f32=out.buf, y_op=yop, stats=out.st)
+
+            def bwd():
+                g_out = gact(out)
+                go = to_op(g_out, Co, Hh, Ww)
+                da2 = P.buf("d_a2", Nf * hw * Co * osz)
+                dgrad(go, Co, Hh, Ww, c2.weight, Co, 3, out_op=da2)
+                draw = None
+                if has_skip:
+                    wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight, (c2.bias, sk.bias))
+                    draw = P.buf("d_raw", Nf * hw * Ci * osz)
+                    dgrad(go, Co, Hh, Ww, sk.weight, Ci, 1, out_op=draw)
+                    wgrad(raw, opd, Ci, Ci, Hh, Ww, go, Co, 1, 1, sk.weight)
+                else:
+                    wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight, (c2.bias,))
+                    P.op("fdm_accum", N_.AccumArgs, src=g_out, dst=gact(xa), N=Nf, H=Hh, W=Ww, C=Co, pool=0, src_dtype=F32_,
+                         accumulate=acc(xa))
+                gn_bwd(h1_, None, gn2, film_off[id(rb)], da2, None, None, 1)
+                gh = to_op(gact(h1_), Co, Hh, Ww)
+                da1 = P.buf("d_a1", Nf * hw * Ci * osz)
+                dgrad(gh, Co, Hh, Ww, c1.weight, Ci, 3, out_op=da1)
+                wgrad(a1, opd, Ci, Ci, Hh, Ww, gh, Co, 3, 1, c1.weight, (c1.bias,))
+                gn_bwd(xa, xb, gn, None, da1, None, draw, 1)
+            if train:
+                P.tape.append(bwd)
             return out
 
         def attention(ab, x, want_op=False):
@@ -546,6 +770,45 @@ class DenoiserEngine:
             z = new_act("sa_z", Cc, Hh, Ww)
             conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf,
                  y_op=with_op_copy(z) if want_op else None, stats=z.st)
+
+            def bwd():
+                n_tok = Nf * hw
+                # spatial half: z = proj(o2) + yn ; o2 = attn(qkv2) ; qkv2 = qkv(yn_op) ; yn = GN(y)
+                g_z = gact(z)
+                gz = to_op(g_z, Cc, Hh, Ww)
+                do2 = P.buf("d_sa_o", n_tok * Cc * osz)
+                dgrad(gz, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, out_op=do2)
+                wgrad(o2, opd, Cc, Cc, Hh, Ww, gz, Cc, 1, 1, sa.proj_out.weight, (sa.proj_out.bias,))
+                dqkv2 = P.buf("d_sa_qkv", n_tok * 3 * Cc * osz)
+                P.bflops += 10 * hw * hw * Cc * Nf
+                P.op("fdm_attn_spatial_bwd", N_.AttnSpatialBwdArgs, qkv=qkv2, out=o2, dout=do2, dqkv=dqkv2, lse=P.at_lse,
+                     dsum=P.at_dsum, N=Nf, L=hw, C=Cc, heads=sa.num_heads, dtype=opd)
+                P.at_rows = max(P.at_rows, Nf * sa.num_heads * hw)
+                dyn = P.buf("d_sa_yn", n_tok * Cc * osz)
+                dgrad(dqkv2, 3 * Cc, Hh, Ww, sa.qkv.weight, Cc, 1, out_op=dyn)
+                wgrad(yn_op, opd, Cc, Cc, Hh, Ww, dqkv2, 3 * Cc, 1, 1, sa.qkv.weight, (sa.qkv.bias,))
+                gn_bwd(y, None, sa.norm, None, dyn, g_z, None, 0)
+                # temporal half: y = proj(o) + xn ; o = attn_rpe(qkv, R) ; qkv = qkv(xn_op) ; xn = temporalGN(x)
+                g_y = gact(y)
+                gy = to_op(g_y, Cc, Hh, Ww)
+                do = P.buf("d_ta_o", n_tok * Cc * osz)
+                dgrad(gy, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, out_op=do)
+                wgrad(o, opd, Cc, Cc, Hh, Ww, gy, Cc, 1, 1, ta.proj_out.weight, (ta.proj_out.bias,))
+                dqkv = P.buf("d_ta_qkv", n_tok * 3 * Cc * osz)
+                P.bflops += 25 * T * T * Cc * B * hw
+                P.op("fdm_attn_temporal_bwd", N_.AttnTemporalBwdArgs, qkv=qkv, out=o, Rq=R[(id(ab), "rpe_q")],
+                     Rk=R[(id(ab), "rpe_k")], Rv=R[(id(ab), "rpe_v")], mask=P.mask, dout=do, dqkv=dqkv,
+                     dRq=dRb[(id(ab), "rpe_q")], dRk=dRb[(id(ab), "rpe_k")], dRv=dRb[(id(ab), "rpe_v")], lse=P.at_lse,
+                     dsum=P.at_dsum, B=B, T=T, HW=hw, C=Cc, heads=ta.num_heads, dtype=opd)
+                P.at_rows = max(P.at_rows, B * ta.num_heads * T * hw)
+                dxn = P.buf("d_ta_xn", n_tok * Cc * osz)
+                dgrad(dqkv, 3 * Cc, Hh, Ww, ta.qkv.weight, Cc, 1, out_op=dxn)
+                wgrad(xn_op, opd, Cc, Cc, Hh, Ww, dqkv, 3 * Cc, 1, 1, ta.qkv.weight, (ta.qkv.bias,))
+                P.op("fdm_temporal_gn_bwd", N_.TemporalGnBwdArgs, x=x.buf, gamma=f32(ta.norm.weight), dy_op=dxn, dy_f32=g_y,
+                     gx=gact(x), dgamma=pg(ta.norm.weight), dbeta=pg(ta.norm.bias), B=B, T=T, HW=hw, C=Cc, op_dtype=opd,
+                     accumulate=acc(x), eps=ta.norm.eps)
+            if train:
+                P.tape.append(bwd)
             return z
 
         def resample(layer, x, down):
@@ -553,7 +816,8 @@ class DenoiserEngine:
             Ho, Wo = (x.H // 2, x.W // 2) if down else (x.H * 2, x.W * 2)
             out = new_act("down" if down else "up", x.C, Ho, Wo)
             Hc, Wc = (x.H, x.W) if down else (Ho, Wo)  # spatial size of the conv's input
-            if self.use_tc and self.tc_ok(x.C, 0, x.C, 3, 2 if down else 1, 0, Ho, Wo):
+            a = None
+            if (self.use_tc and self.tc_ok(x.C, 0, x.C, 3, 2 if down else 1, 0, Ho, Wo)) or (train and not down):
                 if down and x.op is not None:
                     a = x.op  # the producing conv already stored the bf16 operand copy
                 else:
@@ -567,6 +831,26 @@ class DenoiserEngine:
                 # the CUDA-core engine gathers straight from the fp32 stream (stride 2 / folded nearest upsample)
                 conv(x.buf, x.C, x.H, x.W, cv.weight, x.C, 3, stride=2 if down else 1, upsample=0 if down else 1,
                      bias=f32(cv.bias), y_f32=out.buf, stats=out.st, a_dtype=N_.F32)
+
+            def bwd():
+                Cc = x.C
+                g_out = gact(out)
+                go = to_op(g_out, Cc, Ho, Wo)
+                if down:
+                    # dgrad of the stride-2 conv = stride-1 conv over the zero-inserted gradient, accumulated in place into g_x
+                    z_ = to_op(g_out, Cc, Ho, Wo, up=2)
+                    gx = gact(x)
+                    dgrad(z_, Cc, Hc, Wc, cv.weight, Cc, 3, out_f32=gx, resid=gx if acc(x) else None)
+                    wgrad(a if a is not None else x.buf, opd if a is not None else F32_, Cc, Cc, Hc, Wc, go, Cc, 3, 2, cv.weight,
+                          (cv.bias,))
+                else:
+                    da = P.buf("d_up_a", Nf * Ho * Wo * Cc * osz)
+                    dgrad(go, Cc, Ho, Wo, cv.weight, Cc, 3, out_op=da)
+                    wgrad(a, opd, Cc, Cc, Ho, Wo, go, Cc, 3, 1, cv.weight, (cv.bias,))
+                    P.op("fdm_accum", N_.AccumArgs, src=da, dst=gact(x), N=Nf, H=x.H, W=x.W, C=Cc, pool=1, src_dtype=opd,
+                         accumulate=acc(x))
+            if train:
+                P.tape.append(bwd)
             return out
 
         names = {id(mod): name for name, mod in m.named_modules()}
@@ -584,6 +868,13 @@ class DenoiserEngine:
                         conv(xin, Cin, H, W, layer.weight, layer.out_channels, 3, bias=f32(layer.bias), y_f32=out.buf,
                              stats=out.st, a_dtype=N_.F32)
                     h = out
+
+                    def bwd(layer=layer, out=out):
+                        go = to_op(gact(out), layer.out_channels, H, W)
+                        wgrad(xin, N_.BF16 if stem_tc else F32_, 8 if stem_tc else Cin, Cin, H, W, go, layer.out_channels, 3, 1,
+                              layer.weight, (layer.bias,))
+                    if train:
+                        P.tape.append(bwd)
                 elif isinstance(layer, ResBlock):
                     h = res_block(layer, h, skip, want_op=want_op)
                     skip = None
@@ -615,6 +906,37 @@ class DenoiserEngine:
              film_stride=0, film_off=0, silu=1, op_dtype=opd, eps=gn.eps)
         conv(a, h.C, H, W, cv.weight, m.out_channels, 3, bias=f32(cv.bias), y_f32=P.eps, out_nchw=1)
 
+        if train:
+            h_last, head_a, Co_ = h, a, m.out_channels
+            P.geps = P.buf("geps", Nf * Co_ * H * W * 4, True)
+            P.at_rows = 1
+            P.at_lse, P.at_dsum = P.buf("attn_lse", 256), P.buf("attn_dsum", 256)
+
+            def head_bwd():
+                tc_head = self.use_tc and self.tc_ok(8, 0, h_last.C, 3, 1, 0, H, W) and Co_ <= 8
+                Cp = 8 if tc_head else Co_
+                ge_p = P.buf("geps_op", Nf * H * W * Cp * osz)
+                P.op("fdm_nchw_to_nhwc", N_.NchwToNhwcArgs, src=P.geps, dst=ge_p, N=Nf, C=Co_, H=H, W=W, Cpad=Cp, op_dtype=opd)
+                ge = ge_p
+                if Cp != Co_:
+                    ge = P.buf("geps_op_true", Nf * H * W * Co_ * osz)
+                    P.op("fdm_nchw_to_nhwc", N_.NchwToNhwcArgs, src=P.geps, dst=ge, N=Nf, C=Co_, H=H, W=W, Cpad=Co_, op_dtype=opd)
+                da = P.buf("d_head_a", Nf * H * W * h_last.C * osz)
+                dgrad(ge_p, Cp, H, W, cv.weight, h_last.C, 3, out_op=da)
+                wgrad(head_a, opd, h_last.C, h_last.C, H, W, ge, Co_, 3, 1, cv.weight, (cv.bias,))
+                gn_bwd(h_last, None, gn, None, da, None, None, 1)
+            P.tape.append(head_bwd)
+            P.cur = P.bops
+            for emit in reversed(P.tape):
+                emit()
+            P.cur = P.ops
+            P.at_lse.nbytes = P.at_dsum.nbytes = (P.at_rows * 4 + 255) // 256 * 256
+            dev_ = th.zeros(len(P.pack_problems) * C.sizeof(N_.PackProblem), dtype=th.uint8, device=device)
+            P.pending.append((dev_, N_.PackProblem, [dict(src=s_, src2=s2_, dst=d_, co=co_, ci=ci_, k=k_, mode=mo_)
+                                                    for s_, s2_, d_, co_, ci_, k_, mo_ in P.pack_problems]))
+            pack_fields.update(problems=dev_, count=len(P.pack_problems),
+                               max_elems=max(co_ * ci_ * k_ * k_ for _, _, _, co_, ci_, k_, _ in P.pack_problems))
+
         P.join_at = next((i for i, (fn, _, _) in enumerate(P.ops) if fn == "fdm_attn_temporal"), len(P.ops))
         if (th.device(device).type == "cuda" and P.side_end > P.side_begin and P.join_at >= P.side_end
                 and os.environ.get("FDM_SIDE_STREAM", "1") != "0"):
@@ -639,6 +961,16 @@ class DenoiserEngine:
                 arr[i].C, arr[i].te_off = pr["C"], pr["te_off"]
             dev.copy_(th.frombuffer(bytearray(bytes(arr)), dtype=th.uint8))
         self._pending_groups, self._pending_rh = [], None
+        for dev, cls, items in P.pending:
+            arr = (cls * len(items))()
+            for i, it in enumerate(items):
+                for k, v in it.items():
+                    setattr(arr[i], k, P.ptr(v) if isinstance(v, (Buf, tuple, th.Tensor)) or v is None else v)
+            dev.copy_(th.frombuffer(bytearray(bytes(arr)), dtype=th.uint8))
+            P.keep.append(dev)
+        if train:
+            P.geps_view = P.view(P.geps, (B, T, m.out_channels, H, W), th.float32)
+            P.n_bwd_launches = len(P.bcalls)
         # typed views of the I/O buffers
         Cx = Cin - 1
         P.x_view = P.view(P.x, (B, T, Cx, H, W), th.float32)
@@ -659,6 +991,12 @@ class DenoiserEngine:
         P.fi_view.copy_(frame_indices)
         P.obs_view.copy_(obs_mask.reshape(P.B, P.T))
         th.clamp(obs_mask.reshape(P.B, P.T) + latent_mask.reshape(P.B, P.T), max=1, out=P.mask_view)
+
+    def forward_train(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask):
+        """Differentiable forward (w.r.t. the parameters) through the native forward + backward schedules."""
+        if frame_indices is None:
+            raise ValueError("frame_indices is required (temporal RPE, rpe.py:146)")
+        return _DenoiserFn.apply(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, *self.model.parameters())
 
     def forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask):
         B, T, Cx, H, W = x.shape

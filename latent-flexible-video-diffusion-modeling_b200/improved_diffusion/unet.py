@@ -9,6 +9,8 @@ the modules; it hands (x, x0, t, frame_indices, masks) to a `DenoiserEngine`, wh
 kernel schedule per input shape (NHWC activations, fused GroupNorm/SiLU/FiLM, implicit-GEMM convs,
 RPE attention kernels) and replays it.
 """
+import os
+
 import torch as th
 import torch.nn as nn
 
@@ -155,8 +157,12 @@ class UNetVideoModel(nn.Module):
             out = differentiable_forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, attns=attns)
             return out, attns
         needs_grad = th.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad and x.is_cuda and os.environ.get("FDM_TRAIN_ENGINE", "native") != "autograd":
+            # training on the GPU: native forward AND backward kernel schedules behind one autograd node (engine._DenoiserFn)
+            return self.engine().forward_train(x, x0, timesteps, frame_indices, obs_mask, latent_mask), None
         if needs_grad:
-            # training: interim PyTorch-autograd expression of the same network (see autograd_path.py / DESIGN.md)
+            # CPU (tests, the drop-in TrainLoop check) or FDM_TRAIN_ENGINE=autograd (A/B): PyTorch-autograd expression of the
+            # same network over the same parameters (autograd_path.py)
             from .autograd_path import differentiable_forward
             return differentiable_forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask), None
         if not x.is_cuda:

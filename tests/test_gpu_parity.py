@@ -222,3 +222,74 @@ def test_pixel_space_128px_vs_oracle(precision):
     e = O.rel_l2(eps.cpu(), ref)
     print(f"128px [{precision}] eps rel-L2 = {e:.3e}")
     assert eps.shape == (1, 2, 3, 128, 128) and e <= TOL[precision]
+
+
+def _grad_errors(got, ref):
+    """rel-L2 per parameter, with the denominator floored at 5 % of the median gradient norm: several parameters have an
+    analytically ZERO gradient (conv biases feeding a GroupNorm, the rpe_k output bias: softmax shift invariance) and only
+    carry rounding noise (~1e-10 in fp32, ~1e-5 in bf16 against a median norm of ~2e-3) on either side."""
+    floor = 5e-2 * float(torch.stack([v.double().norm() for v in ref.values()]).median())
+    return sorted(((float((got[k].double() - ref[k].double()).norm() / max(float(ref[k].double().norm()), floor)), k)
+                   for k in ref), reverse=True)
+
+
+def _train_grads(model, diffusion, inp, t, noise, engine, monkeypatch, precision=None):
+    monkeypatch.setenv("FDM_TRAIN_ENGINE", engine)
+    if precision is not None:
+        monkeypatch.setattr(model, "precision", precision)
+    # the autograd side must be true fp32 in BACKWARD too (cuDNN allows TF32 by default; autograd_path only pins the forward)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    model.zero_grad(set_to_none=True)
+    terms = diffusion.training_losses(model, inp["x0"].cuda(), t.cuda(), model_kwargs=cuda_kw(inp), noise=noise.cuda(),
+                                      latent_mask=inp["latent_mask"].cuda(), eval_mask=inp["latent_mask"].cuda())
+    terms["loss"].mean().backward()
+    torch.cuda.synchronize()
+    return terms["loss"].detach().cpu(), {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", [
+    # model overrides, B, T, n_obs, padded rows
+    (dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32), 2, 5, 2, (1,)),
+    (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 7, 3, ()),
+    (dict(image_size=64, in_channels=3, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 3, 1, ()),
+])
+def test_native_backward_matches_autograd(case, precision, monkeypatch):
+    """The native backward schedule (engine._DenoiserFn: conv dgrad/wgrad, GroupNorm / attention / RPENet backward kernels) against
+    torch.autograd over the PyTorch expression of the same network and parameters, on the same device.  fp32 mode: both sides are
+    exact fp32 -> tight; bf16 mode: bf16 GEMM operands / operand gradients on the native side against the exact fp32 autograd."""
+    over, B, T, n_obs, pad = case
+    model, diffusion, cfg, sd = build(over, precision)
+    model.train()
+    inp = O.synthetic_inputs(cfg, B, T, n_obs, seed=5, video_len=60, pad_rows=pad)
+    g = torch.Generator().manual_seed(11)
+    t = torch.randint(0, diffusion.num_timesteps, (B,), generator=g)
+    noise = torch.randn(inp["x0"].shape, generator=g)
+    loss_n, gn_ = _train_grads(model, diffusion, inp, t, noise, "native", monkeypatch, precision)
+    loss_a, ga_ = _train_grads(model, diffusion, inp, t, noise, "autograd", monkeypatch, "fp32")
+    tol_loss, tol_g = (1e-5, 2e-4) if precision == "fp32" else (3e-2, 2e-1)
+    assert O.rel_l2(loss_n, loss_a) <= tol_loss
+    errs = _grad_errors(gn_, ga_)
+    print(f"native vs autograd [{precision}] worst grad rel-L2 = {errs[0][0]:.3e} at {errs[0][1]}, median {errs[len(errs) // 2][0]:.3e}")
+    assert all(torch.isfinite(v).all() for v in gn_.values())
+    assert errs[0][0] <= tol_g, errs[:5]
+    # a second backward of a fresh forward reproduces the first (buffers are re-zeroed, weights re-packed)
+    loss_n2, gn2 = _train_grads(model, diffusion, inp, t, noise, "native", monkeypatch, precision)
+    assert _grad_errors(gn2, gn_)[0][0] <= 1e-4
+
+
+def test_native_training_step_follows_weight_updates(monkeypatch):
+    """After an optimizer step the training plan must see the new weights (one fdm_pack_weights launch per forward)."""
+    over = dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32)
+    model, diffusion, cfg, sd = build(over, "fp32")
+    model.train()
+    inp = O.synthetic_inputs(cfg, 1, 5, 2, seed=6)
+    t, noise = torch.tensor([17]), torch.randn(inp["x0"].shape, generator=torch.Generator().manual_seed(3))
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    _train_grads(model, diffusion, inp, t, noise, "native", monkeypatch)
+    opt.step()
+    loss_n, gn_ = _train_grads(model, diffusion, inp, t, noise, "native", monkeypatch)
+    loss_a, ga_ = _train_grads(model, diffusion, inp, t, noise, "autograd", monkeypatch)
+    assert O.rel_l2(loss_n, loss_a) <= 1e-5
+    assert _grad_errors(gn_, ga_)[0][0] <= 2e-4
