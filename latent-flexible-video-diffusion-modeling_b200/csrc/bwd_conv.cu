@@ -9,6 +9,10 @@
 
 namespace fdm {
 
+// wgrad_tc.cu: tcgen05 engine; FDM_ERR_UNSUPPORTED for shapes / dtypes it does not take (the caller then runs the CUDA-core kernel)
+int conv_wgrad_tc(const fdm_conv_wgrad_args* a, float* part, int* splits_out, cudaStream_t st);
+size_t conv_wgrad_tc_partial_bytes(const fdm_conv_wgrad_args* a);
+
 constexpr int WG_BM = 64, WG_BN = 64, WG_BK = 16, WG_NT = 256;
 
 struct WgradParams {
@@ -172,6 +176,10 @@ static inline WgradGeom wgrad_geom(const fdm_conv_wgrad_args* a) {
   g.chunk = ((g.M + want - 1) / want + WG_BK - 1) / WG_BK * WG_BK;
   g.splits = (int)((g.M + g.chunk - 1) / g.chunk);
   g.part_bytes = (size_t)g.splits * g.taps * a->C * a->Cout * sizeof(float);
+  if (a->engine == FDM_CONV_TC) {  // either engine may end up running: size for the larger partial buffer
+    const size_t tcb = conv_wgrad_tc_partial_bytes(a);
+    if (tcb > g.part_bytes) g.part_bytes = tcb;
+  }
   g.cs_blocks = (int)(g.M / 64 > 592 ? 592 : (g.M / 64 > 0 ? g.M / 64 : 1));
   g.cs_rows = (g.M + g.cs_blocks - 1) / g.cs_blocks;
   g.cs_blocks = (int)((g.M + g.cs_rows - 1) / g.cs_rows);
@@ -179,7 +187,6 @@ static inline WgradGeom wgrad_geom(const fdm_conv_wgrad_args* a) {
   return g;
 }
 
-int conv_wgrad_tc(const fdm_conv_wgrad_args* a, cudaStream_t st);  // wgrad_tc.cu (returns FDM_ERR_UNSUPPORTED for shapes it does not take)
 
 }  // namespace fdm
 
@@ -200,9 +207,10 @@ extern "C" int fdm_conv_wgrad(const fdm_conv_wgrad_args* a, void* stream) {
   const WgradGeom g = wgrad_geom(a);
   float* part = reinterpret_cast<float*>(a->workspace);
   float* cs_part = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + (g.part_bytes + 255) / 256 * 256);
+  int splits = g.splits;
   bool done = false;
   if (a->engine == FDM_CONV_TC) {
-    const int rc = conv_wgrad_tc(a, st);
+    const int rc = conv_wgrad_tc(a, part, &splits, st);
     if (rc == FDM_OK) done = true;
     else if (rc != FDM_ERR_UNSUPPORTED) return rc;
   }
@@ -218,10 +226,12 @@ extern "C" int fdm_conv_wgrad(const fdm_conv_wgrad_args* a, void* stream) {
     else if (ab) fdm::launch(wgrad_simt_kernel<__nv_bfloat16, float>, grid, dim3(WG_NT), 0, st, p);
     else if (db) fdm::launch(wgrad_simt_kernel<float, __nv_bfloat16>, grid, dim3(WG_NT), 0, st, p);
     else fdm::launch(wgrad_simt_kernel<float, float>, grid, dim3(WG_NT), 0, st, p);
+  }
+  {
     const long long total = (long long)g.taps * a->Cw * a->Cout;
     long long gr = (total + 255) / 256;
     if (gr > 148 * 8) gr = 148 * 8;
-    fdm::launch(wgrad_reduce_kernel, dim3((unsigned)gr), dim3(256), 0, st, (const float*)part, a->dw, g.splits, g.taps, a->C, a->Cw, a->Cout);
+    fdm::launch(wgrad_reduce_kernel, dim3((unsigned)gr), dim3(256), 0, st, (const float*)part, a->dw, splits, g.taps, a->C, a->Cw, a->Cout);
   }
   if (a->dbias != nullptr || a->dbias2 != nullptr) {
     if (a->dy_dtype == FDM_BF16)

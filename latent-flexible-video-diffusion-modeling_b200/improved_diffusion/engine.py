@@ -48,6 +48,7 @@ class Plan:
         self.calls = None    # [(fn, byref(struct))] after finalize()
         self.stats_bytes = 0
         self.graphs = {}     # CUDA graphs captured over this plan (see gaussian_diffusion._graph_sampler)
+        self._warm = set()
         self.debug = os.environ.get("FDM_DEBUG_TAPS", "0") == "1"
         self.taps = {}       # module name -> (Buf, C, H, W) of that layer's fp32 NHWC output (readable when debug)
         self.side_begin = self.side_end = self.join_at = 0  # op index range of the RPE-table branch / its first consumer
@@ -171,6 +172,25 @@ class Plan:
         esz = th.empty((), dtype=dtype).element_size()
         return self.arena[b.offset:b.offset + n * esz].view(dtype).view(*shape)
 
+    def run_graphed(self, which, device):
+        """Training: the forward ("fwd") / backward ("bwd") schedule as ONE CUDA graph replay.  The first call of each runs
+        eagerly (lazy module loading, cudaFuncSetAttribute), the second captures; FDM_NO_GRAPH=1 keeps everything eager."""
+        body = self.run if which == "fwd" else self.run_backward
+        cur = lambda: th.cuda.current_stream(device).cuda_stream
+        if os.environ.get("FDM_NO_GRAPH", "0") == "1":
+            return body(cur())
+        key = ("train", which)
+        if key not in self.graphs:
+            if key not in self._warm:
+                self._warm.add(key)
+                return body(cur())
+            th.cuda.current_stream(device).synchronize()
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g, capture_error_mode="thread_local"):
+                body(cur())
+            self.graphs[key] = g
+        self.graphs[key].replay()
+
     def run_backward(self, stream):
         """Launch the backward schedule (training plans): zero the accumulator arena and the flat parameter-gradient buffer,
         then every backward kernel in order on `stream`.  The caller has copied d(loss)/d(eps) into `geps_view`."""
@@ -223,7 +243,7 @@ class _DenoiserFn(th.autograd.Function):
         P.set_t_source(None)
         P.x_view.copy_(x)
         P.t_view.copy_(timesteps.reshape(B).float())
-        P.run(th.cuda.current_stream(x.device).cuda_stream)
+        P.run_graphed("fwd", x.device)
         P.generation = getattr(P, "generation", 0) + 1
         ctx.plan, ctx.generation = P, P.generation
         return P.eps_view.clone()
@@ -235,7 +255,7 @@ class _DenoiserFn(th.autograd.Function):
             raise RuntimeError("the activations of this forward were overwritten by a later forward of the same shape "
                                "(the training plan keeps ONE set of saved activations): call backward before the next forward")
         P.geps_view.copy_(g)
-        P.run_backward(th.cuda.current_stream(g.device).cuda_stream)
+        P.run_graphed("bwd", g.device)
         flat = P.pgrad.clone()  # the plan's buffer is reused by the next backward; autograd owns this copy
         base = P.pgrad.data_ptr()
         grads = tuple(flat[(v.data_ptr() - base) // 4:(v.data_ptr() - base) // 4 + v.numel()].view(v.shape) for v in P.pgrad_views)
@@ -841,8 +861,12 @@ class DenoiserEngine:
                     z_ = to_op(g_out, Cc, Ho, Wo, up=2)
                     gx = gact(x)
                     dgrad(z_, Cc, Hc, Wc, cv.weight, Cc, 3, out_f32=gx, resid=gx if acc(x) else None)
-                    wgrad(a if a is not None else x.buf, opd if a is not None else F32_, Cc, Cc, Hc, Wc, go, Cc, 3, 2, cv.weight,
-                          (cv.bias,))
+                    if self.use_tc and a is not None:
+                        # tcgen05 wgrad is stride-1: the zero-inserted gradient against the full-resolution input is the same sum
+                        wgrad(a, opd, Cc, Cc, Hc, Wc, z_, Cc, 3, 1, cv.weight, (cv.bias,))
+                    else:
+                        wgrad(a if a is not None else x.buf, opd if a is not None else F32_, Cc, Cc, Hc, Wc, go, Cc, 3, 2,
+                              cv.weight, (cv.bias,))
                 else:
                     da = P.buf("d_up_a", Nf * Ho * Wo * Cc * osz)
                     dgrad(go, Cc, Ho, Wo, cv.weight, Cc, 3, out_op=da)

@@ -179,6 +179,11 @@ WGRAD_CASES = [
     (7, 8, 8, 192, 192, 64, 1, 1),   # 1x1 skip / linear
     (2, 4, 4, 256, 256, 768, 1, 1),  # qkv on a 4x4 map
     (1, 64, 64, 32, 32, 32, 3, 1),
+    (2, 128, 128, 128, 128, 128, 3, 1),  # 128-wide rows: one X block per stage, filter rows paired
+    (3, 64, 64, 128, 128, 256, 3, 1),
+    (3, 32, 32, 256, 256, 128, 1, 1),
+    (2, 16, 16, 192, 192, 384, 3, 1),    # ragged 128-channel chunking of both operands
+    (40, 32, 32, 64, 64, 64, 3, 1),      # many pixel chunks per split
 ]
 
 
