@@ -192,13 +192,21 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def bench_train(dev, world, precision, steps=20, warmup=3):
-    """train samples/s on BASELINE cfg2 (Carla-latent: nc=64, nrb=1, K=5, batch 1 per GPU, 1000-step schedule): one
-    training_losses forward + backward (+ DDP gradient allreduce when world > 1) + AdamW step per iteration.
-    Forward AND backward run on the native kernel schedules (engine._DenoiserFn); the same step through torch.autograd over the
-    PyTorch expression of the network (cuDNN/cuBLAS, FDM_TRAIN_ENGINE=autograd) is timed beside it as `autograd_ms_per_step`."""
+TRAIN_WORKLOADS = {
+    # BASELINE.json configs[1]: Carla-latent, nc = 64, K = 5, batch 1, on 1 B200
+    "cfg2-train": (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 5, 20),
+    # BASELINE.json configs[2]: Carla pixel-scale, nc = 128, K = 20, 128x128x3 frames, batch 2 PER GPU (DDP over the box)
+    "cfg3-train": (dict(image_size=128, in_channels=3, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 2, 20, 6),
+}
+
+
+def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
+    """train samples/s: one training_losses forward + backward (+ DDP gradient allreduce over NCCL when world > 1) + AdamW step
+    per iteration, per-GPU batch fixed (weak scaling).  Forward AND backward run on the native kernel schedules
+    (engine._DenoiserFn, CUDA-graph replays); the same step through torch.autograd over the PyTorch expression of the network
+    (cuDNN/cuBLAS under autocast, FDM_TRAIN_ENGINE=autograd) is timed beside it as `autograd_ms_per_step`."""
     import torch.distributed as dist
-    over = dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000)
+    over, B, K, steps = TRAIN_WORKLOADS[workload]
     model, diffusion, _ = build_native(over, dev)
     model.precision = precision
     model.train()
@@ -207,8 +215,7 @@ def bench_train(dev, world, precision, steps=20, warmup=3):
         from improved_diffusion.sharding import wrap_ddp
         net = wrap_ddp(model, dev)
     opt = th.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0, fused=True)
-    B, K = 1, 5
-    batch = {k: v.to(dev) for k, v in synthetic_batch(over, B, K, 3, 20, seed=1).items()}
+    batch = {k: v.to(dev) for k, v in synthetic_batch(over, B, K, 3, 4 * K, seed=1 + int(os.environ.get("RANK", "0"))).items()}
     g = th.Generator(device=dev).manual_seed(0)
 
     def step():
@@ -218,8 +225,9 @@ def bench_train(dev, world, precision, steps=20, warmup=3):
         opt.zero_grad(set_to_none=True)
         terms["loss"].mean().backward()
         opt.step()
+        return terms["loss"]
 
-    def timed(engine):
+    def timed(engine, n):
         os.environ["FDM_TRAIN_ENGINE"] = engine
         for _ in range(warmup):
             step()
@@ -228,24 +236,33 @@ def bench_train(dev, world, precision, steps=20, warmup=3):
             dist.barrier()
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            step()
+        for _ in range(n):
+            loss = step()
         e1.record()
         th.cuda.synchronize()
+        assert bool(th.isfinite(loss).all()), "training loss is not finite"
         ms = th.tensor([e0.elapsed_time(e1)], device=dev, dtype=th.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()) / n
 
-    ms_auto = timed("autograd")
-    ms = timed("native")
+    ms_auto = timed("autograd", max(2, steps // 2))
+    th.cuda.empty_cache()
+    ms = timed("native", steps)
     plan = next(iter(model.engine().train_plans.values()))
-    return {"metric": "train samples/sec", "value": world * B * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps,
-            "autograd_ms_per_step": ms_auto / steps,
-            "config": {"workload": "cfg2-train", "batch_per_gpu": B, "frames": K, **over, "optimizer": "AdamW (torch fused)"},
-            "launches_per_step": {"forward": plan.n_launches, "backward": plan.n_bwd_launches},
-            "path": "native: forward + backward kernel schedules of libfdm_sm100.so behind one autograd node (conv dgrad on tcgen05, "
-                    "wgrad / GroupNorm / attention / RPENet backward kernels); DDP gradient allreduce when n_gpus > 1"}
+    flops = plan.flops + plan.bflops
+    out = {"metric": "train samples/sec", "value": world * B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+           "autograd_ms_per_step": ms_auto, "steps": steps,
+           "config": {"workload": workload, "batch_per_gpu": B, "frames": K, **over, "optimizer": "AdamW (torch fused)"},
+           "launches_per_step": {"forward": plan.n_launches, "backward": plan.n_bwd_launches},
+           "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                        "flops_per_step": flops, "what": "algorithmic fwd + dgrad + wgrad + attention FLOPs of one step / step time "
+                                                         "(optimizer, loss and host work included in the time)"},
+           "path": "native: forward + backward kernel schedules of libfdm_sm100.so behind one autograd node (conv dgrad and wgrad on "
+                   "tcgen05, GroupNorm / attention / RPENet backward kernels); DDP gradient allreduce when n_gpus > 1"}
+    del opt, net, model
+    th.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -465,7 +482,8 @@ def main():
     # ------------------------------------------------------------------ secondary metric: train samples/s (BASELINE cfg2)
     train = None
     if not args.no_train:
-        train = bench_train(dev, world, args.precision)
+        train = bench_train(dev, world, args.precision, "cfg2-train")
+        train["cfg3"] = bench_train(dev, world, args.precision, "cfg3-train")
 
     if rank == 0:
         line = {"metric": "denoiser frame-steps/sec (sampling)", "value": value, "unit": "frame-steps/s", "n_gpus": world,

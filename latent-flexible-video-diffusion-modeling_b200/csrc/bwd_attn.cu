@@ -339,7 +339,10 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_q_kernel(TABw
   float* rv = rq + T * TB_FC;        // [T][8]  Rv[t, s, chunk]
   float* dsw = rv + T * TB_FC;       // [T][33] dS[s][px]
   float* qw = dsw + T * TB_LD;       // [8][33] q[f][px]
-  const int px0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z;
+  // one CTA per (32 pixels, head, video, round of 8 query frames): the rounds are independent, and on the small feature maps
+  // (8x8: two pixel blocks) they are the only parallelism there is
+  const int rounds = (T + TB_WARPS - 1) / TB_WARPS;
+  const int px0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z / rounds;
   const int px = min(px0 + lane, HW - 1);
   const bool px_ok = px0 + lane < HW;
   const QT* qkv = reinterpret_cast<const QT*>(p.qkv);
@@ -348,8 +351,8 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_q_kernel(TABw
   QT* dqkv = reinterpret_cast<QT*>(p.dqkv);
   const size_t tok = (size_t)3 * C;
   const float* maskb = p.mask ? p.mask + (size_t)b * T : nullptr;
-  const int rounds = (T + TB_WARPS - 1) / TB_WARPS;
-  for (int rd = 0; rd < rounds; ++rd) {
+  {
+    const int rd = blockIdx.z - b * rounds;
     const int t_raw = rd * TB_WARPS + w;
     const bool act = t_raw < T;
     const int t = act ? t_raw : 0;
@@ -479,7 +482,8 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_kv_kernel(TAB
   float* dsw = rv + T * TB_FC;       // [T][33] dS[t][px]
   float* pw = dsw + T * TB_LD;       // [T][33] P[t][px]
   float* kw = pw + T * TB_LD;        // [8][33] k[f][px]
-  const int px0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z;
+  const int rounds = (T + TB_WARPS - 1) / TB_WARPS;
+  const int px0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z / rounds;
   const int px = min(px0 + lane, HW - 1);
   const bool px_ok = px0 + lane < HW;
   const QT* qkv = reinterpret_cast<const QT*>(p.qkv);
@@ -487,8 +491,8 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_kv_kernel(TAB
   QT* dqkv = reinterpret_cast<QT*>(p.dqkv);
   const size_t tok = (size_t)3 * C;
   const float* maskb = p.mask ? p.mask + (size_t)b * T : nullptr;
-  const int rounds = (T + TB_WARPS - 1) / TB_WARPS;
-  for (int rd = 0; rd < rounds; ++rd) {
+  {
+    const int rd = blockIdx.z - b * rounds;
     const int s_raw = rd * TB_WARPS + w;
     const bool act = s_raw < T;
     const int s = act ? s_raw : 0;
@@ -633,7 +637,7 @@ static void launch_ta_bwd(const TABwdParams& p, cudaStream_t st) {
   const int T = p.T;
   const size_t smem_q = ((size_t)2 * T * TB_FC * TB_LD + (size_t)TB_WARPS * (3 * T * TB_FC + T * TB_LD + TB_FC * TB_LD)) * sizeof(float);
   const size_t smem_kv = ((size_t)2 * T * TB_FC * TB_LD + (size_t)TB_WARPS * (3 * T * TB_FC + 2 * T * TB_LD + TB_FC * TB_LD)) * sizeof(float);
-  dim3 grid((p.HW + 31) / 32, p.heads, p.B);
+  dim3 grid((p.HW + 31) / 32, p.heads, p.B * ((T + TB_WARPS - 1) / TB_WARPS));
   cudaFuncSetAttribute(attn_temporal_bwd_q_kernel<TP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
   cudaFuncSetAttribute(attn_temporal_bwd_kv_kernel<TP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);
   fdm::launch(attn_temporal_bwd_q_kernel<TP, QT>, grid, dim3(TB_WARPS * 32), smem_q, st, p);
@@ -645,7 +649,7 @@ extern "C" int fdm_attn_temporal_bwd(const fdm_attn_temporal_bwd_args* a, void* 
               FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->B > 0 && a->T > 0 && a->HW > 0 && a->heads > 0 && a->C % a->heads == 0, FDM_ERR_BAD_ARG);
   const int F = a->C / a->heads;
-  FDM_REQUIRE(F % TB_FC == 0 && a->T <= 40 && a->B <= 65535, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(F % TB_FC == 0 && a->T <= 40 && a->B <= 8000, FDM_ERR_UNSUPPORTED);
   TABwdParams p{a->qkv, a->out, a->dout, a->Rq, a->Rk, a->Rv, a->mask, a->dqkv, a->dRq, a->dRk, a->dRv, a->lse, a->dsum,
                 a->B, a->T, a->HW, a->C, a->heads, F, 1.0f / sqrtf((float)F)};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

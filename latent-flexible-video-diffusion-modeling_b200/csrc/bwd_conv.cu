@@ -108,6 +108,117 @@ __global__ void __launch_bounds__(WG_NT) wgrad_simt_kernel(WgradParams p) {
   }
 }
 
+// ---- skinny layers: stem (<= 8 input channels) and head (<= 8 output channels).  The 64x64 tile above would be >= 87 % zeros
+// there and, with so few (ci, co) tiles, leaves the split-K CTAs walking ~20k pixels each (measured 4.5 ms per launch on the
+// 128-px model).  Here one thread owns a channel of the WIDE side (coalesced global reads) and keeps all taps x narrow-side
+// channels in registers; the narrow side is a warp-uniform (broadcast) load.  grid (ceil(wide/128), splits), block 128.
+constexpr int WG_NARROW = 8;
+
+template <typename AT, typename DT>
+__global__ void __launch_bounds__(128) wgrad_narrow_in_kernel(WgradParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int co = blockIdx.x * 128 + threadIdx.x;
+  const bool ok = co < p.Cout;
+  const int taps = p.ksize * p.ksize, pad = p.ksize >> 1, HWo = p.Ho * p.Wo;
+  const long long m_begin = (long long)blockIdx.y * p.chunk;
+  const long long m_end = m_begin + p.chunk < p.M ? m_begin + p.chunk : p.M;
+  const AT* A = reinterpret_cast<const AT*>(p.a);
+  const DT* DY = reinterpret_cast<const DT*>(p.dy);
+  float acc[9][WG_NARROW];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < WG_NARROW; ++c) acc[t][c] = 0.f;
+  int fn = (int)(m_begin / HWo);
+  int rem = (int)(m_begin - (long long)fn * HWo);
+  int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+  for (long long m = m_begin; m < m_end; ++m) {
+    const float dy = ok ? OpType<DT>::load(DY + (size_t)m * p.Cout + co) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (t < taps) {
+        const int r = t / p.ksize, s = t - r * p.ksize;
+        const int ih = oh * p.stride + r - pad, iw = ow * p.stride + s - pad;
+        if (ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win) {  // warp-uniform branch
+          const AT* arow = A + ((size_t)(fn * p.Hin + ih) * p.Win + iw) * p.C;
+          if (sizeof(AT) == 2 && p.C == 8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(arow));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              acc[t][2 * c] = fmaf(dy, __uint_as_float(w[c] << 16), acc[t][2 * c]);
+              acc[t][2 * c + 1] = fmaf(dy, __uint_as_float(w[c] & 0xffff0000u), acc[t][2 * c + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < WG_NARROW; ++c)
+              if (c < p.C) acc[t][c] = fmaf(dy, OpType<AT>::load(arow + c), acc[t][c]);
+          }
+        }
+      }
+    }
+    if (++ow == p.Wo) { ow = 0; if (++oh == p.Ho) { oh = 0; ++fn; } }
+  }
+  if (!ok) return;
+  float* out = p.part + (size_t)blockIdx.y * taps * p.C * p.Cout;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+    if (t < taps) {
+#pragma unroll
+      for (int c = 0; c < WG_NARROW; ++c)
+        if (c < p.C) out[((size_t)t * p.C + c) * p.Cout + co] = acc[t][c];
+    }
+}
+
+template <typename AT, typename DT>
+__global__ void __launch_bounds__(128) wgrad_narrow_out_kernel(WgradParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int ci = blockIdx.x * 128 + threadIdx.x;
+  const bool ok = ci < p.C;
+  const int taps = p.ksize * p.ksize, pad = p.ksize >> 1, HWo = p.Ho * p.Wo;
+  const long long m_begin = (long long)blockIdx.y * p.chunk;
+  const long long m_end = m_begin + p.chunk < p.M ? m_begin + p.chunk : p.M;
+  const AT* A = reinterpret_cast<const AT*>(p.a);
+  const DT* DY = reinterpret_cast<const DT*>(p.dy);
+  float acc[9][WG_NARROW];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < WG_NARROW; ++c) acc[t][c] = 0.f;
+  int fn = (int)(m_begin / HWo);
+  int rem = (int)(m_begin - (long long)fn * HWo);
+  int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+  for (long long m = m_begin; m < m_end; ++m) {
+    float dy[WG_NARROW];
+#pragma unroll
+    for (int c = 0; c < WG_NARROW; ++c) dy[c] = c < p.Cout ? OpType<DT>::load(DY + (size_t)m * p.Cout + c) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (t < taps) {
+        const int r = t / p.ksize, s = t - r * p.ksize;
+        const int ih = oh * p.stride + r - pad, iw = ow * p.stride + s - pad;
+        if (ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win) {
+          const float x = ok ? OpType<AT>::load(A + ((size_t)(fn * p.Hin + ih) * p.Win + iw) * p.C + ci) : 0.f;
+#pragma unroll
+          for (int c = 0; c < WG_NARROW; ++c) acc[t][c] = fmaf(x, dy[c], acc[t][c]);
+        }
+      }
+    }
+    if (++ow == p.Wo) { ow = 0; if (++oh == p.Ho) { oh = 0; ++fn; } }
+  }
+  if (!ok) return;
+  float* out = p.part + (size_t)blockIdx.y * taps * p.C * p.Cout;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+    if (t < taps) {
+#pragma unroll
+      for (int c = 0; c < WG_NARROW; ++c)
+        if (c < p.Cout) out[((size_t)t * p.C + ci) * p.Cout + c] = acc[t][c];
+    }
+}
+
 // dw[co][ci < Cw][kh][kw] = sum_split part[split][tap = kh*k+kw][ci][co]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splits, int taps, int C, int Cw,
                                     int Cout) {
@@ -126,14 +237,44 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   }
 }
 
-// column sums of dy [rows][C]: stage 1 -> part[block][C], stage 2 -> out (and out2)
+// column sums of dy [rows][C]: stage 1 -> part[block][C], stage 2 -> out (and out2).  C % 4 == 0: a thread owns 4 columns and
+// every (256 / (C/4))-th row of the block's range (128/64-bit loads, all lanes busy for any C); other C: one column per thread.
 template <typename DT>
 __global__ void __launch_bounds__(256) colsum_kernel(const DT* __restrict__ x, float* __restrict__ part, long long rows, int C,
                                                      long long rows_per_block) {
   pdl_launch_dependents();
   pdl_wait();
+  __shared__ float4 cs_red[256];
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  const int quads = C / 4;
+  if ((C & 3) == 0 && quads <= 256) {
+    const int q = threadIdx.x % quads, rl = threadIdx.x / quads, nrl = 256 / quads;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < nrl) {
+      long long r = r0 + rl;
+      for (; r + 3 * nrl < r1; r += 4 * nrl) {  // four independent loads in flight
+        const float4 a = OpType<DT>::load4(x + (size_t)r * C + q * 4), b = OpType<DT>::load4(x + (size_t)(r + nrl) * C + q * 4);
+        const float4 c = OpType<DT>::load4(x + (size_t)(r + 2 * nrl) * C + q * 4), d = OpType<DT>::load4(x + (size_t)(r + 3 * nrl) * C + q * 4);
+        s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+        s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+      }
+      for (; r < r1; r += nrl) {
+        const float4 a = OpType<DT>::load4(x + (size_t)r * C + q * 4);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+    }
+    cs_red[threadIdx.x] = s;
+    __syncthreads();
+    if (rl == 0) {
+      for (int k = 1; k < nrl; ++k) {
+        const float4 o = cs_red[k * quads + q];
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+      *reinterpret_cast<float4*>(part + (size_t)blockIdx.x * C + q * 4) = s;
+    }
+    return;
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (long long r = r0; r < r1; ++r) s += OpType<DT>::load(x + (size_t)r * C + c);
@@ -153,7 +294,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 }
 
 struct WgradGeom {
-  int Ho, Wo, taps, splits, ci_tiles, co_tiles, cs_blocks;
+  int Ho, Wo, taps, splits, ci_tiles, co_tiles, cs_blocks, narrow;
   long long M, chunk, cs_rows;
   size_t part_bytes, cs_bytes;
 };
@@ -173,6 +314,14 @@ static inline WgradGeom wgrad_geom(const fdm_conv_wgrad_args* a) {
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
   if (want > 1024) want = 1024;
+  g.narrow = (a->C <= WG_NARROW && a->Cout >= 32) ? 1 : ((a->Cout <= WG_NARROW && a->C >= 32) ? 2 : 0);
+  if (g.narrow) {
+    const long long wide_blocks = ((g.narrow == 1 ? a->Cout : a->C) + 127) / 128;
+    want = (148LL * 8 + wide_blocks - 1) / wide_blocks;
+    if (want > (g.M + 63) / 64) want = (g.M + 63) / 64;
+    if (want < 1) want = 1;
+    if (want > 4096) want = 4096;
+  }
   g.chunk = ((g.M + want - 1) / want + WG_BK - 1) / WG_BK * WG_BK;
   g.splits = (int)((g.M + g.chunk - 1) / g.chunk);
   g.part_bytes = (size_t)g.splits * g.taps * a->C * a->Cout * sizeof(float);
@@ -199,7 +348,8 @@ extern "C" size_t fdm_conv_wgrad_workspace(const fdm_conv_wgrad_args* a) {
 }
 
 extern "C" int fdm_conv_wgrad(const fdm_conv_wgrad_args* a, void* stream) {
-  FDM_REQUIRE(a && a->a && a->dy && a->dw && a->workspace, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a && a->dy && a->workspace && (a->dw == nullptr || a->a != nullptr), FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->dw != nullptr || a->dbias != nullptr || a->dbias2 != nullptr, FDM_ERR_BAD_ARG);  // dw == NULL: bias gradient only
   FDM_REQUIRE(a->N > 0 && a->C > 0 && a->Cout > 0 && a->Cw > 0 && a->Cw <= a->C, FDM_ERR_BAD_ARG);
   FDM_REQUIRE((a->ksize == 1 || a->ksize == 3) && (a->stride == 1 || a->stride == 2), FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->workspace_bytes >= fdm_conv_wgrad_workspace(a), FDM_ERR_BAD_ARG);
@@ -208,8 +358,8 @@ extern "C" int fdm_conv_wgrad(const fdm_conv_wgrad_args* a, void* stream) {
   float* part = reinterpret_cast<float*>(a->workspace);
   float* cs_part = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + (g.part_bytes + 255) / 256 * 256);
   int splits = g.splits;
-  bool done = false;
-  if (a->engine == FDM_CONV_TC) {
+  bool done = a->dw == nullptr;
+  if (!done && a->engine == FDM_CONV_TC) {
     const int rc = conv_wgrad_tc(a, part, &splits, st);
     if (rc == FDM_OK) done = true;
     else if (rc != FDM_ERR_UNSUPPORTED) return rc;
@@ -220,14 +370,25 @@ extern "C" int fdm_conv_wgrad(const fdm_conv_wgrad_args* a, void* stream) {
     p.N = a->N; p.Hin = a->Hin; p.Win = a->Win; p.C = a->C; p.Cout = a->Cout; p.Ho = g.Ho; p.Wo = g.Wo;
     p.ksize = a->ksize; p.stride = a->stride; p.M = g.M; p.chunk = g.chunk; p.ci_tiles = g.ci_tiles;
     dim3 grid(g.ci_tiles * g.co_tiles, g.taps, g.splits);
-    FDM_REQUIRE(grid.z <= 65535, FDM_ERR_UNSUPPORTED);
+    dim3 block(WG_NT);
+    if (g.narrow) {
+      grid = dim3(((g.narrow == 1 ? a->Cout : a->C) + 127) / 128, g.splits, 1);
+      block = dim3(128);
+    }
+    FDM_REQUIRE(grid.z <= 65535 && grid.y <= 65535, FDM_ERR_UNSUPPORTED);
     const bool ab = a->a_dtype == FDM_BF16, db = a->dy_dtype == FDM_BF16;
-    if (ab && db) fdm::launch(wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16>, grid, dim3(WG_NT), 0, st, p);
-    else if (ab) fdm::launch(wgrad_simt_kernel<__nv_bfloat16, float>, grid, dim3(WG_NT), 0, st, p);
-    else if (db) fdm::launch(wgrad_simt_kernel<float, __nv_bfloat16>, grid, dim3(WG_NT), 0, st, p);
-    else fdm::launch(wgrad_simt_kernel<float, float>, grid, dim3(WG_NT), 0, st, p);
+#define FDM_WG_LAUNCH(K)                                                                     \
+  do {                                                                                       \
+    if (ab && db) fdm::launch(K<__nv_bfloat16, __nv_bfloat16>, grid, block, 0, st, p);       \
+    else if (ab) fdm::launch(K<__nv_bfloat16, float>, grid, block, 0, st, p);                \
+    else if (db) fdm::launch(K<float, __nv_bfloat16>, grid, block, 0, st, p);                \
+    else fdm::launch(K<float, float>, grid, block, 0, st, p);                                \
+  } while (0)
+    if (g.narrow == 1) FDM_WG_LAUNCH(wgrad_narrow_in_kernel);
+    else if (g.narrow == 2) FDM_WG_LAUNCH(wgrad_narrow_out_kernel);
+    else FDM_WG_LAUNCH(wgrad_simt_kernel);
   }
-  {
+  if (a->dw != nullptr) {
     const long long total = (long long)g.taps * a->Cw * a->Cout;
     long long gr = (total + 255) / 256;
     if (gr > 148 * 8) gr = 148 * 8;

@@ -42,7 +42,7 @@ __device__ __forceinline__ void gn_group_stats(const GnBwdParams& p, int n, int 
 
 // MODE 0: statistics pass; MODE 1: apply pass.  grid (ceil(HW / pix_per_block), N); block (C/4) * ppi threads.
 template <typename OT, int MODE>
-__global__ void gn_bwd_kernel(GnBwdParams p) {
+__global__ void __launch_bounds__(256, 3) gn_bwd_kernel(GnBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_mean[32], s_rstd[32], s_m1[32], s_m2[32];
@@ -96,45 +96,53 @@ __global__ void gn_bwd_kernel(GnBwdParams p) {
   float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
   const int p0 = blockIdx.x * p.pix_per_block;
   const int p1 = min(p0 + p.pix_per_block, p.HW);
-  for (int px = p0 + pl; px < p1; px += ppi) {
-    const float4 x4 = __ldg(reinterpret_cast<const float4*>(src + (size_t)px * sstride));
-    const size_t o = ((size_t)n * p.HW + px) * C + c;
-    float dy[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.dy_op != nullptr) {
-      const float4 d = OpType<OT>::load4(reinterpret_cast<const OT*>(p.dy_op) + o);
-      dy[0] = d.x; dy[1] = d.y; dy[2] = d.z; dy[3] = d.w;
-    }
-    if (p.dy_f32 != nullptr) {
-      const float4 d = __ldg(reinterpret_cast<const float4*>(p.dy_f32 + o));
-      dy[0] += d.x; dy[1] += d.y; dy[2] += d.z; dy[3] += d.w;
-    }
-    const float x[4] = {x4.x, x4.y, x4.z, x4.w};
-    float dx[4];
+  // GN_U pixels per trip (measured on B200: 2 and 4 are SLOWER than 1 — 111 / 137 registers cut the resident blocks per SM): every load of the trip (x, the upstream gradient(s), the pass-through gradient, the accumulated
+  // destination) is issued before the first use — the kernel is HBM/L2-latency bound, not FMA bound
+  constexpr int GN_U = 1;
+  for (int px0_ = p0 + pl; px0_ < p1; px0_ += GN_U * ppi) {
+    float4 x4[GN_U], d_op[GN_U], d_f32[GN_U], d_raw[GN_U], g_old[GN_U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float xh = (x[j] - mean[j]) * rstd[j];
-      float du = dy[j];
-      if (p.silu) du *= dsilu_f(fmaf(xh, mul[j], add[j]));
-      if (MODE == 0) {
-        accA[j] = fmaf(du, xh, accA[j]);
-        accB[j] += du;
-      } else {
-        dx[j] = rstd[j] * (du * kc[j] - m1[j] - xh * m2[j]);
+    for (int u = 0; u < GN_U; ++u) {
+      const int px = px0_ + u * ppi;
+      if (px >= p1) break;
+      const size_t o = ((size_t)n * p.HW + px) * C + c;
+      x4[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)px * sstride));
+      if (p.dy_op != nullptr) d_op[u] = OpType<OT>::load4(reinterpret_cast<const OT*>(p.dy_op) + o);
+      if (p.dy_f32 != nullptr) d_f32[u] = __ldg(reinterpret_cast<const float4*>(p.dy_f32 + o));
+      if (MODE == 1) {
+        if (p.draw_op != nullptr) d_raw[u] = OpType<OT>::load4(reinterpret_cast<const OT*>(p.draw_op) + o);
+        const float* gsrc = from_a ? p.gxa + ((size_t)n * p.HW + px) * p.Ca + c : p.gxb + ((size_t)n * p.HW + px) * p.Cb + (c - p.Ca);
+        if (from_a ? p.acc_a : p.acc_b) g_old[u] = *reinterpret_cast<const float4*>(gsrc);
       }
     }
-    if (MODE == 1) {
-      if (p.draw_op != nullptr) {
-        const float4 d = OpType<OT>::load4(reinterpret_cast<const OT*>(p.draw_op) + o);
-        dx[0] += d.x; dx[1] += d.y; dx[2] += d.z; dx[3] += d.w;
+#pragma unroll
+    for (int u = 0; u < GN_U; ++u) {
+      const int px = px0_ + u * ppi;
+      if (px >= p1) break;
+      float dy[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.dy_op != nullptr) { dy[0] = d_op[u].x; dy[1] = d_op[u].y; dy[2] = d_op[u].z; dy[3] = d_op[u].w; }
+      if (p.dy_f32 != nullptr) { dy[0] += d_f32[u].x; dy[1] += d_f32[u].y; dy[2] += d_f32[u].z; dy[3] += d_f32[u].w; }
+      const float x[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+      float dx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (x[j] - mean[j]) * rstd[j];
+        float du = dy[j];
+        if (p.silu) du *= dsilu_f(fmaf(xh, mul[j], add[j]));
+        if (MODE == 0) {
+          accA[j] = fmaf(du, xh, accA[j]);
+          accB[j] += du;
+        } else {
+          dx[j] = rstd[j] * (du * kc[j] - m1[j] - xh * m2[j]);
+        }
       }
-      float* gdst = from_a ? p.gxa + ((size_t)n * p.HW + px) * p.Ca + c : p.gxb + ((size_t)n * p.HW + px) * p.Cb + (c - p.Ca);
-      const int acc = from_a ? p.acc_a : p.acc_b;
-      float4 v = make_float4(dx[0], dx[1], dx[2], dx[3]);
-      if (acc) {
-        const float4 e = *reinterpret_cast<const float4*>(gdst);
-        v = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+      if (MODE == 1) {
+        if (p.draw_op != nullptr) { dx[0] += d_raw[u].x; dx[1] += d_raw[u].y; dx[2] += d_raw[u].z; dx[3] += d_raw[u].w; }
+        float* gdst = from_a ? p.gxa + ((size_t)n * p.HW + px) * p.Ca + c : p.gxb + ((size_t)n * p.HW + px) * p.Cb + (c - p.Ca);
+        float4 v = make_float4(dx[0], dx[1], dx[2], dx[3]);
+        if (from_a ? p.acc_a : p.acc_b) v = make_float4(v.x + g_old[u].x, v.y + g_old[u].y, v.z + g_old[u].z, v.w + g_old[u].w);
+        *reinterpret_cast<float4*>(gdst) = v;
       }
-      *reinterpret_cast<float4*>(gdst) = v;
     }
   }
   if (MODE == 0) {
@@ -158,35 +166,50 @@ __global__ void gn_bwd_kernel(GnBwdParams p) {
   }
 }
 
-// one thread per channel: parameter gradients from the per-(n, c) sums
-__global__ void gn_bwd_params_kernel(GnBwdParams p) {
+// parameter gradients from the per-(n, c) sums.  block (32 channels, 8 frame slices): the frames of a video are split over
+// threadIdx.y and combined in shared memory (one thread per channel walking all N frames took 45 us per launch at N = 160).
+__global__ void __launch_bounds__(256) gn_bwd_params_kernel(GnBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= p.C) return;
-  const float ga = p.gamma[c], be = p.beta[c];
+  __shared__ double redA[8][33], redB[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, sl = threadIdx.y;
+  const bool ok = c < p.C;
+  const float ga = ok ? p.gamma[c] : 0.f, be = ok ? p.beta[c] : 0.f;
   const int B = p.N / p.T;
   double dg = 0.0, db = 0.0;
   for (int b = 0; b < B; ++b) {
     double sA = 0.0, sB = 0.0;
-    for (int t = 0; t < p.T; ++t) {
-      const double* ab = p.ab + ((size_t)(b * p.T + t) * p.C + c) * 2;
-      sA += ab[0];
-      sB += ab[1];
-    }
-    double sc = 1.0;
-    if (p.film != nullptr) {
-      sc = 1.0 + (double)p.film[(size_t)b * p.film_stride + p.film_off + c];
-      if (p.dfilm != nullptr) {
-        p.dfilm[(size_t)b * p.film_stride + p.film_off + c] = (float)((double)ga * sA + (double)be * sB);
-        p.dfilm[(size_t)b * p.film_stride + p.film_off + p.C + c] = (float)sB;
+    if (ok)
+      for (int t = sl; t < p.T; t += 8) {
+        const double* ab = p.ab + ((size_t)(b * p.T + t) * p.C + c) * 2;
+        sA += ab[0];
+        sB += ab[1];
       }
+    redA[sl][threadIdx.x] = sA;
+    redB[sl][threadIdx.x] = sB;
+    __syncthreads();
+    if (sl == 0 && ok) {
+      for (int k = 1; k < 8; ++k) {
+        sA += redA[k][threadIdx.x];
+        sB += redB[k][threadIdx.x];
+      }
+      double sc = 1.0;
+      if (p.film != nullptr) {
+        sc = 1.0 + (double)p.film[(size_t)b * p.film_stride + p.film_off + c];
+        if (p.dfilm != nullptr) {
+          p.dfilm[(size_t)b * p.film_stride + p.film_off + c] = (float)((double)ga * sA + (double)be * sB);
+          p.dfilm[(size_t)b * p.film_stride + p.film_off + p.C + c] = (float)sB;
+        }
+      }
+      dg += sc * sA;
+      db += sc * sB;
     }
-    dg += sc * sA;
-    db += sc * sB;
+    __syncthreads();
   }
-  p.dgamma[c] = (float)dg;
-  p.dbeta[c] = (float)db;
+  if (sl == 0 && ok) {
+    p.dgamma[c] = (float)dg;
+    p.dbeta[c] = (float)db;
+  }
 }
 
 // ---------------- temporal GroupNorm backward -----------------------------------------------------------------------
@@ -306,6 +329,7 @@ extern "C" int fdm_gn_bwd(const fdm_gn_bwd_args* a, void* stream) {
   FDM_REQUIRE(p.C % 32 == 0 && p.Ca % 4 == 0 && p.Cb % 4 == 0 && p.C <= 4096, FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->N > 0 && a->HW > 0 && a->N % p.T == 0, FDM_ERR_BAD_ARG);
   const int quads = p.C / 4;
+  FDM_REQUIRE(quads <= 256, FDM_ERR_UNSUPPORTED);  // one thread per channel quad, <= 256 threads (register budget of the apply pass)
   int ppi = quads >= 256 ? 1 : 256 / quads;
   if (ppi > a->HW) ppi = a->HW;
   const int threads = quads * ppi;
@@ -316,7 +340,7 @@ extern "C" int fdm_gn_bwd(const fdm_gn_bwd_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->op_dtype == FDM_BF16) fdm::launch(gn_bwd_kernel<__nv_bfloat16, 0>, grid, dim3(threads), 0, st, p);
   else fdm::launch(gn_bwd_kernel<float, 0>, grid, dim3(threads), 0, st, p);
-  fdm::launch(gn_bwd_params_kernel, dim3((p.C + 127) / 128), dim3(128), 0, st, p);
+  fdm::launch(gn_bwd_params_kernel, dim3((p.C + 31) / 32), dim3(32, 8), 0, st, p);
   if (a->op_dtype == FDM_BF16) fdm::launch(gn_bwd_kernel<__nv_bfloat16, 1>, grid, dim3(threads), 0, st, p);
   else fdm::launch(gn_bwd_kernel<float, 1>, grid, dim3(threads), 0, st, p);
   return check_launch();

@@ -607,15 +607,17 @@ class DenoiserEngine:
                  y_f32=out_f32, y_op=out_op, stats=None, N=n or Nf, Hin=Hg, Win=Wg, C0=Cg, C1=0, Cout=Co, ksize=k, stride=1,
                  upsample=0, a_dtype=opd, op_dtype=opd, out_nchw=0, engine=N_.CONV_TC if tc else N_.CONV_SIMT)
 
-        def wgrad(a, a_dtype, Cs, Cw, Hin, Win, gy, Co, k, stride, w, biases=(), n=None):
-            """dW (PyTorch layout, into the flat parameter-gradient buffer) and the bias gradient(s)"""
+        def wgrad(a, a_dtype, Cs, Cw, Hin, Win, gy, Co, k, stride, w, biases=(), n=None, dw=None):
+            """dW (PyTorch layout, into the flat parameter-gradient buffer unless `dw` names a scratch buffer) and the bias
+            gradient(s); a is None: bias gradient only"""
             fields = dict(N=n or Nf, Hin=Hin, Win=Win, C=Cs, Cw=Cw, Cout=Co, ksize=k, stride=stride, a_dtype=a_dtype,
                           dy_dtype=opd, engine=N_.CONV_TC if self.use_tc else N_.CONV_SIMT)
             need = int(lib.fdm_conv_wgrad_workspace(C.byref(N_.ConvWgradArgs(**fields))))
             P.wg_ws.nbytes = max(P.wg_ws.nbytes, (need + 255) // 256 * 256)
             pad_ = k // 2
             P.bflops += 2 * (n or Nf) * ((Hin + 2 * pad_ - k) // stride + 1) * ((Win + 2 * pad_ - k) // stride + 1) * Co * k * k * Cw
-            P.op("fdm_conv_wgrad", N_.ConvWgradArgs, a=a, dy=gy, dw=pg(w), dbias=pg(biases[0]) if biases else None,
+            P.op("fdm_conv_wgrad", N_.ConvWgradArgs, a=a, dy=gy, dw=(dw if dw is not None else pg(w)) if a is not None else None,
+                 dbias=pg(biases[0]) if biases else None,
                  dbias2=pg(biases[1]) if len(biases) > 1 else None, workspace=P.wg_ws, workspace_bytes=need, **fields)
 
         def gn_bwd(xa, xb, gn, foff, dy_op, dy_f32, draw, silu):
@@ -895,6 +897,14 @@ class DenoiserEngine:
 
                     def bwd(layer=layer, out=out):
                         go = to_op(gact(out), layer.out_channels, H, W)
+                        if stem_tc and layer.out_channels % 64 == 0:
+                            # tcgen05 wgrad wants >= 64 stored input channels: a zero-padded bf16 copy of the network input
+                            # (7/8 of the MMA rows are zeros — still ~20x faster than CUDA cores on the 128-px model)
+                            xin64 = P.buf("xin64", Nf * H * W * 64 * 2)
+                            P.op("fdm_input_prep", N_.InputPrepArgs, x=P.x, x0=P.x0, obs_mask=P.obs, xin=None, xin_bf16=xin64,
+                                 N=Nf, C=Cin - 1, H=H, W=W, Cpad=64)
+                            wgrad(xin64, N_.BF16, 64, Cin, H, W, go, layer.out_channels, 3, 1, layer.weight, (layer.bias,))
+                            return
                         wgrad(xin, N_.BF16 if stem_tc else F32_, 8 if stem_tc else Cin, Cin, H, W, go, layer.out_channels, 3, 1,
                               layer.weight, (layer.bias,))
                     if train:
@@ -947,7 +957,18 @@ class DenoiserEngine:
                     P.op("fdm_nchw_to_nhwc", N_.NchwToNhwcArgs, src=P.geps, dst=ge, N=Nf, C=Co_, H=H, W=W, Cpad=Co_, op_dtype=opd)
                 da = P.buf("d_head_a", Nf * H * W * h_last.C * osz)
                 dgrad(ge_p, Cp, H, W, cv.weight, h_last.C, 3, out_op=da)
-                wgrad(head_a, opd, h_last.C, h_last.C, H, W, ge, Co_, 3, 1, cv.weight, (cv.bias,))
+                if tc_head and h_last.C % 64 == 0:
+                    # same trick on the output side: the eps gradient zero-padded to 64 channels feeds the tcgen05 wgrad; the first
+                    # Co_ rows of its [64][C][3][3] result are the head's weight gradient
+                    ge64 = P.buf("geps_op64", Nf * H * W * 64 * osz)
+                    P.op("fdm_nchw_to_nhwc", N_.NchwToNhwcArgs, src=P.geps, dst=ge64, N=Nf, C=Co_, H=H, W=W, Cpad=64, op_dtype=opd)
+                    dw64 = P.buf("head_dw64", 64 * h_last.C * 9 * 4)
+                    wgrad(head_a, opd, h_last.C, h_last.C, H, W, ge64, 64, 3, 1, cv.weight, (), dw=dw64)
+                    P.op("fdm_sum_parts", N_.SumPartsArgs, parts=dw64, out=pg(cv.weight), part_stride=0, n=Co_ * h_last.C * 9,
+                         count=1, accumulate=0)
+                    wgrad(None, opd, h_last.C, h_last.C, H, W, ge, Co_, 3, 1, cv.weight, (cv.bias,))
+                else:
+                    wgrad(head_a, opd, h_last.C, h_last.C, H, W, ge, Co_, 3, 1, cv.weight, (cv.bias,))
                 gn_bwd(h_last, None, gn, None, da, None, None, 1)
             P.tape.append(head_bwd)
             P.cur = P.bops

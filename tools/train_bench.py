@@ -6,4 +6,6 @@ import torch as th
 import bench
 dev = th.device("cuda:0")
 th.cuda.set_device(dev)
-print(json.dumps(bench.bench_train(dev, 1, sys.argv[1] if len(sys.argv) > 1 else "bf16")))
+prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+for wl in (sys.argv[2:] or ["cfg2-train", "cfg3-train"]):
+    print(json.dumps(bench.bench_train(dev, 1, prec, wl)))
