@@ -212,8 +212,10 @@ def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
     model.train()
     net = model
     if world > 1:
-        from improved_diffusion.sharding import wrap_ddp
-        net = wrap_ddp(model, dev)
+        from improved_diffusion import sharding
+        # FDM_DDP=torch: torch DistributedDataParallel exactly as train_util.py:118-125 (drop-in path, per-parameter hooks);
+        # default: one allreduce over the native backward's flat gradient buffer
+        net = sharding.wrap_ddp(model, dev) if os.environ.get("FDM_DDP", "flat") == "torch" else sharding.FlatGradDataParallel(model)
     opt = th.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0, fused=True)
     batch = {k: v.to(dev) for k, v in synthetic_batch(over, B, K, 3, 4 * K, seed=1 + int(os.environ.get("RANK", "0"))).items()}
     g = th.Generator(device=dev).manual_seed(0)
@@ -246,7 +248,7 @@ def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / n
 
-    ms_auto = timed("autograd", max(2, steps // 2))
+    ms_auto = timed("autograd", max(2, steps // 2)) if world == 1 else None  # the A/B arm is a single-GPU comparison
     th.cuda.empty_cache()
     ms = timed("native", steps)
     plan = next(iter(model.engine().train_plans.values()))
@@ -259,7 +261,8 @@ def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
                         "flops_per_step": flops, "what": "algorithmic fwd + dgrad + wgrad + attention FLOPs of one step / step time "
                                                          "(optimizer, loss and host work included in the time)"},
            "path": "native: forward + backward kernel schedules of libfdm_sm100.so behind one autograd node (conv dgrad and wgrad on "
-                   "tcgen05, GroupNorm / attention / RPENet backward kernels); DDP gradient allreduce when n_gpus > 1"}
+                   "tcgen05, GroupNorm / attention / RPENet backward kernels); n_gpus > 1: ONE NCCL allreduce over the flat gradient "
+                   "buffer per step (sharding.FlatGradDataParallel; FDM_DDP=torch selects torch DDP as in train_util.py:118-125)"}
     del opt, net, model
     th.cuda.empty_cache()
     return out

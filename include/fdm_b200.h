@@ -221,6 +221,8 @@ typedef struct {
   void* out;      /* [N][H*f][W*f][C], f = upsample ? 2 : 1;  upsample = 2: ZERO-INSERTION (value at even (h,w), zeros
                      elsewhere): the gradient of a stride-2 conv's output prepared for its dgrad/wgrad as stride-1 convs */
   int32_t N, H, W, C, upsample, op_dtype;
+  float* colsum;  /* optional (upsample = 0): colsum[c] += sum over all pixels of x[.,c] — the bias gradient of the conv whose output */
+  float* colsum2; /* gradient this tensor is (fp32 atomics; zeroed by the caller); colsum2: a second copy (fused 1x1 skip conv bias) */
 } fdm_cast_args; /* which = 9 */
 int fdm_cast(const fdm_cast_args* a, void* stream);
 

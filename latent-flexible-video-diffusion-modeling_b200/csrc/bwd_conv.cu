@@ -231,9 +231,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
     const long long r = i / Cout;
     const int ci = (int)(r % Cw), tap = (int)(r / Cw);
     const float* src = part + ((size_t)tap * C + ci) * Cout + co;
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += src[k * sstride];
-    dw[((size_t)co * Cw + ci) * taps + tap] = s;
+    // fixed summation order, four independent loads in flight (a serial chain of `splits` DRAM latencies otherwise)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 3 < splits; k += 4) {
+      s0 += src[k * sstride];
+      s1 += src[(k + 1) * sstride];
+      s2 += src[(k + 2) * sstride];
+      s3 += src[(k + 3) * sstride];
+    }
+    for (; k < splits; ++k) s0 += src[k * sstride];
+    dw[((size_t)co * Cw + ci) * taps + tap] = (s0 + s1) + (s2 + s3);
   }
 }
 

@@ -53,6 +53,45 @@ __global__ void cast_kernel(const float* __restrict__ x, OT* __restrict__ out, i
   }
 }
 
+// cast + column sums: the fp32 gradient of a conv output becomes the bf16 operand of its dgrad / wgrad, and its column sums ARE
+// the bias gradient — one read instead of a second pass over the tensor (the separate bias-gradient kernels were 7 % of the
+// 128-px training step).  block = (C/4 quads) x ppi pixel lanes; block partials -> fp32 atomics (colsum zeroed by the caller).
+template <typename OT>
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ x, OT* __restrict__ out, float* __restrict__ cs,
+                                                          float* __restrict__ cs2, long long rows, int C, long long rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float4 red[256];
+  const int quads = C / 4;
+  const int q = threadIdx.x % quads, pl = threadIdx.x / quads, ppi = blockDim.x / quads;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = r0 + pl; r < r1; r += 2 * ppi) {
+    const bool two = r + ppi < r1;
+    const float4 a = *reinterpret_cast<const float4*>(x + (size_t)r * C + q * 4);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (two) b = *reinterpret_cast<const float4*>(x + (size_t)(r + ppi) * C + q * 4);
+    OpType<OT>::store4(out + (size_t)r * C + q * 4, a);
+    if (two) OpType<OT>::store4(out + (size_t)(r + ppi) * C + q * 4, b);
+    s.x += a.x + b.x; s.y += a.y + b.y; s.z += a.z + b.z; s.w += a.w + b.w;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (pl == 0) {
+    for (int k = 1; k < ppi; ++k) {
+      const float4 o = red[k * quads + q];
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    float* d = cs + q * 4;
+    atomicAdd(d, s.x); atomicAdd(d + 1, s.y); atomicAdd(d + 2, s.z); atomicAdd(d + 3, s.w);
+    if (cs2 != nullptr) {
+      d = cs2 + q * 4;
+      atomicAdd(d, s.x); atomicAdd(d + 1, s.y); atomicAdd(d + 2, s.z); atomicAdd(d + 3, s.w);
+    }
+  }
+}
+
 // ---------------- A16-A18 fused DDPM posterior update -------------------------------------------------
 __global__ void ddpm_step_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
                                  const float4* __restrict__ noise, const float* __restrict__ coef,
@@ -276,6 +315,22 @@ extern "C" int fdm_input_prep(const fdm_input_prep_args* a, void* stream) {
 extern "C" int fdm_cast(const fdm_cast_args* a, void* stream) {
   FDM_REQUIRE(a && a->x && a->out, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->C % 4 == 0 && a->N > 0, FDM_ERR_UNSUPPORTED);
+  if (a->colsum != nullptr) {
+    FDM_REQUIRE(a->upsample == 0 && a->C / 4 <= 256, FDM_ERR_UNSUPPORTED);
+    const long long rows = (long long)a->N * a->H * a->W;
+    const int quads = a->C / 4;
+    int ppi = 256 / quads;
+    if (ppi > rows) ppi = (int)rows;
+    long long blocks = (rows + 8 * ppi - 1) / (8 * ppi);  // >= 8 rows per thread
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    const long long rpb = ((rows + blocks - 1) / blocks + ppi - 1) / ppi * ppi;
+    blocks = (rows + rpb - 1) / rpb;
+    if (a->op_dtype == FDM_BF16)
+      fdm::launch(cast_colsum_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(quads * ppi), 0, (cudaStream_t)stream, a->x, (__nv_bfloat16*)a->out, a->colsum, a->colsum2, rows, a->C, rpb);
+    else
+      fdm::launch(cast_colsum_kernel<float>, dim3((unsigned)blocks), dim3(quads * ppi), 0, (cudaStream_t)stream, a->x, (float*)a->out, a->colsum, a->colsum2, rows, a->C, rpb);
+    return check_launch();
+  }
   long long total = (long long)a->N * a->H * a->W * (a->upsample ? 4 : 1) * (a->C / 4);
   int g = grid_for(total, 256);
   if (a->op_dtype == FDM_BF16)

@@ -49,7 +49,7 @@ AttnTemporalArgs = _S("AttnTemporalArgs", [("qkv", vp), ("Rq", vp), ("Rk", vp), 
 AttnSpatialArgs = _S("AttnSpatialArgs", [("qkv", vp), ("out", vp), ("N", i32), ("L", i32), ("C", i32), ("heads", i32),
                                          ("qkv_dtype", i32), ("out_dtype", i32), ("engine", i32)])
 CastArgs = _S("CastArgs", [("x", vp), ("out", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32),
-                           ("upsample", i32), ("op_dtype", i32)])
+                           ("upsample", i32), ("op_dtype", i32), ("colsum", vp), ("colsum2", vp)])
 DdpmStepArgs = _S("DdpmStepArgs", [("x", vp), ("eps", vp), ("noise", vp), ("coef", vp), ("t", vp), ("sample", vp),
                                    ("pred_xstart", vp), ("per_video", i64), ("B", i32), ("clip", i32)])
 QSampleArgs = _S("QSampleArgs", [("x0", vp), ("noise", vp), ("coef2", vp), ("t", vp), ("x_t", vp),

@@ -245,7 +245,7 @@ class _DenoiserFn(th.autograd.Function):
         P.t_view.copy_(timesteps.reshape(B).float())
         P.run_graphed("fwd", x.device)
         P.generation = getattr(P, "generation", 0) + 1
-        ctx.plan, ctx.generation = P, P.generation
+        ctx.plan, ctx.generation, ctx.engine = P, P.generation, engine
         return P.eps_view.clone()
 
     @staticmethod
@@ -257,6 +257,9 @@ class _DenoiserFn(th.autograd.Function):
         P.geps_view.copy_(g)
         P.run_graphed("bwd", g.device)
         flat = P.pgrad.clone()  # the plan's buffer is reused by the next backward; autograd owns this copy
+        sync = getattr(ctx.engine.model, "_fdm_grad_sync", None)
+        if sync is not None:  # sharding.FlatGradDataParallel: ONE allreduce over the whole flat gradient
+            sync(flat)
         base = P.pgrad.data_ptr()
         grads = tuple(flat[(v.data_ptr() - base) // 4:(v.data_ptr() - base) // 4 + v.numel()].view(v.shape) for v in P.pgrad_views)
         return (None,) * 7 + grads
@@ -591,11 +594,15 @@ class DenoiserEngine:
             ginit.add(k_)
             return r_
 
-        def to_op(g, Cc, Hh, Ww, n=None, up=0):
-            """fp32 gradient -> operand-dtype copy feeding dgrad / wgrad (up = 2: zero insertion for a stride-2 conv)"""
+        def to_op(g, Cc, Hh, Ww, n=None, up=0, biases=()):
+            """fp32 gradient -> operand-dtype copy feeding dgrad / wgrad (up = 2: zero insertion for a stride-2 conv).  `biases`:
+            bias parameters of the conv whose output gradient this is — their gradient (the column sums) falls out of the same
+            read (fp32 atomics into the zeroed flat gradient buffer)."""
             f_ = 2 if up else 1
             o_ = P.buf("g_op", (n or Nf) * Hh * f_ * Ww * f_ * Cc * osz)
-            P.op("fdm_cast", N_.CastArgs, x=g, out=o_, N=n or Nf, H=Hh, W=Ww, C=Cc, upsample=up, op_dtype=opd)
+            assert not (biases and (up or Cc > 1024))
+            P.op("fdm_cast", N_.CastArgs, x=g, out=o_, N=n or Nf, H=Hh, W=Ww, C=Cc, upsample=up, op_dtype=opd,
+                 colsum=pg(biases[0]) if biases else None, colsum2=pg(biases[1]) if len(biases) > 1 else None)
             return o_
 
         def dgrad(gy, Cg, Hg, Wg, w, Co, k, out_op=None, out_f32=None, resid=None, n=None):
@@ -647,10 +654,10 @@ class DenoiserEngine:
                     Cc = ab.channels
                     for which in ("rpe_q", "rpe_k", "rpe_v"):
                         net, key = getattr(ab.temporal_attention, which).rpe_net, (id(ab), which)
-                        g_ = to_op(dRb[key], Cc, 1, 1, n=BTT)
+                        g_ = to_op(dRb[key], Cc, 1, 1, n=BTT, biases=(net.out.bias,))
                         dh = P.buf("rpe_dhid", BTT * Cc * osz)
                         dgrad(g_, Cc, 1, 1, net.out.weight, Cc, 1, out_op=dh, n=BTT)
-                        wgrad(hid[key], hdt, Cc, Cc, 1, 1, g_, Cc, 1, 1, net.out.weight, (net.out.bias,), n=BTT)
+                        wgrad(hid[key], hdt, Cc, Cc, 1, 1, g_, Cc, 1, 1, net.out.weight, n=BTT)
                         rp.append(dict(wd=f32(net.embed_distances.weight), bd=f32(net.embed_distances.bias), dhidden=dh,
                                        dwd=pg(net.embed_distances.weight), dbd=pg(net.embed_distances.bias), C=Cc,
                                        te_off=te_off[key]))
@@ -737,24 +744,24 @@ class DenoiserEngine:
 
             def bwd():
                 g_out = gact(out)
-                go = to_op(g_out, Co, Hh, Ww)
+                go = to_op(g_out, Co, Hh, Ww, biases=(c2.bias, sk.bias) if has_skip else (c2.bias,))
                 da2 = P.buf("d_a2", Nf * hw * Co * osz)
                 dgrad(go, Co, Hh, Ww, c2.weight, Co, 3, out_op=da2)
                 draw = None
                 if has_skip:
-                    wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight, (c2.bias, sk.bias))
+                    wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight)
                     draw = P.buf("d_raw", Nf * hw * Ci * osz)
                     dgrad(go, Co, Hh, Ww, sk.weight, Ci, 1, out_op=draw)
                     wgrad(raw, opd, Ci, Ci, Hh, Ww, go, Co, 1, 1, sk.weight)
                 else:
-                    wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight, (c2.bias,))
+                    wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight)
                     P.op("fdm_accum", N_.AccumArgs, src=g_out, dst=gact(xa), N=Nf, H=Hh, W=Ww, C=Co, pool=0, src_dtype=F32_,
                          accumulate=acc(xa))
                 gn_bwd(h1_, None, gn2, film_off[id(rb)], da2, None, None, 1)
-                gh = to_op(gact(h1_), Co, Hh, Ww)
+                gh = to_op(gact(h1_), Co, Hh, Ww, biases=(c1.bias,))
                 da1 = P.buf("d_a1", Nf * hw * Ci * osz)
                 dgrad(gh, Co, Hh, Ww, c1.weight, Ci, 3, out_op=da1)
-                wgrad(a1, opd, Ci, Ci, Hh, Ww, gh, Co, 3, 1, c1.weight, (c1.bias,))
+                wgrad(a1, opd, Ci, Ci, Hh, Ww, gh, Co, 3, 1, c1.weight)
                 gn_bwd(xa, xb, gn, None, da1, None, draw, 1)
             if train:
                 P.tape.append(bwd)
@@ -797,10 +804,10 @@ class DenoiserEngine:
                 n_tok = Nf * hw
                 # spatial half: z = proj(o2) + yn ; o2 = attn(qkv2) ; qkv2 = qkv(yn_op) ; yn = GN(y)
                 g_z = gact(z)
-                gz = to_op(g_z, Cc, Hh, Ww)
+                gz = to_op(g_z, Cc, Hh, Ww, biases=(sa.proj_out.bias,))
                 do2 = P.buf("d_sa_o", n_tok * Cc * osz)
                 dgrad(gz, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, out_op=do2)
-                wgrad(o2, opd, Cc, Cc, Hh, Ww, gz, Cc, 1, 1, sa.proj_out.weight, (sa.proj_out.bias,))
+                wgrad(o2, opd, Cc, Cc, Hh, Ww, gz, Cc, 1, 1, sa.proj_out.weight)
                 dqkv2 = P.buf("d_sa_qkv", n_tok * 3 * Cc * osz)
                 P.bflops += 10 * hw * hw * Cc * Nf
                 P.op("fdm_attn_spatial_bwd", N_.AttnSpatialBwdArgs, qkv=qkv2, out=o2, dout=do2, dqkv=dqkv2, lse=P.at_lse,
@@ -812,10 +819,10 @@ class DenoiserEngine:
                 gn_bwd(y, None, sa.norm, None, dyn, g_z, None, 0)
                 # temporal half: y = proj(o) + xn ; o = attn_rpe(qkv, R) ; qkv = qkv(xn_op) ; xn = temporalGN(x)
                 g_y = gact(y)
-                gy = to_op(g_y, Cc, Hh, Ww)
+                gy = to_op(g_y, Cc, Hh, Ww, biases=(ta.proj_out.bias,))
                 do = P.buf("d_ta_o", n_tok * Cc * osz)
                 dgrad(gy, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, out_op=do)
-                wgrad(o, opd, Cc, Cc, Hh, Ww, gy, Cc, 1, 1, ta.proj_out.weight, (ta.proj_out.bias,))
+                wgrad(o, opd, Cc, Cc, Hh, Ww, gy, Cc, 1, 1, ta.proj_out.weight)
                 dqkv = P.buf("d_ta_qkv", n_tok * 3 * Cc * osz)
                 P.bflops += 25 * T * T * Cc * B * hw
                 P.op("fdm_attn_temporal_bwd", N_.AttnTemporalBwdArgs, qkv=qkv, out=o, Rq=R[(id(ab), "rpe_q")],
@@ -846,7 +853,7 @@ class DenoiserEngine:
                     # bf16 operand copy of the fp32 stream (nearest x2 upsample folded into the cast, unet.py:85), then tcgen05
                     a = P.buf("resample_a", Nf * Hc * Wc * x.C * osz)
                     P.op("fdm_cast", N_.CastArgs, x=x.buf, out=a, N=Nf, H=x.H, W=x.W, C=x.C, upsample=0 if down else 1,
-                         op_dtype=opd)
+                         op_dtype=opd, colsum=None, colsum2=None)
                 conv(a, x.C, Hc, Wc, cv.weight, x.C, 3, stride=2 if down else 1, bias=f32(cv.bias), y_f32=out.buf,
                      stats=out.st)
             else:
@@ -857,7 +864,7 @@ class DenoiserEngine:
             def bwd():
                 Cc = x.C
                 g_out = gact(out)
-                go = to_op(g_out, Cc, Ho, Wo)
+                go = to_op(g_out, Cc, Ho, Wo, biases=(cv.bias,))
                 if down:
                     # dgrad of the stride-2 conv = stride-1 conv over the zero-inserted gradient, accumulated in place into g_x
                     z_ = to_op(g_out, Cc, Ho, Wo, up=2)
@@ -865,14 +872,14 @@ class DenoiserEngine:
                     dgrad(z_, Cc, Hc, Wc, cv.weight, Cc, 3, out_f32=gx, resid=gx if acc(x) else None)
                     if self.use_tc and a is not None:
                         # tcgen05 wgrad is stride-1: the zero-inserted gradient against the full-resolution input is the same sum
-                        wgrad(a, opd, Cc, Cc, Hc, Wc, z_, Cc, 3, 1, cv.weight, (cv.bias,))
+                        wgrad(a, opd, Cc, Cc, Hc, Wc, z_, Cc, 3, 1, cv.weight)
                     else:
                         wgrad(a if a is not None else x.buf, opd if a is not None else F32_, Cc, Cc, Hc, Wc, go, Cc, 3, 2,
-                              cv.weight, (cv.bias,))
+                              cv.weight)
                 else:
                     da = P.buf("d_up_a", Nf * Ho * Wo * Cc * osz)
                     dgrad(go, Cc, Ho, Wo, cv.weight, Cc, 3, out_op=da)
-                    wgrad(a, opd, Cc, Cc, Ho, Wo, go, Cc, 3, 1, cv.weight, (cv.bias,))
+                    wgrad(a, opd, Cc, Cc, Ho, Wo, go, Cc, 3, 1, cv.weight)
                     P.op("fdm_accum", N_.AccumArgs, src=da, dst=gact(x), N=Nf, H=x.H, W=x.W, C=Cc, pool=1, src_dtype=opd,
                          accumulate=acc(x))
             if train:
@@ -896,17 +903,17 @@ class DenoiserEngine:
                     h = out
 
                     def bwd(layer=layer, out=out):
-                        go = to_op(gact(out), layer.out_channels, H, W)
+                        go = to_op(gact(out), layer.out_channels, H, W, biases=(layer.bias,))
                         if stem_tc and layer.out_channels % 64 == 0:
                             # tcgen05 wgrad wants >= 64 stored input channels: a zero-padded bf16 copy of the network input
                             # (7/8 of the MMA rows are zeros — still ~20x faster than CUDA cores on the 128-px model)
                             xin64 = P.buf("xin64", Nf * H * W * 64 * 2)
                             P.op("fdm_input_prep", N_.InputPrepArgs, x=P.x, x0=P.x0, obs_mask=P.obs, xin=None, xin_bf16=xin64,
                                  N=Nf, C=Cin - 1, H=H, W=W, Cpad=64)
-                            wgrad(xin64, N_.BF16, 64, Cin, H, W, go, layer.out_channels, 3, 1, layer.weight, (layer.bias,))
+                            wgrad(xin64, N_.BF16, 64, Cin, H, W, go, layer.out_channels, 3, 1, layer.weight)
                             return
                         wgrad(xin, N_.BF16 if stem_tc else F32_, 8 if stem_tc else Cin, Cin, H, W, go, layer.out_channels, 3, 1,
-                              layer.weight, (layer.bias,))
+                              layer.weight)
                     if train:
                         P.tape.append(bwd)
                 elif isinstance(layer, ResBlock):

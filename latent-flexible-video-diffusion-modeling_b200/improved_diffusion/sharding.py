@@ -7,6 +7,9 @@ Multi-GPU data parallelism for the hot path, one process per GPU u
     one-shot all_gather returns the full batch on every rank.
   * training: torch DistributedDataParallel around the model exactly as train_util.py:118-125 (NCCL gradient allreduce
     over NVLink/NVSwitch, 128 MB buckets, broadcast_buffers=False); `wrap_ddp` is that call with the reference's arguments.
+    `FlatGradDataParallel` is the B200-native alternative for the native training path: the backward schedule leaves ALL
+    parameter gradients in one flat fp32 buffer, so the exchange is ONE NCCL allreduce over that buffer (no per-parameter
+    hooks, no bucket copies) issued from inside the autograd node.
 """
 import torch as th
 import torch.distributed as dist
@@ -62,3 +65,33 @@ def wrap_ddp(model, device=None):
     if device is not None and th.device(device).type == "cuda":
         return DDP(model, device_ids=[device], output_device=device, **kw)
     return DDP(model, **kw)
+
+
+def allreduce_mean_(flat, group=None):
+    """In-place mean over the ranks of `group` (one collective; the NCCL kernel runs on NCCL's stream, ordered after the
+    caller's current stream and before its later work)."""
+    _, world = _rank_world(group)
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+    return flat
+
+
+class FlatGradDataParallel(th.nn.Module):
+    """Data-parallel wrapper for the NATIVE training path (engine._DenoiserFn): parameters are broadcast from rank 0 once;
+    every backward ends with ONE allreduce(mean) over the flat parameter-gradient buffer before autograd hands the
+    gradients to the parameters.  Same call signature / state_dict as the wrapped model (`.module`, like DDP)."""
+
+    def __init__(self, model, group=None):
+        super().__init__()
+        self.module, self.group = model, group
+        _, world = _rank_world(group)
+        if world > 1:
+            for p in model.parameters():
+                dist.broadcast(p.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        model._fdm_grad_sync = lambda flat: allreduce_mean_(flat, group)
+
+    def forward(self, x, **kwargs):
+        if not x.is_cuda:
+            raise NotImplementedError("FlatGradDataParallel synchronises the native (CUDA) backward; wrap CPU models with wrap_ddp")
+        return self.module(x, **kwargs)

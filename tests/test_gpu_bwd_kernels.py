@@ -457,3 +457,20 @@ def test_accum_pool_and_nchw_to_nhwc():
     n.call("fdm_nchw_to_nhwc", n.NchwToNhwcArgs(src=ptr(g), dst=ptr(out), N=Nf, C=4, H=H, W=W, Cpad=8, op_dtype=n.BF16), stream())
     torch.cuda.synchronize()
     assert torch.equal(out[..., :4].float(), g.permute(0, 2, 3, 1).to(torch.bfloat16).float()) and float(out[..., 4:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("case", [(5, 32, 32, 64), (3, 8, 8, 192), (1, 4, 4, 1024), (7, 1, 1, 96)])
+def test_cast_with_fused_bias_gradient(case):
+    """fdm_cast with colsum: the operand-dtype copy of a gradient and its column sums (= the conv's bias gradient) in one pass."""
+    n = N_()
+    Nf, H, W, Cc = case
+    torch.manual_seed(10)
+    g = torch.randn(Nf, H, W, Cc, device="cuda")
+    out = torch.empty(Nf, H, W, Cc, device="cuda", dtype=torch.bfloat16)
+    cs, cs2 = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    n.call("fdm_cast", n.CastArgs(x=ptr(g), out=ptr(out), N=Nf, H=H, W=W, C=Cc, upsample=0, op_dtype=n.BF16, colsum=ptr(cs),
+                                  colsum2=ptr(cs2)), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out, g.to(torch.bfloat16))
+    ref = g.double().sum(dim=(0, 1, 2))
+    assert rel(cs, ref) <= 1e-5 and rel(cs2 - 1, ref) <= 1e-5

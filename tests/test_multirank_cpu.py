@@ -94,12 +94,25 @@ def _worker(rank, world, port, what, out_dir):
             floor = 5e-2 * sorted(float(v.norm()) for v in ref.values())[len(ref) // 2]
             worst = max(float((p.grad - ref[k]).norm()) / max(float(ref[k].norm()), floor) for k, p in model.named_parameters())
             assert worst <= 1e-4, worst
+        elif what == "flat":
+            # the collective of FlatGradDataParallel (one mean-allreduce over a flat gradient buffer) and its parameter broadcast
+            flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+            sharding.allreduce_mean_(flat)
+            assert torch.allclose(flat, torch.arange(10, dtype=torch.float32) * (1 + world) / 2)
+            m = FakeDenoiser()
+            with torch.no_grad():
+                m.w.fill_(float(rank + 3))
+            wrapped = sharding.FlatGradDataParallel(m)
+            assert float(m.w) == 3.0 and callable(m._fdm_grad_sync) and wrapped.module is m
+            g = torch.full((4,), float(rank))
+            m._fdm_grad_sync(g)
+            assert torch.allclose(g, torch.full((4,), (world - 1) / 2))
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("what", ["sample", "train"])
+@pytest.mark.parametrize("what", ["sample", "train", "flat"])
 def test_two_ranks_gloo(tmp_path, what):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, what, str(tmp_path)), nprocs=2, join=True)
