@@ -210,6 +210,7 @@ typedef struct {
   int32_t N, L, C, heads;
   int32_t qkv_dtype, out_dtype;
   int32_t engine; /* 0 = auto (tcgen05 kernel for bf16 when L in {16,32,64,128,256} and head dim % 16 == 0, else CUDA cores); 1 = force CUDA cores */
+  float* lse;     /* optional output [N][heads][L] (tcgen05 engine only): log-sum-exp of every score row, consumed by fdm_attn_spatial_bwd */
 } fdm_attn_spatial_args; /* which = 8 */
 int fdm_attn_spatial(const fdm_attn_spatial_args* a, void* stream);
 
@@ -362,6 +363,8 @@ typedef struct {
   const void* dout; void* dqkv;
   float* lse; float* dsum;
   int32_t N, L, C, heads, dtype;
+  int32_t lse_from_forward; /* 1: `lse` holds what fdm_attn_spatial (tcgen05 engine) saved -> the tcgen05 backward kernels may run;
+                               0: CUDA-core kernels, which recompute it into `lse` */
 } fdm_attn_spatial_bwd_args; /* which = 20 */
 int fdm_attn_spatial_bwd(const fdm_attn_spatial_bwd_args* a, void* stream);
 

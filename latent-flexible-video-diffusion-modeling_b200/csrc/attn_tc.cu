@@ -24,6 +24,7 @@ struct SaTcParams {
   int cf;       // 64-wide channel chunks per head = ceil(F / 64)
   int tmem_cols;
   float scale_log2e;
+  float* lse;   // optional [N][heads][L]: natural-log sum-exp of each scaled score row (saved for the backward pass)
 };
 
 // MN-major, 128-byte swizzle: rows (one per K index) of 128 bytes = 64 MN elements; 8-row groups 1024 bytes apart (SBO)
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
   tcgen05_fence_after();
   const float inv = 1.f / sum;
   const int q = q0 + tid;
+  if (p.lse != nullptr && q < L) p.lse[((size_t)n * p.heads + h) * L + q] = mx * p.scale_log2e * 0.6931471805599453f + logf(sum);
   __nv_bfloat16* orow = p.out + ((size_t)n * L + (q < L ? q : 0)) * C + h * F;
   for (int f = 0; f < F; f += 16) {
     uint32_t v[16];
@@ -226,6 +228,7 @@ int attn_spatial_tc_launch(const fdm_attn_spatial_args* a, cudaStream_t st) {
   p.cf = (F + 63) / 64;
   p.tmem_cols = pow2_at_least(L > F ? L : F, 32);
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)F);
+  p.lse = a->lse;
   EncodeTiledFn enc = get_tensormap_encoder();
   FDM_REQUIRE(enc != nullptr, FDM_ERR_UNSUPPORTED);
   CUtensorMap tq;

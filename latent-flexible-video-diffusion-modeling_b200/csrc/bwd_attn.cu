@@ -28,9 +28,13 @@ struct SABwdParams {
 // dst[r][f] (row stride ld) = src[(r0 + r) * row_stride + f], zero for rows >= L
 template <typename QT>
 __device__ __forceinline__ void sa_stage(float* dst, const QT* src, size_t row_stride, int r0, int L, int F, int ld) {
-  for (int i = threadIdx.x; i < SA_KB * F; i += blockDim.x) {
-    const int r = i / F, f = i - r * F;
-    dst[r * ld + f] = (r0 + r < L) ? OpType<QT>::load(src + (size_t)(r0 + r) * row_stride + f) : 0.f;
+  const int fq = F >> 2;  // head dims are multiples of 8: four elements per load
+  for (int i = threadIdx.x; i < SA_KB * fq; i += blockDim.x) {
+    const int r = i / fq, f = (i - r * fq) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < L) v = OpType<QT>::load4(src + (size_t)(r0 + r) * row_stride + f);
+    float* d = dst + r * ld + f;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
 }
 
@@ -608,11 +612,20 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_kv_kernel(TAB
 
 using namespace fdm;
 
+namespace fdm {
+int attn_spatial_bwd_tc_launch(const fdm_attn_spatial_bwd_args* a, cudaStream_t st);  // attn_bwd_tc.cu
+}
+
 extern "C" int fdm_attn_spatial_bwd(const fdm_attn_spatial_bwd_args* a, void* stream) {
   FDM_REQUIRE(a && a->qkv && a->out && a->dout && a->dqkv && a->lse && a->dsum, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->N > 0 && a->L > 0 && a->heads > 0 && a->C % a->heads == 0, FDM_ERR_BAD_ARG);
+  if (a->lse_from_forward) {  // tcgen05 kernels (bf16, forward ran on tcgen05 and saved the log-sum-exp)
+    const int rc = attn_spatial_bwd_tc_launch(a, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != FDM_ERR_UNSUPPORTED) return rc;
+    // shapes the tcgen05 kernels do not take: the CUDA-core kernels below recompute the log-sum-exp into `lse` themselves
+  }
   const int F = a->C / a->heads;
-  FDM_REQUIRE(F <= 32 * SA_MAXU, FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(F <= 32 * SA_MAXU && F % 4 == 0 && a->C % 4 == 0, FDM_ERR_UNSUPPORTED);
   SABwdParams p{a->qkv, a->out, a->dout, a->dqkv, a->lse, a->dsum, a->N, a->L, a->C, a->heads, F, 1.0f / sqrtf((float)F)};
   const int ld = F + 1;
   const size_t smem_q = ((size_t)2 * SA_KB * ld + 8 * (SA_RPW * 2 * F + SA_RPW * SA_KB)) * sizeof(float);

@@ -150,7 +150,18 @@ __global__ void __launch_bounds__(128) linear_bwd_x_kernel(const fdm_linear_bwd_
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int n = 0; n < pr.Nout; ++n) {
+    int n = 0;
+    for (; n + 7 < pr.Nout; n += 8) {  // eight weight rows in flight (a serial chain of Nout DRAM latencies otherwise)
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(pr.w + (size_t)(n + u) * pr.K + k);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (m0 + j < pr.M) acc[j] = fmaf(__ldg(pr.dy + (size_t)(m0 + j) * pr.ldy + n + u), w[u], acc[j]);
+    }
+    for (; n < pr.Nout; ++n) {
       const float w = __ldg(pr.w + (size_t)n * pr.K + k);
 #pragma unroll
       for (int j = 0; j < 8; ++j)

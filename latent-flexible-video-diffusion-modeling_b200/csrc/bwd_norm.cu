@@ -9,8 +9,11 @@
 
 namespace fdm {
 
+// silu'(u) = s + u s (1 - s), s = sigmoid(u).  FAST: ex2.approx / rcp.approx (rel. error ~1e-6, far below the bf16 rounding of the
+// gradients it multiplies; the kernel was 50 % issue-bound with the precise expf + division); the fp32 mode keeps the precise one.
+template <bool FAST>
 __device__ __forceinline__ float dsilu_f(float u) {
-  const float s = 1.f / (1.f + expf(-u));
+  const float s = FAST ? __fdividef(1.f, 1.f + __expf(-u)) : 1.f / (1.f + expf(-u));
   return s * (1.f + u * (1.f - s));
 }
 
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_kernel(GnBwdParams p) {
       for (int j = 0; j < 4; ++j) {
         const float xh = (x[j] - mean[j]) * rstd[j];
         float du = dy[j];
-        if (p.silu) du *= dsilu_f(fmaf(xh, mul[j], add[j]));
+        if (p.silu) du *= dsilu_f<sizeof(OT) == 2>(fmaf(xh, mul[j], add[j]));
         if (MODE == 0) {
           accA[j] = fmaf(du, xh, accA[j]);
           accB[j] += du;

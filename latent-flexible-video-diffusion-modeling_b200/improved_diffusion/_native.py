@@ -47,7 +47,7 @@ AttnTemporalArgs = _S("AttnTemporalArgs", [("qkv", vp), ("Rq", vp), ("Rk", vp), 
                                            ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("heads", i32),
                                            ("qkv_dtype", i32), ("out_dtype", i32), ("Rq_op", vp), ("Rk_op", vp)])
 AttnSpatialArgs = _S("AttnSpatialArgs", [("qkv", vp), ("out", vp), ("N", i32), ("L", i32), ("C", i32), ("heads", i32),
-                                         ("qkv_dtype", i32), ("out_dtype", i32), ("engine", i32)])
+                                         ("qkv_dtype", i32), ("out_dtype", i32), ("engine", i32), ("lse", vp)])
 CastArgs = _S("CastArgs", [("x", vp), ("out", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32),
                            ("upsample", i32), ("op_dtype", i32), ("colsum", vp), ("colsum2", vp)])
 DdpmStepArgs = _S("DdpmStepArgs", [("x", vp), ("eps", vp), ("noise", vp), ("coef", vp), ("t", vp), ("sample", vp),
@@ -75,7 +75,8 @@ TemporalGnBwdArgs = _S("TemporalGnBwdArgs", [("x", vp), ("gamma", vp), ("dy_op",
                                              ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("op_dtype", i32),
                                              ("accumulate", i32), ("eps", f32)])
 AttnSpatialBwdArgs = _S("AttnSpatialBwdArgs", [("qkv", vp), ("out", vp), ("dout", vp), ("dqkv", vp), ("lse", vp), ("dsum", vp),
-                                               ("N", i32), ("L", i32), ("C", i32), ("heads", i32), ("dtype", i32)])
+                                               ("N", i32), ("L", i32), ("C", i32), ("heads", i32), ("dtype", i32),
+                                               ("lse_from_forward", i32)])
 AttnTemporalBwdArgs = _S("AttnTemporalBwdArgs", [("qkv", vp), ("out", vp), ("Rq", vp), ("Rk", vp), ("Rv", vp), ("mask", vp),
                                                  ("dout", vp), ("dqkv", vp), ("dRq", vp), ("dRk", vp), ("dRv", vp),
                                                  ("lse", vp), ("dsum", vp),

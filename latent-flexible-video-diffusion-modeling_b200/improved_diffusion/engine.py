@@ -794,8 +794,10 @@ class DenoiserEngine:
             conv(yn_op, Cc, Hh, Ww, sa.qkv.weight, 3 * Cc, 1, bias=f32(sa.qkv.bias), y_op=qkv2)
             o2 = P.buf("sa_o", Nf * hw * Cc * osz)
             P.flops += 4 * hw * hw * Cc * Nf
+            # training: the tcgen05 forward also saves the log-sum-exp of every score row for the tcgen05 backward kernels
+            sa_lse = P.buf("sa_lse", Nf * sa.num_heads * hw * 4) if (train and self.use_tc) else None
             P.op("fdm_attn_spatial", N_.AttnSpatialArgs, qkv=qkv2, out=o2, N=Nf, L=hw, C=Cc, heads=sa.num_heads,
-                 qkv_dtype=opd, out_dtype=opd, engine=0 if self.use_tc else 1)
+                 qkv_dtype=opd, out_dtype=opd, engine=0 if self.use_tc else 1, lse=sa_lse)
             z = new_act("sa_z", Cc, Hh, Ww)
             conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf,
                  y_op=with_op_copy(z) if want_op else None, stats=z.st)
@@ -810,8 +812,9 @@ class DenoiserEngine:
                 wgrad(o2, opd, Cc, Cc, Hh, Ww, gz, Cc, 1, 1, sa.proj_out.weight)
                 dqkv2 = P.buf("d_sa_qkv", n_tok * 3 * Cc * osz)
                 P.bflops += 10 * hw * hw * Cc * Nf
-                P.op("fdm_attn_spatial_bwd", N_.AttnSpatialBwdArgs, qkv=qkv2, out=o2, dout=do2, dqkv=dqkv2, lse=P.at_lse,
-                     dsum=P.at_dsum, N=Nf, L=hw, C=Cc, heads=sa.num_heads, dtype=opd)
+                P.op("fdm_attn_spatial_bwd", N_.AttnSpatialBwdArgs, qkv=qkv2, out=o2, dout=do2, dqkv=dqkv2,
+                     lse=sa_lse if sa_lse is not None else P.at_lse, dsum=P.at_dsum, N=Nf, L=hw, C=Cc, heads=sa.num_heads,
+                     dtype=opd, lse_from_forward=1 if sa_lse is not None else 0)
                 P.at_rows = max(P.at_rows, Nf * sa.num_heads * hw)
                 dyn = P.buf("d_sa_yn", n_tok * Cc * osz)
                 dgrad(dqkv2, 3 * Cc, Hh, Ww, sa.qkv.weight, Cc, 1, out_op=dyn)

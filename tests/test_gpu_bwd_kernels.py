@@ -303,6 +303,37 @@ def test_temporal_gn_bwd(case, dtype):
     assert rel(dgamma, gamma.grad) <= 2e-5 and rel(dbeta, beta.grad) <= 2e-5
 
 
+@pytest.mark.parametrize("case", [(5, 256, 64, 4), (3, 64, 192, 4), (4, 16, 256, 4), (2, 256, 512, 4), (3, 256, 384, 4), (6, 64, 128, 2)])
+def test_attn_spatial_bwd_tcgen05(case):
+    """tcgen05 backward kernels fed by the log-sum-exp the tcgen05 FORWARD kernel saves (the training pairing)."""
+    n = N_()
+    Nf, L, Cc, heads = case
+    Fd = Cc // heads
+    torch.manual_seed(16)
+    qkv = torch.randn(Nf, L, 3 * Cc, device="cuda").to(torch.bfloat16)
+    dout = torch.randn(Nf, L, Cc, device="cuda").to(torch.bfloat16)
+    out = torch.empty(Nf, L, Cc, device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((Nf * heads * L,), float("nan"), device="cuda")
+    n.call("fdm_attn_spatial", n.AttnSpatialArgs(qkv=ptr(qkv), out=ptr(out), N=Nf, L=L, C=Cc, heads=heads, qkv_dtype=n.BF16,
+                                                 out_dtype=n.BF16, engine=0, lse=ptr(lse)), stream())
+    ref_in = qkv.float().requires_grad_()
+    q, k, v = ref_in.view(Nf, L, 3, heads, Fd).permute(2, 0, 3, 1, 4)
+    w = (q * Fd ** -0.5) @ k.transpose(-1, -2)
+    o_ref = (torch.softmax(w, dim=-1) @ v).permute(0, 2, 1, 3).reshape(Nf, L, Cc)
+    (o_ref * dout.float()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel(lse.view(Nf, heads, L), torch.logsumexp(w.detach(), dim=-1)) <= 1e-5
+    dqkv = torch.full_like(qkv, float("nan"))
+    dsum = torch.empty(Nf * heads * L, device="cuda")
+    a = n.AttnSpatialBwdArgs(qkv=ptr(qkv), out=ptr(out), dout=ptr(dout), dqkv=ptr(dqkv), lse=ptr(lse), dsum=ptr(dsum),
+                             N=Nf, L=L, C=Cc, heads=heads, dtype=n.BF16, lse_from_forward=1)
+    n.call("fdm_attn_spatial_bwd", a, stream())
+    torch.cuda.synchronize()
+    for name, sl in (("dq", slice(0, Cc)), ("dk", slice(Cc, 2 * Cc)), ("dv", slice(2 * Cc, 3 * Cc))):
+        e = rel(dqkv.float()[..., sl], ref_in.grad[..., sl])
+        assert e <= 1.5e-2, (name, e)  # bf16 P / dS operands + bf16 outputs
+
+
 @pytest.mark.parametrize("case", [(5, 256, 64, 4), (3, 64, 96, 4), (4, 16, 128, 4), (2, 256, 512, 4), (2, 100, 64, 2)])
 @pytest.mark.parametrize("dtype", ["bf16", "fp32"])
 def test_attn_spatial_bwd(case, dtype):
