@@ -1,12 +1,11 @@
 """
 Differentiable forward of UNetVideoModel for TRAINING (reference unet.py:428-464, rpe.py:133-174).
 
-INTERIM (round 1): the sampling path (no_grad) runs entirely on the hand-written sm_100a kernels of libfdm_sm100.so;
-the backward kernels (conv dgrad/wgrad on tcgen05, GroupNorm/attention backward) are not written yet, so when
-gradients are required the forward is expressed with stock PyTorch ops over the SAME parameters and autograd does
-the rest.  That keeps the drop-in contract of SURVEY §8b — `training_losses` works, every parameter receives a gradient
-(DDP find_unused_parameters=False, train_util.py:124), DDP wraps the module unchanged — at reference (cuDNN/cuBLAS)
-speed rather than at B200-native speed.  DESIGN.md lists this as the open row of the hot-path table.
+On a CUDA device training runs on the native forward + backward kernel schedules (engine._DenoiserFn); this module is the
+PyTorch-autograd expression of the SAME network over the SAME parameters, kept for three callers: (1) CPU tensors (the host-side
+tests, the drop-in check under the reference's TrainLoop, the 2-rank gloo DDP test), (2) the A/B arm of the training benchmark and
+of the gradient-parity tests (`FDM_TRAIN_ENGINE=autograd`), (3) `return_attn_weights=True` (attention-map logging needs the
+materialised attention matrices).  Every parameter receives a gradient (DDP find_unused_parameters=False, train_util.py:124).
 
 `model.precision == "bf16"` runs the convolutions / linears under torch.autocast(bfloat16) (GroupNorm and softmax
 stay fp32 as in the reference's GroupNorm32 / softmax(w.float())); "fp32" disables TF32 so the 1e-4 contract holds.
