@@ -1,5 +1,5 @@
 // 3x3 stride-1 convolution as implicit GEMM on tcgen05 — the "halo" kernel for the feature maps that carry the FLOPs
-// (W in {16,32,64}: whole image rows per M tile).  Same math / epilogue contract as conv_tc.cu, different data movement.
+// (W in {16,32,64,128}: whole image rows per M tile).  Same math / epilogue contract as conv_tc.cu, different data movement.
 //
 // Why: conv_tc.cu re-loads the A operand once per filter tap (9 x 16 KB per 128-pixel tile) and its B tile once per
 // CTA; measured with in-kernel timestamps the main loop runs at the SM's L2->shared-memory ingest rate (~64 B/clk),
@@ -391,7 +391,9 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   FDM_REQUIRE(a->C0 % 8 == 0 && (a->a1 == nullptr || a->C1 % 8 == 0) && a->Cout % 4 == 0 && a->Cout >= 32, FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->y_op == nullptr || a->op_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
   const int W = a->Win, H = a->Hin;
-  FDM_REQUIRE(W == 16 || W == 32 || W == 64, FDM_ERR_UNSUPPORTED);
+  // W = 128 (the top level of the 128-px model, 40 % of its conv FLOPs): one image row per M tile; the A box of a two-tile item
+  // (4 rows = 64 KB) leaves room for one pipeline stage only, so those layers run one-tile items (3 rows = 48 KB, two stages)
+  FDM_REQUIRE(W == 16 || W == 32 || W == 64 || W == 128, FDM_ERR_UNSUPPORTED);
   const int hbox = 128 / W;
   FDM_REQUIRE(H % hbox == 0, FDM_ERR_UNSUPPORTED);
   HaloParams p;
@@ -408,6 +410,7 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
     const long rounds1 = (tiles + 147) / 148, rounds2 = (tiles / 2 + 147) / 148;
     const bool two_ok = H % (2 * hbox) == 0;
     p.tpi = (two_ok && 20 * rounds2 <= 13 * rounds1) ? 2 : 1;
+    if (W == 128 && bn == 128) p.tpi = 1;
   }
   p.pairs_per_frame = H / (p.tpi * hbox);
   p.n_items = a->N * p.pairs_per_frame * p.ntiles;

@@ -69,6 +69,8 @@ CASES = [
     (2, 16, 16, 192, 96, 3, 1, 96, False),   # Cout = 96: masked N tile
     (1, 64, 64, 128, 128, 3, 1, 0, True),    # W = 64: two image rows per tile
     (1, 128, 128, 64, 64, 3, 1, 0, False),   # W = 128: one row per tile
+    (2, 128, 128, 128, 128, 3, 1, 0, True),  # W = 128 halo, BN = 128: one-tile items, two pipeline stages
+    (2, 128, 128, 256, 128, 3, 1, 128, False),  # W = 128 halo with the 1x1 skip segment (decoder ResBlock of the 128-px model)
     (3, 32, 32, 64, 64, 3, 2, 0, False),     # Downsample conv (stride 2) through TMA element strides
     (5, 16, 16, 128, 128, 3, 2, 0, False),   # stride 2 -> 8x8 outputs, two frames per tile
     (40, 32, 32, 64, 64, 3, 1, 0, True),     # > 148 work items: persistent halo CTAs loop, TMEM double buffering wraps
