@@ -197,7 +197,8 @@ static WgTcGeom wg_tc_geom(const fdm_conv_wgrad_args* a) {
   if (g.stages < 2) return g;
   g.ci_chunks = (a->C + 64 * g.nxb - 1) / (64 * g.nxb);
   const long long base = (long long)g.ci_chunks * g.co_chunks * a->ksize;
-  long long splits = (148LL * 2 + base - 1) / base;
+  // one CTA per SM (shared memory): at most two full waves of 148 CTAs, never a third, nearly empty one
+  long long splits = (148LL * 2) / base;
   if (splits > g.n_chunks) splits = g.n_chunks;
   if (splits < 1) splits = 1;
   g.cps = (int)((g.n_chunks + splits - 1) / splits);

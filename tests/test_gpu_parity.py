@@ -269,14 +269,17 @@ def test_native_backward_matches_autograd(case, precision, monkeypatch):
     loss_n, gn_ = _train_grads(model, diffusion, inp, t, noise, "native", monkeypatch, precision)
     loss_a, ga_ = _train_grads(model, diffusion, inp, t, noise, "autograd", monkeypatch, "fp32")
     tol_loss, tol_g = (1e-5, 2e-4) if precision == "fp32" else (3e-2, 2.5e-1)
-    assert O.rel_l2(loss_n, loss_a) <= tol_loss
+    assert O.rel_l2(loss_n, loss_a) <= tol_loss, O.rel_l2(loss_n, loss_a)
     errs = _grad_errors(gn_, ga_)
     print(f"native vs autograd [{precision}] worst grad rel-L2 = {errs[0][0]:.3e} at {errs[0][1]}, median {errs[len(errs) // 2][0]:.3e}")
     assert all(torch.isfinite(v).all() for v in gn_.values())
     assert errs[0][0] <= tol_g, errs[:5]
     # a second backward of a fresh forward reproduces the first (buffers are re-zeroed, weights re-packed)
     loss_n2, gn2 = _train_grads(model, diffusion, inp, t, noise, "native", monkeypatch, precision)
-    assert _grad_errors(gn2, gn_)[0][0] <= 1e-4
+    # fp32 atomics (RPE-table pixel sums, temporal-GN parameter sums) make the last bits run-dependent; in bf16 mode a flipped
+    # rounding of a gradient operand is a 4e-3 relative step for that element
+    rep = _grad_errors(gn2, gn_)[0]
+    assert rep[0] <= (1e-4 if precision == "fp32" else 1e-2), rep
 
 
 def test_native_training_step_follows_weight_updates(monkeypatch):
