@@ -199,3 +199,60 @@ def test_drop_in_under_reference_trainloop():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_trainloop.py"), str(port)], env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DROPIN_OK" in r.stdout, (r.stdout[-1000:], r.stderr[-2000:])
+
+
+def test_device_resident_video_sampler_host_logic_cpu():
+    """video_sampler.sample_video_with_iterator on CPU with a row-independent stand-in denoiser: the gather / scatter indexing and
+    the iterator protocol against the reference's per-row procedure (scripts/video_sample.py:56-83 restated)."""
+    import torch
+    from improved_diffusion import video_sampler
+
+    class Fake(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.31))
+
+        def forward(self, x, *, x0, timesteps, frame_indices=None, obs_mask=None, latent_mask=None, return_attn_weights=False):
+            fi = frame_indices.float().view(*frame_indices.shape, 1, 1, 1) / 50.0
+            return self.w * torch.tanh(x * (1 - obs_mask) + x0 * obs_mask + fi), None
+
+    class Scheme:
+        def __init__(self, T, n_obs, B):
+            self.T, self.done, self.B = T, n_obs, B
+
+        def set_videos(self, v):
+            self.v = v
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            if self.done >= self.T:
+                raise StopIteration
+            lat = list(range(self.done, min(self.done + 2, self.T)))
+            obs = [0] + list(range(max(1, self.done - 2), self.done))
+            self.done += len(lat)
+            return [obs] * self.B, [lat] * self.B
+
+    _, diffusion = build(dict(image_size=32, in_channels=2, num_channels=32, num_res_blocks=1, diffusion_steps=32, timestep_respacing="4"))
+    diffusion._noise_fn = torch.zeros_like
+    model = Fake()
+    B, T, n_obs = 3, 8, 3
+    batch = torch.randn(B, T, 2, 8, 8, generator=torch.Generator().manual_seed(1)).clamp(-1, 1)
+    torch.manual_seed(0)
+    got, used = video_sampler.sample_video_with_iterator(model, diffusion, batch, Scheme(T, n_obs, B), n_obs, device="cpu")
+    torch.manual_seed(0)
+    samples = torch.zeros_like(batch)
+    samples[:, :n_obs] = batch[:, :n_obs]
+    for obs, lat in Scheme(T, n_obs, B):
+        fi = torch.cat([torch.tensor(obs), torch.tensor(lat)], dim=1).long()
+        x0 = torch.stack([samples[i, f] for i, f in enumerate(fi)])
+        om = torch.cat([torch.ones_like(torch.tensor(obs)), torch.zeros_like(torch.tensor(lat))], dim=1).view(B, -1, 1, 1, 1).float()
+        out, _ = diffusion.p_sample_loop(model, x0.shape, model_kwargs=dict(frame_indices=fi, x0=x0, obs_mask=om, latent_mask=1 - om),
+                                         latent_mask=1 - om)
+        for i, li in enumerate(lat):
+            samples[i, li] = out[i, -len(li):]
+    assert len(used) == 3 and torch.equal(got, samples)
+    just, _ = video_sampler.sample_video_with_iterator(model, diffusion, batch, Scheme(T, n_obs, B), n_obs, device="cpu",
+                                                       just_get_indices=True)
+    assert torch.equal(just, batch)
