@@ -8,6 +8,7 @@
 // Two kernels per attention: a row-owner pass (log-sum-exp, D, dq, dRk) and a column-owner pass (dk, dv, dRq, dRv) that
 // re-forms P from the stored log-sum-exp — no cross-CTA reduction except the pixel sums of the RPE tables (fp32 atomics).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fdm {
 
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(256) attn_spatial_bwd_kv_kernel(SABwdParams p)
 // =====================================================================================================================
 constexpr int TB_FC = 8;     // head-dim chunk
 constexpr int TB_LD = 33;    // padded pixel stride of the staged tiles
-constexpr int TB_WARPS = 8;
+constexpr int TB_WARPS = 8;  // frames per CTA (runtime: blockDim.x / 32)
 
 struct TABwdParams {
   const void* qkv; const void* out; const void* dout; const float* Rq; const float* Rk; const float* Rv; const float* mask;
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_q_kernel(TABw
   float* qw = dsw + T * TB_LD;       // [8][33] q[f][px]
   // one CTA per (32 pixels, head, video, round of 8 query frames): the rounds are independent, and on the small feature maps
   // (8x8: two pixel blocks) they are the only parallelism there is
-  const int rounds = (T + TB_WARPS - 1) / TB_WARPS;
+  const int NW = blockDim.x >> 5;  // frames per CTA
+  const int rounds = (T + NW - 1) / NW;
   const int px0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z / rounds;
   const int px = min(px0 + lane, HW - 1);
   const bool px_ok = px0 + lane < HW;
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_q_kernel(TABw
   const float* maskb = p.mask ? p.mask + (size_t)b * T : nullptr;
   {
     const int rd = blockIdx.z - b * rounds;
-    const int t_raw = rd * TB_WARPS + w;
+    const int t_raw = rd * NW + w;
     const bool act = t_raw < T;
     const int t = act ? t_raw : 0;
     const size_t row = (size_t)(b * T + t) * HW + px;
@@ -486,7 +488,8 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_kv_kernel(TAB
   float* dsw = rv + T * TB_FC;       // [T][33] dS[t][px]
   float* pw = dsw + T * TB_LD;       // [T][33] P[t][px]
   float* kw = pw + T * TB_LD;        // [8][33] k[f][px]
-  const int rounds = (T + TB_WARPS - 1) / TB_WARPS;
+  const int NW = blockDim.x >> 5;  // frames per CTA
+  const int rounds = (T + NW - 1) / NW;
   const int px0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z / rounds;
   const int px = min(px0 + lane, HW - 1);
   const bool px_ok = px0 + lane < HW;
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_kv_kernel(TAB
   const float* maskb = p.mask ? p.mask + (size_t)b * T : nullptr;
   {
     const int rd = blockIdx.z - b * rounds;
-    const int s_raw = rd * TB_WARPS + w;
+    const int s_raw = rd * NW + w;
     const bool act = s_raw < T;
     const int s = act ? s_raw : 0;
     const size_t row = (size_t)(b * T + s) * HW + px;
@@ -648,13 +651,20 @@ extern "C" int fdm_attn_spatial_bwd(const fdm_attn_spatial_bwd_args* a, void* st
 template <int TP, typename QT>
 static void launch_ta_bwd(const TABwdParams& p, cudaStream_t st) {
   const int T = p.T;
-  const size_t smem_q = ((size_t)2 * T * TB_FC * TB_LD + (size_t)TB_WARPS * (3 * T * TB_FC + T * TB_LD + TB_FC * TB_LD)) * sizeof(float);
-  const size_t smem_kv = ((size_t)2 * T * TB_FC * TB_LD + (size_t)TB_WARPS * (3 * T * TB_FC + 2 * T * TB_LD + TB_FC * TB_LD)) * sizeof(float);
-  dim3 grid((p.HW + 31) / 32, p.heads, p.B * ((T + TB_WARPS - 1) / TB_WARPS));
-  cudaFuncSetAttribute(attn_temporal_bwd_q_kernel<TP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
-  cudaFuncSetAttribute(attn_temporal_bwd_kv_kernel<TP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);
-  fdm::launch(attn_temporal_bwd_q_kernel<TP, QT>, grid, dim3(TB_WARPS * 32), smem_q, st, p);
-  fdm::launch(attn_temporal_bwd_kv_kernel<TP, QT>, grid, dim3(TB_WARPS * 32), smem_kv, st, p);
+  // frames (warps) per CTA.  Fewer warps per CTA (more CTAs on the small feature maps, where 8-warp CTAs number only 48-192) was
+  // measured SLOWER on B200 (cfg3: 3.7 -> 4.9 ms per step): every CTA re-stages all T key/value frames, so halving the frames
+  // per CTA doubles the staging traffic and the serial stage -> sync -> compute chain stays as long.  FDM_TA_BWD_WARPS overrides.
+  static const int nw_env = [] { const char* e = getenv("FDM_TA_BWD_WARPS"); return e ? atoi(e) : 0; }();
+  const int nw = (nw_env == 2 || nw_env == 4) ? nw_env : TB_WARPS;
+  const size_t smem_q = ((size_t)2 * T * TB_FC * TB_LD + (size_t)nw * (3 * T * TB_FC + T * TB_LD + TB_FC * TB_LD)) * sizeof(float);
+  const size_t smem_kv = ((size_t)2 * T * TB_FC * TB_LD + (size_t)nw * (3 * T * TB_FC + 2 * T * TB_LD + TB_FC * TB_LD)) * sizeof(float);
+  const size_t smem_q_max = ((size_t)2 * T * TB_FC * TB_LD + (size_t)TB_WARPS * (3 * T * TB_FC + T * TB_LD + TB_FC * TB_LD)) * sizeof(float);
+  const size_t smem_kv_max = ((size_t)2 * T * TB_FC * TB_LD + (size_t)TB_WARPS * (3 * T * TB_FC + 2 * T * TB_LD + TB_FC * TB_LD)) * sizeof(float);
+  dim3 grid((p.HW + 31) / 32, p.heads, p.B * ((T + nw - 1) / nw));
+  cudaFuncSetAttribute(attn_temporal_bwd_q_kernel<TP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q_max);
+  cudaFuncSetAttribute(attn_temporal_bwd_kv_kernel<TP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_max);
+  fdm::launch(attn_temporal_bwd_q_kernel<TP, QT>, grid, dim3(nw * 32), smem_q, st, p);
+  fdm::launch(attn_temporal_bwd_kv_kernel<TP, QT>, grid, dim3(nw * 32), smem_kv, st, p);
 }
 
 extern "C" int fdm_attn_temporal_bwd(const fdm_attn_temporal_bwd_args* a, void* stream) {
