@@ -43,6 +43,8 @@ class Plan:
         self.tape = []       # backward emitters, one per forward block, run in reverse after the forward schedule is built
         self.bzero_bytes = 0  # arena zeroed at the start of every backward (atomic accumulators, GroupNorm-backward sums)
         self.pack_problems = []  # (src param, src2, dst tensor, co, ci, k, mode): re-packed by ONE launch per forward
+        self.bside = set()       # indices into bops of the launches that run on the backward side stream (weight gradients)
+        self.bwd_side_stream = self.ev_bfork = self.ev_bjoin = None
         self.bufs = []
         self.keep = []       # tensors that must outlive the plan (weights views, problem arrays)
         self.calls = None    # [(fn, byref(struct))] after finalize()
@@ -197,10 +199,27 @@ class Plan:
         self.bzero_arena.zero_()
         self.pgrad.zero_()
         s = C.c_void_p(stream)
-        for name, fn, ref in self.bcalls:
-            rc = fn(ref, s)
+        side = self.bwd_side_stream
+        if side is not None:
+            # weight-gradient launches only feed parameter gradients: they run on a side stream (parallel branches of the CUDA
+            # graph), each ordered after the main-stream kernel that produced its gradient operand, so the dgrad / GroupNorm /
+            # attention chain — the critical path — does not wait for them.  Buffers are never reused in training plans; the
+            # split-K workspace is shared only among side-stream launches (serialised there).
+            main = th.cuda.current_stream(self.arena.device)
+            assert main.cuda_stream == stream, "Plan.run_backward expects torch's current stream"
+            ss = C.c_void_p(side.cuda_stream)
+        for i, (name, fn, ref) in enumerate(self.bcalls):
+            if side is not None and i in self.bside:
+                self.ev_bfork.record(main)
+                side.wait_event(self.ev_bfork)
+                rc = fn(ref, ss)
+            else:
+                rc = fn(ref, s)
             if rc != 0:
                 N_.check(rc, name)
+        if side is not None:
+            self.ev_bjoin.record(side)
+            main.wait_event(self.ev_bjoin)
 
     def run(self, stream):
         """Launch the whole schedule on `stream` (the raw cudaStream_t of torch's CURRENT stream).  The caller has filled the
@@ -260,9 +279,8 @@ class _DenoiserFn(th.autograd.Function):
         sync = getattr(ctx.engine.model, "_fdm_grad_sync", None)
         if sync is not None:  # sharding.FlatGradDataParallel: ONE allreduce over the whole flat gradient
             sync(flat)
-        base = P.pgrad.data_ptr()
-        grads = tuple(flat[(v.data_ptr() - base) // 4:(v.data_ptr() - base) // 4 + v.numel()].view(v.shape) for v in P.pgrad_views)
-        return (None,) * 7 + grads
+        views = th._C._nn.unflatten_dense_tensors(flat, P.unflat)
+        return (None,) * 7 + tuple(views[i] for i in P.unflat_pick)
 
 
 class DenoiserEngine:
@@ -278,6 +296,7 @@ class DenoiserEngine:
         self.use_tc = precision == "bf16" and os.environ.get("FDM_CONV_ENGINE", "tc") != "simt"
         self.temporal_mma = os.environ.get("FDM_TEMPORAL_MMA", "0") == "1"
         self.plans = {}
+        self._params = self._n_params = None
         self.train_plans = {}
         self.packed = {}
         self._versions = None
@@ -286,6 +305,18 @@ class DenoiserEngine:
                                       "(the reference default, script_util.py:34)")
 
     # ------------------------------------------------------------------ weights
+    def param_list(self):
+        """The model's parameters in registration order, cached: walking the module tree (nn.Module.parameters -> named_modules)
+        costs ~0.7 ms per traversal for the 390 tensors, and the launch-bound cfg2 training step did it twice per step."""
+        if self._params is None or len(self._params) != self._n_params_registered():
+            self._params = list(self.model.parameters())
+        return self._params
+
+    def _n_params_registered(self):
+        if self._n_params is None:
+            self._n_params = sum(1 for _ in self.model.parameters())
+        return self._n_params
+
     def _param_versions(self):
         return tuple(p._version for p in self.model.parameters()) + (next(self.model.parameters()).data_ptr(),)
 
@@ -340,7 +371,7 @@ class DenoiserEngine:
         if train:
             # training plans survive optimizer steps: their packed weights are refreshed by ONE fdm_pack_weights launch at the
             # head of every forward; they are rebuilt only when a parameter's storage moves (.to(), re-materialisation)
-            key = (B, T, H, W, str(device), tuple(p.data_ptr() for p in self.model.parameters()))
+            key = (B, T, H, W, str(device), tuple(p.data_ptr() for p in self.param_list()))
             if key not in self.train_plans:
                 self.train_plans.clear()
                 with th.cuda.device(device):
@@ -385,8 +416,16 @@ class DenoiserEngine:
             params = list(m.parameters())
             for p_ in params:
                 assert p_.dtype == th.float32 and p_.is_contiguous(), "training plans expect contiguous fp32 master weights"
-            sizes = [(p_.numel() + 63) // 64 * 64 for p_ in params]
+            # densely packed in parameter order: ONE C++ call (unflatten_dense_tensors) turns a clone of it into the per-parameter
+            # gradients — 390 Python-side narrow+view pairs per step were ~2 ms of host time on the launch-bound cfg2 step
+            sizes = [(p_.numel() + 3) // 4 * 4 for p_ in params]  # 16-byte aligned slots (vectorised optimizer kernels)
             P.pgrad = th.zeros(sum(sizes), dtype=th.float32, device=device)
+            P.unflat, P.unflat_pick = [], []  # templates for unflatten_dense_tensors: parameters interleaved with padding stubs
+            for p_, n_ in zip(params, sizes):
+                P.unflat_pick.append(len(P.unflat))
+                P.unflat.append(p_)
+                if n_ != p_.numel():
+                    P.unflat.append(th.empty(n_ - p_.numel()))
             offs, o = {}, 0
             for p_, n_ in zip(params, sizes):
                 offs[id(p_)] = o
@@ -623,6 +662,7 @@ class DenoiserEngine:
             P.wg_ws.nbytes = max(P.wg_ws.nbytes, (need + 255) // 256 * 256)
             pad_ = k // 2
             P.bflops += 2 * (n or Nf) * ((Hin + 2 * pad_ - k) // stride + 1) * ((Win + 2 * pad_ - k) // stride + 1) * Co * k * k * Cw
+            P.bside.add(len(P.bops))
             P.op("fdm_conv_wgrad", N_.ConvWgradArgs, a=a, dy=gy, dw=(dw if dw is not None else pg(w)) if a is not None else None,
                  dbias=pg(biases[0]) if biases else None,
                  dbias2=pg(biases[1]) if len(biases) > 1 else None, workspace=P.wg_ws, workspace_bytes=need, **fields)
@@ -974,6 +1014,7 @@ class DenoiserEngine:
                     P.op("fdm_nchw_to_nhwc", N_.NchwToNhwcArgs, src=P.geps, dst=ge64, N=Nf, C=Co_, H=H, W=W, Cpad=64, op_dtype=opd)
                     dw64 = P.buf("head_dw64", 64 * h_last.C * 9 * 4)
                     wgrad(head_a, opd, h_last.C, h_last.C, H, W, ge64, 64, 3, 1, cv.weight, (), dw=dw64)
+                    P.bside.add(len(P.bops))  # consumes the side-stream wgrad's scratch: same stream
                     P.op("fdm_sum_parts", N_.SumPartsArgs, parts=dw64, out=pg(cv.weight), part_stride=0, n=Co_ * h_last.C * 9,
                          count=1, accumulate=0)
                     wgrad(None, opd, h_last.C, h_last.C, H, W, ge, Co_, 3, 1, cv.weight, (cv.bias,))
@@ -1026,6 +1067,9 @@ class DenoiserEngine:
         if train:
             P.geps_view = P.view(P.geps, (B, T, m.out_channels, H, W), th.float32)
             P.n_bwd_launches = len(P.bcalls)
+            if th.device(device).type == "cuda" and os.environ.get("FDM_BWD_SIDE_STREAM", "1") != "0":
+                P.bwd_side_stream = th.cuda.Stream(device)
+                P.ev_bfork, P.ev_bjoin = th.cuda.Event(), th.cuda.Event()
         # typed views of the I/O buffers
         Cx = Cin - 1
         P.x_view = P.view(P.x, (B, T, Cx, H, W), th.float32)
@@ -1051,7 +1095,7 @@ class DenoiserEngine:
         """Differentiable forward (w.r.t. the parameters) through the native forward + backward schedules."""
         if frame_indices is None:
             raise ValueError("frame_indices is required (temporal RPE, rpe.py:146)")
-        return _DenoiserFn.apply(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, *self.model.parameters())
+        return _DenoiserFn.apply(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, *self.param_list())
 
     def forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask):
         B, T, Cx, H, W = x.shape
