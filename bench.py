@@ -216,7 +216,13 @@ def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
         # FDM_DDP=torch: torch DistributedDataParallel exactly as train_util.py:118-125 (drop-in path, per-parameter hooks);
         # default: one allreduce over the native backward's flat gradient buffer
         net = sharding.wrap_ddp(model, dev) if os.environ.get("FDM_DDP", "flat") == "torch" else sharding.FlatGradDataParallel(model)
-    opt = th.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0, fused=True)
+    # FDM_OPT=torch: torch.optim.AdamW(fused=True) (multi-tensor kernels over the 390 tensors); default: optim.FlatAdamW — the same
+    # update rule as ONE fdm_adamw launch over flat parameter / moment / gradient buffers
+    if os.environ.get("FDM_OPT", "flat") == "torch":
+        opt = th.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0, fused=True)
+    else:
+        from improved_diffusion.optim import FlatAdamW
+        opt = FlatAdamW(model.parameters(), lr=1e-4, weight_decay=0.0)
     batch = {k: v.to(dev) for k, v in synthetic_batch(over, B, K, 3, 4 * K, seed=1 + int(os.environ.get("RANK", "0"))).items()}
     g = th.Generator(device=dev).manual_seed(0)
 
@@ -255,7 +261,7 @@ def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
     flops = plan.flops + plan.bflops
     out = {"metric": "train samples/sec", "value": world * B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
            "autograd_ms_per_step": ms_auto, "steps": steps,
-           "config": {"workload": workload, "batch_per_gpu": B, "frames": K, **over, "optimizer": "AdamW (torch fused)"},
+           "config": {"workload": workload, "batch_per_gpu": B, "frames": K, **over, "optimizer": "AdamW, weight_decay 0 (" + type(opt).__name__ + ")"},
            "launches_per_step": {"forward": plan.n_launches, "backward": plan.n_bwd_launches},
            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                         "flops_per_step": flops, "what": "algorithmic fwd + dgrad + wgrad + attention FLOPs of one step / step time "

@@ -428,6 +428,21 @@ typedef struct {
 } fdm_nchw_to_nhwc_args; /* which = 28 */
 int fdm_nchw_to_nhwc(const fdm_nchw_to_nhwc_args* a, void* stream);
 
+
+/* B7  fused AdamW over FLAT fp32 buffers — torch.optim.AdamW as constructed by train_util.py:127 (`AdamW(master_params, lr, weight_decay)`),
+ *     one launch for the whole model instead of the multi-tensor kernels over 390 tensors.  The native backward
+ *     already leaves all gradients in one flat buffer; improved_diffusion/optim.py keeps the parameters and both moments flat too.
+ *       p *= 1 - lr*wd ;  m = b1 m + (1-b1) g ;  v = b2 v + (1-b2) g^2 ;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+ *     ema (optional): up to two exponential moving averages of the parameters updated in the same pass (nn.py:55-65) */
+typedef struct {
+  float* p; const float* g; float* m; float* v;
+  float* ema0; float* ema1; /* or NULL */
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2_sqrt;
+  float ema_rate0, ema_rate1;
+} fdm_adamw_args; /* which = 29 */
+int fdm_adamw(const fdm_adamw_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

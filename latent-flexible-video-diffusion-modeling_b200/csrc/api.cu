@@ -65,6 +65,7 @@ extern "C" size_t fdm_struct_size(int which) {
     case 26: return sizeof(fdm_sum_parts_args);
     case 27: return sizeof(fdm_accum_args);
     case 28: return sizeof(fdm_nchw_to_nhwc_args);
+    case 29: return sizeof(fdm_adamw_args);
     default: return 0;
   }
 }

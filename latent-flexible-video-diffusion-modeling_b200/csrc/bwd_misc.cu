@@ -256,6 +256,43 @@ __global__ void __launch_bounds__(256) rpe_hidden_bwd_kernel(const float* __rest
   }
 }
 
+
+// ---------------- B7 fused AdamW (+EMA) over flat buffers -----------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_flat_kernel(fdm_adamw_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n4 = a.n >> 2;
+  const float decay = 1.f - a.lr * a.weight_decay, step = a.lr / a.bias_correction1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 p4 = reinterpret_cast<float4*>(a.p)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m4 = reinterpret_cast<float4*>(a.m)[i], v4 = reinterpret_cast<float4*>(a.v)[i];
+    float p[4] = {p4.x, p4.y, p4.z, p4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p[j] *= decay;
+      m[j] = m[j] + (g[j] - m[j]) * (1.f - a.beta1);       // lerp, as torch's fused kernel
+      v[j] = a.beta2 * v[j] + (1.f - a.beta2) * g[j] * g[j];
+      const float denom = sqrtf(v[j]) / a.bias_correction2_sqrt + a.eps;
+      p[j] -= step * (m[j] / denom);
+    }
+    reinterpret_cast<float4*>(a.p)[i] = make_float4(p[0], p[1], p[2], p[3]);
+    reinterpret_cast<float4*>(a.m)[i] = make_float4(m[0], m[1], m[2], m[3]);
+    reinterpret_cast<float4*>(a.v)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    if (a.ema0 != nullptr) {
+      float4 e = reinterpret_cast<float4*>(a.ema0)[i];
+      const float r = a.ema_rate0;
+      reinterpret_cast<float4*>(a.ema0)[i] = make_float4(e.x * r + p[0] * (1.f - r), e.y * r + p[1] * (1.f - r), e.z * r + p[2] * (1.f - r), e.w * r + p[3] * (1.f - r));
+    }
+    if (a.ema1 != nullptr) {
+      float4 e = reinterpret_cast<float4*>(a.ema1)[i];
+      const float r = a.ema_rate1;
+      reinterpret_cast<float4*>(a.ema1)[i] = make_float4(e.x * r + p[0] * (1.f - r), e.y * r + p[1] * (1.f - r), e.z * r + p[2] * (1.f - r), e.w * r + p[3] * (1.f - r));
+    }
+  }
+}
+
 }  // namespace fdm
 
 using namespace fdm;
@@ -316,5 +353,12 @@ extern "C" int fdm_rpe_hidden_bwd(const fdm_rpe_hidden_bwd_args* a, void* stream
     fdm::launch(rpe_hidden_bwd_kernel<__nv_bfloat16>, grid, dim3(32, 8), 0, (cudaStream_t)stream, a->te, a->frame_indices, a->problems, a->dte, a->T, a->te_stride);
   else
     fdm::launch(rpe_hidden_bwd_kernel<float>, grid, dim3(32, 8), 0, (cudaStream_t)stream, a->te, a->frame_indices, a->problems, a->dte, a->T, a->te_stride);
+  return check_launch();
+}
+
+extern "C" int fdm_adamw(const fdm_adamw_args* a, void* stream) {
+  FDM_REQUIRE(a && a->p && a->g && a->m && a->v && a->n > 0, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->n % 4 == 0, FDM_ERR_UNSUPPORTED);  // flat buffers are laid out in 16-byte slots
+  fdm::launch(adamw_flat_kernel, dim3(grid_for_b(a->n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, *a);
   return check_launch();
 }

@@ -1,0 +1,114 @@
+"""
+FlatAdamW — torch.optim.AdamW as the reference constructs it (train_util.py:127: `AdamW(self.master_params, lr=, weight_decay=)`),
+restated over FLAT buffers.
+
+The native backward (engine._DenoiserFn) already returns every parameter gradient as a view of ONE flat fp32 buffer.  Here the
+parameters, `exp_avg` and `exp_avg_sq` are flat buffers too (each parameter's `.data` is re-pointed to its 16-byte aligned slot;
+`Parameter` identity, `state_dict()` keys / shapes and `load_state_dict` are unchanged), so an optimizer step is ONE kernel
+launch (`fdm_adamw`) with ~20 us of host work, instead of torch's multi-tensor path over 390 tensors (~0.7 ms of GPU time and
+~1 ms of host time per step — a quarter of the launch-bound cfg2 training step).  Optionally the EMA copies of the parameters
+(`update_ema`, nn.py:55-65; up to two rates) are updated in the same pass.
+
+Same update rule as torch (decoupled weight decay, bias correction, no amsgrad); `tests/test_gpu_parity.py` checks it against
+torch.optim.AdamW step by step.  Gradients that do not come from the native backward (CPU path, torch DDP buckets, partial
+graphs) are gathered into a flat buffer with one foreach copy first.  CUDA only: there is no CPU fallback.
+"""
+import ctypes as C
+
+import torch as th
+
+from . import _native as N_
+
+
+def flat_slots(params):
+    """(offsets, total) of the 16-byte aligned slots of `params` in a flat fp32 buffer — the layout of the native backward's
+    gradient buffer (engine.py) so that its views line up with the flat parameter buffer."""
+    offs, o = [], 0
+    for p in params:
+        offs.append(o)
+        o += (p.numel() + 3) // 4 * 4
+    return offs, o
+
+
+class FlatAdamW(th.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, ema_rates=()):
+        params = list(params)
+        if any(isinstance(p, dict) for p in params):
+            raise NotImplementedError("FlatAdamW takes one parameter group (as train_util.py:127 builds it)")
+        if len(ema_rates) > 2:
+            raise NotImplementedError("up to two EMA rates are fused into the step")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        ps = self.param_groups[0]["params"]
+        if not ps or not all(p.is_cuda and p.dtype == th.float32 for p in ps):
+            raise RuntimeError("FlatAdamW runs on the sm_100a kernels only: fp32 CUDA parameters (there is no CPU fallback)")
+        self._offs, self._total = flat_slots(ps)
+        dev = ps[0].device
+        self.flat_p = th.zeros(self._total, device=dev)
+        self.flat_m, self.flat_v = th.zeros_like(self.flat_p), th.zeros_like(self.flat_p)
+        self._gather = th.zeros_like(self.flat_p)  # used when the gradients are not already views of one buffer
+        with th.no_grad():
+            for p, o in zip(ps, self._offs):
+                slot = self.flat_p[o:o + p.numel()].view(p.shape)
+                slot.copy_(p.data)
+                p.data = slot  # same Parameter object, storage now inside the flat buffer
+        self._views = lambda flat: [flat[o:o + p.numel()].view(p.shape) for p, o in zip(ps, self._offs)]
+        self._g_views = self._views(self._gather)
+        for p, m, v in zip(ps, self._views(self.flat_m), self._views(self.flat_v)):
+            self.state[p] = {"step": th.zeros((), dtype=th.float32), "exp_avg": m, "exp_avg_sq": v}
+        self._step = 0
+        self.ema_rates = tuple(float(r) for r in ema_rates)
+        self.flat_ema = [self.flat_p.clone() for _ in self.ema_rates]
+
+    def ema_params(self, i):
+        """Per-parameter views of the i-th EMA copy (same shapes / order as the parameters)."""
+        return self._views(self.flat_ema[i])
+
+    def _flat_grad(self, ps):
+        g0 = ps[0].grad
+        if g0 is None:
+            raise RuntimeError("FlatAdamW.step(): parameter without a gradient (find_unused_parameters=False contract)")
+        base = g0.data_ptr()
+        if g0.is_contiguous() and g0.dtype == th.float32 and all(
+                p.grad is not None and p.grad.data_ptr() == base + 4 * o for p, o in zip(ps, self._offs)):
+            return base, None  # the native backward's flat buffer: use it in place
+        th._foreach_copy_(self._g_views, [p.grad for p in ps])
+        return self._gather.data_ptr(), self._gather
+
+    @th.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with th.enable_grad():
+                loss = closure()
+        group = self.param_groups[0]
+        ps = group["params"]
+        if ps[0].data_ptr() != self.flat_p.data_ptr():
+            raise RuntimeError("a parameter's storage was replaced after FlatAdamW flattened it (.to() / .data = ...): rebuild the optimizer")
+        g_ptr, _keep = self._flat_grad(ps)
+        self._step += 1
+        b1, b2 = group["betas"]
+        a = N_.AdamwArgs(p=self.flat_p.data_ptr(), g=g_ptr, m=self.flat_m.data_ptr(), v=self.flat_v.data_ptr(),
+                         ema0=self.flat_ema[0].data_ptr() if len(self.flat_ema) > 0 else None,
+                         ema1=self.flat_ema[1].data_ptr() if len(self.flat_ema) > 1 else None,
+                         n=self._total, lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"],
+                         bias_correction1=1.0 - b1 ** self._step, bias_correction2_sqrt=(1.0 - b2 ** self._step) ** 0.5,
+                         ema_rate0=self.ema_rates[0] if len(self.ema_rates) > 0 else 0.0,
+                         ema_rate1=self.ema_rates[1] if len(self.ema_rates) > 1 else 0.0)
+        N_.check(N_.lib().fdm_adamw(C.byref(a), C.c_void_p(th.cuda.current_stream(self.flat_p.device).cuda_stream)), "fdm_adamw")
+        return loss
+
+    def state_dict(self):
+        for st in self.state.values():
+            st["step"].fill_(self._step)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        ps = self.param_groups[0]["params"]
+        with th.no_grad():  # torch replaced the per-parameter state tensors: copy them back into the flat buffers and re-point
+            for p, m, v in zip(ps, self._views(self.flat_m), self._views(self.flat_v)):
+                st = self.state[p]
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+                self._step = int(st["step"])
+                st["exp_avg"], st["exp_avg_sq"] = m, v
