@@ -8,7 +8,8 @@ over, B, K, steps = bench.TRAIN_WORKLOADS["cfg2-train"]
 dev = th.device("cuda:0")
 model, diffusion, _ = bench.build_native(over, dev)
 model.train()
-opt = th.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0, fused=True)
+from improved_diffusion.optim import FlatAdamW
+opt = FlatAdamW(model.parameters(), lr=1e-4, weight_decay=0.0)
 batch = {k: v.to(dev) for k, v in bench.synthetic_batch(over, B, K, 3, 4 * K, seed=1).items()}
 t = th.randint(0, 1000, (B,), device=dev)
 def step():
@@ -26,4 +27,4 @@ for _ in range(50):
 th.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("cumulative").print_stats(35)
+st.sort_stats("tottime").print_stats(28)
