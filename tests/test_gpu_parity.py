@@ -254,6 +254,8 @@ def _train_grads(model, diffusion, inp, t, noise, engine, monkeypatch, precision
     (dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32), 2, 5, 2, (1,)),
     (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 7, 3, ()),
     (dict(image_size=64, in_channels=3, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 3, 1, ()),
+    # cfg5 family: 64-px latents, nc = 128 (C up to 512, head dims 96 / 128), K = 40 frames (the 40-key temporal kernels)
+    (dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 1, 40, 10, ()),
 ])
 def test_native_backward_matches_autograd(case, precision, monkeypatch):
     """The native backward schedule (engine._DenoiserFn: conv dgrad/wgrad, GroupNorm / attention / RPENet backward kernels) against
