@@ -341,6 +341,9 @@ typedef struct {
   int32_t N, HW, Ca, Cb, T, film_stride, film_off, silu, op_dtype;
   int32_t acc_a, acc_b; /* 1: gx += dx, 0: gx = dx */
   float eps;
+  int32_t phases; /* 0 = all three launches; else a mask: 1 = per-(n,c) sums, 2 = parameter gradients (reads the sums), 4 = apply
+                     (reads the sums).  The parameter-gradient launch only feeds parameter gradients, so the training schedule issues it
+                     on its side stream (mask 2) and keeps the activation-gradient chain (mask 5) short */
 } fdm_gn_bwd_args; /* which = 18 */
 int fdm_gn_bwd(const fdm_gn_bwd_args* a, void* stream);
 

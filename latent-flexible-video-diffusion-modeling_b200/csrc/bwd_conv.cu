@@ -255,20 +255,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const DT* __restrict__ x, f
   __shared__ float4 cs_red[256];
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  const int quads = C / 4;
-  if ((C & 3) == 0 && quads <= 256) {
+  if ((C & 3) == 0) {
+    // blockIdx.y walks column chunks of 1024 (qkv gradients have 3C = 1152..1536 columns)
+    const int c0 = blockIdx.y * 1024;
+    const int quads = min(1024, C - c0) / 4;
     const int q = threadIdx.x % quads, rl = threadIdx.x / quads, nrl = 256 / quads;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const DT* xc = x + c0 + q * 4;
     if (rl < nrl) {
       long long r = r0 + rl;
       for (; r + 3 * nrl < r1; r += 4 * nrl) {  // four independent loads in flight
-        const float4 a = OpType<DT>::load4(x + (size_t)r * C + q * 4), b = OpType<DT>::load4(x + (size_t)(r + nrl) * C + q * 4);
-        const float4 c = OpType<DT>::load4(x + (size_t)(r + 2 * nrl) * C + q * 4), d = OpType<DT>::load4(x + (size_t)(r + 3 * nrl) * C + q * 4);
+        const float4 a = OpType<DT>::load4(xc + (size_t)r * C), b = OpType<DT>::load4(xc + (size_t)(r + nrl) * C);
+        const float4 c = OpType<DT>::load4(xc + (size_t)(r + 2 * nrl) * C), d = OpType<DT>::load4(xc + (size_t)(r + 3 * nrl) * C);
         s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
         s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
       }
       for (; r < r1; r += nrl) {
-        const float4 a = OpType<DT>::load4(x + (size_t)r * C + q * 4);
+        const float4 a = OpType<DT>::load4(xc + (size_t)r * C);
         s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
       }
     }
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const DT* __restrict__ x, f
         const float4 o = cs_red[k * quads + q];
         s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
       }
-      *reinterpret_cast<float4*>(part + (size_t)blockIdx.x * C + q * 4) = s;
+      *reinterpret_cast<float4*>(part + (size_t)blockIdx.x * C + c0 + q * 4) = s;
     }
     return;
   }
@@ -404,9 +407,9 @@ extern "C" int fdm_conv_wgrad(const fdm_conv_wgrad_args* a, void* stream) {
   }
   if (a->dbias != nullptr || a->dbias2 != nullptr) {
     if (a->dy_dtype == FDM_BF16)
-      fdm::launch(colsum_kernel<__nv_bfloat16>, dim3(g.cs_blocks), dim3(256), 0, st, (const __nv_bfloat16*)a->dy, cs_part, g.M, a->Cout, g.cs_rows);
+      fdm::launch(colsum_kernel<__nv_bfloat16>, dim3(g.cs_blocks, (a->Cout + 1023) / 1024), dim3(256), 0, st, (const __nv_bfloat16*)a->dy, cs_part, g.M, a->Cout, g.cs_rows);
     else
-      fdm::launch(colsum_kernel<float>, dim3(g.cs_blocks), dim3(256), 0, st, (const float*)a->dy, cs_part, g.M, a->Cout, g.cs_rows);
+      fdm::launch(colsum_kernel<float>, dim3(g.cs_blocks, (a->Cout + 1023) / 1024), dim3(256), 0, st, (const float*)a->dy, cs_part, g.M, a->Cout, g.cs_rows);
     fdm::launch(colsum_final_kernel, dim3((a->Cout + 127) / 128), dim3(128), 0, st, (const float*)cs_part, a->dbias, a->dbias2, g.cs_blocks, a->Cout);
   }
   return check_launch();

@@ -341,11 +341,16 @@ extern "C" int fdm_gn_bwd(const fdm_gn_bwd_args* a, void* stream) {
   p.pix_per_block = ppb;
   dim3 grid((a->HW + ppb - 1) / ppb, a->N);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->op_dtype == FDM_BF16) fdm::launch(gn_bwd_kernel<__nv_bfloat16, 0>, grid, dim3(threads), 0, st, p);
-  else fdm::launch(gn_bwd_kernel<float, 0>, grid, dim3(threads), 0, st, p);
-  fdm::launch(gn_bwd_params_kernel, dim3((p.C + 31) / 32), dim3(32, 8), 0, st, p);
-  if (a->op_dtype == FDM_BF16) fdm::launch(gn_bwd_kernel<__nv_bfloat16, 1>, grid, dim3(threads), 0, st, p);
-  else fdm::launch(gn_bwd_kernel<float, 1>, grid, dim3(threads), 0, st, p);
+  const int ph = a->phases == 0 ? 7 : a->phases;
+  if (ph & 1) {
+    if (a->op_dtype == FDM_BF16) fdm::launch(gn_bwd_kernel<__nv_bfloat16, 0>, grid, dim3(threads), 0, st, p);
+    else fdm::launch(gn_bwd_kernel<float, 0>, grid, dim3(threads), 0, st, p);
+  }
+  if (ph & 2) fdm::launch(gn_bwd_params_kernel, dim3((p.C + 31) / 32), dim3(32, 8), 0, st, p);
+  if (ph & 4) {
+    if (a->op_dtype == FDM_BF16) fdm::launch(gn_bwd_kernel<__nv_bfloat16, 1>, grid, dim3(threads), 0, st, p);
+    else fdm::launch(gn_bwd_kernel<float, 1>, grid, dim3(threads), 0, st, p);
+  }
   return check_launch();
 }
 

@@ -45,6 +45,7 @@ class Plan:
         self.pack_problems = []  # (src param, src2, dst tensor, co, ci, k, mode): re-packed by ONE launch per forward
         self.bside = set()       # indices into bops of the launches that run on the backward side stream (weight gradients)
         self.bwd_side_stream = self.ev_bfork = self.ev_bjoin = None
+        self.bjoin_before = -1   # index into bops where the main stream first needs side-stream results (conditioning path)
         self.bufs = []
         self.keep = []       # tensors that must outlive the plan (weights views, problem arrays)
         self.calls = None    # [(fn, byref(struct))] after finalize()
@@ -209,6 +210,9 @@ class Plan:
             assert main.cuda_stream == stream, "Plan.run_backward expects torch's current stream"
             ss = C.c_void_p(side.cuda_stream)
         for i, (name, fn, ref) in enumerate(self.bcalls):
+            if side is not None and i == self.bjoin_before:
+                self.ev_bjoin.record(side)
+                main.wait_event(self.ev_bjoin)
             if side is not None and i in self.bside:
                 self.ev_bfork.record(main)
                 side.wait_event(self.ev_bfork)
@@ -367,7 +371,8 @@ class DenoiserEngine:
         return self.packed[key]
 
     # ------------------------------------------------------------------ plan compiler
-    def plan_for(self, B, T, H, W, device, train=False):
+    def plan_for(self, B, T, H, W, device, train=False, slot=0):
+        """`slot`: distinct plans (own arena, own streams) of the same shape — sub-batches run concurrently by the sampler"""
         if train:
             # training plans survive optimizer steps: their packed weights are refreshed by ONE fdm_pack_weights launch at the
             # head of every forward; they are rebuilt only when a parameter's storage moves (.to(), re-materialisation)
@@ -378,7 +383,7 @@ class DenoiserEngine:
                     self.train_plans[key] = self._compile(B, T, H, W, device, train=True)
             return self.train_plans[key]
         self.refresh_weights()
-        key = (B, T, H, W, str(device))
+        key = (B, T, H, W, str(device), slot)
         if key not in self.plans:
             with th.cuda.device(device):
                 self.plans[key] = self._compile(B, T, H, W, device)
@@ -670,13 +675,18 @@ class DenoiserEngine:
         def gn_bwd(xa, xb, gn, foff, dy_op, dy_f32, draw, silu):
             Cc = xa.C + (xb.C if xb else 0)
             ab_ = P.bzero("gn_ab", Nf * Cc * 16)
-            P.op("fdm_gn_bwd", N_.GnBwdArgs, xa=xa.buf, xb=xb.buf if xb else None, stats_a=xa.st,
-                 stats_b=xb.st if xb else None, gamma=f32(gn.weight), beta=f32(gn.bias), film=cond if foff is not None else None,
-                 dy_op=dy_op, dy_f32=dy_f32, draw_op=draw, gxa=gact(xa), gxb=gact(xb) if xb else None, ab=ab_,
-                 dgamma=pg(gn.weight), dbeta=pg(gn.bias), dfilm=dcond if foff is not None else None, N=Nf, HW=xa.H * xa.W,
-                 Ca=xa.C, Cb=xb.C if xb else 0, T=T, film_stride=cond_cols if foff is not None else 0,
-                 film_off=foff if foff is not None else 0, silu=silu, op_dtype=opd, acc_a=acc(xa),
-                 acc_b=acc(xb) if xb else 0, eps=gn.eps)
+            fields = dict(xa=xa.buf, xb=xb.buf if xb else None, stats_a=xa.st,
+                          stats_b=xb.st if xb else None, gamma=f32(gn.weight), beta=f32(gn.bias), film=cond if foff is not None else None,
+                          dy_op=dy_op, dy_f32=dy_f32, draw_op=draw, gxa=gact(xa), gxb=gact(xb) if xb else None, ab=ab_,
+                          dgamma=pg(gn.weight), dbeta=pg(gn.bias), dfilm=dcond if foff is not None else None, N=Nf, HW=xa.H * xa.W,
+                          Ca=xa.C, Cb=xb.C if xb else 0, T=T, film_stride=cond_cols if foff is not None else 0,
+                          film_off=foff if foff is not None else 0, silu=silu, op_dtype=opd, acc_a=acc(xa),
+                          acc_b=acc(xb) if xb else 0, eps=gn.eps)
+            # sums + apply on the main chain; the parameter-gradient launch (dgamma, dbeta, FiLM scale/shift gradients) only reads
+            # the sums and feeds parameter gradients / the conditioning-path backward at the very end: side stream
+            P.op("fdm_gn_bwd", N_.GnBwdArgs, phases=5, **fields)
+            P.bside.add(len(P.bops))
+            P.op("fdm_gn_bwd", N_.GnBwdArgs, phases=2, **fields)
 
         if train:
             P.bflops = 0
@@ -688,6 +698,7 @@ class DenoiserEngine:
                     dRb[(id(ab), which)] = P.bzero("dR", B * T * T * ab.channels * 4)
 
             def cond_bwd():
+                P.bjoin_before = len(P.bops)  # consumes dcond (written on the side stream by the GroupNorm parameter launches)
                 BTT = B * T * T
                 rp = []
                 for ab in attn_blocks:

@@ -184,6 +184,7 @@ WGRAD_CASES = [
     (3, 32, 32, 256, 256, 128, 1, 1),
     (2, 16, 16, 192, 192, 384, 3, 1),    # ragged 128-channel chunking of both operands
     (40, 32, 32, 64, 64, 64, 3, 1),      # many pixel chunks per split
+    (3, 16, 16, 384, 384, 1152, 1, 1),   # qkv linear of the nc = 128 model: 3C = 1152 output columns (two bias-sum column chunks)
 ]
 
 
