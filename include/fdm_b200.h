@@ -341,6 +341,10 @@ typedef struct {
   int32_t N, HW, Ca, Cb, T, film_stride, film_off, silu, op_dtype;
   int32_t acc_a, acc_b; /* 1: gx += dx, 0: gx = dx */
   float eps;
+  void* gop_a;   /* optional: operand-dtype copy of the FINAL gradient of xa (gxa after this launch's contribution), [N][HW][Ca] — when
+                    this GroupNorm is the last contributor to that gradient, the producer's dgrad / wgrad read it without a cast pass */
+  float* cs_a;   /* optional (with gop_a): cs_a[c] += column sums of the final gxa = bias gradient of the conv that produced xa (atomics) */
+  float* cs2_a;  /* optional second copy (bias of a fused 1x1 skip conv) */
   int32_t phases; /* 0 = all three launches; else a mask: 1 = per-(n,c) sums, 2 = parameter gradients (reads the sums), 4 = apply
                      (reads the sums).  The parameter-gradient launch only feeds parameter gradients, so the training schedule issues it
                      on its side stream (mask 2) and keeps the activation-gradient chain (mask 5) short */

@@ -22,6 +22,7 @@ struct GnBwdParams {
   const float* gamma; const float* beta; const float* film;
   const void* dy_op; const float* dy_f32; const void* draw_op;
   float* gxa; float* gxb; double* ab; float* dgamma; float* dbeta; float* dfilm;
+  void* gop_a; float* cs_a; float* cs2_a;
   int N, HW, Ca, Cb, C, T, film_stride, film_off, silu, pix_per_block, acc_a, acc_b;
   float eps;
 };
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_kernel(GnBwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_mean[32], s_rstd[32], s_m1[32], s_m2[32];
-  __shared__ float s_red[MODE == 0 ? 1024 * 8 : 1];
+  __shared__ float s_red[MODE == 0 ? 1024 * 8 : 1024];  // MODE 1: block partials of the fused bias-gradient column sums
   const int n = blockIdx.y, b = n / p.T;
   const int C = p.C, cpg = C / 32, quads = C / 4;
   const int q = threadIdx.x % quads, pl = threadIdx.x / quads, ppi = blockDim.x / quads;
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_kernel(GnBwdParams p) {
     if (MODE == 1) { m1[j] = s_m1[g]; m2[j] = s_m2[g]; }
   }
   float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
+  float accC[4] = {0.f, 0.f, 0.f, 0.f};  // MODE 1: column sums of the final gradient of xa
   const int p0 = blockIdx.x * p.pix_per_block;
   const int p1 = min(p0 + p.pix_per_block, p.HW);
   // GN_U pixels per trip (measured on B200: 2 and 4 are SLOWER than 1 — 111 / 137 registers cut the resident blocks per SM): every load of the trip (x, the upstream gradient(s), the pass-through gradient, the accumulated
@@ -145,6 +147,30 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_kernel(GnBwdParams p) {
         float4 v = make_float4(dx[0], dx[1], dx[2], dx[3]);
         if (from_a ? p.acc_a : p.acc_b) v = make_float4(v.x + g_old[u].x, v.y + g_old[u].y, v.z + g_old[u].z, v.w + g_old[u].w);
         *reinterpret_cast<float4*>(gdst) = v;
+        if (from_a && p.gop_a != nullptr) {
+          // this launch is the LAST contributor to xa's gradient: emit the operand copy its producer's dgrad / wgrad will read,
+          // and the bias gradient (column sums) of that producer — no separate cast pass over the tensor
+          OpType<OT>::store4(reinterpret_cast<OT*>(p.gop_a) + ((size_t)n * p.HW + px) * p.Ca + c, v);
+          accC[0] += v.x; accC[1] += v.y; accC[2] += v.z; accC[3] += v.w;
+        }
+      }
+    }
+  }
+  if (MODE == 1 && p.cs_a != nullptr) {
+    float* r = s_red + (size_t)threadIdx.x * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = accC[j];
+    __syncthreads();
+    if (pl == 0 && from_a) {
+      for (int k = 1; k < ppi; ++k) {
+        const float* o = s_red + (size_t)(k * quads + q) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) accC[j] += o[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(p.cs_a + c + j, accC[j]);
+        if (p.cs2_a != nullptr) atomicAdd(p.cs2_a + c + j, accC[j]);
       }
     }
   }
@@ -327,6 +353,7 @@ extern "C" int fdm_gn_bwd(const fdm_gn_bwd_args* a, void* stream) {
   p.xa = a->xa; p.xb = a->xb; p.sa = a->stats_a; p.sb = a->stats_b; p.gamma = a->gamma; p.beta = a->beta; p.film = a->film;
   p.dy_op = a->dy_op; p.dy_f32 = a->dy_f32; p.draw_op = a->draw_op; p.gxa = a->gxa; p.gxb = a->gxb; p.ab = a->ab;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dfilm = a->dfilm;
+  p.gop_a = a->gop_a; p.cs_a = a->gop_a ? a->cs_a : nullptr; p.cs2_a = a->gop_a ? a->cs2_a : nullptr;
   p.N = a->N; p.HW = a->HW; p.Ca = a->Ca; p.Cb = a->xb ? a->Cb : 0; p.C = p.Ca + p.Cb; p.T = a->T > 0 ? a->T : 1;
   p.film_stride = a->film_stride; p.film_off = a->film_off; p.silu = a->silu; p.acc_a = a->acc_a; p.acc_b = a->acc_b; p.eps = a->eps;
   FDM_REQUIRE(p.C % 32 == 0 && p.Ca % 4 == 0 && p.Cb % 4 == 0 && p.C <= 4096, FDM_ERR_UNSUPPORTED);

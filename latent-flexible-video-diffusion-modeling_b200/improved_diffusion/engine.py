@@ -649,6 +649,15 @@ class DenoiserEngine:
                  colsum=pg(biases[0]) if biases else None, colsum2=pg(biases[1]) if len(biases) > 1 else None)
             return o_
 
+        preop = {}  # id(activation buffer) -> operand-dtype copy of its FINAL gradient, already written (with the bias sums) by the
+        #             GroupNorm backward that was the last contributor to it
+
+        def get_op(act):
+            """operand-dtype copy of the complete gradient of `act` + the bias gradient of its producing conv"""
+            if id(act.buf) in preop:
+                return preop[id(act.buf)]
+            return to_op(gact(act), act.C, act.H, act.W, biases=act.biases)
+
         def dgrad(gy, Cg, Hg, Wg, w, Co, k, out_op=None, out_f32=None, resid=None, n=None):
             """gradient wrt a stride-1 conv's input: fdm_conv over the rotated / channel-swapped weights"""
             tc = self.use_tc and opd == N_.BF16 and self.tc_ok(Cg, 0, Co, k, 1, 0, Hg, Wg) and Co % 4 == 0
@@ -672,22 +681,33 @@ class DenoiserEngine:
                  dbias=pg(biases[0]) if biases else None,
                  dbias2=pg(biases[1]) if len(biases) > 1 else None, workspace=P.wg_ws, workspace_bytes=need, **fields)
 
-        def gn_bwd(xa, xb, gn, foff, dy_op, dy_f32, draw, silu):
+        def gn_bwd(xa, xb, gn, foff, dy_op, dy_f32, draw, silu, last=False):
+            """`last`: this GroupNorm is the LAST contributor (in backward order) to xa's gradient — true for the first forward
+            consumer of a tensor — so the launch also emits the operand copy + bias sums its producer needs (checked after the
+            schedule is complete: no later launch may write that gradient)."""
             Cc = xa.C + (xb.C if xb else 0)
             ab_ = P.bzero("gn_ab", Nf * Cc * 16)
+            gop = None
+            if last and os.environ.get("FDM_FUSE_GRAD_CAST", "1") != "0":
+                gop = P.buf("g_op", Nf * xa.H * xa.W * xa.C * osz)
+                preop[id(xa.buf)] = gop
+                fused_checks.append((len(P.bops), gact(xa)))
             fields = dict(xa=xa.buf, xb=xb.buf if xb else None, stats_a=xa.st,
                           stats_b=xb.st if xb else None, gamma=f32(gn.weight), beta=f32(gn.bias), film=cond if foff is not None else None,
                           dy_op=dy_op, dy_f32=dy_f32, draw_op=draw, gxa=gact(xa), gxb=gact(xb) if xb else None, ab=ab_,
                           dgamma=pg(gn.weight), dbeta=pg(gn.bias), dfilm=dcond if foff is not None else None, N=Nf, HW=xa.H * xa.W,
                           Ca=xa.C, Cb=xb.C if xb else 0, T=T, film_stride=cond_cols if foff is not None else 0,
                           film_off=foff if foff is not None else 0, silu=silu, op_dtype=opd, acc_a=acc(xa),
-                          acc_b=acc(xb) if xb else 0, eps=gn.eps)
+                          acc_b=acc(xb) if xb else 0, eps=gn.eps, gop_a=gop,
+                          cs_a=pg(xa.biases[0]) if (gop is not None and xa.biases) else None,
+                          cs2_a=pg(xa.biases[1]) if (gop is not None and len(xa.biases) > 1) else None)
             # sums + apply on the main chain; the parameter-gradient launch (dgamma, dbeta, FiLM scale/shift gradients) only reads
             # the sums and feeds parameter gradients / the conditioning-path backward at the very end: side stream
             P.op("fdm_gn_bwd", N_.GnBwdArgs, phases=5, **fields)
             P.bside.add(len(P.bops))
             P.op("fdm_gn_bwd", N_.GnBwdArgs, phases=2, **fields)
 
+        fused_checks = []  # (index of the fusing launch in bops, gradient buffer) for the post-compile safety check
         if train:
             P.bflops = 0
             P.wg_ws = P.buf("wgrad_ws", 256)
@@ -753,6 +773,7 @@ class DenoiserEngine:
         class Act:  # residual-stream tensor: fp32 NHWC + its GroupNorm statistics (+ optional bf16 operand copy)
             def __init__(s, buf, st, Cc, Hh, Ww):
                 s.buf, s.st, s.C, s.H, s.W, s.op = buf, st, Cc, Hh, Ww, None
+                s.biases = ()  # bias parameters of the conv that produces this tensor (their gradient = column sums of its gradient)
 
         def with_op_copy(act):
             """Ask the producing conv to also store a bf16 copy (a stride-2 Downsample conv reads it directly: no cast pass)."""
@@ -776,6 +797,7 @@ class DenoiserEngine:
                  raw_op=raw, N=Nf, HW=hw, Ca=xa.C, Cb=xb.C if xb else 0, T=T, film_stride=0, film_off=0, silu=1,
                  op_dtype=opd, eps=gn.eps)
             h1_ = new_act("res_h1", Co, Hh, Ww)
+            h1_.biases = (c1.bias,)
             conv(a1, Ci, Hh, Ww, c1.weight, Co, 3, bias=f32(c1.bias), y_f32=h1_.buf, stats=h1_.st)
             gn2, c2 = rb.out_layers[0], rb.out_layers[3]
             a2 = P.buf("res_a2", Nf * hw * Co * osz)
@@ -785,6 +807,7 @@ class DenoiserEngine:
             out = new_act("res_out", Co, Hh, Ww)
             yop = with_op_copy(out) if want_op else None
             sk = rb.skip_connection
+            out.biases = (c2.bias, sk.bias) if has_skip else (c2.bias,)
             if has_skip:
                 if sk.kernel_size != (1, 1):
                     raise NotImplementedError("ResBlock(use_conv=True) 3x3 skip is never built by create_model")
@@ -795,7 +818,7 @@ class DenoiserEngine:
 
             def bwd():
                 g_out = gact(out)
-                go = to_op(g_out, Co, Hh, Ww, biases=(c2.bias, sk.bias) if has_skip else (c2.bias,))
+                go = get_op(out)
                 da2 = P.buf("d_a2", Nf * hw * Co * osz)
                 dgrad(go, Co, Hh, Ww, c2.weight, Co, 3, out_op=da2)
                 draw = None
@@ -808,12 +831,12 @@ class DenoiserEngine:
                     wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight)
                     P.op("fdm_accum", N_.AccumArgs, src=g_out, dst=gact(xa), N=Nf, H=Hh, W=Ww, C=Co, pool=0, src_dtype=F32_,
                          accumulate=acc(xa))
-                gn_bwd(h1_, None, gn2, film_off[id(rb)], da2, None, None, 1)
-                gh = to_op(gact(h1_), Co, Hh, Ww, biases=(c1.bias,))
+                gn_bwd(h1_, None, gn2, film_off[id(rb)], da2, None, None, 1, last=True)
+                gh = get_op(h1_)
                 da1 = P.buf("d_a1", Nf * hw * Ci * osz)
                 dgrad(gh, Co, Hh, Ww, c1.weight, Ci, 3, out_op=da1)
                 wgrad(a1, opd, Ci, Ci, Hh, Ww, gh, Co, 3, 1, c1.weight)
-                gn_bwd(xa, xb, gn, None, da1, None, draw, 1)
+                gn_bwd(xa, xb, gn, None, da1, None, draw, 1, last=True)
             if train:
                 P.tape.append(bwd)
             return out
@@ -834,6 +857,7 @@ class DenoiserEngine:
                  Rv=R[(id(ab), "rpe_v")], mask=P.mask, out=o, B=B, T=T, HW=hw, C=Cc, heads=ta.num_heads,
                  qkv_dtype=opd, out_dtype=opd, Rq_op=R_op.get((id(ab), "rpe_q")), Rk_op=R_op.get((id(ab), "rpe_k")))
             y = new_act("ta_y", Cc, Hh, Ww)
+            y.biases = (ta.proj_out.bias,)
             conv(o, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, bias=f32(ta.proj_out.bias), resid=xn, y_f32=y.buf, stats=y.st)
             # --- spatial: plain per-frame GroupNorm, attention over the pixels of each frame
             yn = P.buf("sa_yn", Nf * hw * Cc * 4)
@@ -850,6 +874,7 @@ class DenoiserEngine:
             P.op("fdm_attn_spatial", N_.AttnSpatialArgs, qkv=qkv2, out=o2, N=Nf, L=hw, C=Cc, heads=sa.num_heads,
                  qkv_dtype=opd, out_dtype=opd, engine=0 if self.use_tc else 1, lse=sa_lse)
             z = new_act("sa_z", Cc, Hh, Ww)
+            z.biases = (sa.proj_out.bias,)
             conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf,
                  y_op=with_op_copy(z) if want_op else None, stats=z.st)
 
@@ -857,7 +882,7 @@ class DenoiserEngine:
                 n_tok = Nf * hw
                 # spatial half: z = proj(o2) + yn ; o2 = attn(qkv2) ; qkv2 = qkv(yn_op) ; yn = GN(y)
                 g_z = gact(z)
-                gz = to_op(g_z, Cc, Hh, Ww, biases=(sa.proj_out.bias,))
+                gz = get_op(z)
                 do2 = P.buf("d_sa_o", n_tok * Cc * osz)
                 dgrad(gz, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, out_op=do2)
                 wgrad(o2, opd, Cc, Cc, Hh, Ww, gz, Cc, 1, 1, sa.proj_out.weight)
@@ -870,10 +895,10 @@ class DenoiserEngine:
                 dyn = P.buf("d_sa_yn", n_tok * Cc * osz)
                 dgrad(dqkv2, 3 * Cc, Hh, Ww, sa.qkv.weight, Cc, 1, out_op=dyn)
                 wgrad(yn_op, opd, Cc, Cc, Hh, Ww, dqkv2, 3 * Cc, 1, 1, sa.qkv.weight, (sa.qkv.bias,))
-                gn_bwd(y, None, sa.norm, None, dyn, g_z, None, 0)
+                gn_bwd(y, None, sa.norm, None, dyn, g_z, None, 0, last=True)
                 # temporal half: y = proj(o) + xn ; o = attn_rpe(qkv, R) ; qkv = qkv(xn_op) ; xn = temporalGN(x)
                 g_y = gact(y)
-                gy = to_op(g_y, Cc, Hh, Ww, biases=(ta.proj_out.bias,))
+                gy = get_op(y)
                 do = P.buf("d_ta_o", n_tok * Cc * osz)
                 dgrad(gy, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, out_op=do)
                 wgrad(o, opd, Cc, Cc, Hh, Ww, gy, Cc, 1, 1, ta.proj_out.weight)
@@ -898,6 +923,7 @@ class DenoiserEngine:
             cv = layer.op if down else layer.conv
             Ho, Wo = (x.H // 2, x.W // 2) if down else (x.H * 2, x.W * 2)
             out = new_act("down" if down else "up", x.C, Ho, Wo)
+            out.biases = (cv.bias,)
             Hc, Wc = (x.H, x.W) if down else (Ho, Wo)  # spatial size of the conv's input
             a = None
             if (self.use_tc and self.tc_ok(x.C, 0, x.C, 3, 2 if down else 1, 0, Ho, Wo)) or (train and not down):
@@ -918,7 +944,7 @@ class DenoiserEngine:
             def bwd():
                 Cc = x.C
                 g_out = gact(out)
-                go = to_op(g_out, Cc, Ho, Wo, biases=(cv.bias,))
+                go = get_op(out)
                 if down:
                     # dgrad of the stride-2 conv = stride-1 conv over the zero-inserted gradient, accumulated in place into g_x
                     z_ = to_op(g_out, Cc, Ho, Wo, up=2)
@@ -948,6 +974,7 @@ class DenoiserEngine:
                 want_op = feeds_downsample and li == len(layers) - 1 and self.use_tc
                 if isinstance(layer, nn.Conv2d):  # stem
                     out = new_act("stem", layer.out_channels, H, W)
+                    out.biases = (layer.bias,)
                     if stem_tc:
                         conv(xin, 8, H, W, layer.weight, layer.out_channels, 3, bias=f32(layer.bias), y_f32=out.buf,
                              stats=out.st, a_dtype=N_.BF16, flop_c0=Cin)
@@ -957,7 +984,7 @@ class DenoiserEngine:
                     h = out
 
                     def bwd(layer=layer, out=out):
-                        go = to_op(gact(out), layer.out_channels, H, W, biases=(layer.bias,))
+                        go = get_op(out)
                         if stem_tc and layer.out_channels % 64 == 0:
                             # tcgen05 wgrad wants >= 64 stored input channels: a zero-padded bf16 copy of the network input
                             # (7/8 of the MMA rows are zeros — still ~20x faster than CUDA cores on the 128-px model)
@@ -1031,12 +1058,21 @@ class DenoiserEngine:
                     wgrad(None, opd, h_last.C, h_last.C, H, W, ge, Co_, 3, 1, cv.weight, (cv.bias,))
                 else:
                     wgrad(head_a, opd, h_last.C, h_last.C, H, W, ge, Co_, 3, 1, cv.weight, (cv.bias,))
-                gn_bwd(h_last, None, gn, None, da, None, None, 1)
+                gn_bwd(h_last, None, gn, None, da, None, None, 1, last=True)
             P.tape.append(head_bwd)
             P.cur = P.bops
             for emit in reversed(P.tape):
                 emit()
             P.cur = P.ops
+            # a fused operand copy is only valid if nothing writes that gradient afterwards
+            grad_out_fields = ("gxa", "gxb", "dst", "y_f32", "gx")
+            for idx, gbuf in fused_checks:
+                for j in range(idx + 1, len(P.bops)):
+                    fn_j, _, f_j = P.bops[j]
+                    if fn_j == "fdm_gn_bwd" and f_j.get("phases") == 2:
+                        continue  # parameter-gradient launch: does not write activation gradients
+                    if any(f_j.get(k) is gbuf for k in grad_out_fields):
+                        raise AssertionError(f"backward schedule: {fn_j} (#{j}) writes a gradient after its operand copy was fused (#{idx})")
             P.at_lse.nbytes = P.at_dsum.nbytes = (P.at_rows * 4 + 255) // 256 * 256
             dev_ = th.zeros(len(P.pack_problems) * C.sizeof(N_.PackProblem), dtype=th.uint8, device=device)
             P.pending.append((dev_, N_.PackProblem, [dict(src=s_, src2=s2_, dst=d_, co=co_, ci=ci_, k=k_, mode=mo_)

@@ -268,9 +268,16 @@ def test_gn_bwd(case, dtype):
                     gxa=ptr(gxa), gxb=ptr(gxb), ab=ptr(ab), dgamma=ptr(dgamma), dbeta=ptr(dbeta), dfilm=ptr(dfilm),
                     N=Nf, HW=HW, Ca=Ca, Cb=Cb, T=T, film_stride=fs, film_off=fo, silu=int(silu), op_dtype=dt(torch.empty(0, dtype=od)),
                     acc_a=1, acc_b=0, eps=1e-5)
+    # fused outputs: operand-dtype copy of the FINAL gradient of xa and its column sums (bias gradient of xa's producer)
+    gop = torch.full((Nf, HW, Ca), float("nan"), device="cuda", dtype=od)
+    cs, cs2 = torch.zeros(Ca, device="cuda"), torch.ones(Ca, device="cuda")
+    a.gop_a, a.cs_a, a.cs2_a = ptr(gop), ptr(cs), ptr(cs2)
     n.call("fdm_gn_bwd", a, stream())
     torch.cuda.synchronize()
     tol = 2e-5
+    assert torch.equal(gop.float(), gxa.to(od).float())
+    ref_cs = gxa.double().sum(dim=(0, 1))
+    assert rel(cs, ref_cs) <= 1e-5 and rel(cs2 - 1, ref_cs) <= 1e-5
     assert rel(gxa - pre_a, xa.grad) <= tol, rel(gxa - pre_a, xa.grad)
     if Cb:
         assert rel(gxb, xb.grad) <= tol
