@@ -192,6 +192,14 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _peak_tflops():
+    """(dense bf16 TFLOP/s, source): the driver-measured cuBLAS number of this pool's B200s, else the profiling recipe's fallback"""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]), "measured"
+    except Exception:
+        return 1590.0, "fallback"
+
+
 TRAIN_WORKLOADS = {
     # BASELINE.json configs[1]: Carla-latent, nc = 64, K = 5, batch 1, on 1 B200
     "cfg2-train": (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 5, 20),
@@ -263,7 +271,8 @@ def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
            "autograd_ms_per_step": ms_auto, "steps": steps,
            "config": {"workload": workload, "batch_per_gpu": B, "frames": K, **over, "optimizer": "AdamW, weight_decay 0 (" + type(opt).__name__ + ")"},
            "launches_per_step": {"forward": plan.n_launches, "backward": plan.n_bwd_launches},
-           "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+           "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "peak": _peak_tflops()[0],
+                        "peak_source": _peak_tflops()[1], "frac": flops / (ms * 1e-3) / 1e12 / _peak_tflops()[0],
                         "flops_per_step": flops, "what": "algorithmic fwd + dgrad + wgrad + attention FLOPs of one step / step time "
                                                          "(optimizer, loss and host work included in the time)"},
            "path": "native: forward + backward kernel schedules of libfdm_sm100.so behind one autograd node (conv dgrad and wgrad on "

@@ -234,6 +234,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
     // fixed summation order, four independent loads in flight (a serial chain of `splits` DRAM latencies otherwise)
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int k = 0;
+    for (; k + 7 < splits; k += 8) {  // eight loads in flight
+      const float a0 = src[k * sstride], a1 = src[(k + 1) * sstride], a2 = src[(k + 2) * sstride], a3 = src[(k + 3) * sstride];
+      const float a4 = src[(k + 4) * sstride], a5 = src[(k + 5) * sstride], a6 = src[(k + 6) * sstride], a7 = src[(k + 7) * sstride];
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      s0 += a4; s1 += a5; s2 += a6; s3 += a7;
+    }
     for (; k + 3 < splits; k += 4) {
       s0 += src[k * sstride];
       s1 += src[(k + 1) * sstride];
