@@ -95,6 +95,9 @@ class FlatAdamW(th.optim.Optimizer):
                          ema_rate0=self.ema_rates[0] if len(self.ema_rates) > 0 else 0.0,
                          ema_rate1=self.ema_rates[1] if len(self.ema_rates) > 1 else 0.0)
         N_.check(N_.lib().fdm_adamw(C.byref(a), C.c_void_p(th.cuda.current_stream(self.flat_p.device).cuda_stream)), "fdm_adamw")
+        # the kernel wrote the parameters through raw pointers: bump one tensor version so that version-keyed caches (the
+        # inference engine's packed weights, DenoiserEngine.refresh_weights) notice the update
+        ps[0].add_(0)
         return loss
 
     def state_dict(self):

@@ -417,5 +417,20 @@ def test_flat_adamw_matches_torch_adamw(monkeypatch):
     opt_ref.step()
     worst = max(O.rel_l2(a.detach().cpu(), b.detach().cpu()) for a, b in zip(model.parameters(), ref.parameters()))
     assert worst <= 1e-5, worst
+    # the INFERENCE engine (packed weights cached by parameter version) must see every optimizer step
+    model.eval()
+    x, t5 = inp["x"].cuda(), torch.tensor([5.0]).cuda()
+    with torch.no_grad():
+        e0, _ = model(x, timesteps=t5, **cuda_kw(inp))
+    for p in model.parameters():
+        p.grad = torch.randn(p.shape, device="cuda", generator=g)
+    opt.step()
+    with torch.no_grad():
+        e1, _ = model(x, timesteps=t5, **cuda_kw(inp))
+        ref.load_state_dict(model.state_dict())
+        ref.eval()
+        e_ref, _ = ref(x, timesteps=t5, **cuda_kw(inp))
+    assert O.rel_l2(e1.cpu(), e0.cpu()) > 1e-4 and O.rel_l2(e1.cpu(), e_ref.cpu()) <= 1e-5
+    model.train()
     # the model still runs (its training plan was rebuilt over the flat parameter storage) and checkpoints keep their keys
     assert list(model.state_dict().keys()) == list(ref.state_dict().keys())
