@@ -450,6 +450,20 @@ typedef struct {
 } fdm_adamw_args; /* which = 29 */
 int fdm_adamw(const fdm_adamw_args* a, void* stream);
 
+
+/* B8  gradient of the masked squared-error means (fdm_masked_mse) w.r.t. the model output — gaussian_diffusion.py:787-788 backward:
+ *     d_out[b,f,i] = (2 / (per_frame*T)) * (out - target) * (g_mse[b]*m1[b,f] + g_eval[b]*m2[b,f]) */
+typedef struct {
+  const float* out;    /* model output (eps) */
+  const float* target; /* noise (or x_start) */
+  const float* m1; const float* m2; /* [B][T] masks or NULL (= 1) */
+  const float* g_mse; const float* g_eval; /* [B] upstream gradients, either may be NULL (= 0) */
+  float* d_out;
+  int64_t per_frame;
+  int32_t B, T;
+} fdm_masked_mse_bwd_args; /* which = 30 */
+int fdm_masked_mse_bwd(const fdm_masked_mse_bwd_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

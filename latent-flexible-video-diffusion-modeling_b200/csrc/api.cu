@@ -66,6 +66,7 @@ extern "C" size_t fdm_struct_size(int which) {
     case 27: return sizeof(fdm_accum_args);
     case 28: return sizeof(fdm_nchw_to_nhwc_args);
     case 29: return sizeof(fdm_adamw_args);
+    case 30: return sizeof(fdm_masked_mse_bwd_args);
     default: return 0;
   }
 }

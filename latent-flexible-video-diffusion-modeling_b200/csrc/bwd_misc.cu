@@ -293,6 +293,23 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(fdm_adamw_args a) {
   }
 }
 
+
+// ---------------- B8 masked MSE backward: grid (chunks, B*T) ----------------------------------------------------------
+__global__ void __launch_bounds__(256) masked_mse_bwd_kernel(fdm_masked_mse_bwd_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int f = blockIdx.y, b = f / a.T;
+  float w = 0.f;
+  if (a.g_mse != nullptr) w += a.g_mse[b] * (a.m1 ? a.m1[f] : 1.f);
+  if (a.g_eval != nullptr) w += a.g_eval[b] * (a.m2 ? a.m2[f] : 1.f);
+  w *= 2.f / ((float)a.per_frame * (float)a.T);
+  const float* o = a.out + (size_t)f * a.per_frame;
+  const float* t = a.target + (size_t)f * a.per_frame;
+  float* d = a.d_out + (size_t)f * a.per_frame;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.per_frame; i += (long long)gridDim.x * blockDim.x)
+    d[i] = w * (o[i] - t[i]);
+}
+
 }  // namespace fdm
 
 using namespace fdm;
@@ -360,5 +377,14 @@ extern "C" int fdm_adamw(const fdm_adamw_args* a, void* stream) {
   FDM_REQUIRE(a && a->p && a->g && a->m && a->v && a->n > 0, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->n % 4 == 0, FDM_ERR_UNSUPPORTED);  // flat buffers are laid out in 16-byte slots
   fdm::launch(adamw_flat_kernel, dim3(grid_for_b(a->n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, *a);
+  return check_launch();
+}
+
+extern "C" int fdm_masked_mse_bwd(const fdm_masked_mse_bwd_args* a, void* stream) {
+  FDM_REQUIRE(a && a->out && a->target && a->d_out && (a->g_mse || a->g_eval), FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->B > 0 && a->T > 0 && a->per_frame > 0, FDM_ERR_BAD_ARG);
+  int chunks = (int)((a->per_frame + 256 * 4 - 1) / (256 * 4));
+  if (chunks > 64) chunks = 64;
+  fdm::launch(masked_mse_bwd_kernel, dim3(chunks, a->B * a->T), dim3(256), 0, (cudaStream_t)stream, *a);
   return check_launch();
 }

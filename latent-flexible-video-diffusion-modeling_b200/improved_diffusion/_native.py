@@ -100,6 +100,8 @@ NchwToNhwcArgs = _S("NchwToNhwcArgs", [("src", vp), ("dst", vp), ("N", i32), ("C
 AdamwArgs = _S("AdamwArgs", [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema0", vp), ("ema1", vp), ("n", i64),
                              ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32),
                              ("bias_correction1", f32), ("bias_correction2_sqrt", f32), ("ema_rate0", f32), ("ema_rate1", f32)])
+MaskedMseBwdArgs = _S("MaskedMseBwdArgs", [("out", vp), ("target", vp), ("m1", vp), ("m2", vp), ("g_mse", vp), ("g_eval", vp),
+                                           ("d_out", vp), ("per_frame", i64), ("B", i32), ("T", i32)])
 PACK_TC_FWD, PACK_TC_DGRAD, PACK_SIMT_FWD, PACK_SIMT_DGRAD, PACK_SUM2 = 0, 1, 2, 3, 4
 
 # index = `which` of fdm_struct_size (include/fdm_b200.h)
@@ -108,14 +110,14 @@ STRUCTS = [InputPrepArgs, ConvArgs, GnApplyArgs, TemporalGnArgs, TimestepEmbeddi
            LinearProblem, RpeHiddenProblem,
            PackProblem, PackWeightsArgs, ConvWgradArgs, GnBwdArgs, TemporalGnBwdArgs, AttnSpatialBwdArgs, AttnTemporalBwdArgs,
            RpeHiddenBwdProblem, RpeHiddenBwdArgs, LinearBwdProblem, GroupedLinearBwdArgs, SumPartsArgs, AccumArgs,
-           NchwToNhwcArgs, AdamwArgs]
+           NchwToNhwcArgs, AdamwArgs, MaskedMseBwdArgs]
 
 ENTRY_POINTS = ["fdm_input_prep", "fdm_conv", "fdm_gn_apply", "fdm_temporal_gn", "fdm_timestep_embedding",
                 "fdm_grouped_linear", "fdm_rpe_hidden", "fdm_attn_temporal", "fdm_attn_spatial", "fdm_cast",
                 "fdm_ddpm_step", "fdm_q_sample", "fdm_masked_mse",
                 "fdm_pack_weights", "fdm_conv_wgrad", "fdm_gn_bwd", "fdm_temporal_gn_bwd", "fdm_attn_spatial_bwd",
                 "fdm_attn_temporal_bwd", "fdm_rpe_hidden_bwd", "fdm_grouped_linear_bwd", "fdm_sum_parts", "fdm_accum",
-                "fdm_nchw_to_nhwc", "fdm_adamw"]
+                "fdm_nchw_to_nhwc", "fdm_adamw", "fdm_masked_mse_bwd"]
 
 _lib = None
 

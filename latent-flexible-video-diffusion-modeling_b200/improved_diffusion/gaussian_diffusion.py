@@ -376,6 +376,10 @@ class GaussianDiffusion:
         out, _ = model(x_t, timesteps=self._scale_timesteps(t), **model_kwargs)
         target = {ModelMeanType.START_X: x_start, ModelMeanType.EPSILON: noise}[self.model_mean_type]
         assert out.shape == target.shape == x_start.shape
+        if _MaskedMSE.usable(out, target, latent_mask, eval_mask):
+            # one reduction kernel forward, one elementwise kernel backward (instead of ~10 torch kernels and autograd nodes)
+            mse, ev = _MaskedMSE.apply(out, target, latent_mask, eval_mask)
+            return {"mse": mse, "eval-mse": ev, "loss": mse}
         se = (target - out) ** 2
         terms = {"mse": mean_flat(se, mask=latent_mask), "eval-mse": mean_flat(se, mask=eval_mask)}
         terms["loss"] = terms["mse"]
@@ -404,6 +408,49 @@ class GaussianDiffusion:
             raise NotImplementedError("decoding latents to pixels needs the diffusers VAE, which is outside the hot path; "
                                       "call p_sample_loop(..., return_decoded=False) and decode offline")
         return video
+
+
+class _MaskedMSE(th.autograd.Function):
+    """mean_flat((target - out)**2 * mask) for the latent and the eval mask (gaussian_diffusion.py:787-788, nn.py:86-92; the mean is
+    over ALL non-batch elements): fdm_masked_mse forward, fdm_masked_mse_bwd for d(out)."""
+
+    @staticmethod
+    def usable(out, target, m1, m2):
+        ok = out.is_cuda and out.dtype == th.float32 and out.dim() == 5 and target.shape == out.shape and not target.requires_grad
+        for m in (m1, m2):
+            ok = ok and (m is None or (m.numel() == out.shape[0] * out.shape[1] and not m.requires_grad))
+        return ok
+
+    @staticmethod
+    def forward(ctx, out, target, m1, m2):
+        B, T = out.shape[:2]
+        out_c, tgt_c = out.contiguous(), target.contiguous()
+        m1c = None if m1 is None else m1.reshape(B, T).float().contiguous()
+        m2c = None if m2 is None else m2.reshape(B, T).float().contiguous()
+        res = th.zeros(2, B, device=out.device)
+        a = N_.MaskedMseArgs(eps=out_c.data_ptr(), noise=tgt_c.data_ptr(), m1=None if m1c is None else m1c.data_ptr(),
+                             m2=None if m2c is None else m2c.data_ptr(), mse=res[0].data_ptr(), eval=res[1].data_ptr(),
+                             per_frame=out_c[0, 0].numel(), B=B, T=T)
+        N_.call("fdm_masked_mse", a, th.cuda.current_stream(out.device).cuda_stream)
+        ctx.save_for_backward(out_c, tgt_c)
+        ctx.masks = (m1c, m2c)
+        return res[0], res[1]
+
+    @staticmethod
+    def backward(ctx, g_mse, g_eval):
+        out_c, tgt_c = ctx.saved_tensors
+        m1c, m2c = ctx.masks
+        B, T = out_c.shape[:2]
+        d = th.empty_like(out_c)
+        gm = None if g_mse is None else g_mse.float().contiguous()
+        ge = None if g_eval is None else g_eval.float().contiguous()
+        if gm is None and ge is None:
+            return None, None, None, None
+        a = N_.MaskedMseBwdArgs(out=out_c.data_ptr(), target=tgt_c.data_ptr(), m1=None if m1c is None else m1c.data_ptr(),
+                                m2=None if m2c is None else m2c.data_ptr(), g_mse=None if gm is None else gm.data_ptr(),
+                                g_eval=None if ge is None else ge.data_ptr(), d_out=d.data_ptr(), per_frame=out_c[0, 0].numel(), B=B, T=T)
+        N_.call("fdm_masked_mse_bwd", a, th.cuda.current_stream(out_c.device).cuda_stream)
+        return d, None, None, None
 
 
 def _extract_into_tensor(arr, timesteps, broadcast_shape):
