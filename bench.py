@@ -230,7 +230,9 @@ def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
         opt = th.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0, fused=True)
     else:
         from improved_diffusion.optim import FlatAdamW
-        opt = FlatAdamW(model.parameters(), lr=1e-4, weight_decay=0.0)
+        # flat-gradient mode (model=...) needs the flat data-parallel wrapper, not torch DDP's per-parameter hooks
+        opt = FlatAdamW(model.parameters(), lr=1e-4, weight_decay=0.0,
+                        model=None if (world > 1 and os.environ.get("FDM_DDP", "flat") == "torch") else model)
     batch = {k: v.to(dev) for k, v in synthetic_batch(over, B, K, 3, 4 * K, seed=1 + int(os.environ.get("RANK", "0"))).items()}
     g = th.Generator(device=dev).manual_seed(0)
 

@@ -12,6 +12,12 @@ launch (`fdm_adamw`) with ~20 us of host work, instead of torch's multi-tensor p
 Same update rule as torch (decoupled weight decay, bias correction, no amsgrad); `tests/test_gpu_parity.py` checks it against
 torch.optim.AdamW step by step.  Gradients that do not come from the native backward (CPU path, torch DDP buckets, partial
 graphs) are gathered into a flat buffer with one foreach copy first.  CUDA only: there is no CPU fallback.
+
+`FlatAdamW(model.parameters(), ..., model=model)` additionally BINDS the model's gradient path to the optimizer ("flat-gradient
+mode"): every `p.grad` becomes a persistent view of the optimizer's flat gradient buffer, the native backward node takes ONE
+anchor tensor instead of the 390 parameters and hands its flat gradient over with one (allreduce +) copy — or add, when several
+backwards run between `zero_grad()` calls (gradient accumulation).  `p.grad` stays readable / clippable as usual; torch DDP
+(per-parameter hooks) does not apply in this mode — use `sharding.FlatGradDataParallel`.
 """
 import ctypes as C
 
@@ -31,7 +37,7 @@ def flat_slots(params):
 
 
 class FlatAdamW(th.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, ema_rates=()):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, ema_rates=(), model=None):
         params = list(params)
         if any(isinstance(p, dict) for p in params):
             raise NotImplementedError("FlatAdamW takes one parameter group (as train_util.py:127 builds it)")
@@ -58,12 +64,42 @@ class FlatAdamW(th.optim.Optimizer):
         self._step = 0
         self.ema_rates = tuple(float(r) for r in ema_rates)
         self.flat_ema = [self.flat_p.clone() for _ in self.ema_rates]
+        self.bound = None
+        if model is not None:
+            mp = list(model.parameters())
+            if len(mp) != len(ps) or any(a is not b for a, b in zip(mp, ps)):
+                raise ValueError("flat-gradient mode needs exactly the model's parameters, in model.parameters() order")
+            self.bound = model
+            self.flat_g = th.zeros_like(self.flat_p)
+            for p, gview in zip(ps, self._views(self.flat_g)):
+                p.grad = gview  # persistent: the native backward refreshes flat_g, never these tensor objects
+            self.anchor = th.zeros(1, device=dev, requires_grad=True)
+            self._fresh = True
+            model._fdm_flat_sink = self
+
+    def receive(self, flat):
+        """Called by the native backward node with the plan's flat gradient (same slot layout): copy, or add when accumulating."""
+        if flat.numel() != self.flat_g.numel():
+            raise RuntimeError("flat gradient layout mismatch between the training plan and FlatAdamW")
+        if self._fresh:
+            self.flat_g.copy_(flat)
+            self._fresh = False
+        else:
+            self.flat_g.add_(flat)
+
+    def zero_grad(self, set_to_none=True):
+        if self.bound is None:
+            return super().zero_grad(set_to_none=set_to_none)
+        self.flat_g.zero_()  # one memset: gradients that arrive through AccumulateGrad (CPU-style autograd path) add into the views
+        self._fresh = True   # the native backward overwrites (copy) on its first hand-over, adds on later ones
 
     def ema_params(self, i):
         """Per-parameter views of the i-th EMA copy (same shapes / order as the parameters)."""
         return self._views(self.flat_ema[i])
 
     def _flat_grad(self, ps):
+        if self.bound is not None:
+            return self.flat_g.data_ptr(), None
         g0 = ps[0].grad
         if g0 is None:
             raise RuntimeError("FlatAdamW.step(): parameter without a gradient (find_unused_parameters=False contract)")

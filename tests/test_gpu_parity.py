@@ -434,3 +434,45 @@ def test_flat_adamw_matches_torch_adamw(monkeypatch):
     model.train()
     # the model still runs (its training plan was rebuilt over the flat parameter storage) and checkpoints keep their keys
     assert list(model.state_dict().keys()) == list(ref.state_dict().keys())
+
+
+def test_flat_gradient_mode_matches_per_parameter_path(monkeypatch):
+    """FlatAdamW(..., model=model): one autograd anchor instead of 390 parameter inputs, p.grad as persistent views of the flat
+    gradient buffer.  Gradients equal the per-parameter path, two backwards between zero_grad() calls accumulate, and the
+    optimizer step equals torch.optim.AdamW on the same gradients."""
+    import copy
+    from improved_diffusion.optim import FlatAdamW
+    monkeypatch.setenv("FDM_TRAIN_ENGINE", "native")
+    over = dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32)
+    model, diffusion, cfg, sd = build(over, "fp32")
+    model.train()
+    inp = O.synthetic_inputs(cfg, 2, 5, 2, seed=8, pad_rows=(0,))
+    noise = torch.randn(inp["x0"].shape, generator=torch.Generator().manual_seed(4))
+    t = torch.tensor([3, 21])
+
+    def backward(m_):
+        terms = diffusion.training_losses(m_, inp["x0"].cuda(), t.cuda(), model_kwargs=cuda_kw(inp), noise=noise.cuda(),
+                                          latent_mask=inp["latent_mask"].cuda())
+        terms["loss"].mean().backward()
+        return terms["loss"].detach()
+    backward(model)
+    ref_grads = [p.grad.detach().clone() for p in model.parameters()]
+    ref = build(over, "fp32")[0]  # (a model that has run holds compiled plans: build a fresh copy instead of deepcopy)
+    ref.load_state_dict(model.state_dict())
+    opt_ref = torch.optim.AdamW(ref.parameters(), lr=2e-3, weight_decay=0.01)
+    model.zero_grad(set_to_none=True)
+    opt = FlatAdamW(model.parameters(), lr=2e-3, weight_decay=0.01, model=model)
+    views = [p.grad for p in model.parameters()]
+    opt.zero_grad()
+    backward(model)
+    assert all(p.grad is v for p, v in zip(model.parameters(), views)), "p.grad must stay the persistent view"
+    assert _grad_errors({i: g for i, g in enumerate(views)}, {i: g for i, g in enumerate(ref_grads)})[0][0] <= 1e-4
+    backward(model)  # second backward without zero_grad: accumulates
+    assert _grad_errors({i: g for i, g in enumerate(views)}, {i: 2 * g for i, g in enumerate(ref_grads)})[0][0] <= 1e-4
+    opt.zero_grad()
+    backward(model)
+    for q, g_ in zip(ref.parameters(), views):
+        q.grad = g_.detach().clone()
+    opt.step()
+    opt_ref.step()
+    assert max(O.rel_l2(a.detach().cpu(), b.detach().cpu()) for a, b in zip(model.parameters(), ref.parameters())) <= 1e-5
