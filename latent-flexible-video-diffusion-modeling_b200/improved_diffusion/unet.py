@@ -157,7 +157,10 @@ class UNetVideoModel(nn.Module):
             out = differentiable_forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, attns=attns)
             return out, attns
         needs_grad = th.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if needs_grad and x.is_cuda and os.environ.get("FDM_TRAIN_ENGINE", "native") != "autograd":
+        # the native backward differentiates w.r.t. the PARAMETERS (what training needs); a caller that wants d(eps)/d(x) or
+        # d(eps)/d(x0) (guidance-style use) gets the autograd expression below instead of silently missing input gradients
+        wants_input_grad = x.requires_grad or (isinstance(x0, th.Tensor) and x0.requires_grad)
+        if needs_grad and x.is_cuda and not wants_input_grad and os.environ.get("FDM_TRAIN_ENGINE", "native") != "autograd":
             # training on the GPU: native forward AND backward kernel schedules behind one autograd node (engine._DenoiserFn)
             return self.engine().forward_train(x, x0, timesteps, frame_indices, obs_mask, latent_mask), None
         if needs_grad:
