@@ -256,3 +256,46 @@ def test_device_resident_video_sampler_host_logic_cpu():
     just, _ = video_sampler.sample_video_with_iterator(model, diffusion, batch, Scheme(T, n_obs, B), n_obs, device="cpu",
                                                        just_get_indices=True)
     assert torch.equal(just, batch)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("over,B,T", [
+    (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 5),    # cfg2
+    (dict(image_size=128, in_channels=3, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 1, 2),  # cfg3 model, short clip
+    (dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 1, 3),   # cfg5 model, short clip
+])
+def test_training_plan_compiles_and_covers_every_parameter(over, B, T, precision):
+    """Host logic of the training schedule compiler (no GPU: plans are compiled over a CPU arena, nothing is launched): every
+    parameter has a gradient writer in the backward schedule, the weight-packing problems cover every conv / linear weight in
+    both layouts, the fused gradient-cast safety check holds, and side-stream launches never write activation gradients."""
+    import torch
+    from improved_diffusion import _native as N_
+    model, _ = build(over)
+    model.precision = precision
+    S = over["image_size"]
+    P = model.engine()._compile(B, T, S, S, torch.device("cpu"), train=True)
+    refs = set()
+    for fn, cls, f in P.bops:
+        refs.update(v.data_ptr() for v in f.values() if isinstance(v, torch.Tensor))
+    for dev, cls, items in P.pending:
+        for it in items:
+            refs.update(v.data_ptr() for v in it.values() if isinstance(v, torch.Tensor))
+    base = P.pgrad.data_ptr()
+    off = 0
+    missing = []
+    for name, p in model.named_parameters():
+        if base + 4 * off not in refs:
+            missing.append(name)
+        off += (p.numel() + 3) // 4 * 4
+    assert not missing, missing
+    assert off == P.pgrad.numel()
+    # every >= 2-D weight is packed for the forward and (except the stem: no input gradient) for the dgrad conv
+    packed_fwd = {id(s_) for s_, _, _, _, _, _, mode in P.pack_problems if mode in (N_.PACK_TC_FWD, N_.PACK_SIMT_FWD)}
+    convs = [p for n_, p in model.named_parameters() if p.dim() == 4 or (p.dim() == 2 and ("qkv" in n_ or "proj_out" in n_ or n_.endswith("rpe_net.out.weight")))]
+    assert all(id(p) in packed_fwd for p in convs if p.dim() == 4)
+    # side-stream launches only feed parameter gradients
+    for i in P.bside:
+        fn, _, f = P.bops[i]
+        assert fn in ("fdm_conv_wgrad", "fdm_sum_parts") or (fn == "fdm_gn_bwd" and f["phases"] == 2), fn
+    assert 0 <= P.bjoin_before <= len(P.bops)
+    assert len(P.bops) > 2 * len(P.ops) - 40 and P.bflops > 1.9 * P.flops
