@@ -51,6 +51,9 @@ WORKLOADS = {
     # cfg5: long-context temporal attention stress (nc=128, K=40, 4x64x64 latents)
     "cfg5-sampling": dict(over=dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000),
                           B=2, K=40, n_obs=20, video_len=300),
+    # cfg3's model used as a sampler (pixel space, 128x128x3, nc=128, K=20, 2 videos per GPU): the 128-wide halo convs
+    "cfg3-sampling": dict(over=dict(image_size=128, in_channels=3, num_channels=128, num_res_blocks=1, diffusion_steps=1000),
+                          B=2, K=20, n_obs=10, video_len=300),
 }
 DEFAULT_WORKLOAD = "cfg4-sampling"
 
@@ -407,10 +410,10 @@ def main():
     sp = C_.c_void_p(stream.cuda_stream)
 
     def is_halo(st):
-        """launches served by conv_halo_kernel (conv_halo.cu): 3x3 stride-1 tcgen05 convs on 16/32/64-wide maps"""
+        """launches served by conv_halo_kernel (conv_halo.cu): 3x3 stride-1 tcgen05 convs on 16/32/64/128-wide maps"""
         if not (st.engine == N_.CONV_TC and st.ksize == 3 and st.stride == 1 and not st.upsample and not st.out_nchw):
             return False
-        return st.Win in (16, 32, 64) and st.Hin % (128 // st.Win) == 0 and st.Cout >= 32 and st.Cout % 4 == 0 and st.C0 % 8 == 0
+        return st.Win in (16, 32, 64, 128) and st.Hin % max(1, 128 // st.Win) == 0 and st.Cout >= 32 and st.Cout % 4 == 0 and st.C0 % 8 == 0
 
     def conv_flops(st):
         pad = st.ksize // 2
