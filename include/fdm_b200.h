@@ -341,6 +341,8 @@ typedef struct {
   int32_t N, HW, Ca, Cb, T, film_stride, film_off, silu, op_dtype;
   int32_t acc_a, acc_b; /* 1: gx += dx, 0: gx = dx */
   float eps;
+  const float* dpass_a; /* optional fp32 [N][HW][Ca]: a gradient that reaches xa unchanged (the identity residual of a ResBlock,
+                           unet.py:207: out = x + h  =>  g_x += g_out) and is added here instead of by a separate accumulate pass */
   void* gop_a;   /* optional: operand-dtype copy of the FINAL gradient of xa (gxa after this launch's contribution), [N][HW][Ca] — when
                     this GroupNorm is the last contributor to that gradient, the producer's dgrad / wgrad read it without a cast pass */
   float* cs_a;   /* optional (with gop_a): cs_a[c] += column sums of the final gxa = bias gradient of the conv that produced xa (atomics) */

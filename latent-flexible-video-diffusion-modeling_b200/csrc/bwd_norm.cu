@@ -22,7 +22,7 @@ struct GnBwdParams {
   const float* gamma; const float* beta; const float* film;
   const void* dy_op; const float* dy_f32; const void* draw_op;
   float* gxa; float* gxb; double* ab; float* dgamma; float* dbeta; float* dfilm;
-  void* gop_a; float* cs_a; float* cs2_a;
+  const float* dpass_a; void* gop_a; float* cs_a; float* cs2_a;
   int N, HW, Ca, Cb, C, T, film_stride, film_off, silu, pix_per_block, acc_a, acc_b;
   float eps;
 };
@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_kernel(GnBwdParams p) {
       }
       if (MODE == 1) {
         if (p.draw_op != nullptr) { dx[0] += d_raw[u].x; dx[1] += d_raw[u].y; dx[2] += d_raw[u].z; dx[3] += d_raw[u].w; }
+        if (from_a && p.dpass_a != nullptr) {
+          const float4 d = __ldg(reinterpret_cast<const float4*>(p.dpass_a + ((size_t)n * p.HW + px) * p.Ca + c));
+          dx[0] += d.x; dx[1] += d.y; dx[2] += d.z; dx[3] += d.w;
+        }
         float* gdst = from_a ? p.gxa + ((size_t)n * p.HW + px) * p.Ca + c : p.gxb + ((size_t)n * p.HW + px) * p.Cb + (c - p.Ca);
         float4 v = make_float4(dx[0], dx[1], dx[2], dx[3]);
         if (from_a ? p.acc_a : p.acc_b) v = make_float4(v.x + g_old[u].x, v.y + g_old[u].y, v.z + g_old[u].z, v.w + g_old[u].w);
@@ -353,6 +357,7 @@ extern "C" int fdm_gn_bwd(const fdm_gn_bwd_args* a, void* stream) {
   p.xa = a->xa; p.xb = a->xb; p.sa = a->stats_a; p.sb = a->stats_b; p.gamma = a->gamma; p.beta = a->beta; p.film = a->film;
   p.dy_op = a->dy_op; p.dy_f32 = a->dy_f32; p.draw_op = a->draw_op; p.gxa = a->gxa; p.gxb = a->gxb; p.ab = a->ab;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dfilm = a->dfilm;
+  p.dpass_a = a->dpass_a;
   p.gop_a = a->gop_a; p.cs_a = a->gop_a ? a->cs_a : nullptr; p.cs2_a = a->gop_a ? a->cs2_a : nullptr;
   p.N = a->N; p.HW = a->HW; p.Ca = a->Ca; p.Cb = a->xb ? a->Cb : 0; p.C = p.Ca + p.Cb; p.T = a->T > 0 ? a->T : 1;
   p.film_stride = a->film_stride; p.film_off = a->film_off; p.silu = a->silu; p.acc_a = a->acc_a; p.acc_b = a->acc_b; p.eps = a->eps;

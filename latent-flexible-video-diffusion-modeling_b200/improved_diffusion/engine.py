@@ -702,7 +702,7 @@ class DenoiserEngine:
                  dbias=pg(biases[0]) if biases else None,
                  dbias2=pg(biases[1]) if len(biases) > 1 else None, workspace=P.wg_ws, workspace_bytes=need, **fields)
 
-        def gn_bwd(xa, xb, gn, foff, dy_op, dy_f32, draw, silu, last=False):
+        def gn_bwd(xa, xb, gn, foff, dy_op, dy_f32, draw, silu, last=False, dpass=None):
             """`last`: this GroupNorm is the LAST contributor (in backward order) to xa's gradient — true for the first forward
             consumer of a tensor — so the launch also emits the operand copy + bias sums its producer needs (checked after the
             schedule is complete: no later launch may write that gradient)."""
@@ -719,7 +719,7 @@ class DenoiserEngine:
                           dgamma=pg(gn.weight), dbeta=pg(gn.bias), dfilm=dcond if foff is not None else None, N=Nf, HW=xa.H * xa.W,
                           Ca=xa.C, Cb=xb.C if xb else 0, T=T, film_stride=cond_cols if foff is not None else 0,
                           film_off=foff if foff is not None else 0, silu=silu, op_dtype=opd, acc_a=acc(xa),
-                          acc_b=acc(xb) if xb else 0, eps=gn.eps, gop_a=gop,
+                          acc_b=acc(xb) if xb else 0, eps=gn.eps, dpass_a=dpass, gop_a=gop,
                           cs_a=pg(xa.biases[0]) if (gop is not None and xa.biases) else None,
                           cs2_a=pg(xa.biases[1]) if (gop is not None and len(xa.biases) > 1) else None)
             # sums + apply on the main chain; the parameter-gradient launch (dgamma, dbeta, FiLM scale/shift gradients) only reads
@@ -849,15 +849,13 @@ class DenoiserEngine:
                     dgrad(go, Co, Hh, Ww, sk.weight, Ci, 1, out_op=draw)
                     wgrad(raw, opd, Ci, Ci, Hh, Ww, go, Co, 1, 1, sk.weight)
                 else:
-                    wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight)
-                    P.op("fdm_accum", N_.AccumArgs, src=g_out, dst=gact(xa), N=Nf, H=Hh, W=Ww, C=Co, pool=0, src_dtype=F32_,
-                         accumulate=acc(xa))
+                    wgrad(a2, opd, Co, Co, Hh, Ww, go, Co, 3, 1, c2.weight)  # identity residual: g_xa += g_out inside the last gn_bwd
                 gn_bwd(h1_, None, gn2, film_off[id(rb)], da2, None, None, 1, last=True)
                 gh = get_op(h1_)
                 da1 = P.buf("d_a1", Nf * hw * Ci * osz)
                 dgrad(gh, Co, Hh, Ww, c1.weight, Ci, 3, out_op=da1)
                 wgrad(a1, opd, Ci, Ci, Hh, Ww, gh, Co, 3, 1, c1.weight)
-                gn_bwd(xa, xb, gn, None, da1, None, draw, 1, last=True)
+                gn_bwd(xa, xb, gn, None, da1, None, draw, 1, last=True, dpass=None if has_skip else g_out)
             if train:
                 P.tape.append(bwd)
             return out

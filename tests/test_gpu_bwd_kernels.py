@@ -272,6 +272,9 @@ def test_gn_bwd(case, dtype):
     gop = torch.full((Nf, HW, Ca), float("nan"), device="cuda", dtype=od)
     cs, cs2 = torch.zeros(Ca, device="cuda"), torch.ones(Ca, device="cuda")
     a.gop_a, a.cs_a, a.cs2_a = ptr(gop), ptr(cs), ptr(cs2)
+    dpass = torch.randn(Nf, HW, Ca, device="cuda")  # fp32 pass-through gradient of xa (identity residual)
+    a.dpass_a = ptr(dpass)
+    pre_a = pre_a + dpass
     n.call("fdm_gn_bwd", a, stream())
     torch.cuda.synchronize()
     tol = 2e-5
