@@ -476,3 +476,37 @@ def test_flat_gradient_mode_matches_per_parameter_path(monkeypatch):
     opt.step()
     opt_ref.step()
     assert max(O.rel_l2(a.detach().cpu(), b.detach().cpu()) for a, b in zip(model.parameters(), ref.parameters())) <= 1e-5
+
+
+def test_native_training_trajectory_matches_autograd(monkeypatch):
+    """Ten SGD steps (fp32 mode, fresh noise / timesteps per step) on two copies of a model — one through the native forward +
+    backward schedules (CUDA-graph replays, weight re-packing every step), one through torch.autograd — must stay together:
+    the same losses step by step and the same weights at the end."""
+    over = dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32)
+    nat, diffusion, cfg, sd = build(over, "fp32")
+    ref = build(over, "fp32")[0]
+    nat.train()
+    ref.train()
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    inp = O.synthetic_inputs(cfg, 2, 5, 2, seed=12, pad_rows=(1,))
+    opts = [torch.optim.SGD(m_.parameters(), lr=0.05) for m_ in (nat, ref)]
+    g = torch.Generator().manual_seed(21)
+    losses = []
+    for it in range(10):
+        t = torch.randint(0, 32, (2,), generator=g)
+        noise = torch.randn(inp["x0"].shape, generator=g)
+        row = []
+        for m_, o_, eng in ((nat, opts[0], "native"), (ref, opts[1], "autograd")):
+            monkeypatch.setenv("FDM_TRAIN_ENGINE", eng)
+            terms = diffusion.training_losses(m_, inp["x0"].cuda(), t.cuda(), model_kwargs=cuda_kw(inp), noise=noise.cuda(),
+                                              latent_mask=inp["latent_mask"].cuda())
+            o_.zero_grad(set_to_none=True)
+            terms["loss"].mean().backward()
+            o_.step()
+            row.append(float(terms["loss"].detach().mean()))
+        losses.append(row)
+    for a, b in losses:
+        assert abs(a - b) <= 2e-4 * abs(b), losses
+    worst = max(O.rel_l2(p.detach().cpu(), q.detach().cpu()) for p, q in zip(nat.parameters(), ref.parameters()))
+    assert worst <= 2e-4, worst
