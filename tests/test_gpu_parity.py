@@ -254,6 +254,11 @@ def _train_grads(model, diffusion, inp, t, noise, engine, monkeypatch, precision
     (dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32), 2, 5, 2, (1,)),
     (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 7, 3, ()),
     (dict(image_size=64, in_channels=3, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 3, 1, ()),
+    # ragged shapes: three videos of four frames with padded rows; an unconditional batch (no observed frames) of 11 frames.
+    # (T = 2 is not used: the temporal GroupNorm then normalises 4 values per group and amplifies rounding noise ~100x — fp32
+    # gradients still agree to 2e-4, bf16 ones do not; the same ill-conditioning as T = 1 in the forward tests)
+    (dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32), 3, 4, 1, (0, 2)),
+    (dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32), 2, 11, 0, ()),
     # cfg5 family: 64-px latents, nc = 128 (C up to 512, head dims 96 / 128), K = 40 frames (the 40-key temporal kernels)
     (dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 1, 40, 10, ()),
 ])
