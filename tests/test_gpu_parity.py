@@ -286,6 +286,7 @@ def test_native_backward_matches_autograd(case, precision, monkeypatch):
     # fp32 atomics (RPE-table pixel sums, temporal-GN parameter sums) make the last bits run-dependent; in bf16 mode a flipped
     # rounding of a gradient operand is a 4e-3 relative step for that element
     rep = _grad_errors(gn2, gn_)[0]
+    print(f"   repeat run worst grad rel-L2 = {rep[0]:.3e} at {rep[1]}")
     assert rep[0] <= (1e-4 if precision == "fp32" else 1e-2), rep
 
 
@@ -511,7 +512,9 @@ def test_native_training_trajectory_matches_autograd(monkeypatch):
             o_.step()
             row.append(float(terms["loss"].detach().mean()))
         losses.append(row)
+    print("trajectory: max loss rel diff %.2e" % max(abs(a - b) / abs(b) for a, b in losses))
     for a, b in losses:
         assert abs(a - b) <= 2e-4 * abs(b), losses
     worst = max(O.rel_l2(p.detach().cpu(), q.detach().cpu()) for p, q in zip(nat.parameters(), ref.parameters()))
+    print("trajectory: worst weight rel-L2 after 10 steps %.2e" % worst)
     assert worst <= 2e-4, worst
