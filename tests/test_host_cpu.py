@@ -299,3 +299,20 @@ def test_training_plan_compiles_and_covers_every_parameter(over, B, T, precision
         assert fn in ("fdm_conv_wgrad", "fdm_sum_parts") or (fn == "fdm_gn_bwd" and f["phases"] == 2), fn
     assert 0 <= P.bjoin_before <= len(P.bops)
     assert len(P.bops) > 2 * len(P.ops) - 40 and P.bflops > 1.9 * P.flops
+
+
+@pytest.mark.parametrize("name", ["stages_hierarchy-2_T300", "stages_autoreg_T60"])
+def test_stage_fixtures_are_consistent(name):
+    """The stage lists generated from the live reference's sampling schemes (tests/golden/make_stages.py): every stage conditions
+    only on finished frames, never exceeds max_frames, and the stages cover the video exactly once (hierarchy-2 on a
+    300-frame video = 27 stages, 534 model-frames per diffusion step)."""
+    import json
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
+    done, generated = set(range(fx["n_obs"])), []
+    for obs, lat in fx["stages"]:
+        assert set(obs) <= done and len(obs) + len(lat) <= fx["max_frames"] and not (set(lat) & done)
+        done |= set(lat)
+        generated += lat
+    assert done == set(range(fx["video_length"])) and len(generated) == len(set(generated))
+    if name == "stages_hierarchy-2_T300":
+        assert len(fx["stages"]) == 27 and sum(len(o) + len(l) for o, l in fx["stages"]) == 534
