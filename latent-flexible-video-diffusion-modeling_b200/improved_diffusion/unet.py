@@ -164,8 +164,14 @@ class UNetVideoModel(nn.Module):
             # training on the GPU: native forward AND backward kernel schedules behind one autograd node (engine._DenoiserFn)
             return self.engine().forward_train(x, x0, timesteps, frame_indices, obs_mask, latent_mask), None
         if needs_grad:
-            # CPU (tests, the drop-in TrainLoop check) or FDM_TRAIN_ENGINE=autograd (A/B): PyTorch-autograd expression of the
-            # same network over the same parameters (autograd_path.py)
+            # NOT a silent fallback: the PyTorch-autograd expression of the same network (autograd_path.py) only runs when asked
+            # for — FDM_TRAIN_ENGINE=autograd (the A/B arm of the benchmark and of the parity tests) or FDM_ALLOW_TORCH_TRAIN=1
+            # (host-side CPU tests, the drop-in TrainLoop check, gradients w.r.t. the inputs)
+            if os.environ.get("FDM_TRAIN_ENGINE") != "autograd" and os.environ.get("FDM_ALLOW_TORCH_TRAIN") != "1":
+                why = "on a CPU tensor" if not x.is_cuda else "with gradients w.r.t. the inputs"
+                raise RuntimeError(f"UNetVideoModel training {why} is not served by the sm_100a kernels (native training "
+                                   "differentiates w.r.t. the parameters, on a CUDA device; there is no silent CPU / PyTorch "
+                                   "fallback).  Set FDM_ALLOW_TORCH_TRAIN=1 to run the PyTorch-autograd expression instead.")
             from .autograd_path import differentiable_forward
             return differentiable_forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask), None
         if not x.is_cuda:

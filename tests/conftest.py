@@ -10,6 +10,9 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# the host-side (CPU) tests exercise losses / DDP / the drop-in TrainLoop through the PyTorch-autograd expression of the network;
+# the product refuses that path unless asked for (unet.py: no silent fallback)
+os.environ.setdefault("FDM_ALLOW_TORCH_TRAIN", "1")
 
 
 def pytest_configure(config):

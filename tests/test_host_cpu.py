@@ -316,3 +316,19 @@ def test_stage_fixtures_are_consistent(name):
     assert done == set(range(fx["video_length"])) and len(generated) == len(set(generated))
     if name == "stages_hierarchy-2_T300":
         assert len(fx["stages"]) == 27 and sum(len(o) + len(l) for o, l in fx["stages"]) == 534
+
+
+def test_torch_training_path_is_opt_in(monkeypatch):
+    """No silent fallback: differentiating the model on a CPU tensor raises unless the PyTorch-autograd expression is asked for."""
+    import torch
+    model, _ = build(dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32))
+    x = torch.zeros(1, 2, 4, 32, 32)
+    kw = dict(x0=x, timesteps=torch.zeros(1), frame_indices=torch.tensor([[0, 1]]), obs_mask=torch.zeros(1, 2, 1, 1, 1),
+              latent_mask=torch.ones(1, 2, 1, 1, 1))
+    monkeypatch.delenv("FDM_ALLOW_TORCH_TRAIN", raising=False)
+    monkeypatch.delenv("FDM_TRAIN_ENGINE", raising=False)
+    with pytest.raises(RuntimeError, match="no silent CPU / PyTorch fallback"):
+        model(x, **kw)
+    monkeypatch.setenv("FDM_ALLOW_TORCH_TRAIN", "1")
+    out, _ = model(x, **kw)
+    assert out.shape == x.shape and out.requires_grad
