@@ -488,6 +488,7 @@ class DenoiserEngine:
             pack_fields = dict(problems=None, count=0, max_elems=0)
             P.op("fdm_pack_weights", N_.PackWeightsArgs, **pack_fields)
             pack_fields = P.ops[-1][2]
+            pack_fields_d = None
 
         # ---------------- persistent inputs / outputs
         P.x = P.buf("x", Nf * (Cin - 1) * H * W * 4, True)
@@ -607,6 +608,11 @@ class DenoiserEngine:
                 b = p_["hidden"]
                 b.first = idx if b.first is None else b.first
                 b.last = idx
+            if train:
+                # the DGRAD weight layouts are only read by the backward schedule: packed on the side stream (this branch),
+                # off the forward's dependent chain
+                P.op("fdm_pack_weights", N_.PackWeightsArgs, problems=None, count=0, max_elems=0)
+                pack_fields_d = P.ops[-1][2]
             if self.use_tc:
                 self._pending_rpe_tc = rpe_tc  # emitted right after the conv helper is defined
             else:
@@ -1093,11 +1099,16 @@ class DenoiserEngine:
                     if any(f_j.get(k) is gbuf for k in grad_out_fields):
                         raise AssertionError(f"backward schedule: {fn_j} (#{j}) writes a gradient after its operand copy was fused (#{idx})")
             P.at_lse.nbytes = P.at_dsum.nbytes = (P.at_rows * 4 + 255) // 256 * 256
-            dev_ = th.zeros(len(P.pack_problems) * C.sizeof(N_.PackProblem), dtype=th.uint8, device=device)
-            P.pending.append((dev_, N_.PackProblem, [dict(src=s_, src2=s2_, dst=d_, co=co_, ci=ci_, k=k_, mode=mo_)
-                                                    for s_, s2_, d_, co_, ci_, k_, mo_ in P.pack_problems]))
-            pack_fields.update(problems=dev_, count=len(P.pack_problems),
-                               max_elems=max(co_ * ci_ * k_ * k_ for _, _, _, co_, ci_, k_, _ in P.pack_problems))
+            dgrad_modes = (N_.PACK_TC_DGRAD, N_.PACK_SIMT_DGRAD)
+            groups = [(pack_fields, [q_ for q_ in P.pack_problems if pack_fields_d is None or q_[6] not in dgrad_modes])]
+            if pack_fields_d is not None:
+                groups.append((pack_fields_d, [q_ for q_ in P.pack_problems if q_[6] in dgrad_modes]))
+            for fields_, probs_ in groups:
+                dev_ = th.zeros(max(len(probs_), 1) * C.sizeof(N_.PackProblem), dtype=th.uint8, device=device)
+                P.pending.append((dev_, N_.PackProblem, [dict(src=s_, src2=s2_, dst=d_, co=co_, ci=ci_, k=k_, mode=mo_)
+                                                        for s_, s2_, d_, co_, ci_, k_, mo_ in probs_]))
+                fields_.update(problems=dev_, count=len(probs_),
+                               max_elems=max([co_ * ci_ * k_ * k_ for _, _, _, co_, ci_, k_, _ in probs_] or [1]))
 
         P.join_at = next((i for i, (fn, _, _) in enumerate(P.ops) if fn == "fdm_attn_temporal"), len(P.ops))
         if (th.device(device).type == "cuda" and P.side_end > P.side_begin and P.join_at >= P.side_end
