@@ -208,6 +208,10 @@ TRAIN_WORKLOADS = {
     "cfg2-train": (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 5, 20),
     # BASELINE.json configs[2]: Carla pixel-scale, nc = 128, K = 20, 128x128x3 frames, batch 2 PER GPU (DDP over the box)
     "cfg3-train": (dict(image_size=128, in_channels=3, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 2, 20, 6),
+    # BASELINE.json configs[4] as a training shape (not part of the default run): long-context model, K = 40, 4x64x64 latents
+    "cfg5-train": (dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 2, 40, 6),
+    # cfg4's shard shape as a training step (8 videos x 20 frames of 4x32x32 latents, nc = 64)
+    "cfg4-train": (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 8, 20, 10),
 }
 
 
