@@ -299,7 +299,60 @@ struct TABwdParams {
   float scale;
 };
 
-// tile[(s * 8 + f) * 33 + px] = src[((b*T + s) * HW + px0 + px) * row_stride + col0 + f]
+// raw 4-element loads: the conversion to fp32 happens AFTER all loads of a staging step were issued (ncu: 33 % of the stall
+// samples of the first version were the bf16 unpack / staging stores waiting on one global load at a time)
+template <typename QT>
+struct Raw4;
+template <>
+struct Raw4<float> {
+  using T = float4;
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ float4 cvt(T v) { return v; }
+};
+template <>
+struct Raw4<__nv_bfloat16> {
+  using T = uint2;
+  static __device__ __forceinline__ T load(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+  static __device__ __forceinline__ float4 cvt(T u) {
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+  }
+};
+
+// Two tiles staged together (K and V, or Q and dO): tile[(s * 8 + f) * 33 + px] = src[((b*T + s) * HW + px0 + px) * stride + col + f].
+// NL = loads per thread and tile at 256 threads (compile-time: all 2*NL loads are in flight before the first store).
+template <int NL, typename QT>
+__device__ __forceinline__ void tb_stage2(float* tile_a, const QT* src_a, size_t stride_a, int col_a, float* tile_b, const QT* src_b,
+                                          size_t stride_b, int col_b, int b, int T, int HW, int px0) {
+  typename Raw4<QT>::T ra[NL], rb[NL];
+  const int total = T * 32 * (TB_FC / 4);
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int i = threadIdx.x + j * blockDim.x;
+    if (i < total) {
+      const int fq = i % (TB_FC / 4), pl = (i / (TB_FC / 4)) % 32, s = i / (32 * (TB_FC / 4));
+      const size_t rowi = (size_t)(b * T + s) * HW + min(px0 + pl, HW - 1);
+      ra[j] = Raw4<QT>::load(src_a + rowi * stride_a + col_a + fq * 4);
+      if (tile_b != nullptr) rb[j] = Raw4<QT>::load(src_b + rowi * stride_b + col_b + fq * 4);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int i = threadIdx.x + j * blockDim.x;
+    if (i < total) {
+      const int fq = i % (TB_FC / 4), pl = (i / (TB_FC / 4)) % 32, s = i / (32 * (TB_FC / 4));
+      const size_t o = (size_t)(s * TB_FC + fq * 4) * TB_LD + pl;
+      const float4 va = Raw4<QT>::cvt(ra[j]);
+      tile_a[o] = va.x; tile_a[o + TB_LD] = va.y; tile_a[o + 2 * TB_LD] = va.z; tile_a[o + 3 * TB_LD] = va.w;
+      if (tile_b != nullptr) {
+        const float4 vb = Raw4<QT>::cvt(rb[j]);
+        tile_b[o] = vb.x; tile_b[o + TB_LD] = vb.y; tile_b[o + 2 * TB_LD] = vb.z; tile_b[o + 3 * TB_LD] = vb.w;
+      }
+    }
+  }
+}
+
+// tile[(s * 8 + f) * 33 + px] = src[((b*T + s) * HW + px0 + px) * row_stride + col0 + f]   (generic loop: any block size)
 template <typename QT>
 __device__ __forceinline__ void tb_stage(float* tile, const QT* src, size_t row_stride, int b, int T, int HW, int px0, int col0) {
   for (int i = threadIdx.x; i < T * 32 * (TB_FC / 4); i += blockDim.x) {
@@ -330,7 +383,7 @@ __device__ __forceinline__ void tb_pixel_gemm(const float* rows, const float* co
 
 // Row-owner pass.  grid (ceil(HW/32), heads, B), block 256: warp w owns query frames t = w, w+8, ...
 template <int TP, typename QT>
-__global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_q_kernel(TABwdParams p) {
+__global__ void __launch_bounds__(TB_WARPS * 32, (TP <= 24 ? 2 : 1)) attn_temporal_bwd_q_kernel(TABwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) float tb_smem[];
@@ -369,13 +422,37 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_q_kernel(TABw
     float Dt = 0.f;
     for (int f0 = 0; f0 < F; f0 += TB_FC) {
       __syncthreads();
-      tb_stage(ksm, qkv, tok, b, T, HW, px0, C + h * F + f0);
-      tb_stage(vsm, qkv, tok, b, T, HW, px0, 2 * C + h * F + f0);
-      for (int i = lane; i < T * TB_FC; i += 32) {
-        const int s = i / TB_FC, f = i - s * TB_FC;
-        rk[i] = __ldg(p.Rk + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
-        rq[i] = __ldg(p.Rq + (((size_t)(b * T + s) * T + t) * C + h * F + f0 + f));
-        rv[i] = __ldg(p.Rv + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+      if (TP >= 32 && blockDim.x == 256) {  // all loads in flight first: pays for T > 24 (measured: cfg5 10.4 -> 8.8 ms; T = 20 got slower)
+        tb_stage2<(TP * 64 + 255) / 256, QT>(ksm, qkv, tok, C + h * F + f0, vsm, qkv, tok, 2 * C + h * F + f0, b, T, HW, px0);
+      } else {
+        tb_stage(ksm, qkv, tok, b, T, HW, px0, C + h * F + f0);
+        tb_stage(vsm, qkv, tok, b, T, HW, px0, 2 * C + h * F + f0);
+      }
+      if constexpr (TP < 32) {
+        for (int i = lane; i < T * TB_FC; i += 32) {
+          const int s = i / TB_FC, f = i - s * TB_FC;
+          rk[i] = __ldg(p.Rk + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+          rq[i] = __ldg(p.Rq + (((size_t)(b * T + s) * T + t) * C + h * F + f0 + f));
+          rv[i] = __ldg(p.Rv + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+        }
+      } else {
+        constexpr int NR = (TP * TB_FC + 31) / 32;
+        float r1[NR], r2[NR], r3[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          const int i = lane + 32 * j;
+          if (i < T * TB_FC) {
+            const int s = i / TB_FC, f = i - s * TB_FC;
+            r1[j] = __ldg(p.Rk + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+            r2[j] = __ldg(p.Rq + (((size_t)(b * T + s) * T + t) * C + h * F + f0 + f));
+            r3[j] = __ldg(p.Rv + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          const int i = lane + 32 * j;
+          if (i < T * TB_FC) { rk[i] = r1[j]; rq[i] = r2[j]; rv[i] = r3[j]; }
+        }
       }
       float q[TB_FC], dO[TB_FC];
       {
@@ -439,10 +516,28 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_q_kernel(TABw
     // dq and dRk
     for (int f0 = 0; f0 < F; f0 += TB_FC) {
       __syncthreads();
-      tb_stage(ksm, qkv, tok, b, T, HW, px0, C + h * F + f0);
-      for (int i = lane; i < T * TB_FC; i += 32) {
-        const int s = i / TB_FC, f = i - s * TB_FC;
-        rk[i] = __ldg(p.Rk + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+      if (TP >= 32 && blockDim.x == 256) {  // all loads in flight first: pays for T > 24 (measured: cfg5 10.4 -> 8.8 ms; T = 20 got slower)
+        tb_stage2<(TP * 64 + 255) / 256, QT>(ksm, qkv, tok, C + h * F + f0, nullptr, qkv, tok, 0, b, T, HW, px0);
+      } else {
+        tb_stage(ksm, qkv, tok, b, T, HW, px0, C + h * F + f0);
+      }
+      if constexpr (TP < 32) {
+        for (int i = lane; i < T * TB_FC; i += 32) {
+          const int s = i / TB_FC, f = i - s * TB_FC;
+          rk[i] = __ldg(p.Rk + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+        }
+      } else {
+        float r1[(TP * TB_FC + 31) / 32];
+#pragma unroll
+        for (int j = 0; j < (TP * TB_FC + 31) / 32; ++j) {
+          const int i = lane + 32 * j;
+          if (i < T * TB_FC) r1[j] = __ldg(p.Rk + (((size_t)(b * T + t) * T + i / TB_FC) * C + h * F + f0 + (i % TB_FC)));
+        }
+#pragma unroll
+        for (int j = 0; j < (TP * TB_FC + 31) / 32; ++j) {
+          const int i = lane + 32 * j;
+          if (i < T * TB_FC) rk[i] = r1[j];
+        }
       }
       {
         const float4 a = OpType<QT>::load4(qkv + row * tok + h * F + f0), c = OpType<QT>::load4(qkv + row * tok + h * F + f0 + 4);
@@ -473,7 +568,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_q_kernel(TABw
 
 // Column-owner pass.  warp w owns key frames s = w, w+8, ...
 template <int TP, typename QT>
-__global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_kv_kernel(TABwdParams p) {
+__global__ void __launch_bounds__(TB_WARPS * 32, (TP <= 24 ? 2 : 1)) attn_temporal_bwd_kv_kernel(TABwdParams p) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) float tb_smem[];
@@ -509,13 +604,37 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_kv_kernel(TAB
     for (int t = 0; t < TP; ++t) { S[t] = 0.f; dP[t] = 0.f; }
     for (int f0 = 0; f0 < F; f0 += TB_FC) {
       __syncthreads();
-      tb_stage(qsm, qkv, tok, b, T, HW, px0, h * F + f0);
-      tb_stage(dosm, dout, (size_t)C, b, T, HW, px0, h * F + f0);
-      for (int i = lane; i < T * TB_FC; i += 32) {
-        const int t = i / TB_FC, f = i - t * TB_FC;
-        rk[i] = __ldg(p.Rk + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
-        rq[i] = __ldg(p.Rq + (((size_t)(b * T + s) * T + t) * C + h * F + f0 + f));
-        rv[i] = __ldg(p.Rv + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+      if (TP >= 32 && blockDim.x == 256) {  // all loads in flight first: pays for T > 24 (measured: cfg5 10.4 -> 8.8 ms; T = 20 got slower)
+        tb_stage2<(TP * 64 + 255) / 256, QT>(qsm, qkv, tok, h * F + f0, dosm, dout, (size_t)C, h * F + f0, b, T, HW, px0);
+      } else {
+        tb_stage(qsm, qkv, tok, b, T, HW, px0, h * F + f0);
+        tb_stage(dosm, dout, (size_t)C, b, T, HW, px0, h * F + f0);
+      }
+      if constexpr (TP < 32) {
+        for (int i = lane; i < T * TB_FC; i += 32) {
+          const int t = i / TB_FC, f = i - t * TB_FC;
+          rk[i] = __ldg(p.Rk + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+          rq[i] = __ldg(p.Rq + (((size_t)(b * T + s) * T + t) * C + h * F + f0 + f));
+          rv[i] = __ldg(p.Rv + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+        }
+      } else {
+        constexpr int NR = (TP * TB_FC + 31) / 32;
+        float r1[NR], r2[NR], r3[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          const int i = lane + 32 * j;
+          if (i < T * TB_FC) {
+            const int t = i / TB_FC, f = i - t * TB_FC;
+            r1[j] = __ldg(p.Rk + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+            r2[j] = __ldg(p.Rq + (((size_t)(b * T + s) * T + t) * C + h * F + f0 + f));
+            r3[j] = __ldg(p.Rv + (((size_t)(b * T + t) * T + s) * C + h * F + f0 + f));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          const int i = lane + 32 * j;
+          if (i < T * TB_FC) { rk[i] = r1[j]; rq[i] = r2[j]; rv[i] = r3[j]; }
+        }
       }
       float k[TB_FC], v[TB_FC];
       {
@@ -560,8 +679,12 @@ __global__ void __launch_bounds__(TB_WARPS * 32) attn_temporal_bwd_kv_kernel(TAB
     // dk, dv, dRq, dRv
     for (int f0 = 0; f0 < F; f0 += TB_FC) {
       __syncthreads();
-      tb_stage(qsm, qkv, tok, b, T, HW, px0, h * F + f0);
-      tb_stage(dosm, dout, (size_t)C, b, T, HW, px0, h * F + f0);
+      if (TP >= 32 && blockDim.x == 256) {  // all loads in flight first: pays for T > 24 (measured: cfg5 10.4 -> 8.8 ms; T = 20 got slower)
+        tb_stage2<(TP * 64 + 255) / 256, QT>(qsm, qkv, tok, h * F + f0, dosm, dout, (size_t)C, h * F + f0, b, T, HW, px0);
+      } else {
+        tb_stage(qsm, qkv, tok, b, T, HW, px0, h * F + f0);
+        tb_stage(dosm, dout, (size_t)C, b, T, HW, px0, h * F + f0);
+      }
       for (int i = lane; i < T * TB_FC; i += 32) {
         const int t = i / TB_FC, f = i - t * TB_FC;
         rq[i] = __ldg(p.Rq + (((size_t)(b * T + s) * T + t) * C + h * F + f0 + f));

@@ -10,6 +10,7 @@ from improved_diffusion import _native as N_
 CFG = {"cfg2": (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 1, 5),
        "cfg2b8": (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 8, 5),
        "cfg4": (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 8, 20),
+       "cfg5": (dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 2, 40),
        "cfg3": (dict(image_size=128, in_channels=3, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 2, 20)}
 over, B, K = CFG[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
