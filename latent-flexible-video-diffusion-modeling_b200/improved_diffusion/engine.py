@@ -286,9 +286,18 @@ class _DenoiserFn(th.autograd.Function):
             # flat gradient buffer, so the whole hand-over is ONE allreduce (in place, on the plan's buffer) and ONE copy / add —
             # no per-parameter views, AccumulateGrad nodes or zero_grad loops (1.5 ms of host time per step for 390 tensors)
             sync = getattr(ctx.engine.model, "_fdm_grad_sync", None)
-            if sync is not None:
+            if sync is None:
+                sink.receive(P.pgrad)
+            elif not getattr(ctx.engine.model, "_fdm_grad_sync_on", True):  # FlatGradDataParallel.no_sync(): accumulate locally
+                sink.receive(P.pgrad)
+                sink.unsynced = True
+            elif getattr(sink, "unsynced", False):  # first synchronised backward after no_sync(): reduce the accumulated total
+                sink.receive(P.pgrad)
+                sync(sink.flat_g)
+                sink.unsynced = False
+            else:
                 sync(P.pgrad)
-            sink.receive(P.pgrad)
+                sink.receive(P.pgrad)
             return (None,) * 8
         flat = P.pgrad.clone()  # the plan's buffer is reused by the next backward; autograd owns this copy
         sync = getattr(ctx.engine.model, "_fdm_grad_sync", None)

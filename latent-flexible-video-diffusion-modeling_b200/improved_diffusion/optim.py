@@ -75,6 +75,7 @@ class FlatAdamW(th.optim.Optimizer):
                 p.grad = gview  # persistent: the native backward refreshes flat_g, never these tensor objects
             self.anchor = th.zeros(1, device=dev, requires_grad=True)
             self._fresh = True
+            self.unsynced = False  # set by the backward node under FlatGradDataParallel.no_sync()
             model._fdm_flat_sink = self
 
     def receive(self, flat):
@@ -92,6 +93,7 @@ class FlatAdamW(th.optim.Optimizer):
             return super().zero_grad(set_to_none=set_to_none)
         self.flat_g.zero_()  # one memset: gradients that arrive through AccumulateGrad (CPU-style autograd path) add into the views
         self._fresh = True   # the native backward overwrites (copy) on its first hand-over, adds on later ones
+        self.unsynced = False
 
     def ema_params(self, i):
         """Per-parameter views of the i-th EMA copy (same shapes / order as the parameters)."""

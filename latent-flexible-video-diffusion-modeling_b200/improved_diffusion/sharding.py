@@ -11,6 +11,8 @@ Multi-GPU data parallelism for the hot path, one process per GPU u
     parameter gradients in one flat fp32 buffer, so the exchange is ONE NCCL allreduce over that buffer (no per-parameter
     hooks, no bucket copies) issued from inside the autograd node.
 """
+import contextlib
+
 import torch as th
 import torch.distributed as dist
 
@@ -90,6 +92,21 @@ class FlatGradDataParallel(th.nn.Module):
             for p in model.parameters():
                 dist.broadcast(p.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         model._fdm_grad_sync = lambda flat: allreduce_mean_(flat, group)
+        model._fdm_grad_sync_on = True
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Like DDP.no_sync(): backwards inside the context only accumulate locally; the first backward after it allreduces the
+        accumulated gradient once.  Needs the flat-gradient mode (optim.FlatAdamW(..., model=model)), whose flat buffer is what
+        gets reduced; as with DDP, do not mix synchronised and unsynchronised backwards between two zero_grad() calls other than
+        `no_sync ... no_sync, sync`."""
+        if getattr(self.module, "_fdm_flat_sink", None) is None:
+            raise NotImplementedError("FlatGradDataParallel.no_sync() needs optim.FlatAdamW(..., model=model) (flat-gradient mode)")
+        self.module._fdm_grad_sync_on = False
+        try:
+            yield
+        finally:
+            self.module._fdm_grad_sync_on = True
 
     def forward(self, x, **kwargs):
         if not x.is_cuda:

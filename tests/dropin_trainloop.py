@@ -5,6 +5,7 @@ import os
 import sys
 import types
 
+import numpy as np
 import torch as th
 import torch.distributed as dist
 
@@ -49,6 +50,8 @@ loop = train_util.TrainLoop(model=model, diffusion=diffusion, data=data(), batch
                             diffusion_space_kwargs=d["diffusion_space_kwargs"], fp16_scale_growth=1e-3, schedule_sampler=None,
                             weight_decay=0.0, lr_anneal_steps=0, sample_interval=None, pad_with_random_frames=True, max_frames=5,
                             enc_dec_chunk_size=10, args=args)
+th.manual_seed(5)
+np.random.seed(5)
 loop.run_loop()
 changed = sum(int(not th.equal(a, p.detach())) for a, p in zip(before, model.parameters()))
 keys = set().union(*[set(x) for x in logged])
@@ -56,5 +59,33 @@ keys = set().union(*[set(x) for x in logged])
 assert loop.step >= 1 and changed > 50, (loop.step, changed)
 assert {"loss", "mse", "grad_norm", "step"} <= keys, keys
 assert all(th.isfinite(p).all() for p in model.parameters())
+
+# ---- the same two steps through this repo's train_step.NativeTrainStep (host side of the step restated: mask sampling, gather,
+# timestep draw, loss weighting, gradient norm, AdamW, EMA, logging) from the same seeds: identical parameters, EMA and logs
+from improved_diffusion.train_step import NativeTrainStep  # noqa: E402
+
+th.manual_seed(0)
+model2, diffusion2 = create_model_and_diffusion(**d)
+model2.precision = "fp32"
+assert all(th.equal(a, p.detach()) for a, p in zip(before, model2.parameters()))
+stream = data()
+next(stream)  # the reference's constructor takes one batch for visualisation (train_util.py:86-88)
+runner = NativeTrainStep(model2, diffusion2, lr=1e-3, max_frames=5, weight_decay=0.0, ema_rate="0.9999", microbatch=-1,
+                         pad_with_random_frames=True, optimizer="torch")
+th.manual_seed(5)
+np.random.seed(5)
+mine = [runner.run_step(next(stream)[0], next(stream)[0]) for _ in range(loop.step + 1)]
+worst = max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(model.parameters(), model2.parameters()))
+worst_ema = max(float((a - b).abs().max()) for a, b in zip(loop.ema_params[0], runner.ema_params[0]))
+assert worst <= 1e-6 and worst_ema <= 1e-7, (worst, worst_ema)
+ref_logs = [x for x in logged if "loss" in x]
+assert len(ref_logs) == len(mine), (len(ref_logs), len(mine))
+for r, m in zip(ref_logs, mine):
+    for k, v in r.items():
+        if k in m and k not in ("step", "samples"):
+            assert abs(float(v) - m[k]) <= 1e-5 * max(1.0, abs(m[k])), (k, v, m[k])
+    assert {k for k in r if k.startswith(("loss", "mse", "eval-mse", "grad_norm"))} <= set(m), (sorted(r), sorted(m))
+    assert int(r["step"]) == m["step"] and int(r["samples"]) == m["samples"]
+print("TRAINSTEP_OK worst param diff", worst, "ema", worst_ema, "keys", sorted(mine[0])[:8])
 print("DROPIN_OK steps", loop.step + 1, "params changed", changed, "logged", sorted(keys)[:6])
 dist.destroy_process_group()

@@ -332,3 +332,41 @@ def test_torch_training_path_is_opt_in(monkeypatch):
     monkeypatch.setenv("FDM_ALLOW_TORCH_TRAIN", "1")
     out, _ = model(x, **kw)
     assert out.shape == x.shape and out.requires_grad
+
+
+def test_mask_sampler_matches_reference_goldens():
+    """train_step.sample_all_masks / prepare_training_batch / sample_some_indices against outputs of the reference's TrainLoop
+    methods (tests/golden/train_masks.json, made by tests/golden/make_train_masks.py from the live reference): same masks, frame
+    indices, gathered frames AND the same RNG positions afterwards (torch + numpy), bit for bit."""
+    import json
+    import numpy as np
+    from improved_diffusion import train_step as ts
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "train_masks.json")))
+    for c in gold["cases"]:
+        B, T = c["B"], c["T"]
+        b1 = (1000 * torch.arange(B).view(B, 1) + torch.arange(T).view(1, T)).float().view(B, T, 1, 1, 1)
+        b2 = -b1 - 1
+        torch.manual_seed(c["seed"])
+        np.random.seed(c["seed"])
+        batch, fi, obs, lat = ts.sample_all_masks(b1, b2 if c["second"] else None, max_frames=c["max_frames"],
+                                                  pad_with_random_frames=c["pad"])
+        tail = [float(torch.rand(())), float(np.random.rand())]
+        assert fi.tolist() == c["frame_indices"], c["seed"]
+        assert batch.flatten(1).long().tolist() == c["batch"], c["seed"]
+        assert obs.flatten(1).long().tolist() == c["obs"] and lat.flatten(1).long().tolist() == c["latent"], c["seed"]
+        assert obs.shape == (B, len(c["obs"][0]), 1, 1, 1) and obs.dtype == b1.dtype and fi.dtype == torch.int64
+        assert tail == c["tail"], c["seed"]
+    torch.manual_seed(123)
+    np.random.seed(123)
+    draws = [ts.sample_some_indices(n, T) for n, T in [(5, 12), (20, 300), (40, 41), (3, 7), (20, 36)] for _ in range(200)]
+    assert draws == gold["draws"]
+    # gather=False returns the full-length masks; set_masks overrides the first rows
+    torch.manual_seed(0)
+    np.random.seed(0)
+    b1 = torch.zeros(3, 12, 1, 2, 2)
+    preset = {"obs": torch.ones(1, 12, 1, 1, 1), "latent": torch.zeros(1, 12, 1, 1, 1)}
+    same, obs, lat = ts.sample_all_masks(b1, max_frames=5, gather=False, set_masks=preset)
+    assert same is b1 and obs.shape == (3, 12, 1, 1, 1) and float(obs[0].sum()) == 12 and float(lat[0].sum()) == 0
+    assert float((obs[1:] + lat[1:]).flatten(1).sum(1).max()) <= 5
+    with pytest.raises(ValueError):
+        ts.sample_all_masks(torch.zeros(1, 3, 1, 1, 1), max_frames=5)
