@@ -247,23 +247,52 @@ class NativeTrainStep:
                     th._foreach_add_(ema, [p.detach() for p in self.params], alpha=1 - rate)
         return gsq
 
-    def run_step(self, batch1, batch2=None):
+    def run_step(self, batch1, batch2=None, defer=False):
+        """One optimizer step.  Returns this step's log dict; with `defer=True` the read is left in flight (asynchronous copy
+        into pinned memory) and the PREVIOUS step's dict is returned instead (None on the first call; `flush()` returns the last
+        one), so that the host side of step i+1 — mask sampling, gather, upload, launches — overlaps the GPU work of step i
+        instead of waiting for it as every `.item()` of the reference's logging does."""
         logs = self.forward_backward(batch1, batch2)
         gsq = self.optimize()
-        out = self._read_logs(logs, gsq)
-        out.update(step=self.step, samples=(self.step + 1) * batch1.shape[0] * self.world, lr=self.opt.param_groups[0]["lr"])
+        extra = dict(step=self.step, samples=(self.step + 1) * batch1.shape[0] * self.world, lr=self.opt.param_groups[0]["lr"])
         self.step += 1
+        previous = self.flush()
+        self._pending = self._start_read(logs, gsq, extra)
+        return previous if defer else self.flush()
+
+    def flush(self):
+        """Finish the log read left in flight by `run_step(..., defer=True)`; None when there is none."""
+        pending, self._pending = getattr(self, "_pending", None), None
+        if pending is None:
+            return None
+        host, event, keys, sizes, extra = pending
+        if event is not None:
+            event.synchronize()
+        out = self._reduce_logs(host.numpy().astype(np.float64), keys, sizes)
+        out.update(extra)
         return out
 
-    def _read_logs(self, logs, gsq):
+    def _start_read(self, logs, gsq, extra):
         """log_loss_dict (train_util.py:529-535) + _log_grad_norm with ONE device->host read: [t | loss terms ...] per microbatch
         and the squared gradient norm are packed into one tensor; means and per-quartile means are formed on the host."""
         keys = list(logs[0][1].keys())
         packed = th.cat([th.cat([t.float()] + [terms[k].float() for k in keys]) for t, terms in logs] + [gsq.float().reshape(1)])
-        host = packed.cpu().numpy().astype(np.float64)
+        sizes = [t.shape[0] for t, _ in logs]
+        if packed.is_cuda:
+            slot = self._log_slot = 1 - getattr(self, "_log_slot", 0)  # two pinned buffers: one in flight, one being read
+            key = ("log", slot, packed.numel())
+            if key not in self._staging:
+                self._staging[key] = [th.empty(packed.numel(), dtype=th.float32, pin_memory=True), None]
+            host = self._staging[key][0]
+            host.copy_(packed, non_blocking=True)
+            event = th.cuda.Event()
+            event.record()
+            return host, event, keys, sizes, extra
+        return packed, None, keys, sizes, extra
+
+    def _reduce_logs(self, host, keys, sizes):
         out, sums, off = {}, {}, 0
-        for t, _ in logs:
-            n = t.shape[0]
+        for n in sizes:
             ts = host[off:off + n]
             for j, k in enumerate(keys):
                 vals = host[off + (j + 1) * n: off + (j + 2) * n]

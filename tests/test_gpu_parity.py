@@ -518,3 +518,70 @@ def test_native_training_trajectory_matches_autograd(monkeypatch):
     worst = max(O.rel_l2(p.detach().cpu(), q.detach().cpu()) for p, q in zip(nat.parameters(), ref.parameters()))
     print("trajectory: worst weight rel-L2 after 10 steps %.2e" % worst)
     assert worst <= 2e-4, worst
+
+
+def _video_stream(seed, B=2, T=12):
+    g = torch.Generator().manual_seed(seed)
+    while True:
+        yield torch.randn(B, T, 4, 32, 32, generator=g).clamp(-1, 1)
+
+
+def test_native_train_step_matches_torch_stack(monkeypatch):
+    """train_step.NativeTrainStep (host side of TrainLoop.run_step; on CPU it is bit-identical to the reference's TrainLoop,
+    tests/dropin_trainloop.py) over the NATIVE stack — host batch through the pinned staging upload, native forward/backward, flat
+    gradient norm, FlatAdamW+EMA, one log read — against the same class over torch.autograd + torch.optim.AdamW from the same
+    seeds: same random draws, same logged losses / quartiles / gradient norm for three steps.  (Parameters themselves are not
+    compared: Adam turns the rounding-noise gradients of the analytically gradient-free biases into +-lr steps on both sides.)"""
+    import numpy as np
+    from improved_diffusion.train_step import NativeTrainStep
+    from improved_diffusion.sharding import FlatGradDataParallel
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    over = dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32)
+
+    def run(optimizer, engine, microbatch=-1, wrap=False, steps=3, defer=False):
+        model, diffusion, _, _ = build(over, "fp32")
+        model.train()
+        monkeypatch.setenv("FDM_TRAIN_ENGINE", engine)
+        runner = NativeTrainStep(model, diffusion, lr=1e-4, max_frames=5, ema_rate="0.999,0.9999", microbatch=microbatch,
+                                 optimizer=optimizer, lr_anneal_steps=100)
+        if wrap:
+            runner.net = FlatGradDataParallel(model)
+        torch.manual_seed(7)
+        np.random.seed(7)
+        data = _video_stream(3)
+        logs = [runner.run_step(next(data), next(data), defer=defer) for _ in range(steps)]
+        if defer:  # every call returned the previous step's log; the last one is still in flight
+            assert logs[0] is None
+            logs = logs[1:] + [runner.flush()]
+            assert runner.flush() is None
+        tail = (float(torch.rand(())), float(np.random.rand()))
+        return logs, tail, model, runner
+
+    nat, tail_n, model_n, runner_n = run("flat", "native")
+    ref, tail_r, _, _ = run("torch", "autograd")
+    assert tail_n == tail_r  # the same random draws were consumed
+    for a, b in zip(nat, ref):
+        assert set(a) == set(b), (sorted(a), sorted(b))
+        for k in a:
+            assert abs(a[k] - b[k]) <= 3e-4 * max(abs(b[k]), 1e-6), (k, a[k], b[k])
+    assert nat[2]["lr"] == pytest.approx(1e-4 * (1 - 2 / 100)) and nat[2]["step"] == 2 and nat[2]["samples"] == 6
+    assert all(torch.isfinite(e).all() for e in runner_n.ema_params[1])
+    assert not torch.equal(runner_n.ema_params[0][0], next(model_n.parameters()).detach())
+    late = run("flat", "native", defer=True)[0]  # deferred log reads: the same records, one step later
+    for a, b in zip(nat, late):
+        assert set(a) == set(b) and a["step"] == b["step"]
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-5 * max(abs(b[k]), 1e-6), (k, a[k], b[k])
+    # gradient accumulation over microbatches, with and without the data-parallel wrapper's no_sync() (world size 1: the
+    # allreduce is the identity, the deferred-synchronisation bookkeeping is what runs): the same numbers
+    acc, _, model_a, _ = run("flat", "native", microbatch=1, steps=2)
+    accw, _, model_w, runner_w = run("flat", "native", microbatch=1, wrap=True, steps=2)
+    assert runner_w.opt.unsynced is False
+    for a, b in zip(acc, accw):  # not bit-identical: the backward's fp32 atomics (RPE tables, split reductions) reorder run to run
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-5 * max(abs(b[k]), 1e-6), (k, a[k], b[k])
+    refacc, _, _, _ = run("torch", "autograd", microbatch=1, steps=2)
+    for a, b in zip(acc, refacc):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 3e-4 * max(abs(b[k]), 1e-6), (k, a[k], b[k])

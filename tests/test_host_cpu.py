@@ -370,3 +370,41 @@ def test_mask_sampler_matches_reference_goldens():
     assert float((obs[1:] + lat[1:]).flatten(1).sum(1).max()) <= 5
     with pytest.raises(ValueError):
         ts.sample_all_masks(torch.zeros(1, 3, 1, 1, 1), max_frames=5)
+
+
+def test_train_step_host_logic_cpu():
+    """NativeTrainStep on CPU: the flat optimizer refuses (CUDA kernels only, no fallback); the explicit torch arm runs the host
+    logic — microbatches, loss weighting, LR annealing, EMA, deferred log reads — and its records are self-consistent.
+    (Parity of this arm with the reference's TrainLoop: tests/dropin_trainloop.py.)"""
+    import numpy as np
+    from improved_diffusion.train_step import NativeTrainStep, UniformTimesteps
+    model, diffusion = build(dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32))
+    with pytest.raises(RuntimeError):
+        NativeTrainStep(model, diffusion, lr=1e-3, max_frames=5)
+    with pytest.raises(ValueError):
+        NativeTrainStep(model, diffusion, lr=1e-3, max_frames=5, optimizer="sgd")
+    np.random.seed(0)
+    t, w = UniformTimesteps(diffusion).sample(64, "cpu")
+    assert t.dtype == torch.int64 and int(t.min()) >= 0 and int(t.max()) < 32 and torch.all(w == 1) and w.dtype == torch.float32
+    runner = NativeTrainStep(model, diffusion, lr=1e-3, max_frames=5, optimizer="torch", microbatch=1, lr_anneal_steps=10,
+                             ema_rate="0.5")
+    before = [p.detach().clone() for p in model.parameters()]
+    torch.manual_seed(1)
+    np.random.seed(1)
+    g = torch.Generator().manual_seed(2)
+    vids = lambda: torch.randn(2, 12, 4, 32, 32, generator=g).clamp(-1, 1)
+    first = runner.run_step(vids(), vids(), defer=True)
+    second = runner.run_step(vids(), vids(), defer=True)
+    last = runner.flush()
+    assert first is None and second["step"] == 0 and last["step"] == 1 and runner.flush() is None
+    assert second["lr"] == pytest.approx(1e-3) and last["lr"] == pytest.approx(1e-3 * 0.9) and last["samples"] == 4
+    for rec in (second, last):
+        quart = [k for k in rec if k.startswith("loss_q")]
+        assert quart and rec["grad_norm"] > 0 and np.isfinite(rec["loss"])
+        assert min(rec[k] for k in quart) - 1e-9 <= rec["loss"] <= max(rec[k] for k in quart) + 1e-9
+        assert rec["loss"] == pytest.approx(rec["mse"])
+    moved = [i for i, (a, p) in enumerate(zip(before, model.parameters())) if not torch.equal(a, p.detach())]
+    assert len(moved) > 50
+    i = moved[0]  # EMA with rate 0.5 after two steps sits strictly between the start and the current value
+    e, p0, p2 = runner.ema_params[0][i], before[i], list(model.parameters())[i].detach()
+    assert not torch.equal(e, p0) and not torch.equal(e, p2)
