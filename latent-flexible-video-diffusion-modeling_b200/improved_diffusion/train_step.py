@@ -306,6 +306,63 @@ class NativeTrainStep:
         return out
 
 
+    # ---- checkpoint files in the reference's format (train_util.py:373-402 save, :137-173 resume)
+    def save(self, directory, config=None):
+        """Writes what TrainLoop.save() writes, under the same names: `model{step:06d}.pt` and `ema_{rate}_{step:06d}.pt`, each
+        {"state_dict", "config", "step"}, and `opt{step:06d}.pt` (torch.optim.AdamW state_dict layout — FlatAdamW's is the same).
+        `step` is the index of the last completed step, as upstream numbers its files.  Tensors are written as compact CPU copies
+        (the parameters / moments / EMA copies are views of flat device buffers here).  Rank 0 writes; returns the model file's path."""
+        import os
+        step = max(self.step - 1, 0)
+        if self.world > 1 and dist.get_rank() != 0:
+            dist.barrier()
+            return os.path.join(directory, f"model{step:06d}.pt")
+        os.makedirs(directory, exist_ok=True)
+        compact = lambda t: t.detach().cpu().clone()
+        names = [n for n, _ in self.model.named_parameters()]
+
+        def state_dict_of(params):
+            sd = {k: compact(v) for k, v in self.model.state_dict().items()}
+            sd.update({n: compact(p) for n, p in zip(names, params)})
+            return sd
+
+        for rate, params in [(0, self.params)] + list(zip(self.ema_rate, self.ema_params)):
+            name = f"model{step:06d}.pt" if not rate else f"ema_{rate}_{step:06d}.pt"
+            th.save({"state_dict": state_dict_of(params), "config": dict(config or {}), "step": step}, os.path.join(directory, name))
+        osd = self.opt.state_dict()
+        osd = {"state": {i: {k: (compact(v) if th.is_tensor(v) else v) for k, v in st.items()} for i, st in osd["state"].items()},
+               "param_groups": osd["param_groups"]}
+        th.save(osd, os.path.join(directory, f"opt{step:06d}.pt"))
+        if self.world > 1:
+            dist.barrier()
+        return os.path.join(directory, f"model{step:06d}.pt")
+
+    def resume(self, directory):
+        """Loads the newest `model*.pt` of `directory` (find_resume_checkpoint, train_util.py:508-517), the matching EMA files
+        and optimizer state when present, and continues from that file's step number, as TrainLoop.__init__ does.  Files written
+        by the reference's TrainLoop and by `save()` are interchangeable.  Returns the step, or None when there is nothing to resume."""
+        import glob
+        import os
+        found = {int(os.path.basename(f)[5:-3]): f for f in glob.glob(os.path.join(directory, "model*.pt"))}
+        if not found:
+            return None
+        step = max(found)
+        dev = self.device
+        self.model.load_state_dict(th.load(found[step], map_location=dev)["state_dict"])
+        names = [n for n, _ in self.model.named_parameters()]
+        with th.no_grad():
+            for rate, ema in zip(self.ema_rate, self.ema_params):
+                path = os.path.join(directory, f"ema_{rate}_{step:06d}.pt")
+                src = th.load(path, map_location=dev)["state_dict"] if os.path.exists(path) else dict(zip(names, self.params))
+                for n, e in zip(names, ema):
+                    e.copy_(src[n])
+        path = os.path.join(directory, f"opt{step:06d}.pt")
+        if os.path.exists(path):
+            self.opt.load_state_dict(th.load(path, map_location=dev))
+        self.step = step
+        return step
+
+
 class _null:
     def __enter__(self):
         return self

@@ -42,7 +42,8 @@ def data():
         yield th.randn(2, 12, 4, 32, 32, generator=g).clamp(-1, 1), {}
 
 
-train_util.TrainLoop.save = lambda self: None  # checkpoint I/O is out of scope here
+real_save = train_util.TrainLoop.save
+train_util.TrainLoop.save = lambda self: None  # no checkpoint files during the training run (checked separately below)
 args = types.SimpleNamespace(resume_id="", T=12)
 before = [p.detach().clone() for p in model.parameters()]
 loop = train_util.TrainLoop(model=model, diffusion=diffusion, data=data(), batch_size=2, microbatch=-1, lr=1e-3, ema_rate="0.9999",
@@ -87,5 +88,43 @@ for r, m in zip(ref_logs, mine):
     assert {k for k in r if k.startswith(("loss", "mse", "eval-mse", "grad_norm"))} <= set(m), (sorted(r), sorted(m))
     assert int(r["step"]) == m["step"] and int(r["samples"]) == m["samples"]
 print("TRAINSTEP_OK worst param diff", worst, "ema", worst_ema, "keys", sorted(mine[0])[:8])
+
+# ---- checkpoint files: NativeTrainStep.save() -> the reference's TrainLoop resumes from them (its own _load_and_sync_parameters,
+# _load_optimizer_state, _load_ema_parameters), and the reference's TrainLoop.save() -> NativeTrainStep.resume()
+import tempfile  # noqa: E402
+
+work = tempfile.mkdtemp()
+os.chdir(work)
+os.makedirs("checkpoints")
+saved = runner.save(os.path.join("checkpoints", "mine"), config={"T": 12, "max_frames": 5})
+assert os.path.basename(saved) == "model000001.pt" and sorted(os.listdir("checkpoints/mine")) == [
+    "ema_0.9999_000001.pt", "model000001.pt", "opt000001.pt"]
+th.manual_seed(0)
+model3, diffusion3 = create_model_and_diffusion(**d)
+loop3 = train_util.TrainLoop(model=model3, diffusion=diffusion3, data=data(), batch_size=2, microbatch=-1, lr=1e-3, ema_rate="0.9999",
+                             log_interval=1, save_interval=10 ** 9, resume_checkpoint="", use_fp16=False,
+                             diffusion_space_kwargs=d["diffusion_space_kwargs"], fp16_scale_growth=1e-3, schedule_sampler=None,
+                             weight_decay=0.0, lr_anneal_steps=0, sample_interval=None, pad_with_random_frames=True, max_frames=5,
+                             enc_dec_chunk_size=10, args=types.SimpleNamespace(resume_id="mine", T=12))
+assert loop3.step == 1
+assert all(th.equal(a.detach(), b.detach()) for a, b in zip(model3.parameters(), model2.parameters()))
+assert all(th.equal(a.detach(), b) for a, b in zip(loop3.ema_params[0], runner.ema_params[0]))
+for pa, pb in zip(loop3.opt.param_groups[0]["params"], runner.opt.param_groups[0]["params"]):
+    sa, sb = loop3.opt.state[pa], runner.opt.state[pb]
+    assert th.equal(sa["exp_avg"], sb["exp_avg"]) and th.equal(sa["exp_avg_sq"], sb["exp_avg_sq"]) and float(sa["step"]) == float(sb["step"])
+train_util.TrainLoop.save = real_save  # the real one from here on (it was stubbed out for the training run above)
+loop.args = types.SimpleNamespace(resume_id="theirs", T=12)
+loop.step = 1
+loop.save()
+th.manual_seed(0)
+model4, diffusion4 = create_model_and_diffusion(**d)
+runner4 = NativeTrainStep(model4, diffusion4, lr=1e-3, max_frames=5, ema_rate="0.9999", optimizer="torch")
+assert runner4.resume(os.path.join("checkpoints", "nothing-here")) is None
+assert runner4.resume(os.path.join("checkpoints", "theirs")) == 1 and runner4.step == 1
+assert all(th.equal(a.detach(), b.detach()) for a, b in zip(model4.parameters(), model.parameters()))
+assert all(th.equal(a, b.detach()) for a, b in zip(runner4.ema_params[0], loop.ema_params[0]))
+for pa, pb in zip(runner4.opt.param_groups[0]["params"], loop.opt.param_groups[0]["params"]):
+    assert th.equal(runner4.opt.state[pa]["exp_avg_sq"], loop.opt.state[pb]["exp_avg_sq"])
+print("CHECKPOINT_OK both directions")
 print("DROPIN_OK steps", loop.step + 1, "params changed", changed, "logged", sorted(keys)[:6])
 dist.destroy_process_group()

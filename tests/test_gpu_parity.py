@@ -526,7 +526,7 @@ def _video_stream(seed, B=2, T=12):
         yield torch.randn(B, T, 4, 32, 32, generator=g).clamp(-1, 1)
 
 
-def test_native_train_step_matches_torch_stack(monkeypatch):
+def test_native_train_step_matches_torch_stack(monkeypatch, tmp_path):
     """train_step.NativeTrainStep (host side of TrainLoop.run_step; on CPU it is bit-identical to the reference's TrainLoop,
     tests/dropin_trainloop.py) over the NATIVE stack — host batch through the pinned staging upload, native forward/backward, flat
     gradient norm, FlatAdamW+EMA, one log read — against the same class over torch.autograd + torch.optim.AdamW from the same
@@ -585,3 +585,17 @@ def test_native_train_step_matches_torch_stack(monkeypatch):
     for a, b in zip(acc, refacc):
         for k in a:
             assert abs(a[k] - b[k]) <= 3e-4 * max(abs(b[k]), 1e-6), (k, a[k], b[k])
+    # checkpoint round trip around the flat buffers: compact files in the reference's layout, identical state after resume()
+    path = runner_n.save(str(tmp_path), config={})
+    ck = torch.load(path)
+    assert list(ck["state_dict"]) == list(model_n.state_dict()) and ck["step"] == 2
+    assert all(v.device.type == "cpu" and v.untyped_storage().nbytes() == v.numel() * 4 for v in ck["state_dict"].values())
+    model_b = build(over, "fp32", seed=5)[0]
+    model_b.train()
+    runner_b = NativeTrainStep(model_b, runner_n.diffusion, lr=1e-4, max_frames=5, ema_rate="0.999,0.9999")
+    assert runner_b.resume(str(tmp_path)) == 2
+    for name in ("flat_p", "flat_m", "flat_v"):
+        assert torch.equal(getattr(runner_b.opt, name), getattr(runner_n.opt, name)), name
+    assert all(torch.equal(a, b) for a, b in zip(runner_b.opt.flat_ema, runner_n.opt.flat_ema))
+    assert runner_b.opt._step == runner_n.opt._step == 3
+    assert next(model_b.parameters()).data_ptr() == runner_b.opt.flat_p.data_ptr()  # still views of the flat buffer

@@ -372,7 +372,7 @@ def test_mask_sampler_matches_reference_goldens():
         ts.sample_all_masks(torch.zeros(1, 3, 1, 1, 1), max_frames=5)
 
 
-def test_train_step_host_logic_cpu():
+def test_train_step_host_logic_cpu(tmp_path):
     """NativeTrainStep on CPU: the flat optimizer refuses (CUDA kernels only, no fallback); the explicit torch arm runs the host
     logic — microbatches, loss weighting, LR annealing, EMA, deferred log reads — and its records are self-consistent.
     (Parity of this arm with the reference's TrainLoop: tests/dropin_trainloop.py.)"""
@@ -408,3 +408,15 @@ def test_train_step_host_logic_cpu():
     i = moved[0]  # EMA with rate 0.5 after two steps sits strictly between the start and the current value
     e, p0, p2 = runner.ema_params[0][i], before[i], list(model.parameters())[i].detach()
     assert not torch.equal(e, p0) and not torch.equal(e, p2)
+    # checkpoint files in the reference's layout (names, keys), and back
+    path = runner.save(str(tmp_path), config={"max_frames": 5})
+    assert sorted(os.listdir(tmp_path)) == ["ema_0.5_000001.pt", "model000001.pt", "opt000001.pt"]
+    ck = torch.load(path)
+    assert set(ck) == {"state_dict", "config", "step"} and ck["step"] == 1 and list(ck["state_dict"]) == list(model.state_dict())
+    model_b, diffusion_b = build(dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32))
+    runner_b = NativeTrainStep(model_b, diffusion_b, lr=1e-3, max_frames=5, optimizer="torch", ema_rate="0.5")
+    assert runner_b.resume(str(tmp_path)) == 1
+    assert all(torch.equal(a.detach(), b.detach()) for a, b in zip(model.parameters(), model_b.parameters()))
+    assert all(torch.equal(a, b) for a, b in zip(runner.ema_params[0], runner_b.ema_params[0]))
+    sa, sb = runner.opt.state_dict()["state"], runner_b.opt.state_dict()["state"]
+    assert all(torch.equal(sa[i]["exp_avg"], sb[i]["exp_avg"]) and float(sa[i]["step"]) == float(sb[i]["step"]) for i in sa)
