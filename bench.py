@@ -287,9 +287,45 @@ def bench_train(dev, world, precision, workload="cfg2-train", warmup=3):
            "path": "native: forward + backward kernel schedules of libfdm_sm100.so behind one autograd node (conv dgrad and wgrad on "
                    "tcgen05, GroupNorm / attention / RPENet backward kernels); n_gpus > 1: ONE NCCL allreduce over the flat gradient "
                    "buffer per step (sharding.FlatGradDataParallel; FDM_DDP=torch selects torch DDP as in train_util.py:118-125)"}
-    del opt, net, model
+    del opt, net
+    if world == 1:
+        try:
+            out["e2e"] = _train_e2e(model, diffusion, over, B, K, steps)
+        except Exception as ex:  # the device-resident number above stands on its own; say what went wrong instead of hiding it
+            out["e2e"] = {"error": repr(ex)[:300]}
+    del model
     th.cuda.empty_cache()
     return out
+
+
+def _train_e2e(model, diffusion, over, B, K, steps):
+    """The same training step end to end through train_step.NativeTrainStep with HOST video batches (3K frames each): per step
+    mask sampling (the reference's draw order), frame gather, pinned upload, native forward + backward, gradient norm, FlatAdamW +
+    EMA, and one device->host read of the logged scalars (left in flight: `defer=True`).  Wall clock around the loop."""
+    import numpy as np
+    from improved_diffusion.train_step import NativeTrainStep
+    os.environ["FDM_TRAIN_ENGINE"] = "native"
+    runner = NativeTrainStep(model, diffusion, lr=1e-4, max_frames=K, ema_rate="0.9999")
+    C, S, T = over["in_channels"], over["image_size"], 3 * K
+    g = th.Generator().manual_seed(5)
+    pool = [th.randn(B, T, C, S, S, generator=g).clamp(-1, 1) for _ in range(4)]
+    th.manual_seed(6)
+    np.random.seed(6)
+    for i in range(3):
+        runner.run_step(pool[i % 4], pool[(i + 1) % 4], defer=True)
+    runner.flush()
+    th.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        runner.run_step(pool[i % 4], pool[(i + 1) % 4], defer=True)
+    rec = runner.flush()
+    th.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    assert np.isfinite(rec["loss"]) and np.isfinite(rec["grad_norm"]), rec
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+            "h2d_bytes_per_step": B * K * (C * S * S * 4 + 8 + 4 + 4), "d2h_bytes_per_step": (4 * B + 1) * 4,
+            "what": f"NativeTrainStep.run_step on host batches [B={B}, T={T}, {C}, {S}, {S}] fp32 (masks, gather, upload, fwd, bwd, "
+                    "grad norm, AdamW+EMA, log read)"}
 
 
 def main():
