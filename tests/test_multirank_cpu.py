@@ -107,12 +107,34 @@ def _worker(rank, world, port, what, out_dir):
             g = torch.full((4,), float(rank))
             m._fdm_grad_sync(g)
             assert torch.allclose(g, torch.full((4,), (world - 1) / 2))
+        elif what == "trainstep":
+            # train_step.NativeTrainStep (host side of TrainLoop.run_step) under DDP, torch arm: per-rank data and masks, two
+            # microbatches per step (DDP.no_sync() on the first, as train_util.py:311-315), identical weights on both ranks after
+            import numpy as np
+            from improved_diffusion.train_step import NativeTrainStep
+            over = dict(SMALL, timestep_respacing="")
+            model, diffusion = _build(over)
+            model.precision = "fp32"
+            runner = NativeTrainStep(model, diffusion, lr=1e-3, max_frames=4, optimizer="torch", microbatch=1, net=sharding.wrap_ddp(model))
+            torch.manual_seed(100 + rank)
+            np.random.seed(100 + rank)
+            g = torch.Generator().manual_seed(200 + rank)
+            recs = [runner.run_step(torch.randn(2, 9, 4, 32, 32, generator=g).clamp(-1, 1),
+                                    torch.randn(2, 9, 4, 32, 32, generator=g).clamp(-1, 1)) for _ in range(2)]
+            assert recs[1]["samples"] == 2 * 2 * world and recs[1]["step"] == 1 and recs[0]["grad_norm"] > 0
+            flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+            both = [torch.zeros_like(flat) for _ in range(world)]
+            dist.all_gather(both, flat)
+            assert torch.equal(both[0], both[1]), "ranks diverged: the gradient exchange of the microbatched step is broken"
+            losses = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(losses, torch.tensor([recs[0]["loss"]], dtype=torch.float64))
+            assert float(losses[0]) != float(losses[1])  # different data per rank
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("what", ["sample", "train", "flat"])
+@pytest.mark.parametrize("what", ["sample", "train", "flat", "trainstep"])
 def test_two_ranks_gloo(tmp_path, what):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, what, str(tmp_path)), nprocs=2, join=True)
