@@ -22,7 +22,10 @@ def main():
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     over, B, K, T = CFG[name]
     out = {"workload": f"{name}: B={B} videos of {T} frames on the host, max_frames={K}", "steps": steps}
-    for arm, optimizer, engine in (("native", "flat", "native"), ("torch", "torch", "autograd")):
+    arms = (("native", "flat", "native"), ("torch", "torch", "autograd"))
+    if os.environ.get("FDM_TSB_ARMS") == "native":
+        arms = arms[:1]
+    for arm, optimizer, engine in arms:
         os.environ["FDM_TRAIN_ENGINE"] = engine
         os.environ["FDM_ALLOW_TORCH_TRAIN"] = "1"
         d = model_and_diffusion_defaults()
@@ -37,6 +40,8 @@ def main():
         g = torch.Generator().manual_seed(2)
         C, S = over["in_channels"], over["image_size"]
         pool = [torch.randn(B, T, C, S, S, generator=g).clamp(-1, 1) for _ in range(4)]
+        if os.environ.get("FDM_TSB_DEVICE_POOL") == "1":  # videos already on the device: gather there, no upload
+            pool = [v.cuda() for v in pool]
         n_arm = steps if arm == "native" else max(5, steps // 3)
         for i in range(5):
             runner.run_step(pool[i % 4], pool[(i + 1) % 4])
@@ -63,7 +68,8 @@ def main():
                     "loss": log["loss"], "grad_norm": log["grad_norm"]}
         del runner, model
         torch.cuda.empty_cache()
-    out["speedup"] = round(out["torch"]["ms_per_step"] / out["native"]["ms_per_step"], 2)
+    if "torch" in out:
+        out["speedup"] = round(out["torch"]["ms_per_step"] / out["native"]["ms_per_step"], 2)
     print(json.dumps(out))
 
 
