@@ -180,6 +180,7 @@ class NativeTrainStep:
         self.flat = optimizer == "flat"
         self.params = params
         self._staging = {}
+        self._copy_stream = None
 
     # ---- forward_backward (train_util.py:280-333)
     def forward_backward(self, batch1, batch2=None):
@@ -222,9 +223,18 @@ class NativeTrainStep:
         if busy is not None:
             busy.synchronize()  # the previous upload from this buffer (earlier microbatch) must have left the host
         buf.copy_(x)
-        y = buf.to(dev, non_blocking=True)
-        self._staging[key][1] = th.cuda.Event()
-        self._staging[key][1].record()
+        # the copy runs on its own stream so that, with deferred log reads, the upload of step i+1 overlaps the kernels of step i
+        # (on the compute stream it would queue behind them and then delay the forward by its own duration)
+        if self._copy_stream is None:
+            self._copy_stream = th.cuda.Stream(dev)
+        main = th.cuda.current_stream(dev)
+        done = th.cuda.Event()
+        with th.cuda.stream(self._copy_stream):
+            y = buf.to(dev, non_blocking=True)
+            done.record(self._copy_stream)
+        main.wait_event(done)
+        y.record_stream(main)
+        self._staging[key][1] = done
         return y
 
     def grad_norm_sq(self):
