@@ -233,17 +233,22 @@ int fdm_cast(const fdm_cast_args* a, void* stream);
  *     {sqrt_recip_acp, sqrt_recipm1_acp, post_coef1, post_coef2, exp(0.5*log_var)*[t!=0], 0,0,0}
  *   xs = a*x - b*eps; clip; mean = c1*xs + c2*x; sample = mean + sigma*noise
  *   x, eps, noise, sample, pred_xstart: [B][per_video] fp32 (any layout, elementwise); t: [B] int64
+ *   sample may alias x (in-place update of the sampler state).
+ *   noise == NULL (opt-in perf mode, replaces th.randn_like of gaussian_diffusion.py:396): the noise is drawn inside the
+ *   kernel — Philox4x32-10 + Box-Muller, key = philox[0] (seed), counter = (element quad, t[b], philox[1] = stage nonce);
+ *   philox: DEVICE uint64[2], read at run time so a captured CUDA graph sees new seeds / nonces.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* x;
   const float* eps;
-  const float* noise;
+  const float* noise; /* or NULL with philox != NULL */
   const float* coef;
   const int64_t* t;
   float* sample;
   float* pred_xstart; /* or NULL */
   int64_t per_video;
   int32_t B, clip;
+  const uint64_t* philox; /* or NULL */
 } fdm_ddpm_step_args; /* which = 10 */
 int fdm_ddpm_step(const fdm_ddpm_step_args* a, void* stream);
 

@@ -93,18 +93,58 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restric
 }
 
 // ---------------- A16-A18 fused DDPM posterior update -------------------------------------------------
-__global__ void ddpm_step_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
+// Philox4x32-10 (Salmon et al. 2011; the counter-based generator cuRAND / PyTorch use): 4 x 32 random bits per (counter, key)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// two standard normals from two 32-bit words (Box-Muller; u1 in (0,1], precise logf / sincosf)
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (a + 1) / 2^32; a = 2^32-1 rounds to 1.0 -> log = 0
+  const float u2 = (float)b * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
+// x and sample may be the SAME buffer (the graph sampler updates x_t in place): every element is read and then written by
+// the same thread, and neither pointer is declared __restrict__ (no ld.global.nc for x).
+// noise == nullptr: the step's Gaussian noise is generated in the kernel (perf mode: 12 instead of 16 bytes per element and
+// no separate normal_() launch): Philox4x32-10 keyed by philox[0] (seed), counter = (element quad index, t[b], philox[1] (stage
+// nonce)) -> an independent stream per (element, diffusion step, stage).  Not bit-compatible with torch's generator.
+__global__ void ddpm_step_kernel(const float4* x, const float4* __restrict__ eps,
                                  const float4* __restrict__ noise, const float* __restrict__ coef,
-                                 const int64_t* __restrict__ t, float4* __restrict__ sample,
-                                 float4* __restrict__ pred, long long per_video4, int B, int clip) {
+                                 const int64_t* __restrict__ t, float4* sample,
+                                 float4* __restrict__ pred, const unsigned long long* __restrict__ philox,
+                                 long long per_video4, int B, int clip) {
   pdl_launch_dependents();
   pdl_wait();
   long long total = per_video4 * B;
+  unsigned long long seed = 0ull, nonce = 0ull;
+  if (noise == nullptr) { seed = philox[0]; nonce = philox[1]; }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int b = (int)(i / per_video4);
-    const float* c = coef + (size_t)t[b] * 8;
+    const long long tb = t[b];
+    const float* c = coef + (size_t)tb * 8;
     const float ca = c[0], cb = c[1], c1 = c[2], c2 = c[3], sg = c[4];
-    float4 xv = x[i], ev = eps[i], nv = noise[i];
+    float4 xv = x[i], ev = eps[i], nv;
+    if (noise != nullptr) {
+      nv = noise[i];
+    } else {
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), (uint32_t)tb, (uint32_t)nonce),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+      nv = make_float4(n0.x, n0.y, n1.x, n1.y);
+    }
     float xin[4] = {xv.x, xv.y, xv.z, xv.w}, e[4] = {ev.x, ev.y, ev.z, ev.w}, nz[4] = {nv.x, nv.y, nv.z, nv.w};
     float s[4], ps[4];
 #pragma unroll
@@ -341,11 +381,11 @@ extern "C" int fdm_cast(const fdm_cast_args* a, void* stream) {
 }
 
 extern "C" int fdm_ddpm_step(const fdm_ddpm_step_args* a, void* stream) {
-  FDM_REQUIRE(a && a->x && a->eps && a->noise && a->coef && a->t && a->sample, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a && a->x && a->eps && (a->noise || a->philox) && a->coef && a->t && a->sample, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->per_video % 4 == 0 && a->B > 0, FDM_ERR_UNSUPPORTED);
   long long pv4 = a->per_video / 4;
   fdm::launch(ddpm_step_kernel, dim3(grid_for(pv4 * a->B, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)a->x, (const float4*)a->eps, (const float4*)a->noise, a->coef, a->t, (float4*)a->sample,
-      (float4*)a->pred_xstart, pv4, a->B, a->clip);
+      (float4*)a->pred_xstart, (const unsigned long long*)a->philox, pv4, a->B, a->clip);
   return check_launch();
 }
 

@@ -51,7 +51,7 @@ AttnSpatialArgs = _S("AttnSpatialArgs", [("qkv", vp), ("out", vp), ("N", i32), (
 CastArgs = _S("CastArgs", [("x", vp), ("out", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32),
                            ("upsample", i32), ("op_dtype", i32), ("colsum", vp), ("colsum2", vp)])
 DdpmStepArgs = _S("DdpmStepArgs", [("x", vp), ("eps", vp), ("noise", vp), ("coef", vp), ("t", vp), ("sample", vp),
-                                   ("pred_xstart", vp), ("per_video", i64), ("B", i32), ("clip", i32)])
+                                   ("pred_xstart", vp), ("per_video", i64), ("B", i32), ("clip", i32), ("philox", vp)])
 QSampleArgs = _S("QSampleArgs", [("x0", vp), ("noise", vp), ("coef2", vp), ("t", vp), ("x_t", vp),
                                  ("per_video", i64), ("B", i32)])
 MaskedMseArgs = _S("MaskedMseArgs", [("eps", vp), ("noise", vp), ("m1", vp), ("m2", vp), ("mse", vp), ("eval", vp),
@@ -171,4 +171,15 @@ def check(rc, what):
 
 
 def call(name, args, stream):
+    """Launch one entry point on the raw handle `stream`.  The handle must belong to torch's CURRENT device (kernels are launched
+    on the calling thread's current CUDA device): callers with tensors on another GPU wrap the call in
+    `with torch.cuda.device(tensor.device)` — see `device_guard`."""
     check(getattr(lib(), name)(C.byref(args), C.c_void_p(stream)), name)
+
+
+def device_guard(device):
+    """Context manager making `device` torch's current CUDA device for native launches / graph capture (no-op for CPU)."""
+    import contextlib
+    import torch as th
+    d = th.device(device)
+    return th.cuda.device(d) if d.type == "cuda" else contextlib.nullcontext()

@@ -161,7 +161,8 @@ class Plan:
             st.t, st.t_index, st.t_table = self.ptr(self.t), None, None
         else:
             st.t, st.t_index, st.t_table = None, self.ptr(self.t_index), table.data_ptr()
-            self.keep.append(table)
+            if not any(k is table for k in self.keep):
+                self.keep.append(table)
 
     def tap(self, name):
         """fp32 NCHW copy of a layer output (only meaningful with FDM_DEBUG_TAPS=1, after run())."""
@@ -328,6 +329,14 @@ class DenoiserEngine:
         if not model.use_scale_shift_norm:
             raise NotImplementedError("the fused GroupNorm+FiLM kernel implements use_scale_shift_norm=True "
                                       "(the reference default, script_util.py:34)")
+
+    def invalidate(self):
+        """Drop the packed inference weights, inference plans and their captured sampler graphs.  Needed after parameter
+        updates that bypass torch's version counter: writes through `p.data` (p.data.copy_(ema), dist.broadcast(p.data), raw
+        pointer kernels).  load_state_dict / optimizer steps / in-place ops on the Parameter are detected automatically."""
+        self.packed.clear()
+        self.plans.clear()
+        self._versions = None
 
     # ------------------------------------------------------------------ weights
     def param_list(self):
@@ -1181,6 +1190,11 @@ class DenoiserEngine:
         """Differentiable forward (w.r.t. the parameters) through the native forward + backward schedules."""
         if frame_indices is None:
             raise ValueError("frame_indices is required (temporal RPE, rpe.py:146)")
+        if self.model.training and float(getattr(self.model, "dropout", 0) or 0) > 0:
+            # the reference applies nn.Dropout between SiLU and the second conv of every ResBlock (unet.py:167,203-206); the
+            # native schedules have no dropout mask yet -> refuse loudly instead of silently training without it
+            raise NotImplementedError(f"native training implements dropout=0 (the reference default); dropout={self.model.dropout} "
+                                      "needs FDM_TRAIN_ENGINE=autograd (PyTorch expression of the network) or model.eval()")
         sink = getattr(self.model, "_fdm_flat_sink", None)
         if sink is not None:  # flat-gradient mode: ONE anchor tensor stands in for the 390 parameters in the autograd graph
             return _DenoiserFn.apply(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, sink.anchor)

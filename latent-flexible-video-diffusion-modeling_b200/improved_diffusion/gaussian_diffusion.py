@@ -99,6 +99,12 @@ class GaussianDiffusion:
         self.original_dtype = None
         self._dev_tables = {}
         self._noise_fn = th.randn_like  # test hook: lets parity tests inject the reference's noise sequence
+        # "torch": per-step noise from torch's generator (th.randn_like, gaussian_diffusion.py:396 — the reference's stream);
+        # "philox": opt-in perf mode of the graph sampler — the noise is drawn INSIDE fdm_ddpm_step (Philox4x32-10 keyed by
+        # (seed, element, step, stage)): no normal_() launch, 12 instead of 16 bytes per element.  Same distribution, different
+        # stream than torch's generator.
+        self.noise_mode = os.environ.get("FDM_NOISE", "torch")
+        self._philox_stage = 0
         self.setup_enc_dec()
 
     # ------------------------------------------------------------------ device-resident tables
@@ -314,16 +320,24 @@ class GaussianDiffusion:
         tb = self._tables(device)
 
         def run(noise, clip, progress):
+            with N_.device_guard(device):
+                return run_on_device(noise, clip, progress)
+
+        def run_on_device(noise, clip, progress):
             P = eng.plan_for(B, T, H, W, device)
             stream = th.cuda.current_stream(device)
             eng.load_conditioning(P, kw["x0"], kw["frame_indices"], kw["obs_mask"], kw["latent_mask"])
             P.set_t_source(tb["model_t"])
-            key = ("sampler", int(bool(clip)), id(self))
+            philox = self.noise_mode == "philox" and self._noise_fn is th.randn_like
+            # keyed on the coefficient tables the graph bakes in (not id(self): a collected diffusion object's id can be reused)
+            key = ("sampler", int(bool(clip)), int(philox), tb["step"].data_ptr(), tb["model_t"].data_ptr())
             if key not in P.graphs:
-                nbuf = th.empty(shape, device=device, dtype=th.float32)
-                step = N_.DdpmStepArgs(x=P.ptr(P.x), eps=P.ptr(P.eps), noise=nbuf.data_ptr(), coef=tb["step"].data_ptr(),
-                                       t=P.ptr(P.t_index), sample=P.ptr(P.x), pred_xstart=None,
-                                       per_video=T * Cx * H * W, B=B, clip=int(bool(clip)))
+                nbuf = None if philox else th.empty(shape, device=device, dtype=th.float32)
+                pbuf = th.zeros(2, device=device, dtype=th.int64) if philox else None
+                step = N_.DdpmStepArgs(x=P.ptr(P.x), eps=P.ptr(P.eps), noise=None if philox else nbuf.data_ptr(),
+                                       coef=tb["step"].data_ptr(), t=P.ptr(P.t_index), sample=P.ptr(P.x), pred_xstart=None,
+                                       per_video=T * Cx * H * W, B=B, clip=int(bool(clip)),
+                                       philox=pbuf.data_ptr() if philox else None)
 
                 def body():
                     s = th.cuda.current_stream(device).cuda_stream
@@ -334,18 +348,25 @@ class GaussianDiffusion:
                 if os.environ.get("FDM_NO_GRAPH", "0") != "1":
                     P.t_index_view.zero_()
                     P.x_view.zero_()
-                    nbuf.zero_()
+                    if nbuf is not None:
+                        nbuf.zero_()
                     body()  # warm-up outside capture (lazy module loading / function attributes)
                     stream.synchronize()
                     graph = th.cuda.CUDAGraph()
                     with th.cuda.graph(graph):
                         body()
-                P.graphs[key] = (graph, body, nbuf, step)
-            graph, body, nbuf, _ = P.graphs[key]
+                # tb / pbuf: the tables and the Philox key stay alive as long as the graph that reads them
+                P.graphs[key] = (graph, body, nbuf, step, tb, pbuf)
+            graph, body, nbuf = P.graphs[key][:3]
+            pbuf = P.graphs[key][5]
             if noise is not None:
                 P.x_view.copy_(noise)
             else:
                 P.x_view.copy_(th.randn(*shape, device=device))
+            if pbuf is not None:
+                # one seed draw from torch's generator per stage (so th.manual_seed still controls the samples) + a stage nonce
+                self._philox_stage += 1
+                pbuf.copy_(th.tensor([int(th.randint(0, 2 ** 62, (1,)).item()), self._philox_stage], dtype=th.int64))
             steps = range(self.num_timesteps - 1, -1, -1)
             if progress:
                 from tqdm.auto import tqdm
@@ -353,7 +374,8 @@ class GaussianDiffusion:
             with th.no_grad():
                 for i in steps:
                     P.t_index_view.fill_(i)
-                    nbuf.copy_(self._noise_fn(nbuf)) if self._noise_fn is not th.randn_like else nbuf.normal_()
+                    if nbuf is not None:
+                        nbuf.copy_(self._noise_fn(nbuf)) if self._noise_fn is not th.randn_like else nbuf.normal_()
                     if graph is not None:
                         graph.replay()
                     else:
@@ -403,11 +425,35 @@ class GaussianDiffusion:
         return video
 
     @th.no_grad()
+    def denormalize(self, video):
+        """Pre-encoded latents are stored normalised per channel; `video * std + mean` restores the VAE's latent scale
+        (gaussian_diffusion.py:938-939).  The statistics are moved to the video's device once."""
+        if not (self.diffusion_space == "latent" and self.pre_encoded):
+            return video
+        st = self.pre_encoded_stats_dict
+        for k in ("mean", "std"):
+            if st[k].device != video.device:
+                st[k] = st[k].to(video.device)
+        return video * st["std"] + st["mean"]
+
+    @th.no_grad()
     def decode(self, video, chunk_size=20):
-        if self.diffusion_space == "latent" and self.pre_encoded:
-            raise NotImplementedError("decoding latents to pixels needs the diffusers VAE, which is outside the hot path; "
-                                      "call p_sample_loop(..., return_decoded=False) and decode offline")
-        return video
+        """pixel space: identity.  latent space (gaussian_diffusion.py:933-947): de-normalise pre-encoded latents, then decode
+        chunk by chunk with the VAE.  The diffusers VAE itself stays outside the hot path: plug it in as
+        `diffusion.vae_decode = lambda latents: vae.decode(latents.half(), num_frames=1).sample` ([n,C,h,w] -> [n,3,H,W]);
+        without it, ask for latents (`p_sample_loop(..., return_decoded=False)`) and call `denormalize`."""
+        if self.diffusion_space != "latent":
+            return video
+        video = self.denormalize(video)
+        fn = getattr(self, "vae_decode", None)
+        if fn is None:
+            raise NotImplementedError("decoding latents to pixels needs the diffusers VAE, which is outside the hot path: set "
+                                      "diffusion.vae_decode (see decode.__doc__), or call p_sample_loop(..., return_decoded=False) "
+                                      "and diffusion.denormalize(latents)")
+        shape, dev, dt = video.shape, video.device, video.dtype
+        flat = video.flatten(0, 1)
+        out = th.cat([fn(flat[i:i + chunk_size]) for i in range(0, flat.shape[0], chunk_size)])
+        return out.unflatten(0, (shape[0], shape[1])).to(dev).to(self.original_dtype or dt)
 
 
 class _MaskedMSE(th.autograd.Function):

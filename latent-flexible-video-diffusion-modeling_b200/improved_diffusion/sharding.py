@@ -91,6 +91,9 @@ class FlatGradDataParallel(th.nn.Module):
         if world > 1:
             for p in model.parameters():
                 dist.broadcast(p.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            # p.data writes do not bump the parameters' version counters: drop any packed inference weights / sampler graphs
+            for eng in getattr(model, "_engines", {}).values():
+                eng.invalidate()
         model._fdm_grad_sync = lambda flat: allreduce_mean_(flat, group)
         model._fdm_grad_sync_on = True
 

@@ -261,6 +261,9 @@ def _train_grads(model, diffusion, inp, t, noise, engine, monkeypatch, precision
     (dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32), 2, 11, 0, ()),
     # cfg5 family: 64-px latents, nc = 128 (C up to 512, head dims 96 / 128), K = 40 frames (the 40-key temporal kernels)
     (dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 1, 40, 10, ()),
+    # num_res_blocks = 2 — the reference DEFAULT (script_util.py:14): two ResBlock(+attention) stages per level, three per
+    # output level
+    (dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=2, diffusion_steps=32), 2, 5, 2, ()),
 ])
 def test_native_backward_matches_autograd(case, precision, monkeypatch):
     """The native backward schedule (engine._DenoiserFn: conv dgrad/wgrad, GroupNorm / attention / RPENet backward kernels) against
@@ -275,12 +278,30 @@ def test_native_backward_matches_autograd(case, precision, monkeypatch):
     noise = torch.randn(inp["x0"].shape, generator=g)
     loss_n, gn_ = _train_grads(model, diffusion, inp, t, noise, "native", monkeypatch, precision)
     loss_a, ga_ = _train_grads(model, diffusion, inp, t, noise, "autograd", monkeypatch, "fp32")
-    tol_loss, tol_g = (1e-5, 2e-4) if precision == "fp32" else (3e-2, 2.5e-1)
-    assert O.rel_l2(loss_n, loss_a) <= tol_loss, O.rel_l2(loss_n, loss_a)
-    errs = _grad_errors(gn_, ga_)
-    print(f"native vs autograd [{precision}] worst grad rel-L2 = {errs[0][0]:.3e} at {errs[0][1]}, median {errs[len(errs) // 2][0]:.3e}")
     assert all(torch.isfinite(v).all() for v in gn_.values())
-    assert errs[0][0] <= tol_g, errs[:5]
+    errs = _grad_errors(gn_, ga_)
+    if precision == "fp32":
+        assert O.rel_l2(loss_n, loss_a) <= 1e-5, O.rel_l2(loss_n, loss_a)
+        print(f"native vs autograd [fp32] worst grad rel-L2 = {errs[0][0]:.3e} at {errs[0][1]}, median {errs[len(errs) // 2][0]:.3e}")
+        assert errs[0][0] <= 2e-4, errs[:5]
+    else:
+        # CALIBRATED bf16 tolerance: what does torch's own autocast-bf16 backward (cuDNN / cuBLAS bf16 GEMMs, fp32 GroupNorm and
+        # softmax — the same numerical recipe) give against exact fp32 autograd on this very case?  The native bf16 gradients must
+        # be no worse than 1.5x that, in the worst parameter, in the median parameter, and parameter by parameter (against the
+        # larger of that parameter's own autocast error and the autocast median: single small tensors fluctuate).
+        loss_c, gc_ = _train_grads(model, diffusion, inp, t, noise, "autograd", monkeypatch, "bf16")
+        cal = _grad_errors(gc_, ga_)
+        cal_by = {k: e for e, k in cal}
+        worst_c, med_c = cal[0][0], cal[len(cal) // 2][0]
+        worst_n, med_n = errs[0][0], errs[len(errs) // 2][0]
+        print(f"bf16 gradients vs fp32 autograd: native worst {worst_n:.3e} ({errs[0][1]}) median {med_n:.3e} | torch autocast "
+              f"worst {worst_c:.3e} ({cal[0][1]}) median {med_c:.3e} | loss err native {O.rel_l2(loss_n, loss_a):.2e} "
+              f"autocast {O.rel_l2(loss_c, loss_a):.2e}")
+        assert O.rel_l2(loss_n, loss_a) <= max(1.5 * O.rel_l2(loss_c, loss_a), 5e-3)
+        assert worst_n <= 1.5 * worst_c, (errs[:3], cal[:3])
+        assert med_n <= 1.5 * med_c, (med_n, med_c)
+        bad = [(e, k, cal_by[k]) for e, k in errs if e > 1.5 * max(cal_by[k], med_c)]
+        assert not bad, bad[:5]
     # a second backward of a fresh forward reproduces the first (buffers are re-zeroed, weights re-packed)
     loss_n2, gn2 = _train_grads(model, diffusion, inp, t, noise, "native", monkeypatch, precision)
     # fp32 atomics (RPE-table pixel sums, temporal-GN parameter sums) make the last bits run-dependent; in bf16 mode a flipped

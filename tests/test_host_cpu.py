@@ -420,3 +420,55 @@ def test_train_step_host_logic_cpu(tmp_path):
     assert all(torch.equal(a, b) for a, b in zip(runner.ema_params[0], runner_b.ema_params[0]))
     sa, sb = runner.opt.state_dict()["state"], runner_b.opt.state_dict()["state"]
     assert all(torch.equal(sa[i]["exp_avg"], sb[i]["exp_avg"]) and float(sa[i]["step"]) == float(sb[i]["step"]) for i in sa)
+
+
+def test_native_training_refuses_dropout_loudly():
+    """The reference applies nn.Dropout inside every ResBlock when --dropout > 0 (unet.py:167,203-206); the native schedules have
+    no dropout mask, so training with it must raise instead of silently training without."""
+    import pytest as _pt
+    from improved_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
+    d = model_and_diffusion_defaults()
+    d.update(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32, dropout=0.1,
+             diffusion_space_kwargs=dict(PIXEL))
+    model, _ = create_model_and_diffusion(**d)
+    model.train()
+    x = torch.zeros(1, 2, 4, 32, 32)
+    kw = dict(x0=x, timesteps=torch.zeros(1), frame_indices=torch.zeros(1, 2, dtype=torch.long), obs_mask=torch.zeros(1, 2, 1, 1, 1),
+              latent_mask=torch.ones(1, 2, 1, 1, 1))
+    with _pt.raises(NotImplementedError, match="dropout"):
+        model.engine().forward_train(x, kw["x0"], kw["timesteps"], kw["frame_indices"], kw["obs_mask"], kw["latent_mask"])
+    model.eval()  # dropout is the identity in eval mode: the engine must not object (it then fails later only for lack of a GPU)
+    with _pt.raises(Exception) as ei:
+        model.engine().forward_train(x, kw["x0"], kw["timesteps"], kw["frame_indices"], kw["obs_mask"], kw["latent_mask"])
+    assert "dropout" not in str(ei.value)
+
+
+def test_decode_denormalises_pre_encoded_latents():
+    """gaussian_diffusion.py:933-947: pre-encoded latents are de-normalised (video * std + mean) before the VAE decoder; the VAE
+    itself is pluggable (`diffusion.vae_decode`) and stays outside the hot path."""
+    import pytest as _pt
+    from improved_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults
+    mean, std = torch.tensor([0.1, -0.2, 0.3, 0.0]), torch.tensor([1.5, 0.5, 2.0, 1.0])
+    d = model_and_diffusion_defaults()
+    d.update(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32,
+             diffusion_space_kwargs=dict(diffusion_space="latent", pre_encoded=True, pre_encoded_stats_dict=dict(mean=mean, std=std)))
+    _, diffusion = create_model_and_diffusion(**d)
+    z = torch.randn(2, 3, 4, 8, 8)
+    want = z * std.view(1, 1, 4, 1, 1) + mean.view(1, 1, 4, 1, 1)
+    assert torch.equal(diffusion.denormalize(z), want)
+    assert torch.equal(diffusion.encode(z), z)
+    with _pt.raises(NotImplementedError, match="vae_decode"):
+        diffusion.decode(z)
+    seen = []
+
+    def fake_vae(latents):  # [n, 4, h, w] -> [n, 3, 8h, 8w]
+        seen.append(latents.clone())
+        return latents[:, :3].repeat_interleave(8, dim=2).repeat_interleave(8, dim=3)
+    diffusion.vae_decode = fake_vae
+    out = diffusion.decode(z, chunk_size=4)
+    assert out.shape == (2, 3, 3, 64, 64) and [s_.shape[0] for s_ in seen] == [4, 2]
+    assert torch.equal(torch.cat(seen), want.flatten(0, 1))
+    # pixel space: identity, untouched
+    d["diffusion_space_kwargs"] = dict(PIXEL)
+    _, dp = create_model_and_diffusion(**d)
+    assert dp.decode(z) is z and dp.denormalize(z) is z
