@@ -187,6 +187,15 @@ int fdm_rpe_hidden(const fdm_rpe_hidden_args* a, void* stream);
  * A8  temporal attention core with in-kernel RPE and the two-group mask — rpe.py:139-170
  *   qkv: [B*T][HW][3C] (q|k|v, each [heads][F]);  Rq,Rk,Rv: [B][T][T][C] fp32 (R[b,t,s,h,f]);
  *   mask: [B][T] (1/0 group id);  out: [B*T][HW][C] op_dtype
+ *   Two engines behind the same entry point:
+ *     - tcgen05 (attn_temporal_tc.cu; bf16 qkv/out, head dim % 16 == 0, T <= 64): taken when bf16 copies of all three tables
+ *       (Rq_op, Rk_op, Rv_op) and a workspace of fdm_attn_temporal_workspace(a) bytes are given.  Three launches: the
+ *       relative-position score terms as GEMMs over the pixels of each frame, S = QK^T / softmax / O = PV over rows ordered
+ *       (pixel, frame), and the relative-position value term as a GEMM over the pixels.
+ *       Workspace layout: float b2[B][heads][HW][T][TS], float b3[B][heads][HW][T][TS] (TS = T rounded up to an odd multiple of 4), then
+ *       bf16 attn[B][heads][HW][T][64] — the NORMALISED attention weights softmax(S)[t, s] (zero for s >= T): what
+ *       RPEAttention returns as `attn` (rpe.py:164), readable after the call (fdm_attn_temporal_attn_offset(a) bytes in).
+ *     - CUDA cores (attn_simt.cu): fp32 mode and every other shape.
  * A10 spatial attention core — no RPE / no mask; sequence = pixels of one frame.  bf16: S = QK^T and O = PV on tcgen05
  *     (attn_tc.cu: whole score row in TMEM, softmax in fp32 from TMEM); fp32 mode: CUDA-core streaming softmax
  * ---------------------------------------------------------------------------------------------- */
@@ -199,10 +208,17 @@ typedef struct {
   void* out;
   int32_t B, T, HW, C, heads;
   int32_t qkv_dtype, out_dtype;
-  const void* Rq_op; /* optional bf16 copies of Rq / Rk: with bf16 qkv the two relative-position SCORE terms then run as */
-  const void* Rk_op; /* mma.sync GEMMs over pixels (attn_temporal_mma.cu); NULL -> everything on CUDA cores            */
+  const void* Rq_op; /* optional bf16 copies of the three tables ([B][T][T][C]) + workspace: tcgen05 engine */
+  const void* Rk_op;
+  const void* Rv_op;
+  void* workspace;
+  int64_t workspace_bytes;
 } fdm_attn_temporal_args; /* which = 7 */
 int fdm_attn_temporal(const fdm_attn_temporal_args* a, void* stream);
+/* bytes of workspace the tcgen05 engine needs for this shape; 0 = the shape is served by the CUDA-core kernel (no workspace) */
+size_t fdm_attn_temporal_workspace(const fdm_attn_temporal_args* a);
+/* byte offset of the attention-weight tensor inside that workspace */
+size_t fdm_attn_temporal_attn_offset(const fdm_attn_temporal_args* a);
 
 typedef struct {
   const void* qkv; /* [N][L][3C] */

@@ -384,16 +384,27 @@ static int launch_spatial(const SAParams& p, cudaStream_t st) {
 using namespace fdm;
 
 namespace fdm {
-int attn_temporal_mma_launch(const fdm_attn_temporal_args* a, cudaStream_t st);  // attn_temporal_mma.cu
+int attn_temporal_tc_launch(const fdm_attn_temporal_args* a, cudaStream_t st);  // attn_temporal_tc.cu
+size_t attn_temporal_tc_workspace(const fdm_attn_temporal_args* a);
+int tt_row_stride(int T);
+}
+
+extern "C" size_t fdm_attn_temporal_workspace(const fdm_attn_temporal_args* a) { return a ? attn_temporal_tc_workspace(a) : 0; }
+
+extern "C" size_t fdm_attn_temporal_attn_offset(const fdm_attn_temporal_args* a) {
+  if (!a || attn_temporal_tc_workspace(a) == 0) return 0;
+  const size_t rows = (size_t)a->B * a->heads * a->HW * a->T;
+  return 2 * rows * (size_t)tt_row_stride(a->T) * sizeof(float);
 }
 
 extern "C" int fdm_attn_temporal(const fdm_attn_temporal_args* a, void* stream) {
-  FDM_REQUIRE(a && a->qkv && a->Rq && a->Rk && a->Rv && a->out, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a && a->qkv && a->out, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(a->B > 0 && a->T > 0 && a->HW > 0 && a->heads > 0 && a->C % a->heads == 0, FDM_ERR_BAD_ARG);
-  if (a->Rq_op != nullptr && a->Rk_op != nullptr) {
-    int rc = attn_temporal_mma_launch(a, (cudaStream_t)stream);
+  if (a->Rq_op != nullptr && a->Rk_op != nullptr && a->Rv_op != nullptr && a->workspace != nullptr) {
+    int rc = attn_temporal_tc_launch(a, (cudaStream_t)stream);
     if (rc != FDM_ERR_UNSUPPORTED) return rc;
   }
+  FDM_REQUIRE(a->Rq && a->Rk && a->Rv, FDM_ERR_BAD_ARG);  // the CUDA-core kernel reads the fp32 tables
   const int F = a->C / a->heads;
   FDM_REQUIRE(F % TA_FC == 0 && a->T <= 40, FDM_ERR_UNSUPPORTED);
   TAParams p{a->qkv, a->Rq, a->Rk, a->Rv, a->mask, a->out, a->B, a->T, a->HW, a->C, a->heads, F, 1, 1, 1.0f / sqrtf((float)F)};

@@ -45,7 +45,8 @@ RpeHiddenArgs = _S("RpeHiddenArgs", [("te", vp), ("frame_indices", vp), ("proble
                                      ("hidden_dtype", i32)])
 AttnTemporalArgs = _S("AttnTemporalArgs", [("qkv", vp), ("Rq", vp), ("Rk", vp), ("Rv", vp), ("mask", vp), ("out", vp),
                                            ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("heads", i32),
-                                           ("qkv_dtype", i32), ("out_dtype", i32), ("Rq_op", vp), ("Rk_op", vp)])
+                                           ("qkv_dtype", i32), ("out_dtype", i32), ("Rq_op", vp), ("Rk_op", vp), ("Rv_op", vp),
+                                           ("workspace", vp), ("workspace_bytes", i64)])
 AttnSpatialArgs = _S("AttnSpatialArgs", [("qkv", vp), ("out", vp), ("N", i32), ("L", i32), ("C", i32), ("heads", i32),
                                          ("qkv_dtype", i32), ("out_dtype", i32), ("engine", i32), ("lse", vp)])
 CastArgs = _S("CastArgs", [("x", vp), ("out", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32),
@@ -146,6 +147,9 @@ def lib():
             fn.argtypes = [vp, vp]
         L.fdm_conv_wgrad_workspace.restype = C.c_size_t
         L.fdm_conv_wgrad_workspace.argtypes = [vp]
+        for name in ("fdm_attn_temporal_workspace", "fdm_attn_temporal_attn_offset"):
+            getattr(L, name).restype = C.c_size_t
+            getattr(L, name).argtypes = [vp]
         if L.fdm_abi_version() != 1:
             raise NativeError(f"libfdm_sm100.so ABI {L.fdm_abi_version()} != 1")
         _lib = L

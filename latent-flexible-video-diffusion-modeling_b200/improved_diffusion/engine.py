@@ -24,6 +24,10 @@ from . import _native as N_
 from .nn import timestep_freqs
 
 
+class NativeShapeError(RuntimeError):
+    pass
+
+
 class Buf:
     """A region of the plan's arena (or of its statistics arena)."""
     __slots__ = ("name", "nbytes", "offset", "first", "last", "persistent", "arena")
@@ -56,6 +60,7 @@ class Plan:
         self.taps = {}       # module name -> (Buf, C, H, W) of that layer's fp32 NHWC output (readable when debug)
         self.side_begin = self.side_end = self.join_at = 0  # op index range of the RPE-table branch / its first consumer
         self.side_stream = self.ev_fork = self.ev_join = None
+        self.temporal_attn_maps = []  # (workspace Buf, B, T, HW, C, heads) of every tcgen05 temporal attention (attention weights)
         self.flops = 0       # algorithmic 2*MAC of every conv / linear / attention matmul of one forward
         self.conv_flops = 0
 
@@ -176,14 +181,21 @@ class Plan:
         esz = th.empty((), dtype=dtype).element_size()
         return self.arena[b.offset:b.offset + n * esz].view(dtype).view(*shape)
 
-    def run_graphed(self, which, device):
-        """Training: the forward ("fwd") / backward ("bwd") schedule as ONE CUDA graph replay.  The first call of each runs
-        eagerly (lazy module loading, cudaFuncSetAttribute), the second captures; FDM_NO_GRAPH=1 keeps everything eager."""
-        body = self.run if which == "fwd" else self.run_backward
+    def run_graphed(self, which, device, seg=None):
+        """Training: the forward ("fwd") / backward ("bwd") schedule as ONE CUDA graph replay; `seg` = (lo, hi) replays only that
+        range of the backward schedule (its own graph: the overlapped gradient exchange interleaves NCCL calls between the
+        segments).  The first call of each runs eagerly (lazy module loading, cudaFuncSetAttribute), the second captures;
+        FDM_NO_GRAPH=1 keeps everything eager."""
+        if which == "fwd":
+            body = self.run
+        elif seg is None:
+            body = self.run_backward
+        else:
+            body = lambda st: self.run_backward(st, seg[0], seg[1])
         cur = lambda: th.cuda.current_stream(device).cuda_stream
         if os.environ.get("FDM_NO_GRAPH", "0") == "1":
             return body(cur())
-        key = ("train", which)
+        key = ("train", which, seg)
         if key not in self.graphs:
             if key not in self._warm:
                 self._warm.add(key)
@@ -195,11 +207,15 @@ class Plan:
             self.graphs[key] = g
         self.graphs[key].replay()
 
-    def run_backward(self, stream):
-        """Launch the backward schedule (training plans): zero the accumulator arena and the flat parameter-gradient buffer,
-        then every backward kernel in order on `stream`.  The caller has copied d(loss)/d(eps) into `geps_view`."""
-        self.bzero_arena.zero_()
-        self.pgrad.zero_()
+    def run_backward(self, stream, lo=0, hi=None):
+        """Launch the backward schedule (training plans), or its launches [lo, hi): zero the accumulator arena and the flat
+        parameter-gradient buffer (lo == 0 only), then every backward kernel in order on `stream`.  The caller has copied
+        d(loss)/d(eps) into `geps_view`.  A partial range ends with the side stream joined, so that everything it launched —
+        hence every gradient bucket that is final at `hi` — is ordered before whatever the caller enqueues next."""
+        hi = len(self.bcalls) if hi is None else hi
+        if lo == 0:
+            self.bzero_arena.zero_()
+            self.pgrad.zero_()
         s = C.c_void_p(stream)
         side = self.bwd_side_stream
         if side is not None:
@@ -210,21 +226,33 @@ class Plan:
             main = th.cuda.current_stream(self.arena.device)
             assert main.cuda_stream == stream, "Plan.run_backward expects torch's current stream"
             ss = C.c_void_p(side.cuda_stream)
-        for i, (name, fn, ref) in enumerate(self.bcalls):
-            if side is not None and i == self.bjoin_before:
+        used_side = False
+        for i in range(lo, hi):
+            name, fn, ref = self.bcalls[i]
+            if side is not None and i == self.bjoin_before and used_side:
                 self.ev_bjoin.record(side)
                 main.wait_event(self.ev_bjoin)
             if side is not None and i in self.bside:
                 self.ev_bfork.record(main)
                 side.wait_event(self.ev_bfork)
                 rc = fn(ref, ss)
+                used_side = True
             else:
                 rc = fn(ref, s)
             if rc != 0:
                 N_.check(rc, name)
-        if side is not None:
+        if side is not None and used_side:
             self.ev_bjoin.record(side)
             main.wait_event(self.ev_bjoin)
+
+    def backward_segments(self):
+        """[(lo, hi, (first, last+1) of the gradient bucket that is final at hi)]: the backward schedule cut at the completion
+        points of the gradient buckets (see DenoiserEngine._grad_buckets)."""
+        segs, lo = [], 0
+        for b_lo, b_hi, done in self.grad_buckets:
+            segs.append((lo, done + 1, (b_lo, b_hi)))
+            lo = done + 1
+        return segs
 
     def run(self, stream):
         """Launch the whole schedule on `stream` (the raw cudaStream_t of torch's CURRENT stream).  The caller has filled the
@@ -280,13 +308,29 @@ class _DenoiserFn(th.autograd.Function):
             raise RuntimeError("the activations of this forward were overwritten by a later forward of the same shape "
                                "(the training plan keeps ONE set of saved activations): call backward before the next forward")
         P.geps_view.copy_(g)
-        P.run_graphed("bwd", g.device)
         sink = ctx.sink
+        model = ctx.engine.model
+        sync = getattr(model, "_fdm_grad_sync", None)
+        bucket_sync = getattr(model, "_fdm_grad_sync_bucket", None)
+        overlap = (sink is not None and sync is not None and bucket_sync is not None and getattr(model, "_fdm_grad_sync_on", True)
+                   and not getattr(sink, "unsynced", False) and len(P.grad_buckets) > 1)
+        if overlap:
+            # overlapped gradient exchange (reference: DDP's bucketed allreduce during backward, train_util.py:118-125): the backward
+            # schedule runs as one CUDA graph per gradient bucket; as soon as a segment is enqueued, the bucket that is final at its
+            # end is all-reduced (NCCL's stream waits for the segment, the next segment does not wait for NCCL)
+            pending = []
+            for lo, hi, (b_lo, b_hi) in P.backward_segments():
+                P.run_graphed("bwd", g.device, seg=(lo, hi))
+                pending.append(bucket_sync(P.pgrad[b_lo:b_hi]))
+            for finish in pending:
+                finish()
+            sink.receive(P.pgrad)
+            return (None,) * 8
+        P.run_graphed("bwd", g.device)
         if sink is not None:
             # flat-gradient mode (optim.FlatAdamW(..., model=model)): the parameters' .grad are persistent views of the optimizer's
             # flat gradient buffer, so the whole hand-over is ONE allreduce (in place, on the plan's buffer) and ONE copy / add —
             # no per-parameter views, AccumulateGrad nodes or zero_grad loops (1.5 ms of host time per step for 390 tensors)
-            sync = getattr(ctx.engine.model, "_fdm_grad_sync", None)
             if sync is None:
                 sink.receive(P.pgrad)
             elif not getattr(ctx.engine.model, "_fdm_grad_sync_on", True):  # FlatGradDataParallel.no_sync(): accumulate locally
@@ -319,7 +363,8 @@ class DenoiserEngine:
         self.op_size = 2 if precision == "bf16" else 4
         # FDM_CONV_ENGINE=simt forces the CUDA-core implicit GEMM everywhere (debugging / A-B timing of the tcgen05 kernel)
         self.use_tc = precision == "bf16" and os.environ.get("FDM_CONV_ENGINE", "tc") != "simt"
-        self.temporal_mma = os.environ.get("FDM_TEMPORAL_MMA", "0") == "1"
+        # temporal RPE attention on tcgen05 (attn_temporal_tc.cu); FDM_TEMPORAL_TC=0 keeps the CUDA-core kernel (A/B timing)
+        self.temporal_tc = self.use_tc and os.environ.get("FDM_TEMPORAL_TC", "1") != "0"
         self.plans = {}
         self._params = self._n_params = None
         self._train_probe = None
@@ -428,6 +473,69 @@ class DenoiserEngine:
                 self.plans[key] = self._compile(B, T, H, W, device)
         return self.plans[key]
 
+    def _grad_buckets(self, P, params):
+        """Partition the flat parameter-gradient buffer into FDM_GRAD_BUCKETS (default 4) ranges of consecutive slots and find, for
+        each, the backward launch after which it is final: [(first element, one past the last element, index of that launch)].
+        The slots are in gradient-completion order (optim.completion_order), so the `done` indices ascend: bucket k can be
+        all-reduced while launches done_k+1 ... run.  Every parameter must have a writer (DDP find_unused_parameters=False)."""
+        import bisect
+        base, n = P.pgrad.data_ptr(), P.pgrad.numel()
+        by_off = sorted((o, i) for i, o in enumerate(P.flat_offs))
+        starts = [o for o, _ in by_off]
+        last = [-1] * len(params)
+
+        def note(v, j):
+            if isinstance(v, th.Tensor) and base <= v.data_ptr() < base + 4 * n:
+                i = by_off[bisect.bisect_right(starts, (v.data_ptr() - base) // 4) - 1][1]
+                last[i] = max(last[i], j)
+        for j, (_, _, f) in enumerate(P.bops):
+            for v in f.values():
+                note(v, j)
+        for k, (_, _, items) in enumerate(P.pending):
+            j = P.pending_at.get(k)
+            if j is not None:
+                for it in items:
+                    for v in it.values():
+                        note(v, j)
+        names = [nm for nm, _ in self.model.named_parameters()]
+        missing = [names[i] for i in range(len(params)) if last[i] < 0]
+        if missing:
+            raise AssertionError(f"backward schedule: no gradient writer for {missing[:5]} (+{max(0, len(missing) - 5)})")
+        want = max(1, int(os.environ.get("FDM_GRAD_BUCKETS", "4")))
+        order, n_early = P.flat_order, P.n_early
+        size = lambda i: (params[i].numel() + 3) // 4 * 4
+        early_total = sum(size(i) for i in order[:n_early])
+        groups, cur, acc, k = [], [], 0, 1
+        for i in order[:n_early]:
+            cur.append(i)
+            acc += size(i)
+            if want > 2 and acc >= k * early_total / (want - 1) and len(groups) < want - 2:
+                groups.append(cur)
+                cur, k = [], k + 1
+        if cur:
+            groups.append(cur)
+        if order[n_early:]:
+            groups.append(list(order[n_early:]))
+        buckets, done_so_far = [], -1
+        for g in groups:
+            lo = min(P.flat_offs[i] for i in g)
+            hi = max(P.flat_offs[i] + size(i) for i in g)
+            done_so_far = max(done_so_far, max(last[i] for i in g))
+            if buckets and buckets[-1][2] == done_so_far:   # nothing runs between the two completion points: one bucket
+                buckets[-1] = (buckets[-1][0], hi, done_so_far)
+            else:
+                buckets.append((lo, hi, done_so_far))
+        assert buckets[0][0] == 0 and buckets[-1][1] == n and all(a[1] == b[0] for a, b in zip(buckets, buckets[1:])), buckets
+        buckets[-1] = (buckets[-1][0], buckets[-1][1], len(P.bops) - 1)
+        return buckets
+
+    def _temporal_ws(self, B, T, Cc, heads, hw):
+        """Workspace bytes of the tcgen05 temporal attention for this shape, or None when the CUDA-core kernel serves it.
+        hw=None: is the shape family (T, head dim) taken at all (every attention map of the U-Net has HW % 16 == 0)."""
+        a = N_.AttnTemporalArgs(B=B, T=T, HW=hw or 256, C=Cc, heads=heads, qkv_dtype=self.op_dtype, out_dtype=self.op_dtype)
+        n = int(N_.lib().fdm_attn_temporal_workspace(C.byref(a)))
+        return n if n > 0 else None
+
     def tc_ok(self, C0, C1, Cout, k, stride, upsample, Ho, Wo):
         """Shapes the tcgen05 implicit-GEMM kernel takes (conv_tc.cu); everything else runs on the CUDA-core engine."""
         if not self.use_tc or upsample:
@@ -462,18 +570,21 @@ class DenoiserEngine:
                 assert p_.dtype == th.float32 and p_.is_contiguous(), "training plans expect contiguous fp32 master weights"
             # densely packed in parameter order: ONE C++ call (unflatten_dense_tensors) turns a clone of it into the per-parameter
             # gradients — 390 Python-side narrow+view pairs per step were ~2 ms of host time on the launch-bound cfg2 step
-            sizes = [(p_.numel() + 3) // 4 * 4 for p_ in params]  # 16-byte aligned slots (vectorised optimizer kernels)
-            P.pgrad = th.zeros(sum(sizes), dtype=th.float32, device=device)
-            P.unflat, P.unflat_pick = [], []  # templates for unflatten_dense_tensors: parameters interleaved with padding stubs
-            for p_, n_ in zip(params, sizes):
-                P.unflat_pick.append(len(P.unflat))
+            # 16-byte aligned slots (vectorised optimizer kernels) in gradient-COMPLETION order (optim.completion_order): the head and
+            # the last output blocks first, the conditioning path (time MLP, FiLM projections, RPENets) last — a bucket of consecutive
+            # slots is final once the backward schedule passes one point, so its allreduce overlaps the rest of the backward
+            from .optim import model_flat_layout
+            _, offs_list, total, order, n_early = model_flat_layout(m)
+            P.pgrad = th.zeros(total, dtype=th.float32, device=device)
+            P.unflat, P.unflat_pick = [], [0] * len(params)  # templates for unflatten_dense_tensors (flat order) + padding stubs
+            for i in order:
+                p_, n_ = params[i], (params[i].numel() + 3) // 4 * 4
+                P.unflat_pick[i] = len(P.unflat)
                 P.unflat.append(p_)
                 if n_ != p_.numel():
                     P.unflat.append(th.empty(n_ - p_.numel()))
-            offs, o = {}, 0
-            for p_, n_ in zip(params, sizes):
-                offs[id(p_)] = o
-                o += n_
+            offs = {id(p_): o_ for p_, o_ in zip(params, offs_list)}
+            P.flat_order, P.flat_offs, P.n_early = order, offs_list, n_early
             P.pgrad_views = [P.pgrad[offs[id(p_)]:offs[id(p_)] + p_.numel()].view(p_.shape) for p_ in params]
             pg = lambda p_: P.pgrad[offs[id(p_)]:offs[id(p_)] + p_.numel()]  # gradient slot of a parameter
             f32 = lambda p_: p_.detach()
@@ -600,17 +711,19 @@ class DenoiserEngine:
             for which in ("rpe_q", "rpe_k", "rpe_v"):
                 net = getattr(ab.temporal_attention, which).rpe_net
                 hb = P.buf(f"rpe_hidden", B * T * T * Cc * hsz, True)  # side-stream lifetime: never aliased with main-branch buffers
-                rb_ = P.buf(f"rpe_R", B * T * T * Cc * 4, True)
+                # bf16 copies of the tables are the B operands of the tcgen05 temporal attention (attn_temporal_tc.cu); the fp32
+                # tables are only kept where something still reads them: the CUDA-core kernel (shapes the tcgen05 engine does not
+                # take, FDM_TEMPORAL_TC=0) and the backward kernels of training plans
+                tc_here = self.temporal_tc and self._temporal_ws(B, T, ab.channels, ab.temporal_attention.num_heads, None) is not None
+                rop = P.buf(f"rpe_R_op", B * T * T * Cc * 2, True) if tc_here else None
+                rb_ = P.buf(f"rpe_R", B * T * T * Cc * 4, True) if (train or not tc_here) else None
                 hid[(id(ab), which)], R[(id(ab), which)] = hb, rb_
-                # bf16 copies of the score tables feed the mma.sync R-term GEMMs of the experimental temporal attention kernel
-                # (attn_temporal_mma.cu).  Measured on B200 it is NOT faster than the CUDA-core kernel (cfg4 step 2.37 vs
-                # 2.27 ms, cfg5 8.7 vs 8.0 ms), so it is off unless FDM_TEMPORAL_MMA=1.
-                rop = P.buf(f"rpe_R_op", B * T * T * Cc * 2, True) if (self.use_tc and self.temporal_mma and which != "rpe_v") else None
                 R_op[(id(ab), which)] = rop
                 rh_probs.append(dict(wd=f32(net.embed_distances.weight), bd=f32(net.embed_distances.bias), hidden=hb, C=Cc,
                                      te_off=te_off[(id(ab), which)]))
-                out_probs.append(dict(x=hb, w=f32(net.out.weight), b=f32(net.out.bias), y=rb_, M=B * T * T, K=Cc, Nout=Cc,
-                                      ldx=Cc, ldy=Cc, silu_in=0))
+                if not self.use_tc:
+                    out_probs.append(dict(x=hb, w=f32(net.out.weight), b=f32(net.out.bias), y=rb_, M=B * T * T, K=Cc, Nout=Cc,
+                                          ldx=Cc, ldy=Cc, silu_in=0))
                 rpe_tc.append((hb, Cc, net, rb_, rop))
         self._pending_rpe_tc = []
         if rh_probs:
@@ -665,6 +778,7 @@ class DenoiserEngine:
         # ---------------- backward helpers (training plans): every forward block below registers ONE emitter on P.tape;
         # the emitters run in reverse once the forward schedule is complete and append to P.bops
         P.pending = []   # (device byte tensor, struct class, [field dicts]) filled in after finalize()
+        P.pending_at = {}  # index into P.pending -> index of the backward launch that consumes that problem array
         gbufs, ginit = {}, set()
         lib = N_.lib()
         F32_, hdt = N_.F32, (opd if self.use_tc else N_.F32)
@@ -780,12 +894,14 @@ class DenoiserEngine:
                 if rp:
                     dev_ = th.zeros(len(rp) * C.sizeof(N_.RpeHiddenBwdProblem), dtype=th.uint8, device=device)
                     P.pending.append((dev_, N_.RpeHiddenBwdProblem, rp))
+                    P.pending_at[len(P.pending) - 1] = len(P.bops)
                     P.op("fdm_rpe_hidden_bwd", N_.RpeHiddenBwdArgs, te=cond, frame_indices=P.fi, problems=dev_, dte=dcond,
                          B=B, T=T, te_stride=cond_cols, count=len(rp), max_C=max(r_["C"] for r_ in rp), dhidden_dtype=opd)
 
                 def lin_bwd(problems):
                     dev_ = th.zeros(len(problems) * C.sizeof(N_.LinearBwdProblem), dtype=th.uint8, device=device)
                     P.pending.append((dev_, N_.LinearBwdProblem, problems))
+                    P.pending_at[len(P.pending) - 1] = len(P.bops)
                     P.op("fdm_grouped_linear_bwd", N_.GroupedLinearBwdArgs, problems=dev_, count=len(problems),
                          max_M=max(q_["M"] for q_ in problems), max_Nout=max(q_["Nout"] for q_ in problems),
                          max_K=max(q_["K"] for q_ in problems))
@@ -896,9 +1012,17 @@ class DenoiserEngine:
             conv(xn_op, Cc, Hh, Ww, ta.qkv.weight, 3 * Cc, 1, bias=f32(ta.qkv.bias), y_op=qkv)
             o = P.buf("ta_o", Nf * hw * Cc * osz)
             P.flops += 10 * T * T * Cc * B * hw  # QK^T, PV and the three contextual RPE einsums (rpe.py:72-83,144,166)
+            ws_bytes = self._temporal_ws(B, T, Cc, ta.num_heads, hw) if self.temporal_tc else None
+            ws = P.buf("ta_ws", ws_bytes) if ws_bytes else None
+            if ws is None and R[(id(ab), "rpe_q")] is None:
+                raise NativeShapeError(f"temporal attention: no kernel takes T={T}, HW={hw}, C={Cc}, heads={ta.num_heads}")
             P.op("fdm_attn_temporal", N_.AttnTemporalArgs, qkv=qkv, Rq=R[(id(ab), "rpe_q")], Rk=R[(id(ab), "rpe_k")],
                  Rv=R[(id(ab), "rpe_v")], mask=P.mask, out=o, B=B, T=T, HW=hw, C=Cc, heads=ta.num_heads,
-                 qkv_dtype=opd, out_dtype=opd, Rq_op=R_op.get((id(ab), "rpe_q")), Rk_op=R_op.get((id(ab), "rpe_k")))
+                 qkv_dtype=opd, out_dtype=opd, Rq_op=R_op.get((id(ab), "rpe_q")) if ws else None,
+                 Rk_op=R_op.get((id(ab), "rpe_k")) if ws else None, Rv_op=R_op.get((id(ab), "rpe_v")) if ws else None,
+                 workspace=ws, workspace_bytes=ws_bytes or 0)
+            if ws is not None:
+                P.temporal_attn_maps.append((ws, B, T, hw, Cc, ta.num_heads))
             y = new_act("ta_y", Cc, Hh, Ww)
             y.biases = (ta.proj_out.bias,)
             conv(o, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, bias=f32(ta.proj_out.bias), resid=xn, y_f32=y.buf, stats=y.st)
@@ -1116,6 +1240,7 @@ class DenoiserEngine:
                         continue  # parameter-gradient launch: does not write activation gradients
                     if any(f_j.get(k) is gbuf for k in grad_out_fields):
                         raise AssertionError(f"backward schedule: {fn_j} (#{j}) writes a gradient after its operand copy was fused (#{idx})")
+            P.grad_buckets = self._grad_buckets(P, params)
             P.at_lse.nbytes = P.at_dsum.nbytes = (P.at_rows * 4 + 255) // 256 * 256
             dgrad_modes = (N_.PACK_TC_DGRAD, N_.PACK_SIMT_DGRAD)
             groups = [(pack_fields, [q_ for q_ in P.pack_problems if pack_fields_d is None or q_[6] not in dgrad_modes])]

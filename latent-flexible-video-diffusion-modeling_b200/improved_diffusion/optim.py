@@ -26,14 +26,50 @@ import torch as th
 from . import _native as N_
 
 
-def flat_slots(params):
-    """(offsets, total) of the 16-byte aligned slots of `params` in a flat fp32 buffer — the layout of the native backward's
-    gradient buffer (engine.py) so that its views line up with the flat parameter buffer."""
-    offs, o = [], 0
-    for p in params:
-        offs.append(o)
-        o += (p.numel() + 3) // 4 * 4
+def completion_order(names):
+    """Permutation of the parameters (given by name, in model.named_parameters() order) into the order in which their gradients
+    become FINAL in the native backward schedule (engine.py): head first, then output blocks / middle block / input blocks in
+    reverse forward order, and last the conditioning path — time MLP, every ResBlock's FiLM projection (`emb_layers`) and every
+    RPENet — whose gradients are only complete after the whole network has been walked.  The flat gradient / parameter / moment
+    buffers use this order, so a bucket of consecutive slots is complete as soon as the backward passes one point, and its
+    allreduce can overlap the rest of the backward (sharding.FlatGradDataParallel; reference: DDP buckets, train_util.py:118-125).
+    Returns (order, n_early): `order[k]` = index of the parameter stored k-th; the last len(order) - n_early are the late ones."""
+    def late(n):
+        return n.startswith("time_embed.") or ".emb_layers." in n or ".rpe_net." in n
+
+    def rank(n):
+        parts = n.split(".")
+        if parts[0] == "out":
+            return (0, 0)
+        if parts[0] == "output_blocks":
+            return (1, -int(parts[1]))
+        if parts[0] == "middle_block":
+            return (2, 0)
+        if parts[0] == "input_blocks":
+            return (3, -int(parts[1]))
+        return (4, 0)
+    early = sorted((i for i, n in enumerate(names) if not late(n)), key=lambda i: rank(names[i]))  # stable within a block
+    return early + [i for i, n in enumerate(names) if late(n)], len(early)
+
+
+def flat_slots(params, order=None):
+    """(offsets, total) of the 16-byte aligned slots of `params` in a flat fp32 buffer; `offsets[i]` belongs to params[i], slots
+    are laid out in `order` (default: as given).  Shared by the native backward's gradient buffer (engine.py) and FlatAdamW, so
+    their views line up."""
+    offs, o = [0] * len(params), 0
+    for i in (order if order is not None else range(len(params))):
+        offs[i] = o
+        o += (params[i].numel() + 3) // 4 * 4
     return offs, o
+
+
+def model_flat_layout(model):
+    """(parameters, offsets, total, order, n_early) of a model's flat layout in gradient-completion order."""
+    named = list(model.named_parameters())
+    order, n_early = completion_order([n for n, _ in named])
+    params = [p for _, p in named]
+    offs, total = flat_slots(params, order)
+    return params, offs, total, order, n_early
 
 
 class FlatAdamW(th.optim.Optimizer):
@@ -47,7 +83,13 @@ class FlatAdamW(th.optim.Optimizer):
         ps = self.param_groups[0]["params"]
         if not ps or not all(p.is_cuda and p.dtype == th.float32 for p in ps):
             raise RuntimeError("FlatAdamW runs on the sm_100a kernels only: fp32 CUDA parameters (there is no CPU fallback)")
-        self._offs, self._total = flat_slots(ps)
+        order = None
+        if model is not None:
+            mp = list(model.parameters())
+            if len(mp) != len(ps) or any(a is not b for a, b in zip(mp, ps)):
+                raise ValueError("flat-gradient mode needs exactly the model's parameters, in model.parameters() order")
+            order = model_flat_layout(model)[3]  # gradient-completion order: the layout of the native backward's flat buffer
+        self._offs, self._total = flat_slots(ps, order)
         dev = ps[0].device
         self.flat_p = th.zeros(self._total, device=dev)
         self.flat_m, self.flat_v = th.zeros_like(self.flat_p), th.zeros_like(self.flat_p)
@@ -66,9 +108,6 @@ class FlatAdamW(th.optim.Optimizer):
         self.flat_ema = [self.flat_p.clone() for _ in self.ema_rates]
         self.bound = None
         if model is not None:
-            mp = list(model.parameters())
-            if len(mp) != len(ps) or any(a is not b for a, b in zip(mp, ps)):
-                raise ValueError("flat-gradient mode needs exactly the model's parameters, in model.parameters() order")
             self.bound = model
             self.flat_g = th.zeros_like(self.flat_p)
             for p, gview in zip(ps, self._views(self.flat_g)):
@@ -105,7 +144,7 @@ class FlatAdamW(th.optim.Optimizer):
         g0 = ps[0].grad
         if g0 is None:
             raise RuntimeError("FlatAdamW.step(): parameter without a gradient (find_unused_parameters=False contract)")
-        base = g0.data_ptr()
+        base = g0.data_ptr() - 4 * self._offs[0]
         if g0.is_contiguous() and g0.dtype == th.float32 and all(
                 p.grad is not None and p.grad.data_ptr() == base + 4 * o for p, o in zip(ps, self._offs)):
             return base, None  # the native backward's flat buffer: use it in place
@@ -120,7 +159,7 @@ class FlatAdamW(th.optim.Optimizer):
                 loss = closure()
         group = self.param_groups[0]
         ps = group["params"]
-        if ps[0].data_ptr() != self.flat_p.data_ptr():
+        if ps[0].data_ptr() != self.flat_p.data_ptr() + 4 * self._offs[0]:
             raise RuntimeError("a parameter's storage was replaced after FlatAdamW flattened it (.to() / .data = ...): rebuild the optimizer")
         g_ptr, _keep = self._flat_grad(ps)
         self._step += 1

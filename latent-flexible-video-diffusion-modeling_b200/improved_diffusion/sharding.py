@@ -79,12 +79,32 @@ def allreduce_mean_(flat, group=None):
     return flat
 
 
+def allreduce_mean_async(flat, group=None):
+    """Start an in-place mean over the ranks of `group` and return a function that makes the CURRENT stream wait for it.  The
+    collective runs on the process group's own stream, ordered after everything enqueued on the current stream so far; work
+    enqueued on the current stream afterwards (the next backward segment) overlaps it."""
+    _, world = _rank_world(group)
+    if world <= 1:
+        return lambda: None
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group, async_op=True)
+        return work.wait
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def finish():
+        work.wait()
+        flat.div_(world)
+    return finish
+
+
 class FlatGradDataParallel(th.nn.Module):
     """Data-parallel wrapper for the NATIVE training path (engine._DenoiserFn): parameters are broadcast from rank 0 once;
-    every backward ends with ONE allreduce(mean) over the flat parameter-gradient buffer before autograd hands the
-    gradients to the parameters.  Same call signature / state_dict as the wrapped model (`.module`, like DDP)."""
+    the gradient exchange is a mean-allreduce of the flat parameter-gradient buffer, by default in a few BUCKETS that overlap the
+    backward schedule (the buffer is laid out in gradient-completion order: each bucket is launched as soon as the backward has
+    passed the point after which it is final); `overlap=False`: ONE allreduce after the whole backward.  Same call signature / state_dict as the wrapped model (`.module`, like DDP)."""
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, overlap=True):
         super().__init__()
         self.module, self.group = model, group
         _, world = _rank_world(group)
@@ -96,6 +116,13 @@ class FlatGradDataParallel(th.nn.Module):
                 eng.invalidate()
         model._fdm_grad_sync = lambda flat: allreduce_mean_(flat, group)
         model._fdm_grad_sync_on = True
+        # bucketed exchange overlapped with the backward schedule (engine._DenoiserFn.backward); `overlap=False` / FDM_DDP_OVERLAP=0
+        # keeps the single allreduce after the whole backward
+        import os
+        if overlap and os.environ.get("FDM_DDP_OVERLAP", "1") != "0":
+            model._fdm_grad_sync_bucket = lambda flat: allreduce_mean_async(flat, group)
+        elif hasattr(model, "_fdm_grad_sync_bucket"):
+            del model._fdm_grad_sync_bucket
 
     @contextlib.contextmanager
     def no_sync(self):

@@ -177,32 +177,12 @@ def test_conv_tc_head_and_stem(N, H, W, C0, Co):
     assert rel(y, ref) <= 1e-3, rel(y, ref)
 
 
-@pytest.mark.parametrize("B,T,HW,C,heads", [(2, 5, 256, 64, 4), (1, 20, 64, 128, 4), (2, 7, 16, 128, 4), (1, 40, 256, 384, 4),
-                                            (1, 33, 64, 96, 4), (3, 12, 40, 128, 4)])
-@pytest.mark.parametrize("use_mma", [False, True])
-def test_attn_temporal_vs_torch(B, T, HW, C, heads, use_mma):
-    """fdm_attn_temporal (CUDA-core kernel, and the variant with the two R score terms on mma.sync) against
-    softmax(scale (q k^T + q.Rk + k.Rq) + two-group mask) (v + Rv) in torch fp32 (rpe.py:139-170)."""
-    from improved_diffusion import _native as N_
+def _temporal_reference(qkv, Rq, Rk, Rv, mask, B, T, HW, C, heads):
+    """softmax(scale (q k^T + q.Rk + k.Rq) + two-group mask) (v + Rv) in torch fp32 (rpe.py:139-170); returns (out, attn)"""
     F_ = C // heads
-    if use_mma and F_ % 16:
-        pytest.skip("the mma variant needs head dim % 16 == 0 (engine falls back to the CUDA-core kernel)")
-    g = torch.Generator(device="cuda").manual_seed(T * 7 + C)
-    qkv = torch.randn(B * T, HW, 3 * C, device="cuda", generator=g).to(torch.bfloat16)
-    Rq, Rk, Rv = (0.5 * torch.randn(B, T, T, C, device="cuda", generator=g) for _ in range(3))
-    mask = (torch.rand(B, T, device="cuda", generator=g) > 0.3).float()
-    out = torch.empty(B * T, HW, C, device="cuda", dtype=torch.bfloat16)
-    Rq_op, Rk_op = Rq.to(torch.bfloat16), Rk.to(torch.bfloat16)
-    a = N_.AttnTemporalArgs(qkv=qkv.data_ptr(), Rq=Rq.data_ptr(), Rk=Rk.data_ptr(), Rv=Rv.data_ptr(), mask=mask.data_ptr(),
-                            out=out.data_ptr(), B=B, T=T, HW=HW, C=C, heads=heads, qkv_dtype=N_.BF16, out_dtype=N_.BF16,
-                            Rq_op=Rq_op.data_ptr() if use_mma else None, Rk_op=Rk_op.data_ptr() if use_mma else None)
-    N_.call("fdm_attn_temporal", a, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
     x = qkv.float().view(B, T, HW, 3, heads, F_).permute(3, 0, 2, 4, 1, 5)  # 3 B HW H T F
     q, k, v = x[0], x[1], x[2]
-    rq = (Rq_op.float() if use_mma else Rq).view(B, T, T, heads, F_)
-    rk = (Rk_op.float() if use_mma else Rk).view(B, T, T, heads, F_)
-    rv = Rv.view(B, T, T, heads, F_)
+    rq, rk, rv = (r.float().view(B, T, T, heads, F_) for r in (Rq, Rk, Rv))
     w = q @ k.transpose(-1, -2)
     w = w + torch.einsum("bdhtf,btshf->bdhts", q, rk) + torch.einsum("bdhtf,btshf->bdhts", k, rq).transpose(-1, -2)
     w = w * F_ ** -0.5
@@ -210,5 +190,62 @@ def test_attn_temporal_vs_torch(B, T, HW, C, heads, use_mma):
     w = w.masked_fill((allowed == 0).view(B, 1, 1, T, T), float("-inf"))
     p = torch.softmax(w, dim=-1)
     o = p @ v + torch.einsum("bdhts,btshf->bdhtf", p, rv)
-    ref = o.permute(0, 3, 1, 2, 4).reshape(B * T, HW, C)  # B T HW H F
+    return o.permute(0, 3, 1, 2, 4).reshape(B * T, HW, C), p  # out [B T HW H F]; attn [B, HW, H, T, T]
+
+
+@pytest.mark.parametrize("B,T,HW,C,heads", [(2, 5, 256, 64, 4), (1, 20, 64, 128, 4), (2, 7, 16, 128, 4), (1, 40, 256, 384, 4),
+                                            (1, 33, 64, 96, 4), (3, 12, 40, 128, 4)])
+def test_attn_temporal_vs_torch(B, T, HW, C, heads):
+    """fdm_attn_temporal, CUDA-core engine (fp32 tables, no workspace) against torch fp32."""
+    from improved_diffusion import _native as N_
+    g = torch.Generator(device="cuda").manual_seed(T * 7 + C)
+    qkv = torch.randn(B * T, HW, 3 * C, device="cuda", generator=g).to(torch.bfloat16)
+    Rq, Rk, Rv = (0.5 * torch.randn(B, T, T, C, device="cuda", generator=g) for _ in range(3))
+    mask = (torch.rand(B, T, device="cuda", generator=g) > 0.3).float()
+    out = torch.empty(B * T, HW, C, device="cuda", dtype=torch.bfloat16)
+    a = N_.AttnTemporalArgs(qkv=qkv.data_ptr(), Rq=Rq.data_ptr(), Rk=Rk.data_ptr(), Rv=Rv.data_ptr(), mask=mask.data_ptr(),
+                            out=out.data_ptr(), B=B, T=T, HW=HW, C=C, heads=heads, qkv_dtype=N_.BF16, out_dtype=N_.BF16)
+    N_.call("fdm_attn_temporal", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref, _ = _temporal_reference(qkv, Rq, Rk, Rv, mask, B, T, HW, C, heads)
     assert rel(out.float(), ref) <= 6e-3, rel(out.float(), ref)
+
+
+@pytest.mark.parametrize("B,T,HW,C,heads", [
+    (8, 20, 256, 128, 4), (8, 20, 64, 128, 4), (8, 20, 16, 128, 4),      # cfg4's three attention resolutions (F = 32, TP = 32)
+    (2, 40, 256, 384, 4), (2, 40, 64, 512, 4),                           # cfg5 (F = 96 / 128, TP = 64, two channel chunks)
+    (1, 5, 256, 128, 4), (1, 5, 16, 64, 4),                              # cfg2 / cfg1 (TP = 8, F = 32 / 16)
+    (2, 1, 64, 64, 4), (2, 2, 64, 128, 4), (1, 8, 64, 128, 4), (3, 9, 16, 128, 4), (1, 14, 256, 128, 4), (2, 16, 64, 128, 4),
+    (1, 17, 64, 256, 4), (1, 32, 64, 128, 4), (1, 33, 16, 384, 4), (1, 64, 64, 128, 2), (2, 12, 64, 192, 4),
+])
+@pytest.mark.parametrize("masked", [True, False])
+def test_attn_temporal_tcgen05_vs_torch(B, T, HW, C, heads, masked):
+    """fdm_attn_temporal, tcgen05 engine (attn_temporal_tc.cu: bf16 tables + workspace) against torch fp32 over the SAME
+    bf16-rounded operands: the output, and the normalised attention weights it leaves in the workspace (rpe.py:164 `attn`)."""
+    from improved_diffusion import _native as N_
+    import ctypes as C_
+    g = torch.Generator(device="cuda").manual_seed(T * 7 + C + HW)
+    qkv = torch.randn(B * T, HW, 3 * C, device="cuda", generator=g).to(torch.bfloat16)
+    Rq, Rk, Rv = ((0.5 * torch.randn(B, T, T, C, device="cuda", generator=g)).to(torch.bfloat16) for _ in range(3))
+    mask = (torch.rand(B, T, device="cuda", generator=g) > 0.3).float() if masked else None
+    out = torch.full((B * T, HW, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    a = N_.AttnTemporalArgs(qkv=qkv.data_ptr(), Rq=None, Rk=None, Rv=None, mask=mask.data_ptr() if masked else None,
+                            out=out.data_ptr(), B=B, T=T, HW=HW, C=C, heads=heads, qkv_dtype=N_.BF16, out_dtype=N_.BF16,
+                            Rq_op=Rq.data_ptr(), Rk_op=Rk.data_ptr(), Rv_op=Rv.data_ptr())
+    need = int(N_.lib().fdm_attn_temporal_workspace(C_.byref(a)))
+    assert need > 0, "the tcgen05 engine should take this shape"
+    ws = torch.full((need,), 0xFF, device="cuda", dtype=torch.uint8)  # NaN-poisoned: every byte that is read must have been written
+    a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    N_.call("fdm_attn_temporal", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    m = mask if masked else torch.ones(B, T, device="cuda")
+    ref, p_ref = _temporal_reference(qkv, Rq, Rk, Rv, m, B, T, HW, C, heads)
+    e = rel(out.float(), ref)
+    off = int(N_.lib().fdm_attn_temporal_attn_offset(C_.byref(a)))
+    attn = ws[off:off + B * heads * HW * T * 64 * 2].view(torch.bfloat16).view(B, heads, HW, T, 64).float()
+    e_attn = rel(attn[..., :T].permute(0, 2, 1, 3, 4), p_ref)
+    print(f"temporal tcgen05 B={B} T={T} HW={HW} C={C}: out rel-L2 {e:.3e}, attention weights rel-L2 {e_attn:.3e}")
+    assert bool(torch.isfinite(out.float()).all())
+    assert float(attn[..., T:].abs().max()) == 0.0 if T < 64 else True
+    assert e_attn <= 6e-3, e_attn   # P is stored in bf16
+    assert e <= 8e-3, e             # bf16 P feeding both value terms, bf16 output

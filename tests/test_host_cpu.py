@@ -281,14 +281,32 @@ def test_training_plan_compiles_and_covers_every_parameter(over, B, T, precision
         for it in items:
             refs.update(v.data_ptr() for v in it.values() if isinstance(v, torch.Tensor))
     base = P.pgrad.data_ptr()
-    off = 0
-    missing = []
-    for name, p in model.named_parameters():
-        if base + 4 * off not in refs:
-            missing.append(name)
-        off += (p.numel() + 3) // 4 * 4
+    missing = [name for (name, p), off in zip(model.named_parameters(), P.flat_offs) if base + 4 * off not in refs]
     assert not missing, missing
-    assert off == P.pgrad.numel()
+    # flat layout = gradient-completion order (optim.completion_order): dense 16-byte aligned slots, head first, the conditioning
+    # path (time MLP, FiLM projections, RPENets) last; the same layout FlatAdamW uses for parameters / moments / gradients
+    from improved_diffusion.optim import model_flat_layout
+    params, offs, total, order, n_early = model_flat_layout(model)
+    assert offs == P.flat_offs and total == P.pgrad.numel() and sorted(order) == list(range(len(params)))
+    names = [n for n, _ in model.named_parameters()]
+    pos = 0
+    for i in order:
+        assert offs[i] == pos
+        pos += (params[i].numel() + 3) // 4 * 4
+    assert names[order[0]].startswith("out.") and all(
+        n.startswith("time_embed.") or ".emb_layers." in n or ".rpe_net." in n for n in (names[i] for i in order[n_early:]))
+    # gradient buckets: contiguous cover of the buffer, completion points strictly ascending, the last one = end of the schedule
+    bk = P.grad_buckets
+    assert len(bk) >= 2 and bk[0][0] == 0 and bk[-1][1] == total and all(a[1] == b[0] for a, b in zip(bk, bk[1:]))
+    assert all(a[2] < b[2] for a, b in zip(bk, bk[1:])) and bk[-1][2] == len(P.bops) - 1
+    segs = P.backward_segments()
+    assert segs[0][0] == 0 and segs[-1][1] == len(P.bops) and all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+    # no launch after a bucket's completion point writes into it
+    for (b_lo, b_hi, done) in bk[:-1]:
+        for j in range(done + 1, len(P.bops)):
+            for v in P.bops[j][2].values():
+                if isinstance(v, torch.Tensor) and base <= v.data_ptr() < base + 4 * total:
+                    assert not (b_lo <= (v.data_ptr() - base) // 4 < b_hi), (P.bops[j][0], j, done)
     # every >= 2-D weight is packed for the forward and (except the stem: no input gradient) for the dgrad conv
     packed_fwd = {id(s_) for s_, _, _, _, _, _, mode in P.pack_problems if mode in (N_.PACK_TC_FWD, N_.PACK_SIMT_FWD)}
     convs = [p for n_, p in model.named_parameters() if p.dim() == 4 or (p.dim() == 2 and ("qkv" in n_ or "proj_out" in n_ or n_.endswith("rpe_net.out.weight")))]
