@@ -714,7 +714,11 @@ class DenoiserEngine:
                 # bf16 copies of the tables are the B operands of the tcgen05 temporal attention (attn_temporal_tc.cu); the fp32
                 # tables are only kept where something still reads them: the CUDA-core kernel (shapes the tcgen05 engine does not
                 # take, FDM_TEMPORAL_TC=0) and the backward kernels of training plans
-                tc_here = self.temporal_tc and self._temporal_ws(B, T, ab.channels, ab.temporal_attention.num_heads, None) is not None
+                # (training plans keep the CUDA-core forward: its backward kernels re-form P in fp32 from the fp32 tables, and a
+                # forward that rounded P / R to bf16 would leave the analytically-zero gradients (RPE output biases: softmax shift
+                # invariance) with more noise than torch's own autocast backward — measured 0.148 vs 0.14 allowed)
+                tc_here = (self.temporal_tc and not train
+                           and self._temporal_ws(B, T, ab.channels, ab.temporal_attention.num_heads, None) is not None)
                 rop = P.buf(f"rpe_R_op", B * T * T * Cc * 2, True) if tc_here else None
                 rb_ = P.buf(f"rpe_R", B * T * T * Cc * 4, True) if (train or not tc_here) else None
                 hid[(id(ab), which)], R[(id(ab), which)] = hb, rb_
@@ -1012,7 +1016,7 @@ class DenoiserEngine:
             conv(xn_op, Cc, Hh, Ww, ta.qkv.weight, 3 * Cc, 1, bias=f32(ta.qkv.bias), y_op=qkv)
             o = P.buf("ta_o", Nf * hw * Cc * osz)
             P.flops += 10 * T * T * Cc * B * hw  # QK^T, PV and the three contextual RPE einsums (rpe.py:72-83,144,166)
-            ws_bytes = self._temporal_ws(B, T, Cc, ta.num_heads, hw) if self.temporal_tc else None
+            ws_bytes = self._temporal_ws(B, T, Cc, ta.num_heads, hw) if (self.temporal_tc and not train) else None
             ws = P.buf("ta_ws", ws_bytes) if ws_bytes else None
             if ws is None and R[(id(ab), "rpe_q")] is None:
                 raise NativeShapeError(f"temporal attention: no kernel takes T={T}, HW={hw}, C={Cc}, heads={ta.num_heads}")

@@ -13,6 +13,8 @@ Same update rule as torch (decoupled weight decay, bias correction, no amsgrad);
 torch.optim.AdamW step by step.  Gradients that do not come from the native backward (CPU path, torch DDP buckets, partial
 graphs) are gathered into a flat buffer with one foreach copy first.  CUDA only: there is no CPU fallback.
 
+`FlatAdamW(model.parameters(), ..., model=model, bind=False)` only adopts the model's flat layout (gradient-completion order, the
+layout of the native backward's buffer: its per-parameter gradient views are then used in place, without a gather copy).
 `FlatAdamW(model.parameters(), ..., model=model)` additionally BINDS the model's gradient path to the optimizer ("flat-gradient
 mode"): every `p.grad` becomes a persistent view of the optimizer's flat gradient buffer, the native backward node takes ONE
 anchor tensor instead of the 390 parameters and hands its flat gradient over with one (allreduce +) copy — or add, when several
@@ -73,7 +75,7 @@ def model_flat_layout(model):
 
 
 class FlatAdamW(th.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, ema_rates=(), model=None):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, ema_rates=(), model=None, bind=True):
         params = list(params)
         if any(isinstance(p, dict) for p in params):
             raise NotImplementedError("FlatAdamW takes one parameter group (as train_util.py:127 builds it)")
@@ -107,7 +109,7 @@ class FlatAdamW(th.optim.Optimizer):
         self.ema_rates = tuple(float(r) for r in ema_rates)
         self.flat_ema = [self.flat_p.clone() for _ in self.ema_rates]
         self.bound = None
-        if model is not None:
+        if model is not None and bind:
             self.bound = model
             self.flat_g = th.zeros_like(self.flat_p)
             for p, gview in zip(ps, self._views(self.flat_g)):

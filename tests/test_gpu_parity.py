@@ -410,7 +410,7 @@ def test_flat_adamw_matches_torch_adamw(monkeypatch):
     ref = copy.deepcopy(model)
     ref_ema = [p.detach().clone() for p in ref.parameters()]
     opt_ref = torch.optim.AdamW(ref.parameters(), lr=3e-3, weight_decay=0.05)
-    opt = FlatAdamW(model.parameters(), lr=3e-3, weight_decay=0.05, ema_rates=(0.9,))
+    opt = FlatAdamW(model.parameters(), lr=3e-3, weight_decay=0.05, ema_rates=(0.9,), model=model, bind=False)
     assert all(torch.equal(a, b) for a, b in zip(model.parameters(), ref.parameters()))  # flattening kept the values
     inp = O.synthetic_inputs(cfg, 1, 5, 2, seed=6)
     noise = torch.randn(inp["x0"].shape, generator=torch.Generator().manual_seed(3))
@@ -425,7 +425,7 @@ def test_flat_adamw_matches_torch_adamw(monkeypatch):
         # zero-gradient parameters into O(lr) steps of random sign, so two separately differentiated copies drift apart
         for p, q in zip(model.parameters(), ref.parameters()):
             q.grad = p.grad.detach().clone()
-        base = opt.flat_g.data_ptr()
+        base = next(model.parameters()).grad.data_ptr() - 4 * opt._offs[0]
         assert all(p.grad.data_ptr() == base + 4 * o for p, o in zip(model.parameters(), opt._offs)), "gradients are not flat views"
         opt.step()
         opt_ref.step()
