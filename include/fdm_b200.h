@@ -213,6 +213,8 @@ typedef struct {
   const void* Rv_op;
   void* workspace;
   int64_t workspace_bytes;
+  float* attn_mean; /* optional (tcgen05 engine): [B*HW][T][T] fp32, zeroed by the caller; += softmax(S)[t,s] / heads — the map
+                       RPEAttention.forward logs (rpe.py:128-130: mean over heads of `attn`) */
 } fdm_attn_temporal_args; /* which = 7 */
 int fdm_attn_temporal(const fdm_attn_temporal_args* a, void* stream);
 /* bytes of workspace the tcgen05 engine needs for this shape; 0 = the shape is served by the CUDA-core kernel (no workspace) */
@@ -227,6 +229,7 @@ typedef struct {
   int32_t qkv_dtype, out_dtype;
   int32_t engine; /* 0 = auto (tcgen05 kernel for bf16 when L in {16,32,64,128,256} and head dim % 16 == 0, else CUDA cores); 1 = force CUDA cores */
   float* lse;     /* optional output [N][heads][L] (tcgen05 engine only): log-sum-exp of every score row, consumed by fdm_attn_spatial_bwd */
+  float* attn_mean; /* optional (tcgen05 engine only): [N][L][L] fp32, zeroed by the caller; += softmax(S)[q,k] / heads (rpe.py:128-130) */
 } fdm_attn_spatial_args; /* which = 8 */
 int fdm_attn_spatial(const fdm_attn_spatial_args* a, void* stream);
 

@@ -405,6 +405,7 @@ extern "C" int fdm_attn_temporal(const fdm_attn_temporal_args* a, void* stream) 
     if (rc != FDM_ERR_UNSUPPORTED) return rc;
   }
   FDM_REQUIRE(a->Rq && a->Rk && a->Rv, FDM_ERR_BAD_ARG);  // the CUDA-core kernel reads the fp32 tables
+  FDM_REQUIRE(a->attn_mean == nullptr, FDM_ERR_UNSUPPORTED);
   const int F = a->C / a->heads;
   FDM_REQUIRE(F % TA_FC == 0 && a->T <= 40, FDM_ERR_UNSUPPORTED);
   TAParams p{a->qkv, a->Rq, a->Rk, a->Rv, a->mask, a->out, a->B, a->T, a->HW, a->C, a->heads, F, 1, 1, 1.0f / sqrtf((float)F)};
@@ -427,6 +428,7 @@ extern "C" int fdm_attn_spatial(const fdm_attn_spatial_args* a, void* stream) {
     int rc = attn_spatial_tc_launch(a, (cudaStream_t)stream);
     if (rc != FDM_ERR_UNSUPPORTED) return rc;
   }
+  FDM_REQUIRE(a->attn_mean == nullptr, FDM_ERR_UNSUPPORTED);  // attention-map logging is served by the tcgen05 kernels only
   const int F = a->C / a->heads;
   SAParams p{a->qkv, a->out, a->N, a->L, a->C, a->heads, F, 1.0f / sqrtf((float)F)};
   cudaStream_t st = (cudaStream_t)stream;

@@ -25,6 +25,7 @@ struct SaTcParams {
   int tmem_cols;
   float scale_log2e;
   float* lse;   // optional [N][heads][L]: natural-log sum-exp of each scaled score row (saved for the backward pass)
+  float* attn_mean;  // optional [N][L][L]: += softmax weights / heads (attention-map logging, rpe.py:128-130)
 };
 
 // MN-major, 128-byte swizzle: rows (one per K index) of 128 bytes = 64 MN elements; 8-row groups 1024 bytes apart (SBO)
@@ -161,6 +162,30 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
       *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = w;
     }
   }
+  if (p.attn_mean != nullptr) {
+    // materialising variant (logging path): third pass over the score row while S is still in TMEM — the normalised weights,
+    // averaged over the heads by fp32 atomics (the head CTAs of a frame add into the same [L][L] map)
+    const float w = 1.f / (sum * (float)p.heads);
+    const int qq = q0 + tid;
+    float* arow = p.attn_mean + ((size_t)n * L + (qq < L ? qq : 0)) * L;
+    if (L >= 32) {
+      for (int c = 0; c < L; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(trow + c, v);
+        if (qq < L) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(arow + c + j, exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, mneg)) * w);
+        }
+      }
+    } else {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(trow, v);
+      if (qq < L) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(arow + j, exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, mneg)) * w);
+      }
+    }
+  }
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -229,6 +254,7 @@ int attn_spatial_tc_launch(const fdm_attn_spatial_args* a, cudaStream_t st) {
   p.tmem_cols = pow2_at_least(L > F ? L : F, 32);
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)F);
   p.lse = a->lse;
+  p.attn_mean = a->attn_mean;
   EncodeTiledFn enc = get_tensormap_encoder();
   FDM_REQUIRE(enc != nullptr, FDM_ERR_UNSUPPORTED);
   CUtensorMap tq;

@@ -32,6 +32,7 @@ struct TtParams {
   float* b3;               // [B][heads][HW][T(s)][TS(t)]   k_s . Rq[s,t]  (unscaled)
   __nv_bfloat16* P;        // [B][heads][HW][T][64]   normalised attention weights, zero beyond s >= T
   __nv_bfloat16* out;      // [B*T][HW][C]
+  float* attn_mean;        // optional [B*HW][T][T]: += attention weights / heads (attention-map logging, rpe.py:128-130)
   int B, T, HW, C, F, heads;
   int TS;                  // row stride of b2 / b3: tt_row_stride(T) — a multiple of 4 with TS/4 odd (conflict-free float4 rows)
   int Tn;                  // GEMM extent of the frame axis = round_up(T, 16)
@@ -328,6 +329,13 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const __grid_constant__ 
           for (int k = 0; k < TP; ++k) w[k] = e[(g * TP + k) % W];
         }
     }
+    if (p.attn_mean != nullptr) {
+      float* arow = p.attn_mean + (((size_t)b * HW + px) * T + t) * T;
+      const float hw_ = 1.f / (float)p.heads;
+#pragma unroll
+      for (int k = 0; k < TP; ++k)
+        if (k < T) atomicAdd(arow + k, w[k] * hw_);
+    }
     uint4* dst = reinterpret_cast<uint4*>(p.P + (((size_t)bh * HW + px) * T + t) * 64);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -521,6 +529,7 @@ int attn_temporal_tc_launch(const fdm_attn_temporal_args* a, cudaStream_t st) {
   p.b3 = p.b2 + rows * p.TS;
   p.P = reinterpret_cast<__nv_bfloat16*>(p.b3 + rows * p.TS);
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.attn_mean = a->attn_mean;
   const int TP = T <= 8 ? 8 : (T <= 16 ? 16 : (T <= 32 ? 32 : 64));
   const int PL = 128 / TP;
 

@@ -46,9 +46,9 @@ RpeHiddenArgs = _S("RpeHiddenArgs", [("te", vp), ("frame_indices", vp), ("proble
 AttnTemporalArgs = _S("AttnTemporalArgs", [("qkv", vp), ("Rq", vp), ("Rk", vp), ("Rv", vp), ("mask", vp), ("out", vp),
                                            ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("heads", i32),
                                            ("qkv_dtype", i32), ("out_dtype", i32), ("Rq_op", vp), ("Rk_op", vp), ("Rv_op", vp),
-                                           ("workspace", vp), ("workspace_bytes", i64)])
+                                           ("workspace", vp), ("workspace_bytes", i64), ("attn_mean", vp)])
 AttnSpatialArgs = _S("AttnSpatialArgs", [("qkv", vp), ("out", vp), ("N", i32), ("L", i32), ("C", i32), ("heads", i32),
-                                         ("qkv_dtype", i32), ("out_dtype", i32), ("engine", i32), ("lse", vp)])
+                                         ("qkv_dtype", i32), ("out_dtype", i32), ("engine", i32), ("lse", vp), ("attn_mean", vp)])
 CastArgs = _S("CastArgs", [("x", vp), ("out", vp), ("N", i32), ("H", i32), ("W", i32), ("C", i32),
                            ("upsample", i32), ("op_dtype", i32), ("colsum", vp), ("colsum2", vp)])
 DdpmStepArgs = _S("DdpmStepArgs", [("x", vp), ("eps", vp), ("noise", vp), ("coef", vp), ("t", vp), ("sample", vp),

@@ -61,6 +61,7 @@ class Plan:
         self.side_begin = self.side_end = self.join_at = 0  # op index range of the RPE-table branch / its first consumer
         self.side_stream = self.ev_fork = self.ev_join = None
         self.temporal_attn_maps = []  # (workspace Buf, B, T, HW, C, heads) of every tcgen05 temporal attention (attention weights)
+        self.attn_maps = {"spatial": [], "temporal": [], "mixed": []}  # collect_attn plans: (Buf in the zeroed arena, shape)
         self.flops = 0       # algorithmic 2*MAC of every conv / linear / attention matmul of one forward
         self.conv_flops = 0
 
@@ -79,6 +80,13 @@ class Plan:
 
     def stats(self, name, n, c):
         b = Buf(name, n * c * 2 * 8, True, "stats")
+        b.offset = self.stats_bytes
+        self.stats_bytes += b.nbytes
+        return b
+
+    def zeroed(self, name, nbytes):
+        """A buffer in the statistics arena: zeroed at the head of every run (accumulators written with atomics)."""
+        b = Buf(name, nbytes, True, "stats")
         b.offset = self.stats_bytes
         self.stats_bytes += b.nbytes
         return b
@@ -446,7 +454,7 @@ class DenoiserEngine:
         return self.packed[key]
 
     # ------------------------------------------------------------------ plan compiler
-    def plan_for(self, B, T, H, W, device, train=False, slot=0):
+    def plan_for(self, B, T, H, W, device, train=False, slot=0, collect_attn=False):
         """`slot`: distinct plans (own arena, own streams) of the same shape — sub-batches run concurrently by the sampler"""
         if train:
             # training plans survive optimizer steps: their packed weights are refreshed by ONE fdm_pack_weights launch at the
@@ -467,10 +475,10 @@ class DenoiserEngine:
                 self._train_probe = (probe, self.train_plans[key])
             return self.train_plans[key]
         self.refresh_weights()
-        key = (B, T, H, W, str(device), slot)
+        key = (B, T, H, W, str(device), slot, bool(collect_attn))
         if key not in self.plans:
             with th.cuda.device(device):
-                self.plans[key] = self._compile(B, T, H, W, device)
+                self.plans[key] = self._compile(B, T, H, W, device, collect_attn=collect_attn)
         return self.plans[key]
 
     def _grad_buckets(self, P, params):
@@ -550,7 +558,7 @@ class DenoiserEngine:
             return 128 % Wo == 0 and hw % 128 == 0
         return 128 % hw == 0 and (hw % 32 == 0 or 32 % hw == 0)
 
-    def _compile(self, B, T, H, W, device, train=False):
+    def _compile(self, B, T, H, W, device, train=False, collect_attn=False):
         m = self.model
         from .unet import ResBlock, FactorizedAttentionBlock, Downsample, Upsample
         P = Plan(self, B, T, H, W)
@@ -1020,11 +1028,21 @@ class DenoiserEngine:
             ws = P.buf("ta_ws", ws_bytes) if ws_bytes else None
             if ws is None and R[(id(ab), "rpe_q")] is None:
                 raise NativeShapeError(f"temporal attention: no kernel takes T={T}, HW={hw}, C={Cc}, heads={ta.num_heads}")
+            # return_attn_weights=True plans: the tcgen05 kernels also accumulate the head-averaged attention weights — the maps
+            # RPEAttention.forward logs (rpe.py:128-130) — into zero-initialised fp32 buffers
+            t_mean = s_mean = None
+            if collect_attn:
+                if ws is None or not self.use_tc:
+                    raise NativeShapeError("attention-map logging is served by the tcgen05 attention kernels (bf16 mode)")
+                t_mean = P.zeroed("ta_attn_mean", B * hw * T * T * 4)
+                s_mean = P.zeroed("sa_attn_mean", Nf * hw * hw * 4)
+                P.attn_maps["temporal"].append((t_mean, (B * hw, T, T)))
+                P.attn_maps["spatial"].append((s_mean, (Nf, hw, hw)))
             P.op("fdm_attn_temporal", N_.AttnTemporalArgs, qkv=qkv, Rq=R[(id(ab), "rpe_q")], Rk=R[(id(ab), "rpe_k")],
                  Rv=R[(id(ab), "rpe_v")], mask=P.mask, out=o, B=B, T=T, HW=hw, C=Cc, heads=ta.num_heads,
                  qkv_dtype=opd, out_dtype=opd, Rq_op=R_op.get((id(ab), "rpe_q")) if ws else None,
                  Rk_op=R_op.get((id(ab), "rpe_k")) if ws else None, Rv_op=R_op.get((id(ab), "rpe_v")) if ws else None,
-                 workspace=ws, workspace_bytes=ws_bytes or 0)
+                 workspace=ws, workspace_bytes=ws_bytes or 0, attn_mean=t_mean)
             if ws is not None:
                 P.temporal_attn_maps.append((ws, B, T, hw, Cc, ta.num_heads))
             y = new_act("ta_y", Cc, Hh, Ww)
@@ -1043,7 +1061,7 @@ class DenoiserEngine:
             # training: the tcgen05 forward also saves the log-sum-exp of every score row for the tcgen05 backward kernels
             sa_lse = P.buf("sa_lse", Nf * sa.num_heads * hw * 4) if (train and self.use_tc) else None
             P.op("fdm_attn_spatial", N_.AttnSpatialArgs, qkv=qkv2, out=o2, N=Nf, L=hw, C=Cc, heads=sa.num_heads,
-                 qkv_dtype=opd, out_dtype=opd, engine=0 if self.use_tc else 1, lse=sa_lse)
+                 qkv_dtype=opd, out_dtype=opd, engine=0 if self.use_tc else 1, lse=sa_lse, attn_mean=s_mean)
             z = new_act("sa_z", Cc, Hh, Ww)
             z.biases = (sa.proj_out.bias,)
             conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf,
@@ -1329,14 +1347,27 @@ class DenoiserEngine:
             return _DenoiserFn.apply(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, sink.anchor)
         return _DenoiserFn.apply(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, *self.param_list())
 
-    def forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask):
+    def forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, collect_attn=False):
+        """eps, or (eps, attns) with collect_attn: attns = {"spatial": [...], "temporal": [...], "mixed": []}, one head-averaged
+        map per attention block in forward order, as UNetVideoModel.forward(return_attn_weights=True) returns them upstream
+        (unet.py:454-464; spatial [B*T, HW, HW], temporal [B*HW, T, T])."""
         B, T, Cx, H, W = x.shape
-        P = self.plan_for(B, T, H, W, x.device)
         if frame_indices is None:
             raise ValueError("frame_indices is required (temporal RPE, rpe.py:146)")
-        self.load_conditioning(P, x0, frame_indices, obs_mask, latent_mask)
-        P.set_t_source(None)
-        P.x_view.copy_(x)
-        P.t_view.copy_(timesteps.reshape(B).float())
-        P.run(th.cuda.current_stream(x.device).cuda_stream)
-        return P.eps_view.clone()
+        with N_.device_guard(x.device):
+            P = self.plan_for(B, T, H, W, x.device, collect_attn=collect_attn)
+            self.load_conditioning(P, x0, frame_indices, obs_mask, latent_mask)
+            P.set_t_source(None)
+            P.x_view.copy_(x)
+            P.t_view.copy_(timesteps.reshape(B).float())
+            P.run(th.cuda.current_stream(x.device).cuda_stream)
+            eps = P.eps_view.clone()
+            if not collect_attn:
+                return eps
+            attns = {"spatial": [], "temporal": [], "mixed": []}
+            for key in ("spatial", "temporal"):
+                for buf, shape in P.attn_maps[key]:
+                    n = shape[0] * shape[1] * shape[2]
+                    flat = P.stats_arena.view(th.uint8)[buf.offset:buf.offset + 4 * n].view(th.float32)
+                    attns[key].append(flat.view(*shape).clone())
+            return eps, attns

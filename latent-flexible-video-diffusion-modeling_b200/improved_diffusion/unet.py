@@ -150,8 +150,15 @@ class UNetVideoModel(nn.Module):
                 return_attn_weights=False):
         """(eps [B,T,C_out,H,W] fp32, attns) — same contract as unet.py:428-464."""
         if return_attn_weights:
-            # attention-map logging of TrainLoop.log_samples (train_util.py:451-463): needs the materialised T x T / HW x HW
-            # attention matrices, which the fused kernels never form -> PyTorch expression of the same network (slow path)
+            # attention-map logging of TrainLoop.log_samples (train_util.py:451-463).  bf16 mode on CUDA, no gradients: the
+            # tcgen05 attention kernels accumulate the head-averaged maps themselves (materialising variants: attn_tc.cu,
+            # attn_temporal_tc.cu).  Otherwise (fp32 parity mode, CPU, inside autograd): PyTorch expression of the same network.
+            from .engine import NativeShapeError
+            if x.is_cuda and self.precision == "bf16" and not th.is_grad_enabled() and os.environ.get("FDM_ATTN_MAPS", "native") == "native":
+                try:
+                    return self.engine().forward(x, x0, timesteps, frame_indices, obs_mask, latent_mask, collect_attn=True)
+                except NativeShapeError:
+                    pass
             from .autograd_path import differentiable_forward
             attns = {"spatial": [], "temporal": [], "mixed": []}
             out = differentiable_forward(self, x, x0, timesteps, frame_indices, obs_mask, latent_mask, attns=attns)

@@ -275,3 +275,62 @@ def test_philox_sampler_matches_torch_noise_sampler_in_distribution():
     sa, sb = float(a[:, 2:].std()), float(b[:, 2:].std())
     print(f"latent-frame std: torch noise {sa:.4f}, philox noise {sb:.4f}")
     assert abs(sa - sb) <= 0.1 * sa
+
+
+@pytest.mark.parametrize("over,B,T,n_obs,pads", [
+    (dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32), 2, 5, 2, (1,)),
+    (dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000), 2, 20, 10, ()),
+    (dict(image_size=64, in_channels=4, num_channels=128, num_res_blocks=1, diffusion_steps=1000), 1, 40, 20, ()),
+])
+def test_native_attention_maps_match_the_reference(over, B, T, n_obs, pads):
+    """model(..., return_attn_weights=True) (unet.py:454-464, rpe.py:126-131): the head-averaged attention maps of every attention
+    block, produced by the materialising variants of the tcgen05 attention kernels, against the unmodified reference on the GPU."""
+    model, diffusion, ref_model, ref_diffusion, cfg, sd = build_pair(over)
+    model.precision = "bf16"
+    inp = O.synthetic_inputs(cfg, B, T, n_obs, seed=3, video_len=300, pad_rows=pads)
+    ts = O.model_timesteps(O.Tables(cfg), torch.tensor([(53 * (b + 1)) % cfg["diffusion_steps"] for b in range(B)]))
+    kw = cuda_kw(inp)
+    with torch.no_grad():
+        eps_r, attn_r = ref_model(inp["x"].cuda(), timesteps=ts.cuda(), return_attn_weights=True, **kw)
+        with torch.autocast("cuda", dtype=torch.bfloat16):  # calibration: what bf16 GEMM operands cost the reference's own maps
+            _, attn_c = ref_model(inp["x"].cuda(), timesteps=ts.cuda(), return_attn_weights=True, **kw)
+        eps_n, attn_n = model(inp["x"].cuda(), timesteps=ts.cuda(), return_attn_weights=True, **kw)
+        eps_plain, none = model(inp["x"].cuda(), timesteps=ts.cuda(), **kw)
+    assert none is None and O.rel_l2(eps_n.cpu(), eps_plain.cpu()) <= 1e-3  # the logging plan computes the same eps
+    assert O.rel_l2(eps_n.cpu(), eps_r.cpu()) <= TOL["bf16"]
+    assert set(attn_n) == set(attn_r) == {"spatial", "temporal", "mixed"} and attn_n["mixed"] == []
+    plans = model.engine().plans
+    assert any(k[-1] for k in plans), "the maps must come from a collect_attn kernel plan, not from the PyTorch expression"
+    worst = worst_c = 0.0
+    for key in ("spatial", "temporal"):
+        assert len(attn_n[key]) == len(attn_r[key]) == 7
+        for a, r, c in zip(attn_n[key], attn_r[key], attn_c[key]):
+            assert a.shape == r.shape and a.dtype == torch.float32
+            e, e_c = O.rel_l2(a.cpu(), r.cpu()), O.rel_l2(c.float().cpu(), r.cpu())
+            worst, worst_c = max(worst, e), max(worst_c, e_c)
+            # softmax maps amplify score errors; the bound is what torch's own autocast-bf16 run of the reference gives on
+            # the same map (x1.5), with north_star's 2e-2 as the floor
+            assert e <= max(2e-2, 1.5 * e_c), (key, tuple(a.shape), e, e_c)
+            rows = a.sum(dim=-1)
+            assert float((rows - 1).abs().max()) <= 2e-3  # every row of a head-averaged softmax sums to 1
+    print(f"attention maps vs reference-on-GPU: worst rel-L2 {worst:.3e} over 14 maps (B={B}, T={T}); torch autocast-bf16: {worst_c:.3e}")
+
+
+def test_sample_loop_attention_logging_matches_the_reference():
+    """p_sample_loop(return_attn_weights=True): the per-quartile running means of the maps (gaussian_diffusion.py:448-469) through
+    the native maps, against the reference loop with the same seeds (TrainLoop.log_samples' path, train_util.py:451-463)."""
+    over = dict(image_size=32, in_channels=4, num_channels=32, num_res_blocks=1, diffusion_steps=32, timestep_respacing="8")
+    model, diffusion, ref_model, ref_diffusion, cfg, sd = build_pair(over)
+    model.precision = "bf16"
+    inp = O.synthetic_inputs(cfg, 2, 6, 2, seed=4, video_len=40)
+    kw = cuda_kw(inp)
+    shape = tuple(inp["x0"].shape)
+    torch.manual_seed(5)
+    s_n, a_n = diffusion.p_sample_loop(model, shape, model_kwargs=kw, latent_mask=kw["latent_mask"], return_attn_weights=True)
+    torch.manual_seed(5)
+    s_r, a_r = ref_diffusion.p_sample_loop(ref_model, shape, model_kwargs=kw, latent_mask=kw["latent_mask"], return_attn_weights=True)
+    assert set(a_n) == set(a_r) and len(a_n) == 8  # 4 quartiles x {spatial, temporal}
+    for tag in a_r:
+        e = O.rel_l2(a_n[tag].cpu(), a_r[tag].cpu())
+        assert a_n[tag].shape == a_r[tag].shape and e <= 3e-2, (tag, e)
+    assert O.rel_l2(s_n.cpu(), s_r.cpu()) <= 8 * TOL["bf16"]
