@@ -209,22 +209,38 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
   const float inv = 1.f / sum;
   const int q = q0 + tid;
   if (p.lse != nullptr && q < L) p.lse[((size_t)n * p.heads + h) * L + q] = mx * p.scale_log2e * 0.6931471805599453f + logf(sum);
-  __nv_bfloat16* orow = p.out + ((size_t)n * L + (q < L ? q : 0)) * C + h * F;
-  for (int f = 0; f < F; f += 16) {
-    uint32_t v[16];
-    tmem_ld_32x32b_x16(trow + f, v);
-    if (q < L) {
-      uint4 w0 = make_uint4(pack_bf16(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv),
-                            pack_bf16(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv),
-                            pack_bf16(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv),
-                            pack_bf16(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv));
-      uint4 w1 = make_uint4(pack_bf16(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv),
-                            pack_bf16(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv),
-                            pack_bf16(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv),
-                            pack_bf16(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv));
-      *reinterpret_cast<uint4*>(orow + f) = w0;
-      *reinterpret_cast<uint4*>(orow + f + 8) = w1;
+  // O / rowsum -> bf16 -> out, 32 head dims (64 bytes per row) at a time through the warp's staging slice (p_s is dead: the PV
+  // MMAs have retired), 4 lanes per row (see warp_store_rows64)
+  uint8_t* stage = p_s + warp * 2560;
+  const int lane = tid & 31;
+  const size_t row0 = (size_t)n * L + q0 + warp * 32;
+  for (int f = 0; f < F; f += 32) {
+    uint32_t v[32];
+    const bool two = f + 16 < F;  // F % 32 == 16: the last pass holds 16 head dims (2 pieces)
+    {
+      uint32_t a[16];
+      tmem_ld_32x32b_x16(trow + f, a);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = a[j];
+      if (two) {
+        tmem_ld_32x32b_x16(trow + f + 16, a);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 + j] = a[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 + j] = 0u;
+      }
     }
+    uint4 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      w[k] = make_uint4(pack2_bf16(__uint_as_float(v[8 * k]) * inv, __uint_as_float(v[8 * k + 1]) * inv),
+                        pack2_bf16(__uint_as_float(v[8 * k + 2]) * inv, __uint_as_float(v[8 * k + 3]) * inv),
+                        pack2_bf16(__uint_as_float(v[8 * k + 4]) * inv, __uint_as_float(v[8 * k + 5]) * inv),
+                        pack2_bf16(__uint_as_float(v[8 * k + 6]) * inv, __uint_as_float(v[8 * k + 7]) * inv));
+    warp_store_rows64(stage, lane, w, [&](int r) -> uint8_t* {
+      return (q0 + warp * 32 + r < L) ? reinterpret_cast<uint8_t*>(p.out + (row0 + r) * C + h * F + f) : nullptr;
+    }, two ? 4 : 2);
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -128,22 +128,30 @@ __global__ void __launch_bounds__(128) rpe_bias_kernel(const __grid_constant__ C
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const int px = px0 + tid;
   const bool ok = tid < p.rows && px < p.HW;
-  const size_t row = (((size_t)bh * p.HW + (ok ? px : 0)) * p.T + j) * p.TS;
-  for (int c0 = 0; c0 < Tn; c0 += 16) {
+  // 16 fp32 columns (64 bytes per row) at a time through the warp's staging slice (the operand tiles are dead: the MMAs have
+  // retired), 4 lanes per row (warp_store_rows64); columns in [T, Tn) come from zero-filled R rows, [Tn, TS) is never read
+  uint8_t* stage = smem + warp * 2560;
+  const int lane = tid & 31;
+  const int r0 = warp * 32;
+  (void)ok;
+  (void)px;
+  for (int c0 = 0; c0 < Tn && c0 < p.TS; c0 += 16) {
     uint32_t v2[16], v3[16];
     tmem_ld_32x32b_x16(trow + c0, v2);
     tmem_ld_32x32b_x16(trow + Tn + c0, v3);
-    if (ok) {
+    const int pieces = min(4, (p.TS - c0) / 4);
+    auto rowp = [&](float* base, int r) -> uint8_t* {
+      const int rr = r0 + r;
+      if (rr >= p.rows || px0 + rr >= p.HW) return nullptr;
+      return reinterpret_cast<uint8_t*>(base + (((size_t)bh * p.HW + px0 + rr) * p.T + j) * p.TS + c0);
+    };
+    uint4 w[4];
 #pragma unroll
-      for (int q = 0; q < 16; q += 4) {
-        if (c0 + q < p.TS) {  // TS % 4 == 0; columns in [T, Tn) come from zero-filled R rows; [Tn, TS) is never read
-          *reinterpret_cast<float4*>(p.b2 + row + c0 + q) =
-              make_float4(__uint_as_float(v2[q]), __uint_as_float(v2[q + 1]), __uint_as_float(v2[q + 2]), __uint_as_float(v2[q + 3]));
-          *reinterpret_cast<float4*>(p.b3 + row + c0 + q) =
-              make_float4(__uint_as_float(v3[q]), __uint_as_float(v3[q + 1]), __uint_as_float(v3[q + 2]), __uint_as_float(v3[q + 3]));
-        }
-      }
-    }
+    for (int k = 0; k < 4; ++k) w[k] = make_uint4(v2[4 * k], v2[4 * k + 1], v2[4 * k + 2], v2[4 * k + 3]);
+    warp_store_rows64(stage, lane, w, [&](int r) { return rowp(p.b2, r); }, pieces);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = make_uint4(v3[4 * k], v3[4 * k + 1], v3[4 * k + 2], v3[4 * k + 3]);
+    warp_store_rows64(stage, lane, w, [&](int r) { return rowp(p.b3, r); }, pieces);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -316,53 +324,71 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const __grid_constant__ 
     }
     umma_commit(&bar_o);
   }
-  // ---- attention weights of this row -> global (K3's A operand; also what rpe.py:164 returns as `attn`)
-  if (valid) {
-    float w[TP];
+  // ---- attention weights -> global (K3's A operand; also what rpe.py:164 returns as `attn`), while the PV MMAs run.
+  // A row's own TP entries are already in this warp's rows of the swizzled P tile: read them back with 8 lanes per row and store
+  // whole 128-byte rows (s >= TP zero-filled) — 4 rows per instruction, consecutive (pixel, frame) rows are contiguous in P.
+  const int lane = tid & 31;
+  if (p.attn_mean != nullptr && valid) {
+    float* arow = p.attn_mean + (((size_t)b * HW + px) * T + t) * T;
+    const float hw_ = 1.f / (float)p.heads;
 #pragma unroll
-    for (int k = 0; k < TP; ++k) w[k] = e[k];
-    if (TP < 32) {
+    for (int j = 0; j < W; ++j) {
+      const bool own = TP >= 32 ? true : ((j / TP) == sub);
+      if (own && (j % TP) < T) atomicAdd(arow + (j % TP), e[j] * hw_);
+    }
+  }
+  {
+    const int k = lane & 7;  // 16-byte piece of the 128-byte output row: entries s = 8k .. 8k+7
 #pragma unroll
-      for (int g = 1; g < 32 / TP; ++g)
-        if (sub == g) {
-#pragma unroll
-          for (int k = 0; k < TP; ++k) w[k] = e[(g * TP + k) % W];
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 32 + i * 4 + (lane >> 3);  // row of the tile
+      const int rpl = r / TP, rt = r - rpl * TP;
+      if (rt < T && px0 + rpl < HW) {
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (8 * k < TP) {
+          const int gp = ((rpl * TP) >> 3) + k;  // piece of the row's 128 columns holding its own block's entries 8k..8k+7
+          val = *reinterpret_cast<const uint4*>(p_s + (gp >> 3) * 16384 + r * 128 + (((gp & 7) ^ (r & 7)) << 4));
         }
-    }
-    if (p.attn_mean != nullptr) {
-      float* arow = p.attn_mean + (((size_t)b * HW + px) * T + t) * T;
-      const float hw_ = 1.f / (float)p.heads;
-#pragma unroll
-      for (int k = 0; k < TP; ++k)
-        if (k < T) atomicAdd(arow + k, w[k] * hw_);
-    }
-    uint4* dst = reinterpret_cast<uint4*>(p.P + (((size_t)bh * HW + px) * T + t) * 64);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (8 * q < TP)
-        dst[q] = make_uint4(tt_pack(w[(8 * q) % TP], w[(8 * q + 1) % TP]), tt_pack(w[(8 * q + 2) % TP], w[(8 * q + 3) % TP]),
-                            tt_pack(w[(8 * q + 4) % TP], w[(8 * q + 5) % TP]), tt_pack(w[(8 * q + 6) % TP], w[(8 * q + 7) % TP]));
-      else
-        dst[q] = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.P + (((size_t)bh * HW + px0 + rpl) * T + rt) * 64) + k * 16) = val;
+      }
     }
   }
   __syncwarp();
   mbar_wait(&bar_o, 0);
   tcgen05_fence_after();
   {
-    // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, rows beyond T only skip the store
-    __nv_bfloat16* orow = p.out + ((size_t)(b * T + (valid ? t : 0)) * HW + (valid ? px : 0)) * C + h * F;
-    for (int f = 0; f < F; f += 16) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(trow + f, v);
-      if (valid) {
-        uint4 w0 = make_uint4(tt_pack(__uint_as_float(v[0]), __uint_as_float(v[1])), tt_pack(__uint_as_float(v[2]), __uint_as_float(v[3])),
-                              tt_pack(__uint_as_float(v[4]), __uint_as_float(v[5])), tt_pack(__uint_as_float(v[6]), __uint_as_float(v[7])));
-        uint4 w1 = make_uint4(tt_pack(__uint_as_float(v[8]), __uint_as_float(v[9])), tt_pack(__uint_as_float(v[10]), __uint_as_float(v[11])),
-                              tt_pack(__uint_as_float(v[12]), __uint_as_float(v[13])), tt_pack(__uint_as_float(v[14]), __uint_as_float(v[15])));
-        *reinterpret_cast<uint4*>(orow + f) = w0;
-        *reinterpret_cast<uint4*>(orow + f + 8) = w1;
+    // O -> bf16 -> out: 32 head dims (64 bytes per row) at a time through the warp's staging slice (the P tile is dead: the PV
+    // MMAs have retired), 4 lanes per row.  tcgen05.ld is warp-collective: rows beyond T take part and skip the store.
+    // (the slice lies inside this warp's OWN 32 rows of the P tile: a slower warp may still be reading its rows for the store above)
+    uint8_t* stage = p_s + warp * 4096;
+    for (int f = 0; f < F; f += 32) {
+      uint32_t v[32];
+      const bool two = f + 16 < F;
+      {
+        uint32_t a[16];
+        tmem_ld_32x32b_x16(trow + f, a);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = a[j];
+        if (two) {
+          tmem_ld_32x32b_x16(trow + f + 16, a);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[16 + j] = a[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[16 + j] = 0u;
+        }
       }
+      uint4 w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        w[k] = make_uint4(tt_pack(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])), tt_pack(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])),
+                          tt_pack(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])), tt_pack(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
+      warp_store_rows64(stage, lane, w, [&](int rr) -> uint8_t* {
+        const int r = warp * 32 + rr;
+        const int rpl = r / TP, rt = r - rpl * TP;
+        if (rt >= T || px0 + rpl >= HW) return nullptr;
+        return reinterpret_cast<uint8_t*>(p.out + ((size_t)(b * T + rt) * HW + px0 + rpl) * C + h * F + f);
+      }, two ? 4 : 2);
     }
   }
   tcgen05_fence_before();
@@ -432,24 +458,44 @@ __global__ void __launch_bounds__(128) rpe_pv_kernel(const __grid_constant__ CUt
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const int px = px0 + tid;
   const bool ok = tid < p.rows && px < p.HW;
-  __nv_bfloat16* orow = p.out + ((size_t)(b * p.T + t) * p.HW + (ok ? px : 0)) * p.C + h * F;
   const __nv_bfloat16* osrc = o_s + (size_t)(ok ? tid : 0) * F;
-  for (int f = 0; f < F; f += 16) {
-    uint32_t v[16];
-    tmem_ld_32x32b_x16(trow + f, v);
-    if (ok) {
-      uint4 o0 = *reinterpret_cast<const uint4*>(osrc + f), o1 = *reinterpret_cast<const uint4*>(osrc + f + 8);
-      const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-      uint32_t r[8];
+  uint8_t* stage = p_s + warp * 2560;  // the P tile is dead: the MMAs have retired
+  const int lane = tid & 31;
+  for (int f = 0; f < F; f += 32) {
+    uint32_t v[32];
+    const bool two = f + 16 < F;
+    {
+      uint32_t a[16];
+      tmem_ld_32x32b_x16(trow + f, a);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float lo = __uint_as_float(ow[q] << 16) + __uint_as_float(v[2 * q]);
-        const float hi = __uint_as_float(ow[q] & 0xffff0000u) + __uint_as_float(v[2 * q + 1]);
-        r[q] = tt_pack(lo, hi);
+      for (int j = 0; j < 16; ++j) v[j] = a[j];
+      if (two) {
+        tmem_ld_32x32b_x16(trow + f + 16, a);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 + j] = a[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 + j] = 0u;
       }
-      *reinterpret_cast<uint4*>(orow + f) = make_uint4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<uint4*>(orow + f + 8) = make_uint4(r[4], r[5], r[6], r[7]);
     }
+    uint4 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (ok && (k < 2 || two)) o = *reinterpret_cast<const uint4*>(osrc + f + 8 * k);
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+      uint32_t r[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        r[q] = tt_pack(__uint_as_float(ow[q] << 16) + __uint_as_float(v[8 * k + 2 * q]),
+                       __uint_as_float(ow[q] & 0xffff0000u) + __uint_as_float(v[8 * k + 2 * q + 1]));
+      w[k] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    warp_store_rows64(stage, lane, w, [&](int rr) -> uint8_t* {
+      const int r = warp * 32 + rr;
+      if (r >= p.rows || px0 + r >= p.HW) return nullptr;
+      return reinterpret_cast<uint8_t*>(p.out + ((size_t)(b * p.T + t) * p.HW + px0 + r) * p.C + h * F + f);
+    }, two ? 4 : 2);
   }
   tcgen05_fence_before();
   __syncthreads();

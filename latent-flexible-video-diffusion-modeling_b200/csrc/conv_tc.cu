@@ -213,26 +213,40 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + c, v);
       if (direct) {
-        const int m = m_w + lane;
-        if (m < p.M && n_off + c < p.Cout) {
-          __nv_bfloat16* dst = p.y_op + (size_t)m * p.Cout + n_off + c;
+        // lane <-> row out of TMEM: pack this lane's 32 channels (64 bytes), transpose through the warp's staging slice (80-byte
+        // row pitch: conflict-free 16-byte accesses) and store with 4 lanes per row — every store instruction writes whole
+        // 64-byte row segments (8 rows x 64 B) instead of 32 scattered 16-byte pieces (partial-sector writes at the L2)
+        uint8_t* sb = reinterpret_cast<uint8_t*>(stg);
+        const bool cols_ok = n_off + c < p.Cout;
 #pragma unroll
-          for (int q = 0; q < 32; q += 8) {
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (p.bias != nullptr) {
-              b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n_off + c + q));
-              b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n_off + c + q + 4));
-            }
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[q]) + b0.x, __uint_as_float(v[q + 1]) + b0.y);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[q + 2]) + b0.z, __uint_as_float(v[q + 3]) + b0.w);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[q + 4]) + b1.x, __uint_as_float(v[q + 5]) + b1.y);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[q + 6]) + b1.z, __uint_as_float(v[q + 7]) + b1.w);
-            uint4 w;
-            w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
-            w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(dst + q) = w;
+        for (int q = 0; q < 32; q += 8) {
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (p.bias != nullptr && cols_ok) {
+            b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n_off + c + q));
+            b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n_off + c + q + 4));
+          }
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[q]) + b0.x, __uint_as_float(v[q + 1]) + b0.y);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[q + 2]) + b0.z, __uint_as_float(v[q + 3]) + b0.w);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[q + 4]) + b1.x, __uint_as_float(v[q + 5]) + b1.y);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[q + 6]) + b1.z, __uint_as_float(v[q + 7]) + b1.w);
+          uint4 w;
+          w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+          w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(sb + lane * 80 + (q >> 3) * 16) = w;
+        }
+        __syncwarp();
+        if (cols_ok) {
+          const int piece = lane & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2);
+            const int m = m_w + row;
+            if (m < p.M)
+              *reinterpret_cast<uint4*>(p.y_op + (size_t)m * p.Cout + n_off + c + piece * 8) =
+                  *reinterpret_cast<const uint4*>(sb + row * 80 + piece * 16);
           }
         }
+        __syncwarp();
         continue;
       }
 #pragma unroll

@@ -124,6 +124,33 @@ __device__ __forceinline__ bool elect_one_sync() {
 // generic-proxy writes to shared memory (st.shared) must be fenced before the async proxy (tcgen05.mma / TMA) reads them
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Epilogue store helper.  Out of TMEM a lane owns one ROW (tcgen05.ld 32x32b), so a plain per-lane store writes 32 scattered
+// 16-byte pieces per instruction (partial 32-byte sectors at the L2: measured 26.5 -> 20.3 us on the cfg4 qkv linear when
+// replaced).  Here the warp transposes 64 bytes per lane through a private staging slice (32 rows x 80-byte pitch: conflict-free
+// 16-byte accesses) and stores with 4 lanes per row: every instruction writes 8 whole 64-byte row segments.
+//   stage      : 2560 bytes of shared memory private to this warp
+//   w[4]       : this lane's 64 bytes (row = lane)
+//   row_ptr(r) : global address of row r's 64-byte segment, or nullptr to skip the row;  pieces: 16-byte pieces to store (<= 4)
+template <class RowPtr>
+__device__ __forceinline__ void warp_store_rows64(uint8_t* stage, int lane, const uint4 (&w)[4], RowPtr row_ptr, int pieces = 4) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stage + lane * 80 + q * 16) = w[q];
+  __syncwarp();
+  const int piece = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2);
+    uint8_t* d = row_ptr(row);
+    if (d != nullptr && piece < pieces) *reinterpret_cast<uint4*>(d + piece * 16) = *reinterpret_cast<const uint4*>(stage + row * 80 + piece * 16);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
