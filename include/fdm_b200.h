@@ -183,6 +183,30 @@ typedef struct {
 } fdm_rpe_hidden_args; /* which = 6 */
 int fdm_rpe_hidden(const fdm_rpe_hidden_args* a, void* stream);
 
+/* A9 (fused)  every RPENet table of a forward in ONE launch (rpe_tables_tc.cu): the hidden layer is generated straight into shared
+ *   memory as the A operand of a tcgen05 GEMM with W_o (one tensor map per net, kept in a DEVICE blob), b_o added in the epilogue.
+ *   Replaces fdm_rpe_hidden + one fdm_conv per net on inference plans.
+ *   fdm_rpe_tables_prepare fills a HOST blob of fdm_rpe_tables_blob_bytes(count) bytes from a HOST array of problems (device
+ *   pointers inside); the caller copies it to 128-byte aligned device memory once and passes that to fdm_rpe_tables. */
+typedef struct {
+  const float* wd;      /* embed_distances.weight [C][3] */
+  const float* bd;      /* embed_distances.bias   [C]    */
+  const float* bo;      /* out.bias               [C]    */
+  const void* w_packed; /* out.weight packed bf16 [1][round_up(C,16)][round_up(C,64)] (FDM_PACK_TC_FWD layout) */
+  void* out_op;         /* bf16 table [B][T][T][C] or NULL */
+  float* out_f32;       /* fp32 table [B][T][T][C] or NULL */
+  int32_t C, te_off;    /* W_t temb + b_t of this net lives at te[b][te_off .. te_off+C) */
+} fdm_rpe_table_problem; /* which = 31 */
+typedef struct {
+  const float* te;              /* [B][te_stride] */
+  const int64_t* frame_indices; /* [B][T] */
+  const void* blob;             /* DEVICE copy of the prepared blob */
+  int32_t count, B, T, te_stride, max_C;
+} fdm_rpe_tables_args; /* which = 32 */
+size_t fdm_rpe_tables_blob_bytes(int32_t count);
+int fdm_rpe_tables_prepare(const fdm_rpe_table_problem* problems, int32_t count, void* host_blob, size_t blob_bytes);
+int fdm_rpe_tables(const fdm_rpe_tables_args* a, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A8  temporal attention core with in-kernel RPE and the two-group mask — rpe.py:139-170
  *   qkv: [B*T][HW][3C] (q|k|v, each [heads][F]);  Rq,Rk,Rv: [B][T][T][C] fp32 (R[b,t,s,h,f]);

@@ -67,6 +67,8 @@ extern "C" size_t fdm_struct_size(int which) {
     case 28: return sizeof(fdm_nchw_to_nhwc_args);
     case 29: return sizeof(fdm_adamw_args);
     case 30: return sizeof(fdm_masked_mse_bwd_args);
+    case 31: return sizeof(fdm_rpe_table_problem);
+    case 32: return sizeof(fdm_rpe_tables_args);
     default: return 0;
   }
 }

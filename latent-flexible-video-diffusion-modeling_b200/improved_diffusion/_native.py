@@ -103,6 +103,10 @@ AdamwArgs = _S("AdamwArgs", [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema0"
                              ("bias_correction1", f32), ("bias_correction2_sqrt", f32), ("ema_rate0", f32), ("ema_rate1", f32)])
 MaskedMseBwdArgs = _S("MaskedMseBwdArgs", [("out", vp), ("target", vp), ("m1", vp), ("m2", vp), ("g_mse", vp), ("g_eval", vp),
                                            ("d_out", vp), ("per_frame", i64), ("B", i32), ("T", i32)])
+RpeTableProblem = _S("RpeTableProblem", [("wd", vp), ("bd", vp), ("bo", vp), ("w_packed", vp), ("out_op", vp), ("out_f32", vp),
+                                         ("C", i32), ("te_off", i32)])
+RpeTablesArgs = _S("RpeTablesArgs", [("te", vp), ("frame_indices", vp), ("blob", vp), ("count", i32), ("B", i32), ("T", i32),
+                                     ("te_stride", i32), ("max_C", i32)])
 PACK_TC_FWD, PACK_TC_DGRAD, PACK_SIMT_FWD, PACK_SIMT_DGRAD, PACK_SUM2 = 0, 1, 2, 3, 4
 
 # index = `which` of fdm_struct_size (include/fdm_b200.h)
@@ -111,14 +115,14 @@ STRUCTS = [InputPrepArgs, ConvArgs, GnApplyArgs, TemporalGnArgs, TimestepEmbeddi
            LinearProblem, RpeHiddenProblem,
            PackProblem, PackWeightsArgs, ConvWgradArgs, GnBwdArgs, TemporalGnBwdArgs, AttnSpatialBwdArgs, AttnTemporalBwdArgs,
            RpeHiddenBwdProblem, RpeHiddenBwdArgs, LinearBwdProblem, GroupedLinearBwdArgs, SumPartsArgs, AccumArgs,
-           NchwToNhwcArgs, AdamwArgs, MaskedMseBwdArgs]
+           NchwToNhwcArgs, AdamwArgs, MaskedMseBwdArgs, RpeTableProblem, RpeTablesArgs]
 
 ENTRY_POINTS = ["fdm_input_prep", "fdm_conv", "fdm_gn_apply", "fdm_temporal_gn", "fdm_timestep_embedding",
                 "fdm_grouped_linear", "fdm_rpe_hidden", "fdm_attn_temporal", "fdm_attn_spatial", "fdm_cast",
                 "fdm_ddpm_step", "fdm_q_sample", "fdm_masked_mse",
                 "fdm_pack_weights", "fdm_conv_wgrad", "fdm_gn_bwd", "fdm_temporal_gn_bwd", "fdm_attn_spatial_bwd",
                 "fdm_attn_temporal_bwd", "fdm_rpe_hidden_bwd", "fdm_grouped_linear_bwd", "fdm_sum_parts", "fdm_accum",
-                "fdm_nchw_to_nhwc", "fdm_adamw", "fdm_masked_mse_bwd"]
+                "fdm_nchw_to_nhwc", "fdm_adamw", "fdm_masked_mse_bwd", "fdm_rpe_tables"]
 
 _lib = None
 
@@ -147,6 +151,10 @@ def lib():
             fn.argtypes = [vp, vp]
         L.fdm_conv_wgrad_workspace.restype = C.c_size_t
         L.fdm_conv_wgrad_workspace.argtypes = [vp]
+        L.fdm_rpe_tables_blob_bytes.restype = C.c_size_t
+        L.fdm_rpe_tables_blob_bytes.argtypes = [C.c_int32]
+        L.fdm_rpe_tables_prepare.restype = C.c_int
+        L.fdm_rpe_tables_prepare.argtypes = [vp, C.c_int32, vp, C.c_size_t]
         for name in ("fdm_attn_temporal_workspace", "fdm_attn_temporal_attn_offset"):
             getattr(L, name).restype = C.c_size_t
             getattr(L, name).argtypes = [vp]

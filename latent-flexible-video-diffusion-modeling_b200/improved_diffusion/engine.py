@@ -714,11 +714,18 @@ class DenoiserEngine:
         hid = {}
         rh_probs, out_probs, rpe_tc = [], [], []
         hsz = self.op_size if self.use_tc else 4
+        # inference plans whose temporal attentions ALL run on tcgen05: ONE fused launch produces every bf16 table (hidden layer
+        # generated in shared memory as the GEMM's A operand: rpe_tables_tc.cu) instead of fdm_rpe_hidden + one GEMM per net
+        fuse_tables = (self.temporal_tc and not train and os.environ.get("FDM_FUSED_RPE_TABLES", "1") != "0" and bool(attn_blocks)
+                       and max(ab.channels for ab in attn_blocks) <= 512
+                       and all(self._temporal_ws(B, T, ab.channels, ab.temporal_attention.num_heads, None) is not None
+                               for ab in attn_blocks))
         for ab in attn_blocks:
             Cc = ab.channels
             for which in ("rpe_q", "rpe_k", "rpe_v"):
                 net = getattr(ab.temporal_attention, which).rpe_net
-                hb = P.buf(f"rpe_hidden", B * T * T * Cc * hsz, True)  # side-stream lifetime: never aliased with main-branch buffers
+                # (side-stream lifetime: never aliased with main-branch buffers)
+                hb = None if fuse_tables else P.buf(f"rpe_hidden", B * T * T * Cc * hsz, True)
                 # bf16 copies of the tables are the B operands of the tcgen05 temporal attention (attn_temporal_tc.cu); the fp32
                 # tables are only kept where something still reads them: the CUDA-core kernel (shapes the tcgen05 engine does not
                 # take, FDM_TEMPORAL_TC=0) and the backward kernels of training plans
@@ -738,7 +745,28 @@ class DenoiserEngine:
                                           ldx=Cc, ldy=Cc, silu_in=0))
                 rpe_tc.append((hb, Cc, net, rb_, rop))
         self._pending_rpe_tc = []
-        if rh_probs:
+        self._pending_rt = None
+        if fuse_tables:
+            assert all(rop is not None and rb_ is None for _, _, _, rb_, rop in rpe_tc)
+            nbytes = int(N_.lib().fdm_rpe_tables_blob_bytes(len(rpe_tc)))
+            blob = th.zeros(nbytes + 128, dtype=th.uint8, device=device)
+            blob = blob[(-blob.data_ptr()) % 128:][:nbytes]  # tensor maps need 128-byte alignment
+            P.keep.append(blob)
+            self._pending_rt = (blob, [dict(wd=f32(net.embed_distances.weight), bd=f32(net.embed_distances.bias), bo=f32(net.out.bias),
+                                            w_packed=self._pack_tc(net.out.weight), out_op=rop, out_f32=None, C=Cc, te_off=q_["te_off"])
+                                       for (hb, Cc, net, rb_, rop), q_ in zip(rpe_tc, rh_probs)])
+            P.flops += sum(2 * B * T * T * Cc * Cc for _, Cc, _, _, _ in rpe_tc)
+            idx = len(P.ops)
+            P.side_begin = idx
+            P.op("fdm_rpe_tables", N_.RpeTablesArgs, te=cond, frame_indices=P.fi, blob=blob, count=len(rpe_tc), B=B, T=T,
+                 te_stride=cond_cols, max_C=max(Cc for _, Cc, _, _, _ in rpe_tc))
+            for _, _, _, _, rop in rpe_tc:
+                rop.first = idx if rop.first is None else rop.first
+                rop.last = idx
+            P.side_end = len(P.ops)
+            rpe_tc = []
+            self._pending_rh = None
+        elif rh_probs:
             dev = th.zeros(len(rh_probs) * C.sizeof(N_.RpeHiddenProblem), dtype=th.uint8, device=device)
             P.keep.append(dev)
             self._pending_rh = (dev, rh_probs)
@@ -1299,6 +1327,16 @@ class DenoiserEngine:
                 arr[i].C, arr[i].te_off = pr["C"], pr["te_off"]
             dev.copy_(th.frombuffer(bytearray(bytes(arr)), dtype=th.uint8))
         self._pending_groups, self._pending_rh = [], None
+        if getattr(self, "_pending_rt", None) is not None:
+            blob, items = self._pending_rt
+            arr = (N_.RpeTableProblem * len(items))()
+            for i, it in enumerate(items):
+                for k, v in it.items():
+                    setattr(arr[i], k, P.ptr(v) if isinstance(v, (Buf, tuple, th.Tensor)) or v is None else v)
+            host = (C.c_uint8 * blob.numel())()
+            N_.check(N_.lib().fdm_rpe_tables_prepare(C.byref(arr), len(items), C.byref(host), blob.numel()), "fdm_rpe_tables_prepare")
+            blob.copy_(th.frombuffer(bytearray(bytes(host)), dtype=th.uint8))
+            self._pending_rt = None
         for dev, cls, items in P.pending:
             arr = (cls * len(items))()
             for i, it in enumerate(items):

@@ -249,3 +249,50 @@ def test_attn_temporal_tcgen05_vs_torch(B, T, HW, C, heads, masked):
     assert float(attn[..., T:].abs().max()) == 0.0 if T < 64 else True
     assert e_attn <= 6e-3, e_attn   # P is stored in bf16
     assert e <= 8e-3, e             # bf16 P feeding both value terms, bf16 output
+
+
+@pytest.mark.parametrize("B,T,Cs", [(8, 20, (128, 128, 128)), (2, 40, (384, 512, 384, 512)), (1, 5, (64,)), (3, 7, (96, 200))])
+def test_rpe_tables_fused_vs_torch(B, T, Cs):
+    """fdm_rpe_tables (rpe_tables_tc.cu): every RPENet table of a forward in one launch — hidden layer generated in shared memory,
+    W_o GEMM on tcgen05 from per-net tensor maps in a device blob — against the torch expression of rpe.py:20-31 over the same
+    bf16-rounded hidden values and weights."""
+    import ctypes as C_
+    from improved_diffusion import _native as N_
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + T)
+    dev = "cuda"
+    te_stride = sum(Cs) + 16
+    te = torch.randn(B, te_stride, device=dev, generator=g)
+    fi = torch.stack([torch.sort(torch.randperm(300, device=dev, generator=g)[:T]).values for _ in range(B)]).long()
+    probs, keep, refs = (N_.RpeTableProblem * len(Cs))(), [], []
+    off = 16
+    for i, Cc in enumerate(Cs):
+        wd, bd, bo = torch.randn(Cc, 3, device=dev, generator=g), torch.randn(Cc, device=dev, generator=g), torch.randn(Cc, device=dev, generator=g)
+        w = (torch.randn(Cc, Cc, device=dev, generator=g) / Cc ** 0.5)
+        cop, cip = (Cc + 15) // 16 * 16, (Cc + 63) // 64 * 64
+        wp = torch.zeros(1, cop, cip, device=dev, dtype=torch.bfloat16)
+        wp[0, :Cc, :Cc] = w.to(torch.bfloat16)
+        out_op = torch.full((B, T, T, Cc), float("nan"), device=dev, dtype=torch.bfloat16)
+        out_f32 = torch.full((B, T, T, Cc), float("nan"), device=dev) if i % 2 == 0 else None
+        keep += [wd, bd, bo, wp, out_op, out_f32]
+        probs[i] = N_.RpeTableProblem(wd=wd.data_ptr(), bd=bd.data_ptr(), bo=bo.data_ptr(), w_packed=wp.data_ptr(), out_op=out_op.data_ptr(),
+                                      out_f32=out_f32.data_ptr() if out_f32 is not None else None, C=Cc, te_off=off)
+        d = (fi.unsqueeze(-1) - fi.unsqueeze(-2)).float()
+        feats = torch.stack([torch.log(1 + d.clamp(min=0)), torch.log(1 + (-d).clamp(min=0)), (d == 0).float()], dim=-1)
+        e = te[:, off:off + Cc].view(B, 1, 1, Cc) + feats @ wd.t() + bd
+        hidden = torch.nn.functional.silu(e).to(torch.bfloat16).float()
+        refs.append((hidden @ w.to(torch.bfloat16).float().t() + bo, out_op, out_f32))
+        off += Cc
+    n = int(N_.lib().fdm_rpe_tables_blob_bytes(len(Cs)))
+    host = (C_.c_uint8 * n)()
+    N_.check(N_.lib().fdm_rpe_tables_prepare(C_.byref(probs), len(Cs), C_.byref(host), n), "prepare")
+    raw = torch.zeros(n + 128, dtype=torch.uint8, device=dev)
+    blob = raw[(-raw.data_ptr()) % 128:][:n]
+    blob.copy_(torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8))
+    a = N_.RpeTablesArgs(te=te.data_ptr(), frame_indices=fi.data_ptr(), blob=blob.data_ptr(), count=len(Cs), B=B, T=T,
+                         te_stride=te_stride, max_C=max(Cs))
+    N_.call("fdm_rpe_tables", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for ref, out_op, out_f32 in refs:
+        assert rel(out_op.float(), ref) <= 4e-3, rel(out_op.float(), ref)
+        if out_f32 is not None:
+            assert rel(out_f32, ref) <= 2e-4, rel(out_f32, ref)
