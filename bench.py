@@ -564,16 +564,32 @@ def kernel_classes(P, N_, B, K, Cx, S, osz=2):
         elif name == "fdm_gn_apply":
             el = st.N * st.HW * (st.Ca + st.Cb)
             add("gn_apply (GroupNorm+FiLM+SiLU)", "hbm", fn, ref, 0,
-                el * (4 + (osz if st.out_op else 0) + (4 if st.out_f32 else 0) + (osz if st.raw_op else 0)))
+                el * ((2 if st.xa_bf16 else 4) + (osz if st.out_op else 0) + (4 if st.out_f32 else 0) + (osz if st.raw_op else 0)))
         elif name == "fdm_temporal_gn":
             el = st.B * st.T * st.HW * st.C
             add("temporal_gn", "hbm", fn, ref, 0, el * (4 + 4 + osz))
         elif name == "fdm_attn_temporal":
             tok = st.B * st.T * st.HW
-            add("attn_temporal (RPE)", "tensor", fn, ref, 10 * st.T * st.T * st.C * st.B * st.HW,
-                tok * st.C * (3 * osz + osz) + 3 * st.B * st.T * st.T * st.C * 4)
+            # tcgen05 engine (workspace given): 3 launches per call; bytes = qkv read + out written + bf16 tables + the fp32 score-term
+            # tables written and read back + the bf16 attention weights written and read back
+            tc = bool(st.workspace)
+            extra = 0
+            if tc:
+                ts = (st.T + 3) // 4 * 4
+                ts += 4 if (ts // 4) % 2 == 0 else 0
+                rows = st.B * st.heads * st.HW * st.T
+                extra = 2 * (2 * rows * ts * 4) + 2 * rows * 64 * 2
+            add("attn_temporal (RPE; 3 tcgen05 kernels per call)" if tc else "attn_temporal (RPE, CUDA cores)", "tensor", fn, ref,
+                10 * st.T * st.T * st.C * st.B * st.HW,
+                tok * st.C * (3 * osz + osz) + 3 * st.B * st.T * st.T * st.C * (2 if tc else 4) + extra)
         elif name == "fdm_attn_spatial":
             add("attn_spatial (tcgen05)", "tensor", fn, ref, 4 * st.L * st.L * st.C * st.N, st.N * st.L * st.C * 4 * osz)
+        elif name == "fdm_rpe_tables":
+            # every RPENet table in one launch: count x [B*T*T x C] . [C x C] GEMMs; bytes = weights + bf16 tables written
+            cs = getattr(P, "rpe_table_channels", [])
+            m_rows = st.B * st.T * st.T
+            add("rpe_tables (all RPENet tables, one tcgen05 launch, side stream)", "tensor", fn, ref,
+                sum(2 * m_rows * c * c for c in cs), sum(c * c * 2 + m_rows * c * 2 for c in cs))
         elif name in ("fdm_cast", "fdm_input_prep"):
             add("cast / input_prep", "hbm", fn, ref, 0, 0)
         else:
@@ -776,6 +792,9 @@ def main():
         th.cuda.synchronize()
         return c0.elapsed_time(c1) / reps
 
+    # kernels per step: every entry point is one launch, except the tcgen05 temporal attention (3) ; + the statistics memset,
+    # the fused posterior update and the two ATen launches of the step (step-index fill, noise draw)
+    kernel_launches = sum(3 if (nm == "fdm_attn_temporal" and st_.workspace) else 1 for (nm, _, _), st_ in zip(P.calls, P._structs)) + 4
     classes = kernel_classes(P, N_, B, K, C, S, 2 if args.precision == "bf16" else 4)
     table, conv_ms, conv_fl, n_convs = [], 0.0, 0, 0
     for cls, c in classes.items():
@@ -894,8 +913,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
                 "config": config_dict(args.workload, wl, world),
-                "clocks": clk, "e2e": e2e, "gpu_launches": args.steps * (len(P.calls) + 1),
-                "launches_per_step": len(P.calls) + 1, "parity": parity, "roofline": roofline, "roofline_table": table,
+                "clocks": clk, "e2e": e2e, "gpu_launches": args.steps * kernel_launches,
+                "launches_per_step": kernel_launches, "parity": parity, "roofline": roofline, "roofline_table": table,
                 "roofline_all_convs": all_convs, "step_roofline": step_roofline,
                 "cpu_baseline": cpu, "gpu_eager": eager, "train": train}
         if train is not None:  # promoted copies of the training numbers (BASELINE.json metric part 2: train samples/sec)

@@ -104,7 +104,7 @@ int fdm_conv(const fdm_conv_args* a, void* stream);
  *   v = (x - mean_g) * rstd_g * gamma + beta;  if film: v = v*(1+film[b][c]) + film[b][C+c];  if silu: v*=sigmoid(v)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  const float* xa;      /* [N][HW][Ca] */
+  const void* xa;       /* [N][HW][Ca] fp32, or bf16 when xa_bf16 != 0 */
   const float* xb;      /* [N][HW][Cb] or NULL */
   const double* stats_a; /* [N][Ca][2] */
   const double* stats_b; /* [N][Cb][2] or NULL */
@@ -118,6 +118,7 @@ typedef struct {
   int32_t film_stride, film_off;
   int32_t silu, op_dtype;
   float eps;
+  int32_t xa_bf16;      /* 1: xa holds bf16 (a conv output that only this normalisation reads is stored once, in bf16: inference) */
 } fdm_gn_apply_args; /* which = 2 */
 int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream);
 

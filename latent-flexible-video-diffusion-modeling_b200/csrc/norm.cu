@@ -7,15 +7,22 @@
 namespace fdm {
 
 struct GnParams {
-  const float* xa; const float* xb; const double* sa; const double* sb;
+  const void* xa; const float* xb; const double* sa; const double* sb;
   const float* gamma; const float* beta; const float* film;
   void* out_op; float* out_f32; void* raw_op;
   int N, HW, Ca, Cb, C, T, film_stride, film_off, silu, pix_per_block;
   float eps;
 };
 
+__device__ __forceinline__ float4 gn_load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 gn_load4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+
 // grid: (ceil(HW / pix_per_block), N); block: (C/4) * ppi threads  (ppi pixels per iteration)
-template <typename OT>
+// IT = element type of source A (bf16: single-source launches only)
+template <typename OT, typename IT>
 __global__ void gn_apply_kernel(GnParams p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -26,7 +33,8 @@ __global__ void gn_apply_kernel(GnParams p) {
   const int q = threadIdx.x % quads, pl = threadIdx.x / quads, ppi = blockDim.x / quads;
   const int c = q * 4;
   const bool from_a = c < p.Ca;  // Ca, Cb are multiples of 4: a quad never straddles the concat boundary
-  const float* src = from_a ? p.xa + (size_t)n * p.HW * p.Ca + c : p.xb + (size_t)n * p.HW * p.Cb + (c - p.Ca);
+  const IT* src = from_a ? reinterpret_cast<const IT*>(p.xa) + (size_t)n * p.HW * p.Ca + c
+                         : reinterpret_cast<const IT*>(p.xb) + (size_t)n * p.HW * p.Cb + (c - p.Ca);  // (xb only with IT = float)
   const int sstride = from_a ? p.Ca : p.Cb;
   const int p0 = blockIdx.x * p.pix_per_block;
   const int p1 = min(p0 + p.pix_per_block, p.HW);
@@ -35,7 +43,7 @@ __global__ void gn_apply_kernel(GnParams p) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int pp = p0 + pl + u * ppi;
-    if (pp < p1) xs[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)pp * sstride));
+    if (pp < p1) xs[u] = gn_load4(src + (size_t)pp * sstride);
   }
   if (threadIdx.x < 32) {
     const int g = threadIdx.x;
@@ -77,7 +85,7 @@ __global__ void gn_apply_kernel(GnParams p) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int pp = px + u * ppi;
-        if (pp < p1) xs[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)pp * sstride));
+        if (pp < p1) xs[u] = gn_load4(src + (size_t)pp * sstride);
       }
     }
 #pragma unroll
@@ -205,8 +213,11 @@ extern "C" int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream) {
   p.pix_per_block = ppb;
   dim3 grid((a->HW + ppb - 1) / ppb, a->N);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->op_dtype == FDM_BF16) fdm::launch(gn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(threads), 0, st, p);
-  else fdm::launch(gn_apply_kernel<float>, dim3(grid), dim3(threads), 0, st, p);
+  if (a->xa_bf16) {
+    FDM_REQUIRE(a->xb == nullptr && a->op_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
+    fdm::launch(gn_apply_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(threads), 0, st, p);
+  } else if (a->op_dtype == FDM_BF16) fdm::launch(gn_apply_kernel<__nv_bfloat16, float>, dim3(grid), dim3(threads), 0, st, p);
+  else fdm::launch(gn_apply_kernel<float, float>, dim3(grid), dim3(threads), 0, st, p);
   return check_launch();
 }
 

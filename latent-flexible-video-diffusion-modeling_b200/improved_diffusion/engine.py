@@ -756,6 +756,7 @@ class DenoiserEngine:
                                             w_packed=self._pack_tc(net.out.weight), out_op=rop, out_f32=None, C=Cc, te_off=q_["te_off"])
                                        for (hb, Cc, net, rb_, rop), q_ in zip(rpe_tc, rh_probs)])
             P.flops += sum(2 * B * T * T * Cc * Cc for _, Cc, _, _, _ in rpe_tc)
+            P.rpe_table_channels = [Cc for _, Cc, _, _, _ in rpe_tc]
             idx = len(P.ops)
             P.side_begin = idx
             P.op("fdm_rpe_tables", N_.RpeTablesArgs, te=cond, frame_indices=P.fi, blob=blob, count=len(rpe_tc), B=B, T=T,
@@ -997,14 +998,22 @@ class DenoiserEngine:
                  stats_b=xb.st if xb else None, gamma=f32(gn.weight), beta=f32(gn.bias), film=None, out_op=a1, out_f32=None,
                  raw_op=raw, N=Nf, HW=hw, Ca=xa.C, Cb=xb.C if xb else 0, T=T, film_stride=0, film_off=0, silu=1,
                  op_dtype=opd, eps=gn.eps)
-            h1_ = new_act("res_h1", Co, Hh, Ww)
+            # the first conv's output is read by ONE consumer, the second GroupNorm: inference plans in bf16 mode store it once, in
+            # bf16 (statistics still come from the fp32 accumulators in the conv epilogue): 6 instead of 10 bytes per element through
+            # conv epilogue + GN-apply.  Training plans keep it in fp32 (the GroupNorm backward re-reads it).
+            h1_bf16 = self.use_tc and not train and os.environ.get("FDM_H1_BF16", "1") != "0"
+            if h1_bf16:
+                h1_ = Act(P.buf("res_h1_op", Nf * hw * Co * osz), P.stats("res_h1", Nf, Co), Co, Hh, Ww)
+                conv(a1, Ci, Hh, Ww, c1.weight, Co, 3, bias=f32(c1.bias), y_op=h1_.buf, stats=h1_.st)
+            else:
+                h1_ = new_act("res_h1", Co, Hh, Ww)
+                conv(a1, Ci, Hh, Ww, c1.weight, Co, 3, bias=f32(c1.bias), y_f32=h1_.buf, stats=h1_.st)
             h1_.biases = (c1.bias,)
-            conv(a1, Ci, Hh, Ww, c1.weight, Co, 3, bias=f32(c1.bias), y_f32=h1_.buf, stats=h1_.st)
             gn2, c2 = rb.out_layers[0], rb.out_layers[3]
             a2 = P.buf("res_a2", Nf * hw * Co * osz)
             P.op("fdm_gn_apply", N_.GnApplyArgs, xa=h1_.buf, xb=None, stats_a=h1_.st, stats_b=None, gamma=f32(gn2.weight),
                  beta=f32(gn2.bias), film=cond, out_op=a2, out_f32=None, raw_op=None, N=Nf, HW=hw, Ca=Co, Cb=0, T=T,
-                 film_stride=cond_cols, film_off=film_off[id(rb)], silu=1, op_dtype=opd, eps=gn2.eps)
+                 film_stride=cond_cols, film_off=film_off[id(rb)], silu=1, op_dtype=opd, eps=gn2.eps, xa_bf16=1 if h1_bf16 else 0)
             out = new_act("res_out", Co, Hh, Ww)
             yop = with_op_copy(out) if want_op else None
             sk = rb.skip_connection
