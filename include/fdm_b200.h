@@ -119,6 +119,8 @@ typedef struct {
   int32_t silu, op_dtype;
   float eps;
   int32_t xa_bf16;      /* 1: xa holds bf16 (a conv output that only this normalisation reads is stored once, in bf16: inference) */
+  int32_t film_add;     /* 1: use_scale_shift_norm=False (unet.py:204-206): film row holds C values e, y = GN(x + e) (statistics of x + e are
+                           derived from those of x); 0: scale/shift FiLM, y = GN(x) * (1 + scale) + shift */
 } fdm_gn_apply_args; /* which = 2 */
 int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream);
 

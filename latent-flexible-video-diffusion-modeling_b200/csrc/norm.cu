@@ -12,6 +12,7 @@ struct GnParams {
   void* out_op; float* out_f32; void* raw_op;
   int N, HW, Ca, Cb, C, T, film_stride, film_off, silu, pix_per_block;
   float eps;
+  int film_add;  // 1: use_scale_shift_norm=False (unet.py:204-206): the embedding is ADDED before the norm, h = GN(x + e[n, c])
 };
 
 __device__ __forceinline__ float4 gn_load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -51,8 +52,15 @@ __global__ void gn_apply_kernel(GnParams p) {
     for (int j = 0; j < cpg; ++j) {
       int cc = g * cpg + j;
       const double* st = cc < p.Ca ? p.sa + ((size_t)n * p.Ca + cc) * 2 : p.sb + ((size_t)n * p.Cb + (cc - p.Ca)) * 2;
-      s += st[0];
-      ss += st[1];
+      double s1 = st[0], s2 = st[1];
+      if (p.film_add) {
+        // statistics of x + e from those of x (e is constant over the pixels of a channel): exact algebra on the fp64 sums
+        const double e = (double)p.film[(size_t)(n / p.T) * p.film_stride + p.film_off + cc];
+        s2 += 2.0 * e * s1 + (double)p.HW * e * e;
+        s1 += (double)p.HW * e;
+      }
+      s += s1;
+      ss += s2;
     }
     const double cnt = (double)cpg * (double)p.HW;
     const double mean = s / cnt;
@@ -69,7 +77,9 @@ __global__ void gn_apply_kernel(GnParams p) {
       int g = (c + j) / cpg;
       float ga = p.gamma[c + j] * s_rstd[g];
       float be = p.beta[c + j] - s_mean[g] * ga;
-      if (p.film != nullptr) {
+      if (p.film != nullptr && p.film_add) {
+        be = fmaf(p.film[(size_t)b * p.film_stride + p.film_off + c + j], ga, be);  // (x + e) * ga + be
+      } else if (p.film != nullptr) {
         const float* f = p.film + (size_t)b * p.film_stride + p.film_off;
         float sc = 1.f + f[c + j], sh = f[C + c + j];
         ga *= sc;
@@ -200,6 +210,7 @@ extern "C" int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream) {
   p.film = a->film; p.out_op = a->out_op; p.out_f32 = a->out_f32; p.raw_op = a->raw_op;
   p.N = a->N; p.HW = a->HW; p.Ca = a->Ca; p.Cb = a->xb ? a->Cb : 0; p.C = p.Ca + p.Cb; p.T = a->T > 0 ? a->T : 1;
   p.film_stride = a->film_stride; p.film_off = a->film_off; p.silu = a->silu; p.eps = a->eps;
+  p.film_add = (a->film != nullptr && a->film_add) ? 1 : 0;
   FDM_REQUIRE(p.C % 32 == 0 && p.Ca % 4 == 0 && p.Cb % 4 == 0 && p.C <= 4096, FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->N > 0 && a->HW > 0, FDM_ERR_BAD_ARG);
   const int quads = p.C / 4;

@@ -32,7 +32,7 @@ GnApplyArgs = _S("GnApplyArgs", [("xa", vp), ("xb", vp), ("stats_a", vp), ("stat
                                  ("film", vp), ("out_op", vp), ("out_f32", vp), ("raw_op", vp),
                                  ("N", i32), ("HW", i32), ("Ca", i32), ("Cb", i32), ("T", i32),
                                  ("film_stride", i32), ("film_off", i32), ("silu", i32), ("op_dtype", i32), ("eps", f32),
-                                 ("xa_bf16", i32)])
+                                 ("xa_bf16", i32), ("film_add", i32)])
 TemporalGnArgs = _S("TemporalGnArgs", [("x", vp), ("gamma", vp), ("beta", vp), ("out_f32", vp), ("out_op", vp),
                                        ("B", i32), ("T", i32), ("HW", i32), ("C", i32), ("op_dtype", i32), ("eps", f32)])
 TimestepEmbeddingArgs = _S("TimestepEmbeddingArgs", [("t", vp), ("t_index", vp), ("t_table", vp), ("freqs", vp), ("out", vp),

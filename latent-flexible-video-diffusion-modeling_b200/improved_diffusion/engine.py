@@ -379,9 +379,9 @@ class DenoiserEngine:
         self.train_plans = {}
         self.packed = {}
         self._versions = None
-        if not model.use_scale_shift_norm:
-            raise NotImplementedError("the fused GroupNorm+FiLM kernel implements use_scale_shift_norm=True "
-                                      "(the reference default, script_util.py:34)")
+        # use_scale_shift_norm=False (unet.py:204-206: h = GN(h + emb)) is served on the inference path (fdm_gn_apply film_add);
+        # the GroupNorm backward kernels implement the scale/shift form only (forward_train raises)
+        self.film_cols = 2 if model.use_scale_shift_norm else 1
 
     def invalidate(self):
         """Drop the packed inference weights, inference plans and their captured sampler graphs.  Needed after parameter
@@ -651,7 +651,7 @@ class DenoiserEngine:
         film_off, te_off = {}, {}
         for rb in res_blocks:
             film_off[id(rb)] = cols
-            cols += 2 * rb.out_channels
+            cols += self.film_cols * rb.out_channels
         for ab in attn_blocks:
             for which in ("rpe_q", "rpe_k", "rpe_v"):
                 te_off[(id(ab), which)] = cols
@@ -697,7 +697,7 @@ class DenoiserEngine:
         for rb in res_blocks:
             lin = rb.emb_layers[1]
             probs.append(dict(x=emb, w=f32(lin.weight), b=f32(lin.bias), y=(cond, film_off[id(rb)] * 4), M=B, K=ted,
-                              Nout=2 * rb.out_channels, ldx=ted, ldy=cond_cols, silu_in=1, lin=lin,
+                              Nout=self.film_cols * rb.out_channels, ldx=ted, ldy=cond_cols, silu_in=1, lin=lin,
                               off=film_off[id(rb)]))
         for ab in attn_blocks:
             for which in ("rpe_q", "rpe_k", "rpe_v"):
@@ -1013,7 +1013,8 @@ class DenoiserEngine:
             a2 = P.buf("res_a2", Nf * hw * Co * osz)
             P.op("fdm_gn_apply", N_.GnApplyArgs, xa=h1_.buf, xb=None, stats_a=h1_.st, stats_b=None, gamma=f32(gn2.weight),
                  beta=f32(gn2.bias), film=cond, out_op=a2, out_f32=None, raw_op=None, N=Nf, HW=hw, Ca=Co, Cb=0, T=T,
-                 film_stride=cond_cols, film_off=film_off[id(rb)], silu=1, op_dtype=opd, eps=gn2.eps, xa_bf16=1 if h1_bf16 else 0)
+                 film_stride=cond_cols, film_off=film_off[id(rb)], silu=1, op_dtype=opd, eps=gn2.eps, xa_bf16=1 if h1_bf16 else 0,
+                 film_add=0 if m.use_scale_shift_norm else 1)
             out = new_act("res_out", Co, Hh, Ww)
             yop = with_op_copy(out) if want_op else None
             sk = rb.skip_connection
@@ -1384,6 +1385,9 @@ class DenoiserEngine:
         """Differentiable forward (w.r.t. the parameters) through the native forward + backward schedules."""
         if frame_indices is None:
             raise ValueError("frame_indices is required (temporal RPE, rpe.py:146)")
+        if not self.model.use_scale_shift_norm:
+            raise NotImplementedError("native training implements use_scale_shift_norm=True (the reference default, script_util.py:34); "
+                                      "use FDM_TRAIN_ENGINE=autograd for the additive-embedding ResBlocks (unet.py:204-206)")
         if self.model.training and float(getattr(self.model, "dropout", 0) or 0) > 0:
             # the reference applies nn.Dropout between SiLU and the second conv of every ResBlock (unet.py:167,203-206); the
             # native schedules have no dropout mask yet -> refuse loudly instead of silently training without it

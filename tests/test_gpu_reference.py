@@ -334,3 +334,26 @@ def test_sample_loop_attention_logging_matches_the_reference():
         e = O.rel_l2(a_n[tag].cpu(), a_r[tag].cpu())
         assert a_n[tag].shape == a_r[tag].shape and e <= 3e-2, (tag, e)
     assert O.rel_l2(s_n.cpu(), s_r.cpu()) <= 8 * TOL["bf16"]
+
+
+def test_additive_embedding_resblocks_match_the_reference():
+    """use_scale_shift_norm=False (unet.py:204-206): h = out_layers(h + emb_out) — the embedding is added BEFORE the second
+    GroupNorm.  Served by fdm_gn_apply's film_add mode (statistics of h + e derived from those of h in fp64); native training of
+    this variant raises (the GroupNorm backward kernels implement the scale/shift form)."""
+    over = dict(image_size=32, in_channels=4, num_channels=64, num_res_blocks=1, diffusion_steps=1000, use_scale_shift_norm=False)
+    model, diffusion, ref_model, ref_diffusion, cfg, sd = build_pair(over)
+    assert sd["input_blocks.1.0.emb_layers.1.weight"].shape[0] == 64  # C outputs, not 2C
+    inp = O.synthetic_inputs(cfg, 2, 6, 2, seed=12, video_len=100, pad_rows=(0,))
+    ts = O.model_timesteps(O.Tables(cfg), torch.tensor([17, 803]))
+    kw = cuda_kw(inp)
+    with torch.no_grad():
+        ref, _ = ref_model(inp["x"].cuda(), timesteps=ts.cuda(), **kw)
+        for precision in ("fp32", "bf16"):
+            model.precision = precision
+            eps, _ = model(inp["x"].cuda(), timesteps=ts.cuda(), **kw)
+            e = O.rel_l2(eps.cpu(), ref.cpu())
+            print(f"additive-embedding ResBlocks [{precision}] eps rel-L2 = {e:.3e}")
+            assert e <= TOL[precision], (precision, e)
+    model.train()
+    with pytest.raises(NotImplementedError, match="use_scale_shift_norm"):
+        diffusion.training_losses(model, inp["x0"].cuda(), torch.tensor([3, 5]).cuda(), model_kwargs=kw)
