@@ -659,9 +659,11 @@ class DenoiserEngine:
         cond_cols = cols
         freqs = timestep_freqs(mc).to(device)
         P.keep.append(freqs)
-        temb = P.buf("temb", B * mc * 4)
-        h1 = P.buf("time_h1", B * ted * 4)
-        emb = P.buf("emb", B * ted * 4)
+        # (persistent: the conditioning chain runs on the side stream, concurrently with main-stream launches whose buffers must
+        # not alias these)
+        temb = P.buf("temb", B * mc * 4, True)
+        h1 = P.buf("time_h1", B * ted * 4, True)
+        emb = P.buf("emb", B * ted * 4, True)
         cond = P.buf("cond", B * cond_cols * 4, True)  # live for the whole forward
         P.temb_op = len(P.ops)
         P.op("fdm_timestep_embedding", N_.TimestepEmbeddingArgs, t=P.t, t_index=None, t_table=None, freqs=freqs, out=temb,
@@ -1313,7 +1315,21 @@ class DenoiserEngine:
                 fields_.update(problems=dev_, count=len(probs_),
                                max_elems=max([co_ * ci_ * k_ * k_ for _, _, _, co_, ci_, k_, _ in probs_] or [1]))
 
-        P.join_at = next((i for i, (fn, _, _) in enumerate(P.ops) if fn == "fdm_attn_temporal"), len(P.ops))
+        # The whole conditioning chain — timestep embedding, time MLP, FiLM / RPE time projections, RPENet tables: everything that
+        # depends only on (t, frame_indices) — runs on a side stream and is joined before its first consumer on the main stream
+        # (the first FiLM GroupNorm-apply, or the first temporal attention), so it overlaps input prep, stem and the first convs
+        # instead of heading every step.  Inside a CUDA-graph capture the fork / join become graph edges.
+        cond_bufs = {id(cond)} | {id(v) for v in R.values() if v is not None} | {id(v) for v in R_op.values() if v is not None}
+
+        def reads_cond(fields):
+            for v in fields.values():
+                b_ = v[0] if isinstance(v, tuple) else v
+                if isinstance(b_, Buf) and id(b_) in cond_bufs:
+                    return True
+            return False
+        if os.environ.get("FDM_SIDE_COND", "1") != "0" and not train and P.side_end > P.side_begin:
+            P.side_begin = P.temb_op
+        P.join_at = next((i for i, (fn, _, f_) in enumerate(P.ops) if i >= P.side_end and reads_cond(f_)), len(P.ops))
         if (th.device(device).type == "cuda" and P.side_end > P.side_begin and P.join_at >= P.side_end
                 and os.environ.get("FDM_SIDE_STREAM", "1") != "0"):
             P.side_stream = th.cuda.Stream(device)
