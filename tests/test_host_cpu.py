@@ -136,9 +136,12 @@ def test_training_losses_and_grads_match_reference(golden):
     grads = dict(model.named_parameters())
     for k, ref in g["grads"].items():
         assert O.rel_l2(grads[k].grad, ref) <= 1e-4, k
+    # analytically-zero gradients (biases in front of a GroupNorm: 1e-10..1e-8 of pure summation-order noise, which differs
+    # between hosts / thread counts) are held to an absolute floor relative to the largest gradient of the case
+    floor = 1e-7 * max(g["grad_norms"].values())
     for k, nrm in g["grad_norms"].items():
         assert grads[k].grad is not None, k
-        assert abs(float(grads[k].grad.norm()) - nrm) <= 1e-3 * max(nrm, 1e-6), k
+        assert abs(float(grads[k].grad.norm()) - nrm) <= 1e-3 * nrm + floor, k
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/improved_diffusion"), reason="reference checkout only exists in the build container")
