@@ -69,6 +69,7 @@ extern "C" size_t fdm_struct_size(int which) {
     case 30: return sizeof(fdm_masked_mse_bwd_args);
     case 31: return sizeof(fdm_rpe_table_problem);
     case 32: return sizeof(fdm_rpe_tables_args);
+    case 33: return sizeof(fdm_norm_linear_args);
     default: return 0;
   }
 }

@@ -108,6 +108,10 @@ RpeTableProblem = _S("RpeTableProblem", [("wd", vp), ("bd", vp), ("bo", vp), ("w
                                          ("C", i32), ("te_off", i32)])
 RpeTablesArgs = _S("RpeTablesArgs", [("te", vp), ("frame_indices", vp), ("blob", vp), ("count", i32), ("B", i32), ("T", i32),
                                      ("te_stride", i32), ("max_C", i32)])
+NormLinearArgs = _S("NormLinearArgs", [("a_op", vp), ("x", vp), ("stats", vp), ("tstats", vp), ("gamma", vp), ("beta", vp), ("w", vp),
+                                       ("bias", vp), ("resid", vp), ("y_f32", vp), ("y_op", vp), ("out_stats", vp),
+                                       ("B", i32), ("T", i32), ("HW", i32), ("K", i32), ("Cout", i32),
+                                       ("a_mode", i32), ("resid_mode", i32), ("eps", f32)])
 PACK_TC_FWD, PACK_TC_DGRAD, PACK_SIMT_FWD, PACK_SIMT_DGRAD, PACK_SUM2 = 0, 1, 2, 3, 4
 
 # index = `which` of fdm_struct_size (include/fdm_b200.h)
@@ -116,14 +120,14 @@ STRUCTS = [InputPrepArgs, ConvArgs, GnApplyArgs, TemporalGnArgs, TimestepEmbeddi
            LinearProblem, RpeHiddenProblem,
            PackProblem, PackWeightsArgs, ConvWgradArgs, GnBwdArgs, TemporalGnBwdArgs, AttnSpatialBwdArgs, AttnTemporalBwdArgs,
            RpeHiddenBwdProblem, RpeHiddenBwdArgs, LinearBwdProblem, GroupedLinearBwdArgs, SumPartsArgs, AccumArgs,
-           NchwToNhwcArgs, AdamwArgs, MaskedMseBwdArgs, RpeTableProblem, RpeTablesArgs]
+           NchwToNhwcArgs, AdamwArgs, MaskedMseBwdArgs, RpeTableProblem, RpeTablesArgs, NormLinearArgs]
 
 ENTRY_POINTS = ["fdm_input_prep", "fdm_conv", "fdm_gn_apply", "fdm_temporal_gn", "fdm_timestep_embedding",
                 "fdm_grouped_linear", "fdm_rpe_hidden", "fdm_attn_temporal", "fdm_attn_spatial", "fdm_cast",
                 "fdm_ddpm_step", "fdm_q_sample", "fdm_masked_mse",
                 "fdm_pack_weights", "fdm_conv_wgrad", "fdm_gn_bwd", "fdm_temporal_gn_bwd", "fdm_attn_spatial_bwd",
                 "fdm_attn_temporal_bwd", "fdm_rpe_hidden_bwd", "fdm_grouped_linear_bwd", "fdm_sum_parts", "fdm_accum",
-                "fdm_nchw_to_nhwc", "fdm_adamw", "fdm_masked_mse_bwd", "fdm_rpe_tables"]
+                "fdm_nchw_to_nhwc", "fdm_adamw", "fdm_masked_mse_bwd", "fdm_rpe_tables", "fdm_norm_linear"]
 
 _lib = None
 
@@ -159,6 +163,8 @@ def lib():
         for name in ("fdm_attn_temporal_workspace", "fdm_attn_temporal_attn_offset"):
             getattr(L, name).restype = C.c_size_t
             getattr(L, name).argtypes = [vp]
+        L.fdm_norm_linear_supported.restype = C.c_int
+        L.fdm_norm_linear_supported.argtypes = [vp]
         if L.fdm_abi_version() != 1:
             raise NativeError(f"libfdm_sm100.so ABI {L.fdm_abi_version()} != 1")
         _lib = L

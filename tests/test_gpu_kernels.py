@@ -296,3 +296,114 @@ def test_rpe_tables_fused_vs_torch(B, T, Cs):
         assert rel(out_op.float(), ref) <= 4e-3, rel(out_op.float(), ref)
         if out_f32 is not None:
             assert rel(out_f32, ref) <= 2e-4, rel(out_f32, ref)
+
+
+def _nl_inputs(B, T, HW, Cout, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    C = 128
+    dev = "cuda"
+    # activations with per-channel offsets and scales, so that the normalisation actually matters
+    x = torch.randn(B * T, HW, C, device=dev, generator=g) * (0.5 + torch.rand(C, device=dev, generator=g)) + torch.randn(C, device=dev, generator=g)
+    gamma = 1 + 0.3 * torch.randn(C, device=dev, generator=g)
+    beta = 0.3 * torch.randn(C, device=dev, generator=g)
+    w = torch.randn(Cout, C, device=dev, generator=g) / C ** 0.5
+    bias = 0.2 * torch.randn(Cout, device=dev, generator=g)
+    return x, gamma, beta, w, bias, g
+
+
+def _frame_gn(x, gamma, beta, eps):
+    # GroupNorm32 per frame over (C/32 channels x HW): x [N][HW][C]
+    return F.group_norm(x.permute(0, 2, 1).double(), 32, gamma.double(), beta.double(), eps).permute(0, 2, 1).float()
+
+
+def _temporal_gn(x, B, T, gamma, beta, eps):
+    # rpe.py:135-137: statistics over (C/32 channels x T frames) per (video, pixel)
+    N, HW, C = x.shape
+    v = x.view(B, T, HW, C).permute(0, 2, 3, 1).reshape(B * HW, C, T).double()
+    v = F.group_norm(v, 32, gamma.double(), beta.double(), eps)
+    return v.view(B, HW, C, T).permute(0, 3, 1, 2).reshape(N, HW, C).float()
+
+
+def _frame_stats(x):
+    return torch.stack([x.double().sum(1), (x.double() ** 2).sum(1)], dim=-1).contiguous()  # [N][C][2]
+
+
+NL_SHAPES = [(8, 20, 256), (2, 5, 64), (3, 7, 16), (1, 40, 64), (2, 2, 256), (1, 1, 64), (5, 20, 16)]
+
+
+@pytest.mark.parametrize("B,T,HW", NL_SHAPES)
+@pytest.mark.parametrize("a_mode", [1, 2])
+def test_norm_linear_qkv(B, T, HW, a_mode):
+    """fdm_norm_linear (lin_tc.cu), qkv case: GroupNorm (per frame from the producer's sums / temporal, in the tile) in the
+    operand path of the C -> 3C linear, against torch group_norm -> bf16 -> linear on the same bf16-rounded weights."""
+    from improved_diffusion import _native as N_
+    C, Cout, eps = 128, 384, 1e-5
+    x, gamma, beta, w, bias, _ = _nl_inputs(B, T, HW, Cout, seed=B * 1000 + T * 10 + a_mode)
+    wp = w.to(torch.bfloat16).contiguous()
+    y = torch.full((B * T, HW, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stats = _frame_stats(x)
+    tstats = torch.full((B, HW, 32, 2), float("nan"), device="cuda")
+    a = N_.NormLinearArgs(a_op=None, x=x.data_ptr(), stats=stats.data_ptr() if a_mode == 1 else None,
+                          tstats=tstats.data_ptr() if a_mode == 2 else None, gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+                          w=wp.data_ptr(), bias=bias.data_ptr(), resid=None, y_f32=None, y_op=y.data_ptr(), out_stats=None,
+                          B=B, T=T, HW=HW, K=C, Cout=Cout, a_mode=a_mode, resid_mode=0, eps=eps)
+    assert N_.lib().fdm_norm_linear_supported(C_byref(a))
+    N_.call("fdm_norm_linear", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    xn = _frame_gn(x, gamma, beta, eps) if a_mode == 1 else _temporal_gn(x, B, T, gamma, beta, eps)
+    ref = xn.to(torch.bfloat16).float() @ wp.float().t() + bias
+    assert torch.isfinite(y.float()).all()
+    e = rel(y.float(), ref)
+    assert e <= 5e-3, e   # bf16 output rounding (2^-9) + operand rounding flips at the bf16 boundary
+    if a_mode == 2:
+        v = x.view(B, T, HW, 32, 4).permute(0, 2, 3, 1, 4).reshape(B, HW, 32, T * 4).double()
+        mean, var = v.mean(-1), v.var(-1, unbiased=False)
+        assert rel(tstats[..., 0], mean.float()) <= 1e-5
+        assert rel(tstats[..., 1], (var + eps).rsqrt().float()) <= 1e-4
+
+
+def C_byref(a):
+    import ctypes
+    return ctypes.byref(a)
+
+
+@pytest.mark.parametrize("B,T,HW", NL_SHAPES)
+@pytest.mark.parametrize("resid_mode", [0, 1, 2, 3])
+def test_norm_linear_proj(B, T, HW, resid_mode):
+    """fdm_norm_linear, proj_out case: bf16 operand by TMA, residual = plain fp32 tensor / temporal GN of x recomputed from the
+    saved (mean, rstd) pairs / per-frame GN of x recomputed from its sums; fp32 + bf16 outputs and the GroupNorm statistics of
+    the result."""
+    from improved_diffusion import _native as N_
+    C, eps = 128, 1e-5
+    x, gamma, beta, w, bias, g = _nl_inputs(B, T, HW, C, seed=B * 1000 + T * 10 + resid_mode + 5)
+    M = B * T * HW
+    h = torch.randn(M, C, device="cuda", generator=g).to(torch.bfloat16)
+    wp = w.to(torch.bfloat16).contiguous()
+    y = torch.full((M, C), float("nan"), device="cuda")
+    yop = torch.full((M, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ostats = torch.zeros(B * T, C, 2, device="cuda", dtype=torch.float64)
+    stats = _frame_stats(x)
+    if resid_mode == 1:
+        r = torch.randn(M, C, device="cuda", generator=g)
+    elif resid_mode == 2:
+        r = _temporal_gn(x, B, T, gamma, beta, eps).reshape(M, C)
+    elif resid_mode == 3:
+        r = _frame_gn(x, gamma, beta, eps).reshape(M, C)
+    else:
+        r = torch.zeros(M, C, device="cuda")
+    v = x.view(B, T, HW, 32, 4).permute(0, 2, 3, 1, 4).reshape(B, HW, 32, T * 4).double()
+    tstats = torch.stack([v.mean(-1), (v.var(-1, unbiased=False) + eps).rsqrt()], dim=-1).float().contiguous()
+    a = N_.NormLinearArgs(a_op=h.data_ptr(), x=x.data_ptr(), stats=stats.data_ptr(), tstats=tstats.data_ptr(),
+                          gamma=gamma.data_ptr(), beta=beta.data_ptr(), w=wp.data_ptr(), bias=bias.data_ptr(),
+                          resid=r.data_ptr() if resid_mode == 1 else None, y_f32=y.data_ptr(), y_op=yop.data_ptr(),
+                          out_stats=ostats.data_ptr(), B=B, T=T, HW=HW, K=C, Cout=C, a_mode=0, resid_mode=resid_mode, eps=eps)
+    if HW % 32 and HW != 16:
+        assert not N_.lib().fdm_norm_linear_supported(C_byref(a))
+        return
+    N_.call("fdm_norm_linear", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = h.float() @ wp.float().t() + bias + r
+    assert rel(y, ref) <= 2e-5, rel(y, ref)
+    assert rel(yop.float(), ref) <= 4e-3
+    rs = _frame_stats(ref.view(B * T, HW, C))
+    assert rel(ostats, rs) <= 1e-5, rel(ostats, rs)
