@@ -568,6 +568,12 @@ def kernel_classes(P, N_, B, K, Cx, S, osz=2):
         elif name == "fdm_temporal_gn":
             el = st.B * st.T * st.HW * st.C
             add("temporal_gn", "hbm", fn, ref, 0, el * (4 + 4 + osz))
+        elif name == "fdm_norm_linear":
+            # GroupNorm in the operand path of the qkv linear: fp32 activations read once, bf16 qkv written once (+ weights);
+            # bound by the output (an SM drains ~15 B/clk of stores: lin_tc.cu)
+            rows = st.B * st.T * st.HW
+            add("norm_qkv (GroupNorm in the operand path of the qkv linear, persistent tcgen05)", "hbm", fn, ref,
+                2 * rows * st.K * st.Cout, rows * (st.K * 4 + st.Cout * osz) + st.K * st.Cout * 2)
         elif name == "fdm_attn_temporal":
             tok = st.B * st.T * st.HW
             # tcgen05 engine (workspace given): 3 launches per call; bytes = qkv read + out written + bf16 tables + the fp32 score-term

@@ -94,6 +94,17 @@ typedef struct {
   int32_t N, Hin, Win, C0, C1, Cout;
   int32_t ksize, stride, upsample;
   int32_t a_dtype, op_dtype, out_nchw, engine;
+  /* residual = GroupNorm32 of `resid`, recomputed in the epilogue instead of read from a normalised copy (rpe.py:136,173:
+   * x = norm(x) ... return x + proj_out(h)).  tcgen05 per-tap engine, ksize 1, Cout = 128 (a group = one float4):
+   *   0: `resid` is added as it is;  2: temporal GN, (mean, rstd) per (video, pixel, group) from rn_tstats (written by
+   *   fdm_norm_linear a_mode 2);  3: per-frame GN from the (sum, sum of squares) pairs rn_stats */
+  int32_t resid_norm;
+  int32_t rn_T;            /* frames per video (resid_norm 2) */
+  float rn_eps;
+  const float* rn_tstats;  /* [B][HW][32][2] */
+  const double* rn_stats;  /* [N][Cout][2] */
+  const float* rn_gamma;   /* [Cout] */
+  const float* rn_beta;
 } fdm_conv_args; /* which = 1 */
 int fdm_conv(const fdm_conv_args* a, void* stream);
 
@@ -211,36 +222,29 @@ int fdm_rpe_tables_prepare(const fdm_rpe_table_problem* problems, int32_t count,
 int fdm_rpe_tables(const fdm_rpe_tables_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * A7/A8/A10  the linears of an RPEAttention with its GroupNorm in the operand path (lin_tc.cu) — rpe.py:111-113 (norm, qkv,
- * proj_out), :135-140 (x = norm(x); qkv = self.qkv(x)), :170-173 (return x + proj_out(h): the residual is the NORMALISED x).
- *   y[m, :] = W . A[m, :] + bias (+ residual),  m over the B*T*HW rows of the [B*T][HW][K] activations, K = 128
- *   a_mode 0: A = a_op, a bf16 operand (the attention output);
- *   a_mode 1: A = GroupNorm32(x) per frame, from x (fp32) and the per-(frame, channel) (sum, sum of squares) pairs `stats`;
- *   a_mode 2: A = the temporal GroupNorm of x (statistics over K/32 channels x T frames per (video, pixel), rpe.py:135-137),
+ * A7/A8/A10  the qkv linear of an RPEAttention with its GroupNorm in the operand path (lin_tc.cu) — rpe.py:111-113 (norm, qkv),
+ * :135-140 (x = norm(x); qkv = self.qkv(x)).  The normalised tensor is never written:
+ *   y_op[m, :] = W . GN(x)[m, :] + bias,  m over the B*T*HW rows of the [B*T][HW][K] activations, K = 128, y_op bf16
+ *   a_mode 1: GroupNorm32 per frame, from x (fp32) and the per-(frame, channel) (sum, sum of squares) pairs `stats`;
+ *   a_mode 2: the temporal GroupNorm of x (statistics over K/32 channels x T frames per (video, pixel), rpe.py:135-137),
  *             computed inside the tile; the per-(video, pixel, group) (mean, rstd) pairs are written to `tstats` when given.
- *   resid_mode 0: none; 1: + resid[m, :] (fp32); 2: + temporal GN of x recomputed from `tstats`; 3: + per-frame GN of x
- *             recomputed from `stats`   (modes 2, 3: Cout = K; gamma / beta are the norm's affine parameters in every mode)
- *   outputs: y_op (bf16; alone = the qkv case) or y_f32 (+ optional y_op copy, + optional out_stats: (sum, sum of squares) of y
- *            per (frame, channel), added with fp64 atomics into a zeroed buffer).
- *   Persistent CTAs, W resident in shared memory, tcgen05 accumulators in a ring of TMEM slots.  fdm_norm_linear_supported()
- *   tells whether a shape is taken (K = 128, Cout in {128, 256, 384}); callers otherwise run fdm_temporal_gn / fdm_gn_apply +
- *   fdm_conv.
+ *   The matching proj_out (rpe.py:173: return x + proj_out(h) with the NORMALISED x) is fdm_conv with resid = x and
+ *   resid_norm = 3 (stats) / 2 (tstats): it recomputes the residual instead of reading a normalised copy.
+ *   Persistent CTAs, W resident in shared memory, tcgen05 accumulators in TMEM, the output tile staged whole and drained by TMA
+ *   stores.  fdm_norm_linear_supported() tells whether a shape is taken (K = 128, Cout in {128, 256, 384}, HW % 16 == 0,
+ *   a_mode 2: T <= 20); callers otherwise run fdm_temporal_gn / fdm_gn_apply + fdm_conv.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  const void* a_op;     /* a_mode 0: [M][K] bf16 */
-  const float* x;       /* a_mode 1, 2 and resid_mode 2, 3: [B*T][HW][K] fp32 */
-  const double* stats;  /* a_mode 1 / resid_mode 3: [B*T][K][2] */
-  float* tstats;        /* a_mode 2: written, resid_mode 2: read; [B][HW][32][2] (mean, rstd) */
+  const float* x;       /* [B*T][HW][K] fp32 */
+  const double* stats;  /* a_mode 1: [B*T][K][2] */
+  float* tstats;        /* a_mode 2: written (may be NULL); [B][HW][32][2] (mean, rstd) */
   const float* gamma;   /* [K] */
   const float* beta;
   const void* w;        /* bf16 [Cout][K] (the packed 1x1 layout of fdm_conv's tcgen05 engine) */
   const float* bias;    /* [Cout] */
-  const float* resid;   /* resid_mode 1: [M][Cout] fp32 */
-  float* y_f32;         /* [M][Cout] or NULL */
-  void* y_op;           /* [M][Cout] bf16 or NULL */
-  double* out_stats;    /* [B*T][Cout][2] or NULL */
+  void* y_op;           /* [B*T*HW][Cout] bf16 */
   int32_t B, T, HW, K, Cout;
-  int32_t a_mode, resid_mode;
+  int32_t a_mode;
   float eps;
 } fdm_norm_linear_args; /* which = 33 */
 int fdm_norm_linear(const fdm_norm_linear_args* a, void* stream);

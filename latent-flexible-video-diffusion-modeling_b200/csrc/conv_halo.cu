@@ -388,6 +388,7 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
 int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   FDM_REQUIRE(a->a_dtype == FDM_BF16 && (a->ksize == 3 || a->ksize == 1) && a->stride == 1 && !a->upsample && !a->out_nchw,
               FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(a->resid_norm == 0, FDM_ERR_UNSUPPORTED);  // the recomputed-GroupNorm residual lives in the per-tap kernel's epilogue
   FDM_REQUIRE(a->C0 % 8 == 0 && (a->a1 == nullptr || a->C1 % 8 == 0) && a->Cout % 4 == 0 && a->Cout >= 32, FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->y_op == nullptr || a->op_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
   const int W = a->Win, H = a->Hin;

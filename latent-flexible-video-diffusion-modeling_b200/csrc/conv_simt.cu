@@ -267,5 +267,6 @@ extern "C" int fdm_conv(const fdm_conv_args* a, void* stream) {
   }
   if (a->engine == FDM_CONV_TC_TAP) return conv_tc_launch(a, st);
   FDM_REQUIRE(a->engine == FDM_CONV_SIMT, FDM_ERR_BAD_ARG);
+  FDM_REQUIRE(a->resid_norm == 0, FDM_ERR_UNSUPPORTED);
   return conv_simt_launch(a, st);
 }

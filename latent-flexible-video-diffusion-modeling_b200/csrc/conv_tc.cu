@@ -41,6 +41,13 @@ struct TcParams {
   int nr;           // filter rows grouped into one pipeline stage: 1, or 3 (one TMA box of weights per filter column)
   int a_slot;       // bytes of the A region of a stage = nr * 16 KB
   int stage_bytes;  // nr * (16 KB + BN * 128)
+  // residual = GroupNorm of `resid` recomputed here (0: plain residual; 2: temporal GN from rn_tstats; 3: per-frame GN from rn_stats)
+  int resid_norm, rn_T;
+  float rn_eps;
+  const float* rn_tstats;
+  const double* rn_stats;
+  const float* rn_gamma;
+  const float* rn_beta;
 };
 
 constexpr int TC_MAX_STAGES = 8;
@@ -55,8 +62,11 @@ struct TcSmem {
   static_assert(STAGE_BYTES >= 4 * 32 * TC_STG_ROW * 4, "one stage must hold the epilogue staging");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap ta0,
+// RN: the residual is GroupNorm(resid) recomputed in the epilogue (a separate instantiation: the extra live values cost the plain
+// kernel 20-40 registers — its third resident CTA per SM — and 15-35 % when the code was merely predicated; the RN instantiations
+// are held to 112 registers so that they keep three CTAs per SM too)
+template <int BN, bool RN>
+__global__ void __launch_bounds__(TC_THREADS, RN ? 3 : 0) conv_tc_kernel(const __grid_constant__ CUtensorMap ta0,
                                                             const __grid_constant__ CUtensorMap tw0,
                                                             const __grid_constant__ CUtensorMap ta1,
                                                             const __grid_constant__ CUtensorMap tw1, const TcParams p) {
@@ -67,6 +77,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float4 rn_tab[RN ? 4 : 1][2][2][RN ? 32 : 1];  // [epilogue warp][frame half][mul | add][group]
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -201,9 +212,42 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     float* stg = reinterpret_cast<float*>(smem) + g * 32 * TC_STG_ROW;
     const int sub = lane >> 3, cq = (lane & 7) * 4;
     const int m_w = m0 + g * 32;  // first row of this warp
+    const bool two_frames = p.HWo < 32;  // HWo == 16: rows [0,16) and [16,32) of the warp belong to different frames
+    // RN: frame / video of the warp's rows (one integer division per warp instead of two per row and chunk).  Per-frame
+    // statistics: lane l computes scale / shift of group l (columns n_off + 4l .. + 3) for the one or two frames of this warp's
+    // rows — fp64 arithmetic and a global round trip, done once per warp while the MMAs are still running — into the warp's own
+    // slice of a small shared-memory table the chunk loop reads back by column.
+    int rn_n[2] = {0, 0}, rn_b[2] = {0, 0};
+    if (RN) {
+      rn_n[0] = min(m_w, p.M - 1) / p.HWo;
+      rn_n[1] = two_frames ? min(m_w + 16, p.M - 1) / p.HWo : rn_n[0];
+      rn_b[0] = rn_n[0] / p.rn_T;
+      rn_b[1] = rn_n[1] / p.rn_T;
+      if (p.resid_norm == 3) {
+        const int col = n_off + 4 * lane;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), ad = mu;
+          if ((hh == 0 || two_frames) && col < p.Cout && 4 * lane < BN && m_w + hh * 16 < p.M) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.rn_gamma + col));
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.rn_beta + col));
+            const double2* st = reinterpret_cast<const double2*>(p.rn_stats + ((size_t)rn_n[hh] * p.Cout + col) * 2);
+            const double2 s0 = st[0], s1_ = st[1], s2_ = st[2], s3 = st[3];
+            const double cnt = 4.0 * (double)p.HWo;
+            const double mean = (s0.x + s1_.x + s2_.x + s3.x) / cnt;
+            const double var = fmax((s0.y + s1_.y + s2_.y + s3.y) / cnt - mean * mean, 0.0);
+            const float mf = (float)mean, rs = (float)(1.0 / sqrt(var + (double)p.rn_eps));
+            mu = make_float4(gm.x * rs, gm.y * rs, gm.z * rs, gm.w * rs);
+            ad = make_float4(bt.x - mf * mu.x, bt.y - mf * mu.y, bt.z - mf * mu.z, bt.w - mf * mu.w);
+          }
+          rn_tab[g][hh][0][lane] = mu;
+          rn_tab[g][hh][1][lane] = ad;
+        }
+        __syncwarp();
+      }
+    }
     mbar_wait(&tmem_full_bar, 0);
     tcgen05_fence_after();
-    const bool two_frames = p.HWo < 32;  // HWo == 16: rows [0,16) and [16,32) of the warp belong to different frames
     // bf16-only outputs without residual / statistics (the qkv linears): each lane owns 32 consecutive channels of its row =
     // 64 contiguous bytes -> packed 16-byte stores straight from the TMEM registers, no shared-memory transpose
     const bool direct = BN >= 32 && p.y_f32 == nullptr && p.y_op != nullptr && p.resid == nullptr && p.stats == nullptr &&
@@ -275,6 +319,42 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           const int m = m_w + i * 4 + sub;
           res[i] = (p.resid != nullptr && col_ok && m < p.M) ? __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)m * p.Cout + col))
                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (RN && p.resid_norm != 0 && col_ok) {
+          // the residual is GroupNorm(resid) (rpe.py:136,173), recomputed from the statistics instead of read from a normalised
+          // copy: this lane's 4 channels are one group (Cout = 128)
+          if (p.resid_norm == 2) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.rn_gamma + col));
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.rn_beta + col));
+            float2 ms[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = m_w + i * 4 + sub;
+              const int px = m - rn_n[i >> 2] * p.HWo;
+              ms[i] = m < p.M ? __ldg(reinterpret_cast<const float2*>(p.rn_tstats + (((size_t)rn_b[i >> 2] * p.HWo + px) * 32 + (col >> 2)) * 2))
+                              : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              res[i].x = (res[i].x - ms[i].x) * ms[i].y * gm.x + bt.x;
+              res[i].y = (res[i].y - ms[i].x) * ms[i].y * gm.y + bt.y;
+              res[i].z = (res[i].z - ms[i].x) * ms[i].y * gm.z + bt.z;
+              res[i].w = (res[i].w - ms[i].x) * ms[i].y * gm.w + bt.w;
+            }
+          } else {
+            const int grp = (c + cq) >> 2;  // this lane's group inside the N tile
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const float4 mu = rn_tab[g][two_frames ? hh : 0][0][grp], ad = rn_tab[g][two_frames ? hh : 0][1][grp];
+#pragma unroll
+              for (int i = 4 * hh; i < 4 * hh + 4; ++i) {
+                res[i].x = fmaf(res[i].x, mu.x, ad.x);
+                res[i].y = fmaf(res[i].y, mu.y, ad.y);
+                res[i].z = fmaf(res[i].z, mu.z, ad.z);
+                res[i].w = fmaf(res[i].w, mu.w, ad.w);
+              }
+            }
+          }
         }
         float s1[2][4], s2[2][4];
 #pragma unroll
@@ -380,15 +460,15 @@ static bool encode_w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int 
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
+template <int BN, bool RN = false>
 static int launch_tc(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
                      TcParams& p, cudaStream_t st) {
   using S = TcSmem<BN>;
-  constexpr int SMEM_MAX = 226 * 1024;
+  constexpr int SMEM_MAX = (RN ? 216 : 226) * 1024;  // RN: 8.3 KB of static shared memory (the coefficient table)
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<BN, RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
   });
   if (attr_err != cudaSuccess) {
     set_last_error(attr_err);
@@ -406,7 +486,7 @@ static int launch_tc(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUten
   if (stages > iters) stages = iters;
   if (stages < 1) return FDM_ERR_UNSUPPORTED;
   p.stages = stages;
-  fdm::launch(conv_tc_kernel<BN>, dim3(grid), dim3(TC_THREADS), stages * p.stage_bytes + S::EXTRA_BYTES, st, ta0, tw0, ta1, tw1, p);
+  fdm::launch(conv_tc_kernel<BN, RN>, dim3(grid), dim3(TC_THREADS), stages * p.stage_bytes + S::EXTRA_BYTES, st, ta0, tw0, ta1, tw1, p);
   return check_launch();
 }
 
@@ -447,6 +527,14 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.klast0 = (a->C0 - (p.kchunks0 - 1) * TC_BK + 15) / 16;
   p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * TC_BK + 15) / 16 : 0;
   p.out_nchw = a->out_nchw;
+  p.resid_norm = a->resid_norm; p.rn_T = a->rn_T > 0 ? a->rn_T : 1; p.rn_eps = a->rn_eps;
+  p.rn_tstats = a->rn_tstats; p.rn_stats = a->rn_stats; p.rn_gamma = a->rn_gamma; p.rn_beta = a->rn_beta;
+  if (a->resid_norm != 0) {
+    FDM_REQUIRE(a->resid_norm == 2 || a->resid_norm == 3, FDM_ERR_BAD_ARG);
+    FDM_REQUIRE(a->resid != nullptr && a->rn_gamma != nullptr && a->rn_beta != nullptr, FDM_ERR_BAD_ARG);
+    FDM_REQUIRE(a->resid_norm == 2 ? a->rn_tstats != nullptr : a->rn_stats != nullptr, FDM_ERR_BAD_ARG);
+    FDM_REQUIRE(a->Cout == 128 && a->ksize == 1 && !a->out_nchw && (HWo % 32 == 0 || HWo == 16), FDM_ERR_UNSUPPORTED);
+  }
   // N tile: as wide as Cout allows, but narrowed while the grid would leave most SMs idle (small feature maps)
   int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : (a->Cout > 16 ? 32 : 16));
   const int mtiles = (p.M + TC_BM - 1) / TC_BM;
@@ -468,6 +556,11 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
     tw1 = tw0;
   }
   FDM_REQUIRE(ok, FDM_ERR_UNSUPPORTED);
+  if (p.resid_norm != 0) {
+    if (bn == 128) return launch_tc<128, true>(ta0, tw0, ta1, tw1, p, st);
+    if (bn == 64) return launch_tc<64, true>(ta0, tw0, ta1, tw1, p, st);
+    return launch_tc<32, true>(ta0, tw0, ta1, tw1, p, st);
+  }
   if (bn == 128) return launch_tc<128>(ta0, tw0, ta1, tw1, p, st);
   if (bn == 64) return launch_tc<64>(ta0, tw0, ta1, tw1, p, st);
   if (bn == 32) return launch_tc<32>(ta0, tw0, ta1, tw1, p, st);

@@ -27,7 +27,9 @@ ConvArgs = _S("ConvArgs", [("a0", vp), ("w0", vp), ("a1", vp), ("w1", vp), ("bia
                            ("y_f32", vp), ("y_op", vp), ("stats", vp),
                            ("N", i32), ("Hin", i32), ("Win", i32), ("C0", i32), ("C1", i32), ("Cout", i32),
                            ("ksize", i32), ("stride", i32), ("upsample", i32),
-                           ("a_dtype", i32), ("op_dtype", i32), ("out_nchw", i32), ("engine", i32)])
+                           ("a_dtype", i32), ("op_dtype", i32), ("out_nchw", i32), ("engine", i32),
+                           ("resid_norm", i32), ("rn_T", i32), ("rn_eps", f32), ("rn_tstats", vp), ("rn_stats", vp),
+                           ("rn_gamma", vp), ("rn_beta", vp)])
 GnApplyArgs = _S("GnApplyArgs", [("xa", vp), ("xb", vp), ("stats_a", vp), ("stats_b", vp), ("gamma", vp), ("beta", vp),
                                  ("film", vp), ("out_op", vp), ("out_f32", vp), ("raw_op", vp),
                                  ("N", i32), ("HW", i32), ("Ca", i32), ("Cb", i32), ("T", i32),
@@ -108,10 +110,9 @@ RpeTableProblem = _S("RpeTableProblem", [("wd", vp), ("bd", vp), ("bo", vp), ("w
                                          ("C", i32), ("te_off", i32)])
 RpeTablesArgs = _S("RpeTablesArgs", [("te", vp), ("frame_indices", vp), ("blob", vp), ("count", i32), ("B", i32), ("T", i32),
                                      ("te_stride", i32), ("max_C", i32)])
-NormLinearArgs = _S("NormLinearArgs", [("a_op", vp), ("x", vp), ("stats", vp), ("tstats", vp), ("gamma", vp), ("beta", vp), ("w", vp),
-                                       ("bias", vp), ("resid", vp), ("y_f32", vp), ("y_op", vp), ("out_stats", vp),
-                                       ("B", i32), ("T", i32), ("HW", i32), ("K", i32), ("Cout", i32),
-                                       ("a_mode", i32), ("resid_mode", i32), ("eps", f32)])
+NormLinearArgs = _S("NormLinearArgs", [("x", vp), ("stats", vp), ("tstats", vp), ("gamma", vp), ("beta", vp), ("w", vp), ("bias", vp),
+                                       ("y_op", vp), ("B", i32), ("T", i32), ("HW", i32), ("K", i32), ("Cout", i32),
+                                       ("a_mode", i32), ("eps", f32)])
 PACK_TC_FWD, PACK_TC_DGRAD, PACK_SIMT_FWD, PACK_SIMT_DGRAD, PACK_SUM2 = 0, 1, 2, 3, 4
 
 # index = `which` of fdm_struct_size (include/fdm_b200.h)

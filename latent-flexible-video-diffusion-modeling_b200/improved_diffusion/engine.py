@@ -797,7 +797,7 @@ class DenoiserEngine:
 
         # ---------------- conv helper
         def conv(a0, C0, Hin, Win, w0, Cout, k, stride=1, upsample=0, a1=None, C1=0, w1=None, bias=None, resid=None,
-                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None, flop_c0=None, n_frames=None):
+                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None, flop_c0=None, n_frames=None, **resid_norm):
             a_dtype = opd if a_dtype is None else a_dtype
             Nf_ = Nf if n_frames is None else n_frames
             Hv, Wv = (Hin * 2, Win * 2) if upsample else (Hin, Win)
@@ -810,7 +810,7 @@ class DenoiserEngine:
             P.op("fdm_conv", N_.ConvArgs, a0=a0, w0=pack(w0), a1=a1, w1=pack(w1) if w1 is not None else None, bias=bias,
                  resid=resid, y_f32=y_f32, y_op=y_op, stats=stats, N=Nf_, Hin=Hin, Win=Win, C0=C0, C1=C1, Cout=Cout,
                  ksize=k, stride=stride, upsample=upsample, a_dtype=a_dtype, op_dtype=opd, out_nchw=out_nchw,
-                 engine=N_.CONV_TC if tc else N_.CONV_SIMT)
+                 engine=N_.CONV_TC if tc else N_.CONV_SIMT, **resid_norm)
             return Ho, Wo
 
         for hb, Cc, net, rb_, rop in self._pending_rpe_tc:
@@ -1055,13 +1055,36 @@ class DenoiserEngine:
         def attention(ab, x, want_op=False):
             Cc, Hh, Ww, hw = x.C, x.H, x.W, x.H * x.W
             ta, sa = ab.temporal_attention, ab.spatial_attention
+            # Inference plans in bf16 mode: the GroupNorm of each half runs in the operand path of its qkv linear (fdm_norm_linear:
+            # the normalised tensor is never written) and the proj_out epilogue recomputes the residual GN(x) from x and the
+            # saved statistics (fdm_conv resid_norm) — 2 launches and 24 bytes per element less per attention block.
+            def nl_ok(a_mode):
+                if not self.use_tc or train or os.environ.get("FDM_FUSED_QKV", "1") == "0":
+                    return False
+                probe = N_.NormLinearArgs(B=B, T=T, HW=hw, K=Cc, Cout=3 * Cc, a_mode=a_mode)
+                return bool(lib.fdm_norm_linear_supported(C.byref(probe)))
+
+            def norm_qkv(src, a_mode, norm, lin, out, stats=None, tstats=None):
+                P.op("fdm_norm_linear", N_.NormLinearArgs, x=src, stats=stats, tstats=tstats, gamma=f32(norm.weight),
+                     beta=f32(norm.bias), w=pack_fwd(lin.weight, True), bias=f32(lin.bias), y_op=out, B=B, T=T, HW=hw, K=Cc,
+                     Cout=3 * Cc, a_mode=a_mode, eps=norm.eps)
+                fl = 2 * Nf * hw * 3 * Cc * Cc
+                P.flops += fl
+                P.conv_flops += fl
+
             # --- temporal: GN over (C/32 x T) per (b, pixel)
-            xn = P.buf("ta_xn", Nf * hw * Cc * 4)
-            xn_op = P.buf("ta_xn_op", Nf * hw * Cc * osz)
-            P.op("fdm_temporal_gn", N_.TemporalGnArgs, x=x.buf, gamma=f32(ta.norm.weight), beta=f32(ta.norm.bias),
-                 out_f32=xn, out_op=xn_op, B=B, T=T, HW=hw, C=Cc, op_dtype=opd, eps=ta.norm.eps)
             qkv = P.buf("ta_qkv", Nf * hw * 3 * Cc * osz)
-            conv(xn_op, Cc, Hh, Ww, ta.qkv.weight, 3 * Cc, 1, bias=f32(ta.qkv.bias), y_op=qkv)
+            t_fused = nl_ok(2)
+            if t_fused:
+                xn = None
+                tst = P.buf("ta_tstats", B * hw * 32 * 2 * 4)
+                norm_qkv(x.buf, 2, ta.norm, ta.qkv, qkv, tstats=tst)
+            else:
+                xn = P.buf("ta_xn", Nf * hw * Cc * 4)
+                xn_op = P.buf("ta_xn_op", Nf * hw * Cc * osz)
+                P.op("fdm_temporal_gn", N_.TemporalGnArgs, x=x.buf, gamma=f32(ta.norm.weight), beta=f32(ta.norm.bias),
+                     out_f32=xn, out_op=xn_op, B=B, T=T, HW=hw, C=Cc, op_dtype=opd, eps=ta.norm.eps)
+                conv(xn_op, Cc, Hh, Ww, ta.qkv.weight, 3 * Cc, 1, bias=f32(ta.qkv.bias), y_op=qkv)
             o = P.buf("ta_o", Nf * hw * Cc * osz)
             P.flops += 10 * T * T * Cc * B * hw  # QK^T, PV and the three contextual RPE einsums (rpe.py:72-83,144,166)
             ws_bytes = self._temporal_ws(B, T, Cc, ta.num_heads, hw) if (self.temporal_tc and not train) else None
@@ -1087,15 +1110,25 @@ class DenoiserEngine:
                 P.temporal_attn_maps.append((ws, B, T, hw, Cc, ta.num_heads))
             y = new_act("ta_y", Cc, Hh, Ww)
             y.biases = (ta.proj_out.bias,)
-            conv(o, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, bias=f32(ta.proj_out.bias), resid=xn, y_f32=y.buf, stats=y.st)
+            if t_fused:
+                conv(o, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, bias=f32(ta.proj_out.bias), resid=x.buf, y_f32=y.buf, stats=y.st,
+                     resid_norm=2, rn_T=T, rn_eps=ta.norm.eps, rn_tstats=tst, rn_gamma=f32(ta.norm.weight),
+                     rn_beta=f32(ta.norm.bias))
+            else:
+                conv(o, Cc, Hh, Ww, ta.proj_out.weight, Cc, 1, bias=f32(ta.proj_out.bias), resid=xn, y_f32=y.buf, stats=y.st)
             # --- spatial: plain per-frame GroupNorm, attention over the pixels of each frame
-            yn = P.buf("sa_yn", Nf * hw * Cc * 4)
-            yn_op = P.buf("sa_yn_op", Nf * hw * Cc * osz)
-            P.op("fdm_gn_apply", N_.GnApplyArgs, xa=y.buf, xb=None, stats_a=y.st, stats_b=None, gamma=f32(sa.norm.weight),
-                 beta=f32(sa.norm.bias), film=None, out_op=yn_op, out_f32=yn, raw_op=None, N=Nf, HW=hw, Ca=Cc, Cb=0, T=T,
-                 film_stride=0, film_off=0, silu=0, op_dtype=opd, eps=sa.norm.eps)
             qkv2 = P.buf("sa_qkv", Nf * hw * 3 * Cc * osz)
-            conv(yn_op, Cc, Hh, Ww, sa.qkv.weight, 3 * Cc, 1, bias=f32(sa.qkv.bias), y_op=qkv2)
+            s_fused = nl_ok(1)
+            if s_fused:
+                yn = None
+                norm_qkv(y.buf, 1, sa.norm, sa.qkv, qkv2, stats=y.st)
+            else:
+                yn = P.buf("sa_yn", Nf * hw * Cc * 4)
+                yn_op = P.buf("sa_yn_op", Nf * hw * Cc * osz)
+                P.op("fdm_gn_apply", N_.GnApplyArgs, xa=y.buf, xb=None, stats_a=y.st, stats_b=None, gamma=f32(sa.norm.weight),
+                     beta=f32(sa.norm.bias), film=None, out_op=yn_op, out_f32=yn, raw_op=None, N=Nf, HW=hw, Ca=Cc, Cb=0, T=T,
+                     film_stride=0, film_off=0, silu=0, op_dtype=opd, eps=sa.norm.eps)
+                conv(yn_op, Cc, Hh, Ww, sa.qkv.weight, 3 * Cc, 1, bias=f32(sa.qkv.bias), y_op=qkv2)
             o2 = P.buf("sa_o", Nf * hw * Cc * osz)
             P.flops += 4 * hw * hw * Cc * Nf
             # training: the tcgen05 forward also saves the log-sum-exp of every score row for the tcgen05 backward kernels
@@ -1104,8 +1137,13 @@ class DenoiserEngine:
                  qkv_dtype=opd, out_dtype=opd, engine=0 if self.use_tc else 1, lse=sa_lse, attn_mean=s_mean)
             z = new_act("sa_z", Cc, Hh, Ww)
             z.biases = (sa.proj_out.bias,)
-            conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf,
-                 y_op=with_op_copy(z) if want_op else None, stats=z.st)
+            if s_fused:
+                conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=y.buf, y_f32=z.buf,
+                     y_op=with_op_copy(z) if want_op else None, stats=z.st, resid_norm=3, rn_eps=sa.norm.eps, rn_stats=y.st,
+                     rn_gamma=f32(sa.norm.weight), rn_beta=f32(sa.norm.bias))
+            else:
+                conv(o2, Cc, Hh, Ww, sa.proj_out.weight, Cc, 1, bias=f32(sa.proj_out.bias), resid=yn, y_f32=z.buf,
+                     y_op=with_op_copy(z) if want_op else None, stats=z.st)
 
             def bwd():
                 n_tok = Nf * hw

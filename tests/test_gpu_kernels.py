@@ -334,8 +334,9 @@ NL_SHAPES = [(8, 20, 256), (2, 5, 64), (3, 7, 16), (1, 40, 64), (2, 2, 256), (1,
 @pytest.mark.parametrize("B,T,HW", NL_SHAPES)
 @pytest.mark.parametrize("a_mode", [1, 2])
 def test_norm_linear_qkv(B, T, HW, a_mode):
-    """fdm_norm_linear (lin_tc.cu), qkv case: GroupNorm (per frame from the producer's sums / temporal, in the tile) in the
-    operand path of the C -> 3C linear, against torch group_norm -> bf16 -> linear on the same bf16-rounded weights."""
+    """fdm_norm_linear (lin_tc.cu): GroupNorm (per frame from the producer's sums / temporal, in the tile) in the operand path of
+    the C -> 3C linear, against torch group_norm -> bf16 -> linear on the same bf16-rounded weights."""
+    import ctypes
     from improved_diffusion import _native as N_
     C, Cout, eps = 128, 384, 1e-5
     x, gamma, beta, w, bias, _ = _nl_inputs(B, T, HW, Cout, seed=B * 1000 + T * 10 + a_mode)
@@ -343,11 +344,15 @@ def test_norm_linear_qkv(B, T, HW, a_mode):
     y = torch.full((B * T, HW, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
     stats = _frame_stats(x)
     tstats = torch.full((B, HW, 32, 2), float("nan"), device="cuda")
-    a = N_.NormLinearArgs(a_op=None, x=x.data_ptr(), stats=stats.data_ptr() if a_mode == 1 else None,
+    a = N_.NormLinearArgs(x=x.data_ptr(), stats=stats.data_ptr() if a_mode == 1 else None,
                           tstats=tstats.data_ptr() if a_mode == 2 else None, gamma=gamma.data_ptr(), beta=beta.data_ptr(),
-                          w=wp.data_ptr(), bias=bias.data_ptr(), resid=None, y_f32=None, y_op=y.data_ptr(), out_stats=None,
-                          B=B, T=T, HW=HW, K=C, Cout=Cout, a_mode=a_mode, resid_mode=0, eps=eps)
-    assert N_.lib().fdm_norm_linear_supported(C_byref(a))
+                          w=wp.data_ptr(), bias=bias.data_ptr(), y_op=y.data_ptr(),
+                          B=B, T=T, HW=HW, K=C, Cout=Cout, a_mode=a_mode, eps=eps)
+    if a_mode == 2 and T > 20:
+        # the temporal form keeps a pixel's T rows in registers: longer clips run fdm_temporal_gn + fdm_conv
+        assert not N_.lib().fdm_norm_linear_supported(ctypes.byref(a))
+        return
+    assert N_.lib().fdm_norm_linear_supported(ctypes.byref(a))
     N_.call("fdm_norm_linear", a, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     xn = _frame_gn(x, gamma, beta, eps) if a_mode == 1 else _temporal_gn(x, B, T, gamma, beta, eps)
@@ -362,45 +367,32 @@ def test_norm_linear_qkv(B, T, HW, a_mode):
         assert rel(tstats[..., 1], (var + eps).rsqrt().float()) <= 1e-4
 
 
-def C_byref(a):
-    import ctypes
-    return ctypes.byref(a)
-
-
 @pytest.mark.parametrize("B,T,HW", NL_SHAPES)
-@pytest.mark.parametrize("resid_mode", [0, 1, 2, 3])
-def test_norm_linear_proj(B, T, HW, resid_mode):
-    """fdm_norm_linear, proj_out case: bf16 operand by TMA, residual = plain fp32 tensor / temporal GN of x recomputed from the
-    saved (mean, rstd) pairs / per-frame GN of x recomputed from its sums; fp32 + bf16 outputs and the GroupNorm statistics of
-    the result."""
+@pytest.mark.parametrize("resid_norm", [2, 3])
+def test_conv_proj_recomputed_groupnorm_residual(B, T, HW, resid_norm):
+    """fdm_conv (per-tap tcgen05 engine), proj_out form: the residual is GroupNorm(x) RECOMPUTED in the epilogue — temporal GN from
+    the saved (mean, rstd) pairs (resid_norm 2) / per-frame GN from the sums (resid_norm 3) — instead of a normalised fp32 copy
+    (rpe.py:136,173); fp32 + bf16 outputs and the GroupNorm statistics of the result."""
     from improved_diffusion import _native as N_
     C, eps = 128, 1e-5
-    x, gamma, beta, w, bias, g = _nl_inputs(B, T, HW, C, seed=B * 1000 + T * 10 + resid_mode + 5)
+    x, gamma, beta, w, bias, g = _nl_inputs(B, T, HW, C, seed=B * 1000 + T * 10 + resid_norm + 5)
     M = B * T * HW
+    side = int(HW ** 0.5)
     h = torch.randn(M, C, device="cuda", generator=g).to(torch.bfloat16)
     wp = w.to(torch.bfloat16).contiguous()
     y = torch.full((M, C), float("nan"), device="cuda")
     yop = torch.full((M, C), float("nan"), device="cuda", dtype=torch.bfloat16)
     ostats = torch.zeros(B * T, C, 2, device="cuda", dtype=torch.float64)
     stats = _frame_stats(x)
-    if resid_mode == 1:
-        r = torch.randn(M, C, device="cuda", generator=g)
-    elif resid_mode == 2:
-        r = _temporal_gn(x, B, T, gamma, beta, eps).reshape(M, C)
-    elif resid_mode == 3:
-        r = _frame_gn(x, gamma, beta, eps).reshape(M, C)
-    else:
-        r = torch.zeros(M, C, device="cuda")
+    r = (_temporal_gn(x, B, T, gamma, beta, eps) if resid_norm == 2 else _frame_gn(x, gamma, beta, eps)).reshape(M, C)
     v = x.view(B, T, HW, 32, 4).permute(0, 2, 3, 1, 4).reshape(B, HW, 32, T * 4).double()
     tstats = torch.stack([v.mean(-1), (v.var(-1, unbiased=False) + eps).rsqrt()], dim=-1).float().contiguous()
-    a = N_.NormLinearArgs(a_op=h.data_ptr(), x=x.data_ptr(), stats=stats.data_ptr(), tstats=tstats.data_ptr(),
-                          gamma=gamma.data_ptr(), beta=beta.data_ptr(), w=wp.data_ptr(), bias=bias.data_ptr(),
-                          resid=r.data_ptr() if resid_mode == 1 else None, y_f32=y.data_ptr(), y_op=yop.data_ptr(),
-                          out_stats=ostats.data_ptr(), B=B, T=T, HW=HW, K=C, Cout=C, a_mode=0, resid_mode=resid_mode, eps=eps)
-    if HW % 32 and HW != 16:
-        assert not N_.lib().fdm_norm_linear_supported(C_byref(a))
-        return
-    N_.call("fdm_norm_linear", a, torch.cuda.current_stream().cuda_stream)
+    a = N_.ConvArgs(a0=h.data_ptr(), w0=wp.data_ptr(), a1=None, w1=None, bias=bias.data_ptr(), resid=x.data_ptr(), y_f32=y.data_ptr(),
+                    y_op=yop.data_ptr(), stats=ostats.data_ptr(), N=B * T, Hin=side, Win=side, C0=C, C1=0, Cout=C, ksize=1, stride=1,
+                    upsample=0, a_dtype=N_.BF16, op_dtype=N_.BF16, out_nchw=0, engine=N_.CONV_TC, resid_norm=resid_norm, rn_T=T,
+                    rn_eps=eps, rn_tstats=tstats.data_ptr(), rn_stats=stats.data_ptr(), rn_gamma=gamma.data_ptr(),
+                    rn_beta=beta.data_ptr())
+    N_.call("fdm_conv", a, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     ref = h.float() @ wp.float().t() + bias + r
     assert rel(y, ref) <= 2e-5, rel(y, ref)

@@ -42,22 +42,21 @@ for B, T, HW in [(8, 20, 256), (8, 20, 64), (8, 20, 16)]:
     xn_op = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
     side = int(HW ** 0.5)
 
-    def nl(a_mode, resid_mode, Cout):
-        f32 = Cout == 128
-        a = N_.NormLinearArgs(a_op=h.data_ptr(), x=x.data_ptr(), stats=stats.data_ptr(), tstats=tstats.data_ptr(), gamma=gamma.data_ptr(),
-                              beta=beta.data_ptr(), w=(wp if f32 else wq).data_ptr(), bias=bias.data_ptr(), resid=xn.data_ptr(),
-                              y_f32=y.data_ptr() if f32 else None, y_op=None if f32 else qkv.data_ptr(),
-                              out_stats=ostats.data_ptr() if f32 else None, B=B, T=T, HW=HW, K=C, Cout=Cout, a_mode=a_mode,
-                              resid_mode=resid_mode, eps=eps)
+    def nl(a_mode):
+        a = N_.NormLinearArgs(x=x.data_ptr(), stats=stats.data_ptr(), tstats=tstats.data_ptr(), gamma=gamma.data_ptr(),
+                              beta=beta.data_ptr(), w=wq.data_ptr(), bias=bias.data_ptr(), y_op=qkv.data_ptr(), B=B, T=T, HW=HW, K=C,
+                              Cout=384, a_mode=a_mode, eps=eps)
         return lambda: N_.call("fdm_norm_linear", a, st)
 
-    def conv(a0, Cout, resid):
+    def conv(a0, Cout, resid, resid_norm=0):
         f32 = Cout == 128
+        rn = dict(resid_norm=resid_norm, rn_T=T, rn_eps=eps, rn_tstats=tstats.data_ptr(), rn_stats=stats.data_ptr(),
+                  rn_gamma=gamma.data_ptr(), rn_beta=beta.data_ptr()) if resid_norm else {}
         a = N_.ConvArgs(a0=a0.data_ptr(), w0=(wp if f32 else wq).data_ptr(), a1=None, w1=None, bias=bias.data_ptr(),
-                        resid=xn.data_ptr() if resid else None, y_f32=y.data_ptr() if f32 else None,
+                        resid=(x if resid_norm else xn).data_ptr() if resid else None, y_f32=y.data_ptr() if f32 else None,
                         y_op=None if f32 else qkv.data_ptr(), stats=ostats.data_ptr() if f32 else None, N=B * T, Hin=side, Win=side,
                         C0=C, C1=0, Cout=Cout, ksize=1, stride=1, upsample=0, a_dtype=N_.BF16, op_dtype=N_.BF16, out_nchw=0,
-                        engine=N_.CONV_TC)
+                        engine=N_.CONV_TC, **rn)
         return lambda: N_.call("fdm_conv", a, st)
 
     tg = N_.TemporalGnArgs(x=x.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(), out_f32=xn.data_ptr(), out_op=xn_op.data_ptr(),
@@ -70,11 +69,9 @@ for B, T, HW in [(8, 20, 256), (8, 20, 64), (8, 20, 16)]:
         "gn_apply": timed(lambda: N_.call("fdm_gn_apply", ga, st)),
         "conv qkv": timed(conv(xn_op, 384, False)),
         "conv proj+res": timed(conv(h, 128, True)),
-        "nl qkv plain(a0)": None,
-        "nl qkv spatial(a1)": timed(nl(1, 0, 384)),
-        "nl qkv temporal(a2)": timed(nl(2, 0, 384)),
-        "nl proj res1": timed(nl(0, 1, 128)),
-        "nl proj res2": timed(nl(0, 2, 128)),
-        "nl proj res3": timed(nl(0, 3, 128)),
+        "conv proj+GN(x) temporal": timed(conv(h, 128, True, 2)),
+        "conv proj+GN(x) frame": timed(conv(h, 128, True, 3)),
+        "nl qkv spatial(a1)": timed(nl(1)),
+        "nl qkv temporal(a2)": timed(nl(2)),
     }
     print(f"B={B} T={T} HW={HW}: " + "  ".join(f"{k} {v:.1f}us" for k, v in r.items() if v is not None), flush=True)
