@@ -182,9 +182,19 @@ __global__ void __launch_bounds__(NL_WORKERS, 1) nl_qkv_kernel(const __grid_cons
           xr[i] = (ok && i < p.T) ? __ldg(reinterpret_cast<const float4*>(src + i * fstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    if (blockIdx.x < p.tiles) fetch(blockIdx.x);
+    // Work items are (tile, 128-column slice) pairs, handed out as contiguous ranges: 320 tiles over 148 CTAs quantise to 3 vs
+    // 2.16 tiles (the kernel is bound by what each SM has to store), 960 slices to 7 vs 6.5.  A tile that straddles two CTAs is
+    // transformed by both; each computes and stores only its own slices.
+    const int items = p.tiles * p.NS;
+    const int item_lo = (int)(((long long)blockIdx.x * items) / gridDim.x);
+    const int item_hi = (int)(((long long)(blockIdx.x + 1) * items) / gridDim.x);
+    const int tile_lo = item_lo / p.NS, tile_hi = (item_hi + p.NS - 1) / p.NS;  // tiles [tile_lo, tile_hi)
+    uint32_t mma_ph = 0;  // bit j: parity of the next completion of mma_bar[j]
+    if (tile_lo < tile_hi) fetch(tile_lo);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+      const int j_lo = tile == tile_lo ? item_lo - tile * p.NS : 0;
+      const int j_hi = min(p.NS, item_hi - tile * p.NS);
       if (threadIdx.x == 0) NL_TRACE(8 + 8 * it + 0);
       if (p.a_mode == 1) {
 #pragma unroll
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(NL_WORKERS, 1) nl_qkv_kernel(const __grid_cons
       if (threadIdx.x == 0) NL_TRACE(8 + 8 * it + 1);
 
       // the next tile's raw rows: in flight under the MMAs and the epilogue
-      if (tile + (int)gridDim.x < p.tiles) fetch(tile + gridDim.x);
+      if (tile + 1 < tile_hi) fetch(tile + 1);
 
       if (warp == 0) {
         // MMA issue (one elected lane of warp 0; 8 warps keep the register budget at 255 per thread — a ninth, control-only warp
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(NL_WORKERS, 1) nl_qkv_kernel(const __grid_cons
         if (elect_one_sync()) {
           constexpr uint32_t idesc = make_idesc(128);
           const uint32_t a_lo = smem_desc_lo(smem_u32(a_s));
-          for (int j = 0; j < p.NS; ++j) {
+          for (int j = j_lo; j < j_hi; ++j) {
             const uint32_t d = tmem_base + j * 128;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -272,10 +282,11 @@ __global__ void __launch_bounds__(NL_WORKERS, 1) nl_qkv_kernel(const __grid_cons
       named_bar(1 + g, 128);
       const int vb = p.a_mode == 2 ? tile / p.tpv : 0;
       const int px0 = p.a_mode == 2 ? (tile - vb * p.tpv) * p.PL : 0;
-      for (int j = 0; j < p.NS; ++j) {
+      for (int j = j_lo; j < j_hi; ++j) {
         const int gcol = j * 128 + g * 64;
-        mbar_wait(&mma_bar[j], it & 1);
-        if (threadIdx.x == 0 && j == 0) NL_TRACE(8 + 8 * it + 4);
+        mbar_wait(&mma_bar[j], (mma_ph >> j) & 1);
+        mma_ph ^= 1u << j;
+        if (threadIdx.x == 0 && j == j_lo) NL_TRACE(8 + 8 * it + 4);
         tcgen05_fence_after();
         uint8_t* blk = stg_s + (j * 2 + g) * NL_STG_BLOCK;
         uint8_t* myrow = blk + erow * 128;
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(NL_WORKERS, 1) nl_qkv_kernel(const __grid_cons
       tcgen05_fence_before();  // orders this tile's TMEM reads before the arrive on a_ready of the next tile
       if (threadIdx.x == 0) NL_TRACE(8 + 8 * it + 5);
     }
-    if (leader) bulk_wait0();
+    if (leader) bulk_wait_read0();  // shared memory must outlive the stores' reads; grid completion orders the writes themselves
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -403,7 +414,8 @@ extern "C" int fdm_norm_linear(const fdm_norm_linear_args* a, void* stream) {
     set_last_error(attr_err);
     return FDM_ERR_CUDA;
   }
-  const int grid = p.tiles < 148 ? p.tiles : 148;
+  const int items = p.tiles * p.NS;
+  const int grid = items < 148 ? items : 148;
   fdm::launch(nl_qkv_kernel, dim3(grid), dim3(NL_WORKERS), (size_t)smem, reinterpret_cast<cudaStream_t>(stream), tw, ty, p);
   return check_launch();
 }
