@@ -13,6 +13,10 @@
 //     overlaps the main loop of item i+1 inside the same CTA (warp-specialised: TMA / MMA / 4 epilogue warps).
 //   * GroupNorm statistics: per-warp column sums are combined across the 4 epilogue warps and both tiles in shared
 //     memory before the fp64 atomics (8x fewer atomics than one per warp).
+//   * CG = 2 (CTA pairs, `cta_group::2`): the two CTAs of a cluster run two such work items (different rows / frames, SAME output
+//     channels) as ONE stream of M = 256 MMAs issued by the leader.  Each CTA stages its own A box and only HALF of the weight
+//     tile (BN/2 rows per tap): single-CTA MMAs at N <= 128 are bound by shared-memory operand reads (A + B per MMA, measured
+//     86 clk per 128x128x16 against a tensor floor of 64); the pair reads A + B/2 per SM and halves the weight TMA traffic.
 #include "tc_common.cuh"
 #include <mutex>
 
@@ -41,7 +45,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, int TPI>
+template <int BN, int TPI, int CG>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap ta0,
                                                                    const __grid_constant__ CUtensorMap tw0,
                                                                    const __grid_constant__ CUtensorMap ta1,
@@ -55,7 +59,13 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
   constexpr int TMEM_COLS = 4 * BN;  // 2 accumulator buffers x 2 M tiles
-  constexpr int B_TAP_BYTES = BN * 128;
+  constexpr int B_TAP_BYTES = (BN / CG) * 128;  // a CTA of a pair stages its half of the weight tile's rows
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int cid = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // work-item stream of this CTA (pair)
+  const int cstride = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_q = p.n_items / CG;
+  // work item of this CTA for stream position q: the CTAs of a pair take the item pairs 2k, 2k+1 of the SAME N tile
+  auto item_of = [&](int q) { return CG == 2 ? ((2 * (q / p.ntiles) + (int)rank) * p.ntiles + q % p.ntiles) : q; };
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,16 +87,22 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 8);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[i], 8 * CG);  // one arrival per epilogue warp (of both CTAs: the leader's copy is the live one)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   pdl_wait();  // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail
@@ -95,7 +111,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
     {
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const uint32_t full0 = CG == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;  // the leader's full barriers (pairs)
+      const int b_row = CG == 2 ? (int)rank * (BN / 2) : 0;                         // this CTA's rows of the weight tile
+      for (int q = cid; q < n_q; q += cstride) {
+        const int item = item_of(q);
         const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
         const int n = pair / p.pairs_per_frame, h0 = (pair - n * p.pairs_per_frame) * TPI * p.hbox;
         const int pad = p.ks >> 1;
@@ -106,11 +125,17 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
             uint8_t* b_dst = a_dst + p.a_bytes;
             if (elect_one_sync()) {
-              mbar_expect_tx(&full_bar[stage], p.a_bytes0 + p.ks * B_TAP_BYTES);
-              tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - pad, h0 - pad, n);
               // weights are packed filter-column major ([s][r][co][ci]): the three filter rows of column s are ONE box
               // (a TMA instruction costs ~450 clk + 0.4 clk/row on this part, measured: tools/tma_bench.cu)
-              tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * 64, n_off, s * p.ks);
+              if (CG == 2) {
+                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (p.a_bytes0 + p.ks * B_TAP_BYTES));  // both CTAs' bytes
+                tma_load_4d_cg2(a_dst, &ta0, full0 + stage * 8, kc * 64, s - pad, h0 - pad, n);
+                tma_load_3d_cg2(b_dst, &tw0, full0 + stage * 8, kc * 64, n_off + b_row, s * p.ks);
+              } else {
+                mbar_expect_tx(&full_bar[stage], p.a_bytes0 + p.ks * B_TAP_BYTES);
+                tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - pad, h0 - pad, n);
+                tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * 64, n_off, s * p.ks);
+              }
             }
             __syncwarp();
           }
@@ -120,23 +145,37 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
           uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
           if (elect_one_sync()) {
-            mbar_expect_tx(&full_bar[stage], TPI * 128 * 128 + B_TAP_BYTES);
-            tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * 64, 0, h0, n);
-            tma_load_3d(a_dst + p.a_bytes, &tw1, &full_bar[stage], kc * 64, n_off, 0);
+            if (CG == 2) {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (TPI * 128 * 128 + B_TAP_BYTES));
+              tma_load_4d_cg2(a_dst, &ta1, full0 + stage * 8, kc * 64, 0, h0, n);
+              tma_load_3d_cg2(a_dst + p.a_bytes, &tw1, full0 + stage * 8, kc * 64, n_off + b_row, 0);
+            } else {
+              mbar_expect_tx(&full_bar[stage], TPI * 128 * 128 + B_TAP_BYTES);
+              tma_load_4d(a_dst, &ta1, &full_bar[stage], kc * 64, 0, h0, n);
+              tma_load_3d(a_dst + p.a_bytes, &tw1, &full_bar[stage], kc * 64, n_off, 0);
+            }
           }
           __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
-    {
-      constexpr uint32_t idesc = make_idesc(BN);
+    // ===================== MMA issuer (whole warp converged; one elected lane issues; pairs: the leader CTA only) =====================
+    if (CG == 1 || rank == 0) {
+      constexpr uint32_t idesc = make_idesc_mn(128 * CG, BN);
+      auto mma = [](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+        if (CG == 2) umma_bf16_lo_pair(d, a_lo, b_lo, idesc, acc);
+        else umma_bf16_lo(d, a_lo, b_lo, idesc, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if (CG == 2) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
       const uint32_t row16 = ((uint32_t)p.W * 128) >> 4;         // one image row of the A box, in descriptor units (16 B)
       const uint32_t tile_rows16 = (uint32_t)p.hbox * row16;     // second M tile starts hbox rows further down
       uint32_t it = 0, local = 0;
       long long t_wait_tmem = 0, t_wait_full = 0, t_begin = clock64();
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      for (int q = cid; q < n_q; q += cstride, ++local) {
         const uint32_t buf = local & 1;
         long long c0 = clock64();
         mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);
@@ -161,20 +200,20 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
                 for (int j = 0; j < TPI; ++j) {
                   const uint32_t a_lo = a_lo0 + (j ? tile_rows16 : 0u) + r * row16;
                   const uint32_t b_lo = b_lo0 + r * (B_TAP_BYTES >> 4);
-                  umma_bf16_lo(acc0 + j * BN, a_lo, b_lo, idesc, r == 0 ? first : 1u);
-                  umma_bf16_lo(acc0 + j * BN, a_lo + 2, b_lo + 2, idesc, 1u);
-                  umma_bf16_lo(acc0 + j * BN, a_lo + 4, b_lo + 4, idesc, 1u);
-                  umma_bf16_lo(acc0 + j * BN, a_lo + 6, b_lo + 6, idesc, 1u);
+                  mma(acc0 + j * BN, a_lo, b_lo, r == 0 ? first : 1u);
+                  mma(acc0 + j * BN, a_lo + 2, b_lo + 2, 1u);
+                  mma(acc0 + j * BN, a_lo + 4, b_lo + 4, 1u);
+                  mma(acc0 + j * BN, a_lo + 6, b_lo + 6, 1u);
                 }
               }
             } else {
               for (int r = 0; r < p.ks; ++r)
                 for (int j = 0; j < TPI; ++j)
                   for (int k = 0; k < nk; ++k)
-                    umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + r * row16 + 2 * k,
-                                 b_lo0 + r * (B_TAP_BYTES >> 4) + 2 * k, idesc, (r | k) == 0 ? first : 1u);
+                    mma(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + r * row16 + 2 * k,
+                        b_lo0 + r * (B_TAP_BYTES >> 4) + 2 * k, (r | k) == 0 ? first : 1u);
             }
-            umma_commit(&empty_bar[stage]);
+            commit(&empty_bar[stage]);
             }
             __syncwarp();
           }
@@ -190,12 +229,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < TPI; ++j)
               for (int k = 0; k < nk; ++k)
-                umma_bf16_lo(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + 2 * k, b_lo0 + 2 * k, idesc, 1u);
-            umma_commit(&empty_bar[stage]);
+                mma(acc0 + j * BN, a_lo0 + (j ? tile_rows16 : 0u) + 2 * k, b_lo0 + 2 * k, 1u);
+            commit(&empty_bar[stage]);
           }
           __syncwarp();
         }
-        if (elect_one_sync()) umma_commit(&tmem_full_bar[buf]);
+        if (elect_one_sync()) commit(&tmem_full_bar[buf]);
         __syncwarp();
       }
       if (p.trace != nullptr && lane == 0) {
@@ -220,7 +259,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
     uint32_t local = 0;
     long long e_wait = 0, e_begin = clock64(), e_stats = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+    const uint32_t tmem_empty0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;  // the leader's (pairs)
+    for (int q = cid; q < n_q; q += cstride, ++local) {
+      const int item = item_of(q);
       const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
       const uint32_t buf = local & 1;
       const size_t m_pair = (size_t)pair * TPI * 128;
@@ -291,7 +332,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       }
       // all TMEM reads of this warp's part of the accumulator buffer are complete (tcgen05.wait::ld inside the load helper)
       tcgen05_fence_before();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tmem_empty0 + buf * 8);
+        else mbar_arrive(&tmem_empty_bar[buf]);
+      }
       long long c3 = clock64();
       if (p.stats != nullptr) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -321,9 +365,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // neither CTA leaves while the other may still signal its barriers or read its shared memory
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -352,14 +398,14 @@ static bool encode3w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int 
 static int g_num_sms = 0;
 static long long* g_trace = nullptr;
 
-template <int BN, int TPI>
-static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
-                       HaloParams& p, cudaStream_t st) {
+template <int BN, int TPI, int CG>
+static int launch_halo_cg(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
+                          HaloParams& p, cudaStream_t st) {
   constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers
   const int extra = 1024 + 8 * 32 * 16 * 4 + 2 * 4 * BN * 2 * 4;  // alignment slack + staging + statbuf
   p.a_bytes0 = (p.tpi * p.hbox + p.ks - 1) * p.W * 128;
   p.a_bytes = p.a_bytes0 > p.tpi * 128 * 128 ? p.a_bytes0 : p.tpi * 128 * 128;  // the skip segment's box has no halo
-  p.stage_bytes = p.a_bytes + p.ks * BN * 128;
+  p.stage_bytes = p.a_bytes + p.ks * (BN / CG) * 128;  // a CTA of a pair stages half of the weight tile
   p.stages = (SMEM_MAX - extra) / p.stage_bytes;
   if (p.stages > HALO_MAX_STAGES) p.stages = HALO_MAX_STAGES;
   if (p.stages < 2) return FDM_ERR_UNSUPPORTED;
@@ -367,7 +413,7 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN, TPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN, TPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (g_num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);
@@ -379,9 +425,21 @@ static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUt
     return FDM_ERR_CUDA;
   }
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
-  const int grid = p.n_items < sms ? p.n_items : sms;
-  fdm::launch(conv_halo_kernel<BN, TPI>, dim3(grid), dim3(HALO_THREADS), smem, st, ta0, tw0, ta1, tw1, p);
+  if (CG == 2) {
+    const int pairs = sms / 2, n_q = p.n_items / 2;
+    fdm::launch_cluster(conv_halo_kernel<BN, TPI, CG>, dim3(2 * (n_q < pairs ? n_q : pairs)), dim3(HALO_THREADS), smem, st, 2, ta0, tw0, ta1, tw1, p);
+  } else {
+    const int grid = p.n_items < sms ? p.n_items : sms;
+    fdm::launch(conv_halo_kernel<BN, TPI, CG>, dim3(grid), dim3(HALO_THREADS), smem, st, ta0, tw0, ta1, tw1, p);
+  }
   return check_launch();
+}
+
+template <int BN, int TPI>
+static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
+                       HaloParams& p, bool pair, cudaStream_t st) {
+  if (pair) return launch_halo_cg<BN, TPI, 2>(ta0, tw0, ta1, tw1, p, st);
+  return launch_halo_cg<BN, TPI, 1>(ta0, tw0, ta1, tw1, p, st);
 }
 
 // FDM_ERR_UNSUPPORTED => the caller falls back to the per-tap kernel of conv_tc.cu
@@ -422,24 +480,33 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.klast0 = (a->C0 - (p.kchunks0 - 1) * 64 + 15) / 16;
   p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * 64 + 15) / 16 : 0;
   const int co_pad = (a->Cout + 15) / 16 * 16;
+  // CTA pairs (cta_group::2) when the item pairs come out even, so that both CTAs of a pair always have an item; the weight box
+  // of a pair CTA holds half of the tile's rows.
+  // Measured on B200 (profiles/r02_halo_cta_pairs.txt): 1.10-1.32x on layers with >= 9 pipeline stages per item (Cin >= 192 or a wide
+  // skip segment; 384->384 at 32x32 reaches 1474 TFLOP/s), 0.85-1.0x on shallower ones, where the cross-CTA signalling latency of the
+  // few stages is not amortised -> pairs only for the deep layers.  FDM_HALO_CG=1 forces single CTAs, =2 pairs wherever possible.
+  static const int cg_env = [] { const char* e = getenv("FDM_HALO_CG"); return e ? atoi(e) : 0; }();
+  const int stages_per_item = p.kchunks0 * p.ks + p.kchunks1;
+  const bool pair = cg_env != 1 && (cg_env == 2 || stages_per_item >= 9) && ((long)a->N * p.pairs_per_frame) % 2 == 0;
+  const int brows = pair ? bn / 2 : bn;
   CUtensorMap ta0, tw0, ta1, tw1;
   bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, p.tpi * hbox + a->ksize - 1) &&
-            encode3w(&tw0, a->w0, a->ksize * a->ksize, co_pad, p.kchunks0 * 64, bn, a->ksize);
+            encode3w(&tw0, a->w0, a->ksize * a->ksize, co_pad, p.kchunks0 * 64, brows, a->ksize);
   if (ok && a->a1) {
-    ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, p.tpi * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, bn, 1);
+    ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, p.tpi * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, brows, 1);
   } else {
     ta1 = ta0;
     tw1 = tw0;
   }
   FDM_REQUIRE(ok, FDM_ERR_UNSUPPORTED);
   if (p.tpi == 2) {
-    if (bn == 128) return launch_halo<128, 2>(ta0, tw0, ta1, tw1, p, st);
-    if (bn == 64) return launch_halo<64, 2>(ta0, tw0, ta1, tw1, p, st);
-    return launch_halo<32, 2>(ta0, tw0, ta1, tw1, p, st);
+    if (bn == 128) return launch_halo<128, 2>(ta0, tw0, ta1, tw1, p, pair, st);
+    if (bn == 64) return launch_halo<64, 2>(ta0, tw0, ta1, tw1, p, pair, st);
+    return launch_halo<32, 2>(ta0, tw0, ta1, tw1, p, pair, st);
   }
-  if (bn == 128) return launch_halo<128, 1>(ta0, tw0, ta1, tw1, p, st);
-  if (bn == 64) return launch_halo<64, 1>(ta0, tw0, ta1, tw1, p, st);
-  return launch_halo<32, 1>(ta0, tw0, ta1, tw1, p, st);
+  if (bn == 128) return launch_halo<128, 1>(ta0, tw0, ta1, tw1, p, pair, st);
+  if (bn == 64) return launch_halo<64, 1>(ta0, tw0, ta1, tw1, p, pair, st);
+  return launch_halo<32, 1>(ta0, tw0, ta1, tw1, p, pair, st);
 }
 
 }  // namespace fdm

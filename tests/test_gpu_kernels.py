@@ -79,6 +79,13 @@ CASES = [
     (6, 32, 32, 32, 32, 3, 1, 0, True),      # BN = 32
     (40, 16, 16, 128, 384, 1, 1, 0, False),  # qkv linear through the halo kernel's pointwise mode, 3 N tiles, > 148 items
     (40, 16, 16, 128, 128, 1, 1, 0, True),   # proj_out + residual, pointwise mode
+    # CTA pairs (cta_group::2; layers with >= 9 pipeline stages per item and an even number of item pairs)
+    (80, 32, 32, 192, 64, 3, 1, 0, False),   # 320 items -> 160 pair items on 74 clusters: the pair loop and the TMEM buffers wrap
+    (6, 64, 64, 256, 256, 3, 1, 0, True),    # two N tiles per pair, residual epilogue, W = 64
+    (4, 16, 16, 384, 192, 3, 1, 128, False), # Cout = 192 -> BN = 64 pairs (32 weight rows per CTA), 3 N tiles + skip segment
+    (2, 16, 16, 192, 96, 3, 1, 0, False),    # Cout = 96: BN = 64, second N tile half masked, 48-row weight boxes cross Cout
+    (3, 16, 16, 256, 128, 3, 1, 0, True),    # odd number of item pairs (3): falls back to single CTAs
+    (2, 128, 128, 192, 128, 3, 1, 0, False), # W = 128 one-tile items as pairs
 ]
 
 
