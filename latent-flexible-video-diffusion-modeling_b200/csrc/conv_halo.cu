@@ -469,10 +469,7 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
     const long rounds1 = (tiles + 147) / 148, rounds2 = (tiles / 2 + 147) / 148;
     const bool two_ok = H % (2 * hbox) == 0;
     p.tpi = (two_ok && 20 * rounds2 <= 13 * rounds1) ? 2 : 1;
-    if (W == 128 && bn == 128) p.tpi = 1;
   }
-  p.pairs_per_frame = H / (p.tpi * hbox);
-  p.n_items = a->N * p.pairs_per_frame * p.ntiles;
   p.trace = g_trace;
   p.ks = a->ksize;
   p.kchunks0 = (a->C0 + 63) / 64;
@@ -487,7 +484,17 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   // few stages is not amortised -> pairs only for the deep layers.  FDM_HALO_CG=1 forces single CTAs, =2 pairs wherever possible.
   static const int cg_env = [] { const char* e = getenv("FDM_HALO_CG"); return e ? atoi(e) : 0; }();
   const int stages_per_item = p.kchunks0 * p.ks + p.kchunks1;
-  const bool pair = cg_env != 1 && (cg_env == 2 || stages_per_item >= 9) && ((long)a->N * p.pairs_per_frame) % 2 == 0;
+  // (W = 128, BN = 128: always worth it, 1.1-1.4x — only pairs can run the two-tile items there, see below)
+  bool pair = cg_env != 1 && (cg_env == 2 || stages_per_item >= 9 || (W == 128 && bn == 128)) &&
+              ((long)a->N * (H / (p.tpi * hbox))) % 2 == 0;
+  // W = 128 with BN = 128: a single CTA's two-tile stage (64 KB of A + 48 KB of weights) fits only once -> one-tile items (3 image
+  // rows loaded per row computed); a pair CTA stages 24 KB of weights, so two stages of two-tile items fit (4 rows per 2 computed)
+  if (W == 128 && bn == 128 && !(pair && p.tpi == 2)) {
+    p.tpi = 1;
+    pair = pair && ((long)a->N * (H / hbox)) % 2 == 0;
+  }
+  p.pairs_per_frame = H / (p.tpi * hbox);
+  p.n_items = a->N * p.pairs_per_frame * p.ntiles;
   const int brows = pair ? bn / 2 : bn;
   CUtensorMap ta0, tw0, ta1, tw1;
   bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, p.tpi * hbox + a->ksize - 1) &&
