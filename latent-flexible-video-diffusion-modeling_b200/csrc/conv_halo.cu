@@ -449,7 +449,15 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   FDM_REQUIRE(a->resid_norm == 0, FDM_ERR_UNSUPPORTED);  // the recomputed-GroupNorm residual lives in the per-tap kernel's epilogue
   FDM_REQUIRE(a->C0 % 8 == 0 && (a->a1 == nullptr || a->C1 % 8 == 0) && a->Cout % 4 == 0 && a->Cout >= 32, FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->y_op == nullptr || a->op_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
-  const int W = a->Win, H = a->Hin;
+  int W = a->Win, H = a->Hin, N = a->N;
+  // pointwise layers without per-frame statistics see a flat pixel list: maps the row-halo tiling does not take (8x8, 4x4) run as
+  // [N*H*W / 256] "frames" of two 128-pixel rows (the wide qkv linears of the 8x8 levels)
+  if (a->ksize == 1 && a->stats == nullptr && !((W == 16 || W == 32 || W == 64 || W == 128) && H % (128 / W) == 0) &&
+      ((long)N * H * W) % 256 == 0) {
+    N = (int)(((long)N * H * W) / 256);
+    H = 2;
+    W = 128;
+  }
   // W = 128 (the top level of the 128-px model, 40 % of its conv FLOPs): one image row per M tile; the A box of a two-tile item
   // (4 rows = 64 KB) leaves room for one pipeline stage only, so those layers run one-tile items (3 rows = 48 KB, two stages)
   FDM_REQUIRE(W == 16 || W == 32 || W == 64 || W == 128, FDM_ERR_UNSUPPORTED);
@@ -465,7 +473,7 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   // size whose rounds-on-148-SMs x per-item cost is smaller (measured on B200: one-tile items cost ~30 % more per tile —
   // no B sharing, relatively larger halo — so they only pay when two-tile items waste a whole round)
   {
-    const long tiles = (long)a->N * (H / hbox) * p.ntiles;
+    const long tiles = (long)N * (H / hbox) * p.ntiles;
     const long rounds1 = (tiles + 147) / 148, rounds2 = (tiles / 2 + 147) / 148;
     const bool two_ok = H % (2 * hbox) == 0;
     p.tpi = (two_ok && 20 * rounds2 <= 13 * rounds1) ? 2 : 1;
@@ -486,21 +494,21 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   const int stages_per_item = p.kchunks0 * p.ks + p.kchunks1;
   // (W = 128, BN = 128: always worth it, 1.1-1.4x — only pairs can run the two-tile items there, see below)
   bool pair = cg_env != 1 && (cg_env == 2 || stages_per_item >= 9 || (W == 128 && bn == 128)) &&
-              ((long)a->N * (H / (p.tpi * hbox))) % 2 == 0;
+              ((long)N * (H / (p.tpi * hbox))) % 2 == 0;
   // W = 128 with BN = 128: a single CTA's two-tile stage (64 KB of A + 48 KB of weights) fits only once -> one-tile items (3 image
   // rows loaded per row computed); a pair CTA stages 24 KB of weights, so two stages of two-tile items fit (4 rows per 2 computed)
   if (W == 128 && bn == 128 && !(pair && p.tpi == 2)) {
     p.tpi = 1;
-    pair = pair && ((long)a->N * (H / hbox)) % 2 == 0;
+    pair = pair && ((long)N * (H / hbox)) % 2 == 0;
   }
   p.pairs_per_frame = H / (p.tpi * hbox);
-  p.n_items = a->N * p.pairs_per_frame * p.ntiles;
+  p.n_items = N * p.pairs_per_frame * p.ntiles;
   const int brows = pair ? bn / 2 : bn;
   CUtensorMap ta0, tw0, ta1, tw1;
-  bool ok = encode4(&ta0, a->a0, a->N, H, W, a->C0, p.tpi * hbox + a->ksize - 1) &&
+  bool ok = encode4(&ta0, a->a0, N, H, W, a->C0, p.tpi * hbox + a->ksize - 1) &&
             encode3w(&tw0, a->w0, a->ksize * a->ksize, co_pad, p.kchunks0 * 64, brows, a->ksize);
   if (ok && a->a1) {
-    ok = encode4(&ta1, a->a1, a->N, H, W, a->C1, p.tpi * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, brows, 1);
+    ok = encode4(&ta1, a->a1, N, H, W, a->C1, p.tpi * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, brows, 1);
   } else {
     ta1 = ta0;
     tw1 = tw0;

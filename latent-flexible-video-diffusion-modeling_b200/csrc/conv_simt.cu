@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
 
 int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st);    // conv_tc.cu (one TMA box per filter tap)
 int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st);  // conv_halo.cu (3x3 s1, row-halo reuse, persistent)
+int conv_head_launch(const fdm_conv_args* a, cudaStream_t st);  // conv_head.cu (3x3 head conv, <= 4 output channels, NCHW fp32 out)
 
 static int conv_simt_launch(const fdm_conv_args* a, cudaStream_t st) {
   ConvParams p;
@@ -261,8 +262,15 @@ extern "C" int fdm_conv(const fdm_conv_args* a, void* stream) {
   if (a->engine == FDM_CONV_TC) {
     // the halo kernel also has a pointwise mode, but measured slower than the per-tap kernel for the 1x1 qkv / proj_out
     // linears on B200 (35 vs 28 us, 30 vs 17 us: two short K stages cannot amortise the persistent pipeline) -> 3x3 only
+    // — but with >= 4 K chunks (Cin >= 256: the wide models' qkv / proj_out) it wins: 43.6 -> 29.2 us for 384 -> 1152 at 16x16
     static const bool pw = getenv("FDM_HALO_POINTWISE") != nullptr;
-    int rc = (a->ksize == 3 || pw) ? conv_halo_launch(a, st) : FDM_ERR_UNSUPPORTED;
+    static const bool no_pw = getenv("FDM_HALO_NO_POINTWISE") != nullptr;
+    static const bool no_head = getenv("FDM_NO_HEAD_KERNEL") != nullptr;
+    if (a->out_nchw && a->ksize == 3 && !no_head) {
+      const int rh = conv_head_launch(a, st);
+      if (rh != FDM_ERR_UNSUPPORTED) return rh;
+    }
+    int rc = (a->ksize == 3 || pw || (a->C0 >= 256 && !no_pw)) ? conv_halo_launch(a, st) : FDM_ERR_UNSUPPORTED;
     return rc == FDM_ERR_UNSUPPORTED ? conv_tc_launch(a, st) : rc;
   }
   if (a->engine == FDM_CONV_TC_TAP) return conv_tc_launch(a, st);

@@ -123,6 +123,70 @@ def test_conv_tc_vs_torch(case, engine):
     assert rel(y, y2) <= 1e-3
 
 
+@pytest.mark.parametrize("case", [
+    # N, H, W, C0, Cout, resid, stats
+    (16, 16, 16, 384, 1152, False, False),  # wide qkv linear: halo kernel's pointwise mode (Cin >= 256), 9 N tiles
+    (16, 16, 16, 384, 384, True, True),     # wide proj_out + residual + statistics
+    (16, 8, 8, 512, 1536, False, False),    # 8x8 map without statistics: runs as a flat pixel list of 128-wide rows
+    (12, 4, 4, 512, 512, True, False),      # 4x4, 192 pixels: not a multiple of 256 -> per-tap kernel
+    (16, 8, 8, 512, 512, True, True),       # 8x8 with statistics -> per-tap kernel
+], ids=lambda c: "x".join(map(str, c)))
+def test_wide_pointwise_vs_torch(case):
+    from improved_diffusion import _native as N_
+    N, H, W, C0, Co, use_resid, want_stats = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case[:5]))
+    x = torch.randn(N, H, W, C0, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, C0, 1, 1, device="cuda", generator=g) / C0 ** 0.5
+    bias = 0.1 * torch.randn(Co, device="cuda", generator=g)
+    resid = torch.randn(N, H, W, Co, device="cuda", generator=g) if use_resid else None
+    y, yop, stats = run_conv(x, w, bias, engine=N_.CONV_TC, resid=resid, want_op=True, want_stats=want_stats)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias).permute(0, 2, 3, 1)
+    if use_resid:
+        ref = ref + resid
+    assert rel(y, ref) <= 1e-3, rel(y, ref)
+    assert rel(yop.float(), ref) <= 6e-3
+    if want_stats:
+        ref_stats = torch.stack([ref.sum(dim=(1, 2)), (ref * ref).sum(dim=(1, 2))], dim=-1)
+        assert rel(stats, ref_stats) <= 1e-3
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, W, C0, Cout
+    (20, 32, 32, 64, 4),    # cfg4 head
+    (3, 64, 64, 128, 4),    # cfg5 head: two 64-channel chunks
+    (2, 128, 128, 128, 3),  # cfg3 head: 3 output channels, 128-wide rows
+    (5, 16, 16, 192, 4),    # three chunks, whole frame in one strip
+    (3, 8, 8, 64, 3),       # small map: partial MMA tile
+    (2, 24, 40, 64, 4),     # non-square, W not a power of two
+], ids=lambda c: "x".join(map(str, c)))
+def test_head_conv_vs_torch(case):
+    """conv_head.cu (taps in the GEMM's N dimension, shifts applied to the output) against torch and against the per-tap kernel"""
+    from improved_diffusion import _native as N_
+    N, H, W, C0, Co = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, H, W, C0, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, C0, 3, 3, device="cuda", generator=g) / (9 * C0) ** 0.5
+    bias = 0.1 * torch.randn(Co, device="cuda", generator=g)
+    w0p = pack_tc(w)
+    outs = []
+    for engine in (N_.CONV_TC, N_.CONV_TC_TAP):
+        y = torch.full((N, Co, H, W), float("nan"), device="cuda")
+        a = N_.ConvArgs(a0=x.data_ptr(), w0=w0p.data_ptr(), a1=None, w1=None, bias=bias.data_ptr(), resid=None, y_f32=y.data_ptr(),
+                        y_op=None, stats=None, N=N, Hin=H, Win=W, C0=C0, C1=0, Cout=Co, ksize=3, stride=1, upsample=0,
+                        a_dtype=N_.BF16, op_dtype=N_.BF16, out_nchw=1, engine=engine)
+        try:
+            N_.call("fdm_conv", a, torch.cuda.current_stream().cuda_stream)
+        except N_.NativeError:
+            assert engine == N_.CONV_TC_TAP  # the per-tap kernel does not take every map shape; the head kernel must
+            continue
+        torch.cuda.synchronize()
+        outs.append(y)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1)
+    assert rel(outs[0], ref) <= 1e-3, rel(outs[0], ref)
+    if len(outs) > 1:
+        assert rel(outs[0], outs[1]) <= 1e-3
+
+
 def test_conv_simt_fp32_exact():
     from improved_diffusion import _native as N_
     g = torch.Generator(device="cuda").manual_seed(3)
