@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);  // [8 warps][32][16], XOR-swizzled
-  float* statbuf = staging + 8 * 32 * 16;                                              // [2 tiles][4 lane groups][BN][2]
+  float* statbuf = staging + 8 * 32 * 16;                                              // [2 buffers][2 tiles][4 lane groups][BN][2]
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&ta0) : "memory");
@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       const uint32_t buf = local & 1;
       const size_t m_pair = (size_t)pair * TPI * 128;
       const size_t m_w = m_pair + j * 128 + g * 32;  // first row of this warp's 32 rows
+      float* sbuf = statbuf + (size_t)(local & 1) * (8 * BN * 2);
       // bias for this lane's 4 columns of every 16-column chunk: loaded before the accumulator wait (latency hidden)
       float4 biasv[CW / 16];
 #pragma unroll
@@ -314,19 +315,19 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           }
         }
         if (p.stats != nullptr) {
+          // 8 values per lane (4 columns x 2 moments) summed over the 8 lanes that hold the same columns (sub = lane bits 2..4):
+          // a transposing butterfly — each step halves the values a lane keeps and exchanges the other half — needs 4 + 2 + 1
+          // shuffles instead of 8 x 3, and leaves ONE finished sum in every lane: moment = bit 4, column = bits 3, 2.
+          const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+          float k4[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 4; ++q) k4[q] = (b4 ? s2[q] : s1[q]) + __shfl_xor_sync(0xffffffffu, b4 ? s1[q] : s2[q], 16);
+          float k2[2];
 #pragma unroll
-            for (int off = 4; off <= 16; off <<= 1) {
-              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], off);
-              s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], off);
-            }
-          }
-          if (sub == 0) {
-            float* d = statbuf + ((size_t)(hslot * 4 + g) * BN + c + cq4 * 4) * 2;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { d[2 * q] = s1[q]; d[2 * q + 1] = s2[q]; }
-          }
+          for (int q = 0; q < 2; ++q) k2[q] = (b3 ? k4[2 + q] : k4[q]) + __shfl_xor_sync(0xffffffffu, b3 ? k4[q] : k4[2 + q], 8);
+          const float k1 = (b2 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? k2[0] : k2[1], 4);
+          const int qcol = (b3 ? 2 : 0) + (b2 ? 1 : 0);
+          sbuf[((size_t)(hslot * 4 + g) * BN + c + cq4 * 4 + qcol) * 2 + (b4 ? 1 : 0)] = k1;
         }
         __syncwarp();  // staging is overwritten by the next chunk
       }
@@ -338,6 +339,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       }
       long long c3 = clock64();
       if (p.stats != nullptr) {
+        // (the partials alternate between two buffers: the next item's partial writes need no second barrier — a thread reaches the
+        //  next item's barrier only after its reads below, and this buffer is not written again before that barrier)
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // both tiles lie in one frame (a pair never straddles frames): 8 partials per (column, moment), fixed order
         const int frame = (int)(m_pair / p.HW);
@@ -348,11 +351,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             // that drained this half of the columns
             const int k0 = TPI == 2 ? 0 : (cc < BN / 2 ? 0 : 4), k1 = TPI == 2 ? 8 : k0 + 4;
             float acc = 0.f;
-            for (int k = k0; k < k1; ++k) acc += statbuf[(size_t)k * BN * 2 + i];
+            for (int k = k0; k < k1; ++k) acc += sbuf[(size_t)k * BN * 2 + i];
             atomicAdd(p.stats + ((size_t)frame * p.Cout + n_off + cc) * 2 + (i & 1), (double)acc);
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       e_stats += clock64() - c3;
     }
@@ -402,7 +404,7 @@ template <int BN, int TPI, int CG>
 static int launch_halo_cg(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
                           HaloParams& p, cudaStream_t st) {
   constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers
-  const int extra = 1024 + 8 * 32 * 16 * 4 + 2 * 4 * BN * 2 * 4;  // alignment slack + staging + statbuf
+  const int extra = 1024 + 8 * 32 * 16 * 4 + 2 * 2 * 4 * BN * 2 * 4;  // alignment slack + staging + statbuf (two buffers)
   p.a_bytes0 = (p.tpi * p.hbox + p.ks - 1) * p.W * 128;
   p.a_bytes = p.a_bytes0 > p.tpi * 128 * 128 ? p.a_bytes0 : p.tpi * 128 * 128;  // the skip segment's box has no halo
   p.stage_bytes = p.a_bytes + p.ks * (BN / CG) * 128;  // a CTA of a pair stages half of the weight tile
