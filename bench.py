@@ -532,6 +532,15 @@ def kernel_classes(P, N_, B, K, Cx, S, osz=2):
             return False
         return st.Win in (16, 32, 64, 128) and st.Hin % max(1, 128 // st.Win) == 0 and st.Cout >= 32 and st.Cout % 4 == 0 and st.C0 % 8 == 0
 
+    def is_halo_pointwise(st):
+        # wide 1x1 linears (Cin >= 256) run through the halo kernel's pointwise mode (conv_simt.cu: fdm_conv dispatch)
+        if not (st.engine == N_.CONV_TC and st.ksize == 1 and st.stride == 1 and st.C0 >= 256 and not st.out_nchw and not st.resid_norm):
+            return False
+        if st.Cout < 32 or st.Cout % 4 or st.C0 % 8:
+            return False
+        tiled = st.Win in (16, 32, 64, 128) and st.Hin % max(1, 128 // st.Win) == 0
+        return tiled or (not st.stats and (st.N * st.Hin * st.Win) % 256 == 0)
+
     def conv_work(st):
         pad = st.ksize // 2
         ho = (st.Hin + 2 * pad - st.ksize) // st.stride + 1
@@ -555,12 +564,18 @@ def kernel_classes(P, N_, B, K, Cx, S, osz=2):
             fl, by = conv_work(st)
             if st.engine != N_.CONV_TC:
                 add("conv_simt (CUDA-core implicit GEMM)", "fp32", fn, ref, fl, by)
-            elif is_halo(st):
-                add("conv_halo (3x3 s1, tcgen05)", "tensor", fn, ref, fl, by)
+            elif is_halo(st) or is_halo_pointwise(st):
+                add("conv_halo (3x3 s1 and wide 1x1, tcgen05; CTA pairs on deep layers)", "tensor", fn, ref, fl, by)
             elif st.Hin == 1 and st.Win == 1:
                 add("rpe_out_linear (21 RPENet GEMMs, tcgen05, side stream)", "tensor", fn, ref, fl, by)
+            elif st.out_nchw and st.ksize == 3 and st.Cout <= 4 and st.C0 % 64 == 0:
+                add("conv_head (3x3 -> eps, filter taps in the GEMM's N, tcgen05)", "hbm", fn, ref, fl, by)
+            elif st.ksize == 1:
+                add("conv_tc 1x1 (proj_out + residual, per-tap kernel, tcgen05)", "tensor", fn, ref, fl, by)
+            elif st.stride == 2:
+                add("conv_tc stride-2 (Downsample, per-tap kernel, tcgen05)", "tensor", fn, ref, fl, by)
             else:
-                add("conv_tc (per-tap: 1x1 qkv/proj, s2, 8x8/4x4, stem, head; tcgen05)", "tensor", fn, ref, fl, by)
+                add("conv_tc 3x3 on 8x8 / 4x4 maps (per-tap kernel, tcgen05)", "tensor", fn, ref, fl, by)
         elif name == "fdm_gn_apply":
             el = st.N * st.HW * (st.Ca + st.Cb)
             add("gn_apply (GroupNorm+FiLM+SiLU)", "hbm", fn, ref, 0,

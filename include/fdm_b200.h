@@ -75,11 +75,16 @@ int fdm_input_prep(const fdm_input_prep_args* a, void* stream);
  *   Weight layouts:  engine FDM_CONV_SIMT: fp32 [tap = kh*k + kw][ci][co];  engine FDM_CONV_TC: bf16 [tap = kw*k + kh][co_pad][ci_pad]
  *   (filter-column major so one TMA box covers a filter column; ci_pad = ci rounded up to 64, co_pad to 16), both produced by
  *   the host from PyTorch's [co][ci][kh][kw].
+ *   FDM_CONV_TC with upsample (3x3, stride 1, Win in {16,32,64,128}): the upsampled tensor is never formed — output pixel
+ *   (2y+a, 2x+b) sees input rows y + {a-1, a} and columns x + {b-1, b}; w0 holds the four 2x2 filters of the output phases,
+ *   bf16 [phase = 2a + b][tap = 2s' + r'][co_pad][ci_pad], each tap the fp32 SUM of the 3x3 weights that land on that input
+ *   pixel (rows: a = 0: {kh 0}, {kh 1, 2};  a = 1: {kh 0, 1}, {kh 2};  columns alike in kw).  4/9 of the FLOPs.
  *   Outputs (any subset): y_f32 [.,Cout] fp32; y_op [.,Cout] in op_dtype; stats (sum,sumsq per frame,
  *   channel); out_nchw: y_f32 is written as [N][Cout][Ho][Wo] (the head conv producing eps).
  * ---------------------------------------------------------------------------------------------- */
-/* FDM_CONV_TC: tcgen05; picks the row-halo persistent kernel (conv_halo.cu) for 3x3 stride-1 convs on 16/32/64-wide maps,
- * else the per-tap kernel (conv_tc.cu).  FDM_CONV_TC_TAP forces the per-tap kernel (tests / A-B timing). */
+/* FDM_CONV_TC: tcgen05; picks the row-halo persistent kernel (conv_halo.cu; CTA pairs / cta_group::2 on deep layers) for 3x3
+ * stride-1 convs on 16/32/64/128-wide maps and for wide 1x1 linears (Cin >= 256), the head kernel (conv_head.cu) for the 3x3 conv
+ * to <= 4 channels with out_nchw, else the per-tap kernel (conv_tc.cu).  FDM_CONV_TC_TAP forces the per-tap kernel (tests / A-B timing). */
 enum { FDM_CONV_SIMT = 0, FDM_CONV_TC = 1, FDM_CONV_TC_TAP = 2 };
 typedef struct {
   const void* a0;   /* segment-0 input  [N][Hin][Win][C0], a_dtype */

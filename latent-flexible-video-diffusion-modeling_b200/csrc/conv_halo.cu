@@ -13,6 +13,10 @@
 //     overlaps the main loop of item i+1 inside the same CTA (warp-specialised: TMA / MMA / 4 epilogue warps).
 //   * GroupNorm statistics: per-warp column sums are combined across the 4 epilogue warps and both tiles in shared
 //     memory before the fp64 atomics (8x fewer atomics than one per warp).
+//   * nearest x2 upsample + 3x3 conv (unet.py:85-93) WITHOUT the upsampled tensor: output pixel (2y+a, 2x+b) only sees a 2x2
+//     neighbourhood of the low-resolution input, with the 3x3 weights that land on the same input pixel pre-summed (fp32, then bf16)
+//     per output phase (a, b).  A work item is (tiles, N tile, phase): a 2x2-tap conv over the low-resolution rows whose rows are
+//     stored to the phase's pixels of the output — 4/9 of the MMAs of the conv on the upsampled tensor, a 4x smaller operand.
 //   * CG = 2 (CTA pairs, `cta_group::2`): the two CTAs of a cluster run two such work items (different rows / frames, SAME output
 //     channels) as ONE stream of M = 256 MMAs issued by the leader.  Each CTA stages its own A box and only HALF of the weight
 //     tile (BN/2 rows per tap): single-CTA MMAs at N <= 128 are bound by shared-memory operand reads (A + B per MMA, measured
@@ -37,7 +41,8 @@ struct HaloParams {
   int stages, a_bytes, stage_bytes;
   int tpi;       // M tiles per work item: 2 (B shared by two tiles) or 1 (finer items when 2-tile items quantise badly on 148 SMs)
   int a_bytes0;  // bytes of the segment-0 A box ((2*hbox + ks - 1) rows); a_bytes is the slot size
-  int ks;  // filter size 3 (row halo of 2) or 1 (pointwise: no halo, one 'column', one 'row')
+  int ks;  // filter size 3 (row halo of 2), 1 (pointwise: no halo, one 'column', one 'row') or 2 (the per-phase filter of `up`)
+  int up, nph, H, log2W;  // up: nearest-x2-upsample mode, nph = 4 output phases per tile set (else 1)
   long long* trace;  // debug (fdm_debug_set_trace): per-CTA cycle counters, NULL in production
 };
 
@@ -45,7 +50,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, int TPI, int CG>
+template <int BN, int TPI, int CG, bool UP>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap ta0,
                                                                    const __grid_constant__ CUtensorMap tw0,
                                                                    const __grid_constant__ CUtensorMap ta1,
@@ -65,7 +70,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
   const int cstride = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int n_q = p.n_items / CG;
   // work item of this CTA for stream position q: the CTAs of a pair take the item pairs 2k, 2k+1 of the SAME N tile
-  auto item_of = [&](int q) { return CG == 2 ? ((2 * (q / p.ntiles) + (int)rank) * p.ntiles + q % p.ntiles) : q; };
+  // (with `up` an N tile comes in 4 phases: per_pair = ntiles * nph items share the tiles, the pair CTAs take the same one of them)
+  const int per_pair = p.ntiles * p.nph;
+  auto item_of = [&](int q) { return CG == 2 ? ((2 * (q / per_pair) + (int)rank) * per_pair + q % per_pair) : q; };
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,9 +122,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
       const int b_row = CG == 2 ? (int)rank * (BN / 2) : 0;                         // this CTA's rows of the weight tile
       for (int q = cid; q < n_q; q += cstride) {
         const int item = item_of(q);
-        const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
+        const int pair = item / per_pair, rest = item - pair * per_pair;
+        const int phase = rest % p.nph, n_off = (rest / p.nph) * BN;
         const int n = pair / p.pairs_per_frame, h0 = (pair - n * p.pairs_per_frame) * TPI * p.hbox;
-        const int pad = p.ks >> 1;
+        // up: phase (a, b) reads input rows y + {a-1, a} and columns x + {b-1, b}; its 4 taps are rows phase*4 .. +3 of the weights
+        const int pad = UP ? 1 - (phase >> 1) : p.ks >> 1, pad_x = UP ? 1 - (phase & 1) : p.ks >> 1;
+        const int tap0 = phase * 4;
         for (int kc = 0; kc < p.kchunks0; ++kc) {
           for (int s = 0; s < p.ks; ++s, ++it) {
             const int stage = it % p.stages;
@@ -129,12 +139,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
               // (a TMA instruction costs ~450 clk + 0.4 clk/row on this part, measured: tools/tma_bench.cu)
               if (CG == 2) {
                 if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (p.a_bytes0 + p.ks * B_TAP_BYTES));  // both CTAs' bytes
-                tma_load_4d_cg2(a_dst, &ta0, full0 + stage * 8, kc * 64, s - pad, h0 - pad, n);
-                tma_load_3d_cg2(b_dst, &tw0, full0 + stage * 8, kc * 64, n_off + b_row, s * p.ks);
+                tma_load_4d_cg2(a_dst, &ta0, full0 + stage * 8, kc * 64, s - pad_x, h0 - pad, n);
+                tma_load_3d_cg2(b_dst, &tw0, full0 + stage * 8, kc * 64, n_off + b_row, tap0 + s * p.ks);
               } else {
                 mbar_expect_tx(&full_bar[stage], p.a_bytes0 + p.ks * B_TAP_BYTES);
-                tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - pad, h0 - pad, n);
-                tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * 64, n_off, s * p.ks);
+                tma_load_4d(a_dst, &ta0, &full_bar[stage], kc * 64, s - pad_x, h0 - pad, n);
+                tma_load_3d(b_dst, &tw0, &full_bar[stage], kc * 64, n_off, tap0 + s * p.ks);
               }
             }
             __syncwarp();
@@ -262,11 +272,16 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
     const uint32_t tmem_empty0 = CG == 2 ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;  // the leader's (pairs)
     for (int q = cid; q < n_q; q += cstride, ++local) {
       const int item = item_of(q);
-      const int pair = item / p.ntiles, n_off = (item - pair * p.ntiles) * BN;
+      const int pair = item / per_pair, rest = item - pair * per_pair;
+      const int phase = rest % p.nph, n_off = (rest / p.nph) * BN;
       const uint32_t buf = local & 1;
       const size_t m_pair = (size_t)pair * TPI * 128;
       const size_t m_w = m_pair + j * 128 + g * 32;  // first row of this warp's 32 rows
       float* sbuf = statbuf + (size_t)(local & 1) * (8 * BN * 2);
+      // up: this warp's first low-resolution pixel inside its frame, and the offset of the frame's phase-(a, b) origin in the output
+      const unsigned fr_up = UP ? (unsigned)(m_pair / (unsigned)p.HW) : 0u;
+      const int lp0 = UP ? (int)(m_w - (size_t)fr_up * p.HW) : 0;
+      const size_t up_base = UP ? (((size_t)fr_up * 2 * p.H + (phase >> 1)) * (2 * p.W) + (phase & 1)) * p.Cout : 0;
       // bias for this lane's 4 columns of every 16-column chunk: loaded before the accumulator wait (latency hidden)
       float4 biasv[CW / 16];
 #pragma unroll
@@ -309,7 +324,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
 #pragma unroll
           for (int q = 0; q < 4; ++q) { s1[q] += o[q]; s2[q] = fmaf(o[q], o[q], s2[q]); }
           if (col_ok) {
-            const size_t off = (m_w + row) * p.Cout + col;
+            size_t off = (m_w + row) * p.Cout + col;
+            if (UP) {
+              // low-resolution pixel (frame, y, x) -> pixel (2y + a, 2x + b) of the output
+              const int lp = lp0 + row, yy = lp >> p.log2W, xx = lp & (p.W - 1);
+              off = up_base + ((size_t)(2 * yy) * (2 * p.W) + 2 * xx) * p.Cout + col;
+            }
             if (p.y_f32 != nullptr) *reinterpret_cast<float4*>(p.y_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
             if (p.y_op != nullptr) OpType<__nv_bfloat16>::store4(p.y_op + off, make_float4(o[0], o[1], o[2], o[3]));
           }
@@ -400,7 +420,7 @@ static bool encode3w(CUtensorMap* m, const void* ptr, int taps, int co_pad, int 
 static int g_num_sms = 0;
 static long long* g_trace = nullptr;
 
-template <int BN, int TPI, int CG>
+template <int BN, int TPI, int CG, bool UP>
 static int launch_halo_cg(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
                           HaloParams& p, cudaStream_t st) {
   constexpr int SMEM_MAX = 226 * 1024;  // 227 KB per CTA minus the static barriers
@@ -415,7 +435,7 @@ static int launch_halo_cg(const CUtensorMap& ta0, const CUtensorMap& tw0, const 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN, TPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    attr_err = cudaFuncSetAttribute(conv_halo_kernel<BN, TPI, CG, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (g_num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);
@@ -429,10 +449,10 @@ static int launch_halo_cg(const CUtensorMap& ta0, const CUtensorMap& tw0, const 
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   if (CG == 2) {
     const int pairs = sms / 2, n_q = p.n_items / 2;
-    fdm::launch_cluster(conv_halo_kernel<BN, TPI, CG>, dim3(2 * (n_q < pairs ? n_q : pairs)), dim3(HALO_THREADS), smem, st, 2, ta0, tw0, ta1, tw1, p);
+    fdm::launch_cluster(conv_halo_kernel<BN, TPI, CG, UP>, dim3(2 * (n_q < pairs ? n_q : pairs)), dim3(HALO_THREADS), smem, st, 2, ta0, tw0, ta1, tw1, p);
   } else {
     const int grid = p.n_items < sms ? p.n_items : sms;
-    fdm::launch(conv_halo_kernel<BN, TPI, CG>, dim3(grid), dim3(HALO_THREADS), smem, st, ta0, tw0, ta1, tw1, p);
+    fdm::launch(conv_halo_kernel<BN, TPI, CG, UP>, dim3(grid), dim3(HALO_THREADS), smem, st, ta0, tw0, ta1, tw1, p);
   }
   return check_launch();
 }
@@ -440,14 +460,24 @@ static int launch_halo_cg(const CUtensorMap& ta0, const CUtensorMap& tw0, const 
 template <int BN, int TPI>
 static int launch_halo(const CUtensorMap& ta0, const CUtensorMap& tw0, const CUtensorMap& ta1, const CUtensorMap& tw1,
                        HaloParams& p, bool pair, cudaStream_t st) {
-  if (pair) return launch_halo_cg<BN, TPI, 2>(ta0, tw0, ta1, tw1, p, st);
-  return launch_halo_cg<BN, TPI, 1>(ta0, tw0, ta1, tw1, p, st);
+  if (p.up) {
+    // upsample convs map C -> C channels of the U-Net's block widths: BN = 32 is not instantiated for them
+    if (BN == 32) return FDM_ERR_UNSUPPORTED;
+    constexpr int BU = BN == 32 ? 64 : BN;
+    if (pair) return launch_halo_cg<BU, TPI, 2, true>(ta0, tw0, ta1, tw1, p, st);
+    return launch_halo_cg<BU, TPI, 1, true>(ta0, tw0, ta1, tw1, p, st);
+  }
+  if (pair) return launch_halo_cg<BN, TPI, 2, false>(ta0, tw0, ta1, tw1, p, st);
+  return launch_halo_cg<BN, TPI, 1, false>(ta0, tw0, ta1, tw1, p, st);
 }
 
 // FDM_ERR_UNSUPPORTED => the caller falls back to the per-tap kernel of conv_tc.cu
 int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
-  FDM_REQUIRE(a->a_dtype == FDM_BF16 && (a->ksize == 3 || a->ksize == 1) && a->stride == 1 && !a->upsample && !a->out_nchw,
-              FDM_ERR_UNSUPPORTED);
+  FDM_REQUIRE(a->a_dtype == FDM_BF16 && (a->ksize == 3 || a->ksize == 1) && a->stride == 1 && !a->out_nchw, FDM_ERR_UNSUPPORTED);
+  // upsample: Hin x Win is the LOW-resolution input, the output is 2Hin x 2Win, and w0 holds the 4 x (2x2) per-phase filters
+  // ([phase = 2a + b][tap = 2s' + r'][co_pad][ci_pad], see include/fdm_b200.h)
+  const int up = a->upsample ? 1 : 0;
+  FDM_REQUIRE(!up || (a->ksize == 3 && a->a1 == nullptr && a->resid == nullptr), FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->resid_norm == 0, FDM_ERR_UNSUPPORTED);  // the recomputed-GroupNorm residual lives in the per-tap kernel's epilogue
   FDM_REQUIRE(a->C0 % 8 == 0 && (a->a1 == nullptr || a->C1 % 8 == 0) && a->Cout % 4 == 0 && a->Cout >= 32, FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->y_op == nullptr || a->op_dtype == FDM_BF16, FDM_ERR_UNSUPPORTED);
@@ -469,19 +499,22 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.bias = a->bias; p.resid = a->resid; p.y_f32 = a->y_f32; p.y_op = reinterpret_cast<__nv_bfloat16*>(a->y_op);
   p.stats = reinterpret_cast<double*>(a->stats);
   p.Cout = a->Cout; p.W = W; p.HW = H * W; p.hbox = hbox;
+  p.up = up; p.nph = up ? 4 : 1; p.H = H;
+  p.log2W = 0;
+  while ((1 << p.log2W) < W) ++p.log2W;
   const int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : 32);
   p.ntiles = (a->Cout + bn - 1) / bn;
   // items of two M tiles share the weight tiles, but a grid of persistent CTAs finishes with its slowest CTA: pick the item
   // size whose rounds-on-148-SMs x per-item cost is smaller (measured on B200: one-tile items cost ~30 % more per tile —
   // no B sharing, relatively larger halo — so they only pay when two-tile items waste a whole round)
   {
-    const long tiles = (long)N * (H / hbox) * p.ntiles;
+    const long tiles = (long)N * (H / hbox) * p.ntiles * p.nph;
     const long rounds1 = (tiles + 147) / 148, rounds2 = (tiles / 2 + 147) / 148;
     const bool two_ok = H % (2 * hbox) == 0;
     p.tpi = (two_ok && 20 * rounds2 <= 13 * rounds1) ? 2 : 1;
   }
   p.trace = g_trace;
-  p.ks = a->ksize;
+  p.ks = up ? 2 : a->ksize;
   p.kchunks0 = (a->C0 + 63) / 64;
   p.kchunks1 = a->a1 ? (a->C1 + 63) / 64 : 0;
   p.klast0 = (a->C0 - (p.kchunks0 - 1) * 64 + 15) / 16;
@@ -504,11 +537,11 @@ int conv_halo_launch(const fdm_conv_args* a, cudaStream_t st) {
     pair = pair && ((long)N * (H / hbox)) % 2 == 0;
   }
   p.pairs_per_frame = H / (p.tpi * hbox);
-  p.n_items = N * p.pairs_per_frame * p.ntiles;
+  p.n_items = N * p.pairs_per_frame * p.ntiles * p.nph;
   const int brows = pair ? bn / 2 : bn;
   CUtensorMap ta0, tw0, ta1, tw1;
-  bool ok = encode4(&ta0, a->a0, N, H, W, a->C0, p.tpi * hbox + a->ksize - 1) &&
-            encode3w(&tw0, a->w0, a->ksize * a->ksize, co_pad, p.kchunks0 * 64, brows, a->ksize);
+  bool ok = encode4(&ta0, a->a0, N, H, W, a->C0, p.tpi * hbox + p.ks - 1) &&
+            encode3w(&tw0, a->w0, up ? 16 : a->ksize * a->ksize, co_pad, p.kchunks0 * 64, brows, p.ks);
   if (ok && a->a1) {
     ok = encode4(&ta1, a->a1, N, H, W, a->C1, p.tpi * hbox) && encode3w(&tw1, a->w1, 1, co_pad, p.kchunks1 * 64, brows, 1);
   } else {

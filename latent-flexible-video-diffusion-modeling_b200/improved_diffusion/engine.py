@@ -441,6 +441,31 @@ class DenoiserEngine:
             self.packed[key] = out
         return self.packed[key]
 
+    def _pack_tc_up(self, w):
+        """nearest x2 upsample + 3x3 conv (unet.py:85-93) without the upsampled tensor: output pixel (2y+a, 2x+b) sees the input rows
+        y + {a-1, a} and columns x + {b-1, b}; the 3x3 weights that land on the same input pixel are summed in fp32.
+        [co][ci][3][3] -> bf16 [phase = 2a + b][tap = 2s' + r'][co_pad][ci_pad]  (conv_halo.cu `up` mode, include/fdm_b200.h)"""
+        key = ("tcup", w.data_ptr())
+        if key not in self.packed:
+            w4 = w.detach().float()
+            co, ci, _, _ = w4.shape
+            cip, cop = (ci + 63) // 64 * 64, (co + 15) // 16 * 16
+            sets = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+            out = th.zeros(16, cop, cip, dtype=th.bfloat16, device=w.device)
+            for a in (0, 1):
+                for b in (0, 1):
+                    for sp in (0, 1):
+                        for rp in (0, 1):
+                            ws = w4[:, :, sets[a][rp], :][:, :, :, sets[b][sp]].sum(dim=(2, 3))
+                            out[(2 * a + b) * 4 + 2 * sp + rp, :co, :ci] = ws.to(th.bfloat16)
+            self.packed[key] = out
+        return self.packed[key]
+
+    def up_tc_ok(self, Cc, H, W):
+        """Upsample convs the halo kernel's phase mode takes (H x W = the LOW-resolution input): whole image rows per 128-pixel tile"""
+        return (self.use_tc and os.environ.get("FDM_UP_PHASES", "1") != "0" and W in (16, 32, 64, 128) and H % (128 // W) == 0
+                and Cc % 8 == 0 and Cc >= 32 and Cc % 4 == 0)
+
     def _f32(self, p):
         key = ("f32", p.data_ptr())
         if key not in self.packed:
@@ -803,10 +828,13 @@ class DenoiserEngine:
             Hv, Wv = (Hin * 2, Win * 2) if upsample else (Hin, Win)
             Ho, Wo = (Hv + 2 * (k // 2) - k) // stride + 1, (Wv + 2 * (k // 2) - k) // stride + 1
             tc = a_dtype == N_.BF16 and self.tc_ok(C0, C1, Cout, k, stride, upsample, Ho, Wo) and (out_nchw or Cout % 4 == 0)
+            up_tc = bool(upsample) and a_dtype == N_.BF16 and k == 3 and C0 == Cout and not train and self.up_tc_ok(C0, Hin, Win)
             fl = 2 * Nf_ * Ho * Wo * Cout * (k * k * (flop_c0 or C0) + C1)  # algorithmic: padded channels do not count
             P.flops += fl
             P.conv_flops += fl
             pack = lambda w_: pack_fwd(w_, tc)
+            if up_tc:
+                tc, pack = True, self._pack_tc_up
             P.op("fdm_conv", N_.ConvArgs, a0=a0, w0=pack(w0), a1=a1, w1=pack(w1) if w1 is not None else None, bias=bias,
                  resid=resid, y_f32=y_f32, y_op=y_op, stats=stats, N=Nf_, Hin=Hin, Win=Win, C0=C0, C1=C1, Cout=Cout,
                  ksize=k, stride=stride, upsample=upsample, a_dtype=a_dtype, op_dtype=opd, out_nchw=out_nchw,
@@ -1193,7 +1221,15 @@ class DenoiserEngine:
             out.biases = (cv.bias,)
             Hc, Wc = (x.H, x.W) if down else (Ho, Wo)  # spatial size of the conv's input
             a = None
-            if (self.use_tc and self.tc_ok(x.C, 0, x.C, 3, 2 if down else 1, 0, Ho, Wo)) or (train and not down):
+            if not down and not train and self.up_tc_ok(x.C, x.H, x.W):
+                # inference: four 2x2-tap phase convs over the LOW-resolution operand copy (4/9 of the FLOPs, a 4x smaller cast)
+                a = x.op
+                if a is None:
+                    a = P.buf("resample_a", Nf * x.H * x.W * x.C * osz)
+                    P.op("fdm_cast", N_.CastArgs, x=x.buf, out=a, N=Nf, H=x.H, W=x.W, C=x.C, upsample=0, op_dtype=opd, colsum=None,
+                         colsum2=None)
+                conv(a, x.C, x.H, x.W, cv.weight, x.C, 3, upsample=1, bias=f32(cv.bias), y_f32=out.buf, stats=out.st)
+            elif (self.use_tc and self.tc_ok(x.C, 0, x.C, 3, 2 if down else 1, 0, Ho, Wo)) or (train and not down):
                 if down and x.op is not None:
                     a = x.op  # the producing conv already stored the bf16 operand copy
                 else:

@@ -187,6 +187,59 @@ def test_head_conv_vs_torch(case):
         assert rel(outs[0], outs[1]) <= 1e-3
 
 
+def pack_tc_up(w):
+    """[co][ci][3][3] -> bf16 [phase = 2a + b][tap = 2s' + r'][co_pad][ci_pad]: per-phase 2x2 filters of nearest-x2-upsample + conv"""
+    co, ci, _, _ = w.shape
+    cip, cop = (ci + 63) // 64 * 64, (co + 15) // 16 * 16
+    sets = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = torch.zeros(16, cop, cip, dtype=torch.bfloat16, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            for sp in (0, 1):
+                for rp in (0, 1):
+                    ws = w[:, :, sets[a][rp], :][:, :, :, sets[b][sp]].float().sum(dim=(2, 3))
+                    out[(2 * a + b) * 4 + 2 * sp + rp, :co, :ci] = ws.to(torch.bfloat16)
+    return out
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, W (low resolution), C, Cout
+    (20, 16, 16, 128, 128),   # cfg4: 16x16 -> 32x32
+    (6, 32, 32, 256, 256),    # cfg5 top: two N tiles
+    (4, 64, 64, 128, 128),    # cfg3 top: 64 -> 128
+    (5, 16, 16, 384, 384),    # deep: CTA pairs, three N tiles
+    (3, 32, 32, 64, 96),      # masked N tile
+    (3, 16, 16, 128, 64),     # odd number of tile pairs: single CTAs
+], ids=lambda c: "x".join(map(str, c)))
+def test_upsample_conv_vs_torch(case):
+    """nearest x2 upsample + 3x3 conv as four 2x2-tap phase convs over the low-resolution input (conv_halo.cu, `up` mode)"""
+    from improved_diffusion import _native as N_
+    N, H, W, C0, Co = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, H, W, C0, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, C0, 3, 3, device="cuda", generator=g) / (9 * C0) ** 0.5
+    bias = 0.1 * torch.randn(Co, device="cuda", generator=g)
+    wp = pack_tc_up(w)
+    y = torch.full((N, 2 * H, 2 * W, Co), float("nan"), device="cuda")
+    yop = torch.empty(N, 2 * H, 2 * W, Co, device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(N, Co, 2, device="cuda", dtype=torch.float64)
+    a = N_.ConvArgs(a0=x.data_ptr(), w0=wp.data_ptr(), a1=None, w1=None, bias=bias.data_ptr(), resid=None, y_f32=y.data_ptr(),
+                    y_op=yop.data_ptr(), stats=stats.data_ptr(), N=N, Hin=H, Win=W, C0=C0, C1=0, Cout=Co, ksize=3, stride=1,
+                    upsample=1, a_dtype=N_.BF16, op_dtype=N_.BF16, out_nchw=0, engine=N_.CONV_TC)
+    N_.call("fdm_conv", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    xu = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(xu, w, bias, padding=1).permute(0, 2, 3, 1)              # fp32 weights: the phase filters are summed in fp32
+    ref_b = F.conv2d(xu, w.to(torch.bfloat16).float(), bias, padding=1).permute(0, 2, 3, 1)  # what the un-fused bf16 path computes
+    err = rel(y, ref)
+    assert err <= 4e-3, err
+    assert err <= 1.5 * rel(ref_b, ref) + 1e-4, (err, rel(ref_b, ref))      # no worse than rounding each 3x3 weight to bf16
+    assert rel(yop.float(), y) <= 6e-3
+    yc = y.double()
+    ref_stats = torch.stack([yc.sum(dim=(1, 2)), (yc * yc).sum(dim=(1, 2))], dim=-1)
+    assert rel(stats, ref_stats) <= 1e-4
+
+
 def test_conv_simt_fp32_exact():
     from improved_diffusion import _native as N_
     g = torch.Generator(device="cuda").manual_seed(3)
