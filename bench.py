@@ -528,8 +528,10 @@ def kernel_classes(P, N_, B, K, Cx, S, osz=2):
     """Forward launches of the plan grouped by kernel class, each with its algorithmic FLOPs and bytes (per step).
     Bytes = every operand read once + every output written once (what a perfectly cached implementation moves through HBM)."""
     def is_halo(st):
-        if not (st.engine == N_.CONV_TC and st.ksize == 3 and st.stride == 1 and not st.upsample and not st.out_nchw):
+        if not (st.engine == N_.CONV_TC and st.ksize == 3 and st.stride == 1 and not st.out_nchw):
             return False
+        # (upsample convs run in the halo kernel's phase mode on the LOW-resolution Hin x Win input; their FLOPs are counted as the
+        #  3x3 conv over the upsampled tensor — the algorithm the reference runs — although the kernel executes 4/9 of them)
         return st.Win in (16, 32, 64, 128) and st.Hin % max(1, 128 // st.Win) == 0 and st.Cout >= 32 and st.Cout % 4 == 0 and st.C0 % 8 == 0
 
     def is_halo_pointwise(st):
@@ -543,8 +545,9 @@ def kernel_classes(P, N_, B, K, Cx, S, osz=2):
 
     def conv_work(st):
         pad = st.ksize // 2
-        ho = (st.Hin + 2 * pad - st.ksize) // st.stride + 1
-        wo = (st.Win + 2 * pad - st.ksize) // st.stride + 1
+        hv, wv = (2 * st.Hin, 2 * st.Win) if st.upsample else (st.Hin, st.Win)
+        ho = (hv + 2 * pad - st.ksize) // st.stride + 1
+        wo = (wv + 2 * pad - st.ksize) // st.stride + 1
         fl = 2 * st.N * ho * wo * st.Cout * (st.ksize * st.ksize * st.C0 + st.C1)
         asz = 2 if st.a_dtype == N_.BF16 else 4
         by = st.N * st.Hin * st.Win * st.C0 * asz + st.N * ho * wo * st.C1 * asz + st.ksize * st.ksize * st.C0 * st.Cout * asz

@@ -84,6 +84,21 @@ __global__ void __launch_bounds__(256) upsample2_cast_bf16_kernel(const float* _
   }
 }
 
+// plain fp32 -> bf16 cast of a flat tensor: 8 elements per thread (two 16-byte loads, one 16-byte store), no index arithmetic
+__global__ void __launch_bounds__(256) flat_cast_bf16_kernel(const float4* __restrict__ x, uint4* __restrict__ out, long long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 w;
+    w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+    w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+    out[i] = w;
+  }
+}
+
 // cast + column sums: the fp32 gradient of a conv output becomes the bf16 operand of its dgrad / wgrad, and its column sums ARE
 // the bias gradient — one read instead of a second pass over the tensor (the separate bias-gradient kernels were 7 % of the
 // 128-px training step).  block = (C/4 quads) x ppi pixel lanes; block partials -> fp32 atomics (colsum zeroed by the caller).
@@ -406,6 +421,11 @@ extern "C" int fdm_cast(const fdm_cast_args* a, void* stream) {
     const long long tot8 = (long long)a->N * a->H * a->W * (a->C / 8);
     fdm::launch(upsample2_cast_bf16_kernel, dim3(grid_for(tot8, 256)), dim3(256), 0, (cudaStream_t)stream, a->x, (__nv_bfloat16*)a->out, a->N,
                 a->H, a->W, a->C);
+    return check_launch();
+  }
+  if (a->upsample == 0 && a->op_dtype == FDM_BF16 && ((long long)a->N * a->H * a->W * a->C) % 8 == 0) {
+    const long long n8 = (long long)a->N * a->H * a->W * a->C / 8;
+    fdm::launch(flat_cast_bf16_kernel, dim3(grid_for(n8, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)a->x, (uint4*)a->out, n8);
     return check_launch();
   }
   long long total = (long long)a->N * a->H * a->W * (a->upsample ? 4 : 1) * (a->C / 4);

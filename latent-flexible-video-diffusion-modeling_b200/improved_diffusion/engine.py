@@ -464,7 +464,7 @@ class DenoiserEngine:
     def up_tc_ok(self, Cc, H, W):
         """Upsample convs the halo kernel's phase mode takes (H x W = the LOW-resolution input): whole image rows per 128-pixel tile"""
         return (self.use_tc and os.environ.get("FDM_UP_PHASES", "1") != "0" and W in (16, 32, 64, 128) and H % (128 // W) == 0
-                and Cc % 8 == 0 and Cc >= 32 and Cc % 4 == 0)
+                and Cc % 8 == 0 and Cc >= 64)  # (the 32-column tile variant is not instantiated for the phase mode)
 
     def _f32(self, p):
         key = ("f32", p.data_ptr())
