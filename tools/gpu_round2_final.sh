@@ -32,5 +32,12 @@ else
   CMD5="python bench.py --workload cfg5-sampling --steps 3 --warmup 3 --no-train --no-e2e --no-cpu-baseline --no-gpu-eager"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_halo_kernel" -c 24 -f -o gpurun_out/r02_conv_halo_cfg5 $CMD5 > gpurun_out/ncu_full5.log 2>&1
   tail -2 gpurun_out/ncu_full5.log
-  ls -la gpurun_out/*.ncu-rep
+  # the reports are too large to travel back (64 MiB limit): extract the judged tables here and keep the text only
+  for r in r02_conv_halo_head r02_conv_halo_cfg5; do
+    python tools/ncu_extract.py gpurun_out/$r.ncu-rep > gpurun_out/${r}_ncu_full.txt 2>&1
+    python tools/ncu_stalls.py gpurun_out/$r.ncu-rep conv_halo_kernel 16 > gpurun_out/${r}_ncu_stalls.txt 2>&1
+  done
+  python tools/ncu_traffic.py gpurun_out/r02_conv_halo_head.ncu-rep cfg4-sampling > gpurun_out/final_halo_traffic.json 2>&1
+  rm -f gpurun_out/*.ncu-rep
+  du -sh gpurun_out
 fi
