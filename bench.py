@@ -594,15 +594,15 @@ def kernel_classes(P, N_, B, K, Cx, S, osz=2):
                 2 * rows * st.K * st.Cout, rows * (st.K * 4 + st.Cout * osz) + st.K * st.Cout * 2)
         elif name == "fdm_attn_temporal":
             tok = st.B * st.T * st.HW
-            # tcgen05 engine (workspace given): 3 launches per call; bytes = qkv read + out written + bf16 tables + the fp32 score-term
+            # tcgen05 engine (workspace given): 3 launches per call; bytes = qkv read + out written + bf16 tables + the bf16 score-term
             # tables written and read back + the bf16 attention weights written and read back
             tc = bool(st.workspace)
             extra = 0
             if tc:
-                ts = (st.T + 3) // 4 * 4
-                ts += 4 if (ts // 4) % 2 == 0 else 0
+                ts = (st.T + 7) // 8 * 8
+                ts += 8 if (ts // 8) % 2 == 0 else 0
                 rows = st.B * st.heads * st.HW * st.T
-                extra = 2 * (2 * rows * ts * 4) + 2 * rows * 64 * 2
+                extra = 2 * (2 * rows * ts * 2) + 2 * rows * 64 * 2
             add("attn_temporal (RPE; 3 tcgen05 kernels per call)" if tc else "attn_temporal (RPE, CUDA cores)", "tensor", fn, ref,
                 10 * st.T * st.T * st.C * st.B * st.HW,
                 tok * st.C * (3 * osz + osz) + 3 * st.B * st.T * st.T * st.C * (2 if tc else 4) + extra)

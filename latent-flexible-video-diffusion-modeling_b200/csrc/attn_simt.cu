@@ -394,7 +394,7 @@ extern "C" size_t fdm_attn_temporal_workspace(const fdm_attn_temporal_args* a) {
 extern "C" size_t fdm_attn_temporal_attn_offset(const fdm_attn_temporal_args* a) {
   if (!a || attn_temporal_tc_workspace(a) == 0) return 0;
   const size_t rows = (size_t)a->B * a->heads * a->HW * a->T;
-  return 2 * rows * (size_t)tt_row_stride(a->T) * sizeof(float);
+  return 2 * rows * (size_t)tt_row_stride(a->T) * sizeof(__nv_bfloat16);  // past the two bf16 score-term tables
 }
 
 extern "C" int fdm_attn_temporal(const fdm_attn_temporal_args* a, void* stream) {

@@ -28,13 +28,13 @@ namespace fdm {
 
 struct TtParams {
   const float* mask;       // [B][T] or nullptr
-  float* b2;               // [B][heads][HW][T][TS]   q_t . Rk[t,s]      (unscaled)
-  float* b3;               // [B][heads][HW][T(s)][TS(t)]   k_s . Rq[s,t]  (unscaled)
+  __nv_bfloat16* b2;       // [B][heads][HW][T][TS]   q_t . Rk[t,s]      (unscaled; bf16: half the L2 round trip, and K2's tile of both
+  __nv_bfloat16* b3;       // [B][heads][HW][T(s)][TS(t)]   k_s . Rq[s,t]  tables shrinks enough for a FOURTH resident CTA per SM)
   __nv_bfloat16* P;        // [B][heads][HW][T][64]   normalised attention weights, zero beyond s >= T
   __nv_bfloat16* out;      // [B*T][HW][C]
   float* attn_mean;        // optional [B*HW][T][T]: += attention weights / heads (attention-map logging, rpe.py:128-130)
   int B, T, HW, C, F, heads;
-  int TS;                  // row stride of b2 / b3: tt_row_stride(T) — a multiple of 4 with TS/4 odd (conflict-free float4 rows)
+  int TS;                  // row stride of b2 / b3 in elements: tt_row_stride(T) — a multiple of 8 with TS/8 odd (conflict-free 16-byte rows)
   int Tn;                  // GEMM extent of the frame axis = round_up(T, 16)
   int cf;                  // 64-channel chunks per head
   int rows;                // pixels per K1 / K3 tile = min(HW, 128)
@@ -135,22 +135,45 @@ __global__ void __launch_bounds__(128) rpe_bias_kernel(const __grid_constant__ C
   const int r0 = warp * 32;
   (void)ok;
   (void)px;
-  for (int c0 = 0; c0 < Tn && c0 < p.TS; c0 += 16) {
-    uint32_t v2[16], v3[16];
-    tmem_ld_32x32b_x16(trow + c0, v2);
-    tmem_ld_32x32b_x16(trow + Tn + c0, v3);
-    const int pieces = min(4, (p.TS - c0) / 4);
-    auto rowp = [&](float* base, int r) -> uint8_t* {
+  for (int c0 = 0; c0 < Tn && c0 < p.TS; c0 += 32) {
+    // 32 columns -> 32 bf16 = 64 bytes per row and table
+    uint32_t v2[32], v3[32];
+    {
+      uint32_t a[16];
+      tmem_ld_32x32b_x16(trow + c0, a);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v2[k] = a[k];
+      tmem_ld_32x32b_x16(trow + Tn + c0, a);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v3[k] = a[k];
+      if (c0 + 16 < Tn) {
+        tmem_ld_32x32b_x16(trow + c0 + 16, a);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v2[16 + k] = a[k];
+        tmem_ld_32x32b_x16(trow + Tn + c0 + 16, a);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v3[16 + k] = a[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v2[16 + k] = v3[16 + k] = 0u;
+      }
+    }
+    const int pieces = min(4, (p.TS - c0) / 8);
+    auto rowp = [&](__nv_bfloat16* base, int r) -> uint8_t* {
       const int rr = r0 + r;
       if (rr >= p.rows || px0 + rr >= p.HW) return nullptr;
       return reinterpret_cast<uint8_t*>(base + (((size_t)bh * p.HW + px0 + rr) * p.T + j) * p.TS + c0);
     };
     uint4 w[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = make_uint4(v2[4 * k], v2[4 * k + 1], v2[4 * k + 2], v2[4 * k + 3]);
+    for (int k = 0; k < 4; ++k)
+      w[k] = make_uint4(tt_pack(__uint_as_float(v2[8 * k]), __uint_as_float(v2[8 * k + 1])), tt_pack(__uint_as_float(v2[8 * k + 2]), __uint_as_float(v2[8 * k + 3])),
+                        tt_pack(__uint_as_float(v2[8 * k + 4]), __uint_as_float(v2[8 * k + 5])), tt_pack(__uint_as_float(v2[8 * k + 6]), __uint_as_float(v2[8 * k + 7])));
     warp_store_rows64(stage, lane, w, [&](int r) { return rowp(p.b2, r); }, pieces);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = make_uint4(v3[4 * k], v3[4 * k + 1], v3[4 * k + 2], v3[4 * k + 3]);
+    for (int k = 0; k < 4; ++k)
+      w[k] = make_uint4(tt_pack(__uint_as_float(v3[8 * k]), __uint_as_float(v3[8 * k + 1])), tt_pack(__uint_as_float(v3[8 * k + 2]), __uint_as_float(v3[8 * k + 3])),
+                        tt_pack(__uint_as_float(v3[8 * k + 4]), __uint_as_float(v3[8 * k + 5])), tt_pack(__uint_as_float(v3[8 * k + 6]), __uint_as_float(v3[8 * k + 7])));
     warp_store_rows64(stage, lane, w, [&](int r) { return rowp(p.b3, r); }, pieces);
   }
   tcgen05_fence_before();
@@ -201,10 +224,10 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const __grid_constant__ 
   const int TS = p.TS;
   // relative-position score terms of this tile's PL pixels: two CONTIGUOUS blocks [PL][T][TS] of b2 / b3 -> shared memory by
   // bulk copies on the same barrier as the operand tiles (scalar per-thread global loads of these rows were 60 % of the kernel)
-  float* b2_s = reinterpret_cast<float*>(smem + p.cf * 3 * 16384);
-  float* b3_s = b2_s + PL * T * TS;
+  __nv_bfloat16* b2_s = reinterpret_cast<__nv_bfloat16*>(smem + p.cf * 3 * 16384);
+  __nv_bfloat16* b3_s = b2_s + PL * T * TS;
   if (tid == 0) {
-    const uint32_t bias_bytes = (uint32_t)(PL * T * TS * sizeof(float));
+    const uint32_t bias_bytes = (uint32_t)(PL * T * TS * sizeof(__nv_bfloat16));
     mbar_expect_tx(&bar_load, (uint32_t)(p.cf * 3 * 16384) + 2 * bias_bytes);
     for (int c = 0; c < p.cf; ++c) {
       const int ch = h * F + c * 64;
@@ -245,18 +268,19 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const __grid_constant__ 
   float bias[W];
   {
     float bt[TP];  // this row's bias over its own pixel block: b2[px, t, s] + b3[px, s, t]
-    const float4* b2row = reinterpret_cast<const float4*>(b2_s + (size_t)(pl * T + (valid ? t : 0)) * TS);
-    const float* b3col = b3_s + (size_t)pl * T * TS + (valid ? t : 0);
+    const uint4* b2row = reinterpret_cast<const uint4*>(b2_s + (size_t)(pl * T + (valid ? t : 0)) * TS);
+    const __nv_bfloat16* b3col = b3_s + (size_t)pl * T * TS + (valid ? t : 0);
 #pragma unroll
-    for (int k = 0; k < TP / 4; ++k) {
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid && 4 * k < T) r = b2row[k];
-      const float rr[4] = {r.x, r.y, r.z, r.w};
+    for (int k = 0; k < TP / 8; ++k) {
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);  // 8 bf16 of the row (16-byte loads at the odd row stride: conflict-free)
+      if (valid && 8 * k < T) r = b2row[k];
+      const float rr[8] = {__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u),
+                           __uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u), __uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u)};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int s = 4 * k + u;
+      for (int u = 0; u < 8; ++u) {
+        const int s = 8 * k + u;
         const bool okj = valid && s < T && ((((gbits >> s) & 1ull) != 0) == grp);
-        bt[s] = okj ? rr[u] + b3col[(size_t)(s < T ? s : 0) * TS] : -INFINITY;
+        bt[s] = okj ? rr[u] + __bfloat162float(b3col[(size_t)(s < T ? s : 0) * TS]) : -INFINITY;
       }
     }
 #pragma unroll
@@ -512,11 +536,11 @@ static int tt_pow2(int v, int lo) {
   return r;
 }
 static inline int tt_round_up(int v, int m) { return (v + m - 1) / m * m; }
-// row stride (floats) of the bias tables: T rounded up to 4, then to an ODD number of float4s — a thread that reads its own row
-// with 16-byte shared-memory loads while its neighbours read theirs then touches all 8 bank groups (no conflicts)
+// row stride (bf16 elements) of the bias tables: T rounded up to 8, then to an ODD number of 16-byte pieces — rows stay 16-byte aligned
+// (bulk copies, vector reads) and threads reading their own rows side by side touch all bank groups (no conflicts)
 int tt_row_stride(int T) {
-  int ts = tt_round_up(T, 4);
-  if (((ts / 4) & 1) == 0) ts += 4;
+  int ts = tt_round_up(T, 8);
+  if (((ts / 8) & 1) == 0) ts += 8;
   return ts;
 }
 
@@ -535,7 +559,7 @@ size_t attn_temporal_tc_workspace(const fdm_attn_temporal_args* a) {
   if (!tt_shape_ok(a)) return 0;
   const size_t rows = (size_t)a->B * a->heads * a->HW * a->T;
   const size_t TS = tt_row_stride(a->T);
-  return 2 * rows * TS * sizeof(float) + rows * 64 * sizeof(__nv_bfloat16);
+  return 2 * rows * TS * sizeof(__nv_bfloat16) + rows * 64 * sizeof(__nv_bfloat16);
 }
 
 template <typename Kern>
@@ -571,7 +595,7 @@ int attn_temporal_tc_launch(const fdm_attn_temporal_args* a, cudaStream_t st) {
   p.rows = HW < 128 ? HW : 128;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)F);
   const size_t rows = (size_t)B * heads * HW * T;
-  p.b2 = reinterpret_cast<float*>(a->workspace);
+  p.b2 = reinterpret_cast<__nv_bfloat16*>(a->workspace);
   p.b3 = p.b2 + rows * p.TS;
   p.P = reinterpret_cast<__nv_bfloat16*>(p.b3 + rows * p.TS);
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
@@ -619,7 +643,7 @@ int attn_temporal_tc_launch(const fdm_attn_temporal_args* a, cudaStream_t st) {
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, FDM_ERR_UNSUPPORTED);
   }
   const int smem1 = p.cf * (2 * 16384 + 2 * p.Tn * 128) + 1024;
-  const int smem2 = p.cf * 3 * 16384 + 2 * PL * T * p.TS * (int)sizeof(float) + 1024;  // P (32 KB) aliases Q + K; + bias tiles
+  const int smem2 = p.cf * 3 * 16384 + 2 * PL * T * p.TS * (int)sizeof(__nv_bfloat16) + 1024;  // P (32 KB) aliases Q + K; + bias tiles
   const int smem3 = 16384 + p.cf * p.Tn * 128 + p.rows * F * 2 + 1024;
   static std::once_flag once;
   static int attr_rc = FDM_OK;
