@@ -599,8 +599,11 @@ def kernel_classes(P, N_, B, K, Cx, S, osz=2):
             tc = bool(st.workspace)
             extra = 0
             if tc:
-                ts = (st.T + 7) // 8 * 8
-                ts += 8 if (ts // 8) % 2 == 0 else 0
+                t16 = (st.T + 7) // 8 * 8
+                t16 += 8 if (t16 // 8) % 2 == 0 else 0
+                t8 = (st.T + 3) // 4 * 4
+                t8 += 4 if (t8 // 4) % 2 == 0 else 0
+                ts = min(t16, t8)
                 rows = st.B * st.heads * st.HW * st.T
                 extra = 2 * (2 * rows * ts * 2) + 2 * rows * 64 * 2
             add("attn_temporal (RPE; 3 tcgen05 kernels per call)" if tc else "attn_temporal (RPE, CUDA cores)", "tensor", fn, ref,

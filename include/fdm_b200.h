@@ -264,7 +264,7 @@ int fdm_norm_linear_supported(const fdm_norm_linear_args* a);
  *       (Rq_op, Rk_op, Rv_op) and a workspace of fdm_attn_temporal_workspace(a) bytes are given.  Three launches: the
  *       relative-position score terms as GEMMs over the pixels of each frame, S = QK^T / softmax / O = PV over rows ordered
  *       (pixel, frame), and the relative-position value term as a GEMM over the pixels.
- *       Workspace layout: bf16 b2[B][heads][HW][T][TS], bf16 b3[B][heads][HW][T][TS] (TS = T rounded up to an odd multiple of 8), then
+ *       Workspace layout: bf16 b2[B][heads][HW][T][TS], bf16 b3[B][heads][HW][T][TS] (TS = T rounded up to an odd multiple of 8 or of 4, whichever is smaller), then
  *       bf16 attn[B][heads][HW][T][64] — the NORMALISED attention weights softmax(S)[t, s] (zero for s >= T): what
  *       RPEAttention returns as `attn` (rpe.py:164), readable after the call (fdm_attn_temporal_attn_offset(a) bytes in).
  *     - CUDA cores (attn_simt.cu): fp32 mode and every other shape.

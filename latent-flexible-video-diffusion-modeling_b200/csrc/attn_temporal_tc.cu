@@ -34,7 +34,8 @@ struct TtParams {
   __nv_bfloat16* out;      // [B*T][HW][C]
   float* attn_mean;        // optional [B*HW][T][T]: += attention weights / heads (attention-map logging, rpe.py:128-130)
   int B, T, HW, C, F, heads;
-  int TS;                  // row stride of b2 / b3 in elements: tt_row_stride(T) — a multiple of 8 with TS/8 odd (conflict-free 16-byte rows)
+  int TS;                  // row stride of b2 / b3 in elements: tt_row_stride(T) — a multiple of 4 with TS/4 odd (8-byte aligned rows whose
+                           // 8-byte reads by neighbouring threads are bank-conflict free; no padding at T = 20: K2's fourth resident CTA)
   int Tn;                  // GEMM extent of the frame axis = round_up(T, 16)
   int cf;                  // 64-channel chunks per head
   int rows;                // pixels per K1 / K3 tile = min(HW, 128)
@@ -61,6 +62,21 @@ __device__ __forceinline__ void tt_bulk_load(void* dst, const void* src, uint32_
 __device__ __forceinline__ uint32_t tt_pack(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// warp_store_rows64 with 8-byte pieces: rows of the score-term tables are only 8-byte aligned (row stride T rounded up to 4 bf16).
+// Consecutive lanes store consecutive pieces of a row: `np` lanes per row segment.
+template <class RowPtr>
+__device__ __forceinline__ void tt_store_rows8(uint8_t* stage, int lane, const uint4 (&w)[4], RowPtr row_ptr, int np) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stage + lane * 80 + q * 16) = w[q];
+  __syncwarp();
+  for (int idx = lane; idx < 32 * np; idx += 32) {
+    const int row = idx / np, pc = idx - row * np;
+    uint8_t* d = row_ptr(row);
+    if (d != nullptr) *reinterpret_cast<uint2*>(d + pc * 8) = *reinterpret_cast<const uint2*>(stage + row * 80 + pc * 8);
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -158,7 +174,7 @@ __global__ void __launch_bounds__(128) rpe_bias_kernel(const __grid_constant__ C
         for (int k = 0; k < 16; ++k) v2[16 + k] = v3[16 + k] = 0u;
       }
     }
-    const int pieces = min(4, (p.TS - c0) / 8);
+    const int np = min(8, (p.TS - c0) / 4);  // 8-byte pieces of this 64-byte column block that belong to the row
     auto rowp = [&](__nv_bfloat16* base, int r) -> uint8_t* {
       const int rr = r0 + r;
       if (rr >= p.rows || px0 + rr >= p.HW) return nullptr;
@@ -169,12 +185,14 @@ __global__ void __launch_bounds__(128) rpe_bias_kernel(const __grid_constant__ C
     for (int k = 0; k < 4; ++k)
       w[k] = make_uint4(tt_pack(__uint_as_float(v2[8 * k]), __uint_as_float(v2[8 * k + 1])), tt_pack(__uint_as_float(v2[8 * k + 2]), __uint_as_float(v2[8 * k + 3])),
                         tt_pack(__uint_as_float(v2[8 * k + 4]), __uint_as_float(v2[8 * k + 5])), tt_pack(__uint_as_float(v2[8 * k + 6]), __uint_as_float(v2[8 * k + 7])));
-    warp_store_rows64(stage, lane, w, [&](int r) { return rowp(p.b2, r); }, pieces);
+    if ((p.TS & 7) == 0) warp_store_rows64(stage, lane, w, [&](int r) { return rowp(p.b2, r); }, np >> 1);
+    else tt_store_rows8(stage, lane, w, [&](int r) { return rowp(p.b2, r); }, np);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       w[k] = make_uint4(tt_pack(__uint_as_float(v3[8 * k]), __uint_as_float(v3[8 * k + 1])), tt_pack(__uint_as_float(v3[8 * k + 2]), __uint_as_float(v3[8 * k + 3])),
                         tt_pack(__uint_as_float(v3[8 * k + 4]), __uint_as_float(v3[8 * k + 5])), tt_pack(__uint_as_float(v3[8 * k + 6]), __uint_as_float(v3[8 * k + 7])));
-    warp_store_rows64(stage, lane, w, [&](int r) { return rowp(p.b3, r); }, pieces);
+    if ((p.TS & 7) == 0) warp_store_rows64(stage, lane, w, [&](int r) { return rowp(p.b3, r); }, np >> 1);
+    else tt_store_rows8(stage, lane, w, [&](int r) { return rowp(p.b3, r); }, np);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -268,19 +286,28 @@ __global__ void __launch_bounds__(128) attn_rows_kernel(const __grid_constant__ 
   float bias[W];
   {
     float bt[TP];  // this row's bias over its own pixel block: b2[px, t, s] + b3[px, s, t]
-    const uint4* b2row = reinterpret_cast<const uint4*>(b2_s + (size_t)(pl * T + (valid ? t : 0)) * TS);
+    const __nv_bfloat16* b2r = b2_s + (size_t)(pl * T + (valid ? t : 0)) * TS;
     const __nv_bfloat16* b3col = b3_s + (size_t)pl * T * TS + (valid ? t : 0);
+    // this row of b2: 16-byte loads when the rows are 16-byte aligned (TS % 8 == 0), else 8-byte loads — both at an odd number of
+    // units per row, i.e. free of bank conflicts between the threads of a warp
+    auto fin = [&](int s, uint32_t bits) {
+      const bool okj = valid && s < T && ((((gbits >> s) & 1ull) != 0) == grp);
+      bt[s] = okj ? __uint_as_float(bits) + __bfloat162float(b3col[(size_t)(s < T ? s : 0) * TS]) : -INFINITY;
+    };
+    if ((TS & 7) == 0) {
 #pragma unroll
-    for (int k = 0; k < TP / 8; ++k) {
-      uint4 r = make_uint4(0u, 0u, 0u, 0u);  // 8 bf16 of the row (16-byte loads at the odd row stride: conflict-free)
-      if (valid && 8 * k < T) r = b2row[k];
-      const float rr[8] = {__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u),
-                           __uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u), __uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u)};
+      for (int k = 0; k < TP / 8; ++k) {
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if (valid && 8 * k < T) r = reinterpret_cast<const uint4*>(b2r)[k];
+        fin(8 * k, r.x << 16); fin(8 * k + 1, r.x & 0xffff0000u); fin(8 * k + 2, r.y << 16); fin(8 * k + 3, r.y & 0xffff0000u);
+        fin(8 * k + 4, r.z << 16); fin(8 * k + 5, r.z & 0xffff0000u); fin(8 * k + 6, r.w << 16); fin(8 * k + 7, r.w & 0xffff0000u);
+      }
+    } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int s = 8 * k + u;
-        const bool okj = valid && s < T && ((((gbits >> s) & 1ull) != 0) == grp);
-        bt[s] = okj ? rr[u] + __bfloat162float(b3col[(size_t)(s < T ? s : 0) * TS]) : -INFINITY;
+      for (int k = 0; k < TP / 4; ++k) {
+        uint2 r = make_uint2(0u, 0u);
+        if (valid && 4 * k < T) r = reinterpret_cast<const uint2*>(b2r)[k];
+        fin(4 * k, r.x << 16); fin(4 * k + 1, r.x & 0xffff0000u); fin(4 * k + 2, r.y << 16); fin(4 * k + 3, r.y & 0xffff0000u);
       }
     }
 #pragma unroll
@@ -536,12 +563,16 @@ static int tt_pow2(int v, int lo) {
   return r;
 }
 static inline int tt_round_up(int v, int m) { return (v + m - 1) / m * m; }
-// row stride (bf16 elements) of the bias tables: T rounded up to 8, then to an ODD number of 16-byte pieces — rows stay 16-byte aligned
-// (bulk copies, vector reads) and threads reading their own rows side by side touch all bank groups (no conflicts)
+// row stride (bf16 elements) of the bias tables: either T rounded up to an ODD number of 16-byte pieces (16-byte row accesses) or to an
+// odd number of 8-byte pieces (8-byte accesses), whichever pads less — threads reading their own rows side by side then touch all
+// bank groups, and a tile's block of rows stays 16-byte aligned for the bulk copies.  T = 20 -> 20 (K2's smaller tile admits a
+// fourth resident CTA), T = 40 -> 40 (16-byte path).
 int tt_row_stride(int T) {
-  int ts = tt_round_up(T, 8);
-  if (((ts / 8) & 1) == 0) ts += 8;
-  return ts;
+  int t16 = tt_round_up(T, 8);
+  if (((t16 / 8) & 1) == 0) t16 += 8;
+  int t8 = tt_round_up(T, 4);
+  if (((t8 / 4) & 1) == 0) t8 += 4;
+  return t16 <= t8 ? t16 : t8;
 }
 
 static bool tt_shape_ok(const fdm_attn_temporal_args* a) {
