@@ -21,6 +21,10 @@
 //     channels) as ONE stream of M = 256 MMAs issued by the leader.  Each CTA stages its own A box and only HALF of the weight
 //     tile (BN/2 rows per tap): single-CTA MMAs at N <= 128 are bound by shared-memory operand reads (A + B per MMA, measured
 //     86 clk per 128x128x16 against a tensor floor of 64); the pair reads A + B/2 per SM and halves the weight TMA traffic.
+// This kernel does not release its dependents after its dependency wait (common.cuh, pdl_wait): it is ONE wave of persistent CTAs, so
+// the release would come at kernel start and the next kernel's CTAs would sit on the SMs for the whole run (measured: +4 % on the
+// cfg5 / cfg3 steps).  FDM_HALO_LATE_TRIGGER: release when the MMA warp has issued its last work item instead.
+#define FDM_PDL_NO_TRIGGER
 #include "tc_common.cuh"
 #include <mutex>
 
@@ -247,6 +251,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
         if (elect_one_sync()) commit(&tmem_full_bar[buf]);
         __syncwarp();
       }
+#ifdef FDM_HALO_LATE_TRIGGER
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
       if (p.trace != nullptr && lane == 0) {
         p.trace[blockIdx.x * 8 + 0] = clock64() - t_begin;
         p.trace[blockIdx.x * 8 + 1] = t_wait_tmem;
