@@ -1275,6 +1275,12 @@ class DenoiserEngine:
             layers = list(stage)
             for li, layer in enumerate(layers):
                 want_op = feeds_downsample and li == len(layers) - 1 and self.use_tc
+                # inference: the phase-mode upsample conv reads the low-resolution bf16 operand — let the producing conv store it
+                # (one more epilogue store instead of a cast launch)
+                if (not train and h is not None and li + 1 < len(layers) and isinstance(layers[li + 1], Upsample)
+                        and isinstance(layer, (ResBlock, FactorizedAttentionBlock))
+                        and self.up_tc_ok(getattr(layer, "out_channels", h.C), h.H, h.W)):
+                    want_op = True
                 if isinstance(layer, nn.Conv2d):  # stem
                     out = new_act("stem", layer.out_channels, H, W)
                     out.biases = (layer.bias,)
