@@ -259,6 +259,10 @@ extern "C" int fdm_conv(const fdm_conv_args* a, void* stream) {
   FDM_REQUIRE(a->y_f32 != nullptr || a->y_op != nullptr, FDM_ERR_BAD_ARG);
   FDM_REQUIRE(!(a->out_nchw && a->y_f32 == nullptr), FDM_ERR_BAD_ARG);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // the two-tensor skip segment exists in the tcgen05 halo kernel only: everything else fails loudly
+  const bool split1 = a->a1b != nullptr;
+  FDM_REQUIRE(!split1 || (a->a1 != nullptr && a->engine == FDM_CONV_TC && a->ksize == 3 && a->stride == 1 && !a->upsample && !a->out_nchw &&
+                          a->C1a > 0 && a->C1a < a->C1 && a->C1a % 64 == 0), FDM_ERR_UNSUPPORTED);
   if (a->engine == FDM_CONV_TC) {
     // the halo kernel also has a pointwise mode, but measured slower than the per-tap kernel for the 1x1 qkv / proj_out
     // linears on B200 (35 vs 28 us, 30 vs 17 us: two short K stages cannot amortise the persistent pipeline) -> 3x3 only
@@ -271,6 +275,7 @@ extern "C" int fdm_conv(const fdm_conv_args* a, void* stream) {
       if (rh != FDM_ERR_UNSUPPORTED) return rh;
     }
     int rc = (a->ksize == 3 || pw || (a->C0 >= 256 && !no_pw)) ? conv_halo_launch(a, st) : FDM_ERR_UNSUPPORTED;
+    if (rc == FDM_ERR_UNSUPPORTED && split1) return rc;
     return rc == FDM_ERR_UNSUPPORTED ? conv_tc_launch(a, st) : rc;
   }
   if (a->engine == FDM_CONV_TC_TAP) return conv_tc_launch(a, st);

@@ -29,7 +29,7 @@ ConvArgs = _S("ConvArgs", [("a0", vp), ("w0", vp), ("a1", vp), ("w1", vp), ("bia
                            ("ksize", i32), ("stride", i32), ("upsample", i32),
                            ("a_dtype", i32), ("op_dtype", i32), ("out_nchw", i32), ("engine", i32),
                            ("resid_norm", i32), ("rn_T", i32), ("rn_eps", f32), ("rn_tstats", vp), ("rn_stats", vp),
-                           ("rn_gamma", vp), ("rn_beta", vp)])
+                           ("rn_gamma", vp), ("rn_beta", vp), ("a1b", vp), ("C1a", i32)])
 GnApplyArgs = _S("GnApplyArgs", [("xa", vp), ("xb", vp), ("stats_a", vp), ("stats_b", vp), ("gamma", vp), ("beta", vp),
                                  ("film", vp), ("out_op", vp), ("out_f32", vp), ("raw_op", vp),
                                  ("N", i32), ("HW", i32), ("Ca", i32), ("Cb", i32), ("T", i32),

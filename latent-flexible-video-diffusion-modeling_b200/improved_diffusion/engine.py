@@ -466,6 +466,23 @@ class DenoiserEngine:
         return (self.use_tc and os.environ.get("FDM_UP_PHASES", "1") != "0" and W in (16, 32, 64, 128) and H % (128 // W) == 0
                 and Cc % 8 == 0 and Cc >= 64)  # (the 32-column tile variant is not instantiated for the phase mode)
 
+    # Measured (B200, cfg5 / cfg3 samplers): the bf16 copy costs the producing convs' epilogues what the GroupNorm pass saves (gn_apply
+    # -100..-160 us, halo convs +40..+170 us per step: those epilogues drain at ~2.6 TB/s, the GroupNorm pass at 5.7) — the step time does
+    # not move beyond run-to-run noise, with or without a >= 256-channel threshold.  So the scheme is OFF by default (no producer is asked
+    # for the copy); FDM_SPLIT_MIN_C=<channels> enables it for producers at least that wide (0: all).  Results are bit-identical.
+    split_min_c = int(os.environ.get("FDM_SPLIT_MIN_C", str(1 << 30)))
+
+    def halo_map_ok(self, H, W):
+        return W in (16, 32, 64, 128) and H % (128 // W) == 0
+
+    def split_ok(self, xa, xb, Co, H, W, train):
+        """ResBlock skip_connection as a two-tensor K segment of the halo conv (fdm_conv a1 | a1b): both producers stored bf16 copies"""
+        if not self.use_tc or train or os.environ.get("FDM_SPLIT_SKIP", "1") == "0" or not self.halo_map_ok(H, W):
+            return False
+        if xa.op is None or Co < 32 or Co % 4 or xa.C % 8 or xa.C < self.split_min_c:
+            return False
+        return xb is None or (xb.op is not None and xa.C % 64 == 0 and xb.C % 8 == 0)
+
     def _f32(self, p):
         key = ("f32", p.data_ptr())
         if key not in self.packed:
@@ -822,7 +839,8 @@ class DenoiserEngine:
 
         # ---------------- conv helper
         def conv(a0, C0, Hin, Win, w0, Cout, k, stride=1, upsample=0, a1=None, C1=0, w1=None, bias=None, resid=None,
-                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None, flop_c0=None, n_frames=None, **resid_norm):
+                 y_f32=None, y_op=None, stats=None, out_nchw=0, a_dtype=None, flop_c0=None, n_frames=None, a1b=None, C1a=0,
+                 **resid_norm):
             a_dtype = opd if a_dtype is None else a_dtype
             Nf_ = Nf if n_frames is None else n_frames
             Hv, Wv = (Hin * 2, Win * 2) if upsample else (Hin, Win)
@@ -838,7 +856,7 @@ class DenoiserEngine:
             P.op("fdm_conv", N_.ConvArgs, a0=a0, w0=pack(w0), a1=a1, w1=pack(w1) if w1 is not None else None, bias=bias,
                  resid=resid, y_f32=y_f32, y_op=y_op, stats=stats, N=Nf_, Hin=Hin, Win=Win, C0=C0, C1=C1, Cout=Cout,
                  ksize=k, stride=stride, upsample=upsample, a_dtype=a_dtype, op_dtype=opd, out_nchw=out_nchw,
-                 engine=N_.CONV_TC if tc else N_.CONV_SIMT, **resid_norm)
+                 engine=N_.CONV_TC if tc else N_.CONV_SIMT, a1b=a1b, C1a=C1a, **resid_norm)
             return Ho, Wo
 
         for hb, Cc, net, rb_, rop in self._pending_rpe_tc:
@@ -1022,7 +1040,11 @@ class DenoiserEngine:
             hw = Hh * Ww
             has_skip = not isinstance(rb.skip_connection, nn.Identity)
             a1 = P.buf("res_a1", Nf * hw * Ci * osz)
-            raw = P.buf("res_raw", Nf * hw * Ci * osz) if has_skip else None
+            # inference: the 1x1 skip_connection reads the bf16 copies its producers stored (xa.op | xb.op: a two-tensor K segment of
+            # the halo conv) instead of a raw copy of the concat written by the GroupNorm pass — 2 of that pass's 8 bytes per element,
+            # moved into conv epilogues where the store is free
+            split_raw = (has_skip and self.split_ok(xa, xb, Co, Hh, Ww, train))
+            raw = P.buf("res_raw", Nf * hw * Ci * osz) if (has_skip and not split_raw) else None
             gn, c1 = rb.in_layers[0], rb.in_layers[2]
             P.op("fdm_gn_apply", N_.GnApplyArgs, xa=xa.buf, xb=xb.buf if xb else None, stats_a=xa.st,
                  stats_b=xb.st if xb else None, gamma=f32(gn.weight), beta=f32(gn.bias), film=None, out_op=a1, out_f32=None,
@@ -1052,8 +1074,12 @@ class DenoiserEngine:
             if has_skip:
                 if sk.kernel_size != (1, 1):
                     raise NotImplementedError("ResBlock(use_conv=True) 3x3 skip is never built by create_model")
-                conv(a2, Co, Hh, Ww, c2.weight, Co, 3, a1=raw, C1=Ci, w1=sk.weight, bias=bias_sum(c2.bias, sk.bias),
-                     y_f32=out.buf, y_op=yop, stats=out.st)
+                if split_raw:
+                    conv(a2, Co, Hh, Ww, c2.weight, Co, 3, a1=xa.op, C1=Ci, w1=sk.weight, bias=bias_sum(c2.bias, sk.bias),
+                         y_f32=out.buf, y_op=yop, stats=out.st, a1b=xb.op if xb else None, C1a=xa.C if xb else 0)
+                else:
+                    conv(a2, Co, Hh, Ww, c2.weight, Co, 3, a1=raw, C1=Ci, w1=sk.weight, bias=bias_sum(c2.bias, sk.bias),
+                         y_f32=out.buf, y_op=yop, stats=out.st)
             else:
                 conv(a2, Co, Hh, Ww, c2.weight, Co, 3, bias=f32(c2.bias), resid=xa.buf, y_f32=out.buf, y_op=yop, stats=out.st)
 
@@ -1214,7 +1240,7 @@ class DenoiserEngine:
                 P.tape.append(bwd)
             return z
 
-        def resample(layer, x, down):
+        def resample(layer, x, down, want_op=False):
             cv = layer.op if down else layer.conv
             Ho, Wo = (x.H // 2, x.W // 2) if down else (x.H * 2, x.W * 2)
             out = new_act("down" if down else "up", x.C, Ho, Wo)
@@ -1228,7 +1254,8 @@ class DenoiserEngine:
                     a = P.buf("resample_a", Nf * x.H * x.W * x.C * osz)
                     P.op("fdm_cast", N_.CastArgs, x=x.buf, out=a, N=Nf, H=x.H, W=x.W, C=x.C, upsample=0, op_dtype=opd, colsum=None,
                          colsum2=None)
-                conv(a, x.C, x.H, x.W, cv.weight, x.C, 3, upsample=1, bias=f32(cv.bias), y_f32=out.buf, stats=out.st)
+                conv(a, x.C, x.H, x.W, cv.weight, x.C, 3, upsample=1, bias=f32(cv.bias), y_f32=out.buf, stats=out.st,
+                     y_op=with_op_copy(out) if want_op else None)
             elif (self.use_tc and self.tc_ok(x.C, 0, x.C, 3, 2 if down else 1, 0, Ho, Wo)) or (train and not down):
                 if down and x.op is not None:
                     a = x.op  # the producing conv already stored the bf16 operand copy
@@ -1238,7 +1265,7 @@ class DenoiserEngine:
                     P.op("fdm_cast", N_.CastArgs, x=x.buf, out=a, N=Nf, H=x.H, W=x.W, C=x.C, upsample=0 if down else 1,
                          op_dtype=opd, colsum=None, colsum2=None)
                 conv(a, x.C, Hc, Wc, cv.weight, x.C, 3, stride=2 if down else 1, bias=f32(cv.bias), y_f32=out.buf,
-                     stats=out.st)
+                     stats=out.st, y_op=with_op_copy(out) if (want_op and not train) else None)
             else:
                 # the CUDA-core engine gathers straight from the fp32 stream (stride 2 / folded nearest upsample)
                 conv(x.buf, x.C, x.H, x.W, cv.weight, x.C, 3, stride=2 if down else 1, upsample=0 if down else 1,
@@ -1271,10 +1298,17 @@ class DenoiserEngine:
 
         names = {id(mod): name for name, mod in m.named_modules()}
 
-        def run_stage(stage, h, skip=None, feeds_downsample=False):
+        def run_stage(stage, h, skip=None, feeds_downsample=False, out_wants_op=False):
             layers = list(stage)
             for li, layer in enumerate(layers):
                 want_op = feeds_downsample and li == len(layers) - 1 and self.use_tc
+                if out_wants_op and li == len(layers) - 1 and self.use_tc and not train:
+                    # the stage's output is read raw by a ResBlock skip_connection later (as h or as the U-Net skip): bf16 copy from
+                    # its producer when that ResBlock's conv will run on the halo kernel (split_ok)
+                    Hi, Wi = (H, W) if h is None else (h.H, h.W)
+                    Ho_, Wo_ = (Hi // 2, Wi // 2) if isinstance(layer, Downsample) else ((Hi * 2, Wi * 2) if isinstance(layer, Upsample) else (Hi, Wi))
+                    Cout_ = getattr(layer, "out_channels", None) or (h.C if h is not None else 0)
+                    want_op = want_op or (self.halo_map_ok(Ho_, Wo_) and Cout_ >= self.split_min_c)
                 # inference: the phase-mode upsample conv reads the low-resolution bf16 operand — let the producing conv store it
                 # (one more epilogue store instead of a cast launch)
                 if (not train and h is not None and li + 1 < len(layers) and isinstance(layers[li + 1], Upsample)
@@ -1286,7 +1320,7 @@ class DenoiserEngine:
                     out.biases = (layer.bias,)
                     if stem_tc:
                         conv(xin, 8, H, W, layer.weight, layer.out_channels, 3, bias=f32(layer.bias), y_f32=out.buf,
-                             stats=out.st, a_dtype=N_.BF16, flop_c0=Cin)
+                             y_op=with_op_copy(out) if want_op else None, stats=out.st, a_dtype=N_.BF16, flop_c0=Cin)
                     else:
                         conv(xin, Cin, H, W, layer.weight, layer.out_channels, 3, bias=f32(layer.bias), y_f32=out.buf,
                              stats=out.st, a_dtype=N_.F32)
@@ -1312,9 +1346,9 @@ class DenoiserEngine:
                 elif isinstance(layer, FactorizedAttentionBlock):
                     h = attention(layer, h, want_op=want_op)
                 elif isinstance(layer, Downsample):
-                    h = resample(layer, h, True)
+                    h = resample(layer, h, True, want_op=want_op)
                 elif isinstance(layer, Upsample):
-                    h = resample(layer, h, False)
+                    h = resample(layer, h, False, want_op=want_op)
                 else:
                     raise NotImplementedError(type(layer))
                 P.taps[names[id(layer)]] = (h.buf, h.C, h.H, h.W)
@@ -1325,11 +1359,12 @@ class DenoiserEngine:
         for si, stage in enumerate(in_stages):
             nxt = in_stages[si + 1] if si + 1 < len(in_stages) else None
             feeds = nxt is not None and len(nxt) == 1 and isinstance(nxt[0], Downsample)
-            h = run_stage(stage, h, feeds_downsample=feeds)
+            h = run_stage(stage, h, feeds_downsample=feeds, out_wants_op=True)   # pushed as a U-Net skip
             hs.append(h)
-        h = run_stage(m.middle_block, h)
-        for stage in m.output_blocks:
-            h = run_stage(stage, h, hs.pop())
+        h = run_stage(m.middle_block, h, out_wants_op=True)
+        out_stages = list(m.output_blocks)
+        for oi, stage in enumerate(out_stages):
+            h = run_stage(stage, h, hs.pop(), out_wants_op=oi + 1 < len(out_stages))
         gn, cv = m.out[0], m.out[2]
         a = P.buf("head_a", Nf * H * W * h.C * osz)
         P.op("fdm_gn_apply", N_.GnApplyArgs, xa=h.buf, xb=None, stats_a=h.st, stats_b=None, gamma=f32(gn.weight),

@@ -187,6 +187,47 @@ def test_head_conv_vs_torch(case):
         assert rel(outs[0], outs[1]) <= 1e-3
 
 
+@pytest.mark.parametrize("case", [
+    # N, H, W, C0, Cout, C1a, C1b
+    (20, 32, 32, 64, 64, 128, 64),     # cfg4 top level: skip_connection over cat([h (128), skip (64)])
+    (6, 16, 16, 128, 128, 128, 128),   # 16x16 level
+    (4, 64, 64, 128, 128, 256, 128),   # cfg5 / cfg3: deep skip segment, CTA pairs
+    (2, 128, 128, 128, 128, 128, 128), # 128-wide maps, two-tile pair items
+    (3, 16, 16, 384, 384, 512, 328),   # ragged last chunk of the second tensor (328 = 5 * 64 + 8)
+], ids=lambda c: "x".join(map(str, c)))
+def test_conv_split_skip_segment_vs_torch(case):
+    """fdm_conv with the 1x1 skip segment read from two tensors (a1 | a1b = the virtual th.cat of unet.py:460) against the same conv
+    over the materialised concat, and against torch."""
+    from improved_diffusion import _native as N_
+    N, H, W, C0, Co, Ca, Cb = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, H, W, C0, device="cuda", generator=g).to(torch.bfloat16)
+    xa = torch.randn(N, H, W, Ca, device="cuda", generator=g).to(torch.bfloat16)
+    xb = torch.randn(N, H, W, Cb, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, C0, 3, 3, device="cuda", generator=g) / (9 * C0) ** 0.5
+    w1 = torch.randn(Co, Ca + Cb, 1, 1, device="cuda", generator=g) / (Ca + Cb) ** 0.5
+    bias = 0.1 * torch.randn(Co, device="cuda", generator=g)
+    w0p, w1p = pack_tc(w), pack_tc(w1)
+    outs = []
+    for split in (True, False):
+        a1 = xa if split else torch.cat([xa, xb], dim=-1).contiguous()
+        y = torch.full((N, H, W, Co), float("nan"), device="cuda")
+        stats = torch.zeros(N, Co, 2, device="cuda", dtype=torch.float64)
+        a = N_.ConvArgs(a0=x.data_ptr(), w0=w0p.data_ptr(), a1=a1.data_ptr(), w1=w1p.data_ptr(), bias=bias.data_ptr(), resid=None,
+                        y_f32=y.data_ptr(), y_op=None, stats=stats.data_ptr(), N=N, Hin=H, Win=W, C0=C0, C1=Ca + Cb, Cout=Co, ksize=3,
+                        stride=1, upsample=0, a_dtype=N_.BF16, op_dtype=N_.BF16, out_nchw=0, engine=N_.CONV_TC,
+                        a1b=xb.data_ptr() if split else None, C1a=Ca if split else 0)
+        N_.call("fdm_conv", a, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append((y, stats))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1)
+    ref = ref + F.conv2d(torch.cat([xa, xb], dim=-1).float().permute(0, 3, 1, 2), w1.to(torch.bfloat16).float())
+    ref = ref.permute(0, 2, 3, 1)
+    assert rel(outs[0][0], ref) <= 1e-3, rel(outs[0][0], ref)
+    assert torch.equal(outs[0][0], outs[1][0])          # the same MMAs in the same order: bit-identical to the materialised concat
+    assert rel(outs[0][1], outs[1][1]) <= 1e-9
+
+
 def pack_tc_up(w):
     """[co][ci][3][3] -> bf16 [phase = 2a + b][tap = 2s' + r'][co_pad][ci_pad]: per-phase 2x2 filters of nearest-x2-upsample + conv"""
     co, ci, _, _ = w.shape
