@@ -539,7 +539,10 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   int bn = a->Cout % 128 == 0 ? 128 : (a->Cout >= 64 ? 64 : (a->Cout > 16 ? 32 : 16));
   const int mtiles = (p.M + TC_BM - 1) / TC_BM;
   // (small grids run at the per-SM TMA instruction rate, so more CTAs only help while they land on idle SMs: never exceed 148)
-  while (bn > 32 && mtiles * ((a->Cout + bn / 2 - 1) / (bn / 2)) <= 148) bn >>= 1;
+  // (1x1 linears with a short K loop (Cin <= 128: proj_out) are epilogue-bound and light on shared memory — three CTAs per SM are resident —
+  //  so they are narrowed up to 3 x 148 CTAs: 8x8 proj_out 10.7 -> 6.2 us with BN = 32; at 16x16 narrower tiles measured slower)
+  const int cta_cap = (a->ksize == 1 && a->C0 <= 128 && a->a1 == nullptr) ? 3 * 148 : 148;
+  while (bn > 32 && mtiles * ((a->Cout + bn / 2 - 1) / (bn / 2)) <= cta_cap) bn >>= 1;
   const int co_pad = round_up(a->Cout, 16);
   // small grids (one CTA per SM, whole shared memory for the operand ring) run at the TMA INSTRUCTION rate: group the three
   // filter rows of a filter column into one stage so a single weight box serves three taps
