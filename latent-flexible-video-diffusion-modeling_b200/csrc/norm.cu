@@ -12,6 +12,7 @@ struct GnParams {
   void* out_op; float* out_f32; void* raw_op;
   int N, HW, Ca, Cb, C, T, film_stride, film_off, silu, pix_per_block;
   float eps;
+  double inv_cnt;  // 1 / (channels per group * HW)
   int film_add;  // 1: use_scale_shift_norm=False (unet.py:204-206): the embedding is ADDED before the norm, h = GN(x + e[n, c])
 };
 
@@ -62,11 +63,22 @@ __global__ void gn_apply_kernel(GnParams p) {
       s += s1;
       ss += s2;
     }
-    const double cnt = (double)cpg * (double)p.HW;
-    const double mean = s / cnt;
-    const double var = fmax(ss / cnt - mean * mean, 0.0);
-    s_mean[g] = (float)mean;
-    s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
+    // E[x^2] - mean^2 needs the fp64 sums; the final rsqrt does not (bf16-only outputs: two fp64 multiplies and an rsqrtf instead of
+    // two fp64 divisions and a square root on the critical path of every block — these launches are latency-bound on
+    // the small maps).  Launches that keep an fp32 copy (fp32 parity mode) stay in fp64 throughout.
+    if (sizeof(OT) == 2 && p.out_f32 == nullptr) {
+      const double inv = p.inv_cnt;  // 1 / (cpg * HW), divided on the host
+      const double mean = s * inv;
+      const double var = fmax(ss * inv - mean * mean, 0.0);
+      s_mean[g] = (float)mean;
+      s_rstd[g] = rsqrtf((float)var + p.eps);
+    } else {
+      const double cnt = (double)cpg * (double)p.HW;
+      const double mean = s / cnt;
+      const double var = fmax(ss / cnt - mean * mean, 0.0);
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
   }
   __syncthreads();
   float mul[4], add[4];  // v = x*mul + add, folding mean/rstd/gamma/beta/FiLM
@@ -211,6 +223,7 @@ extern "C" int fdm_gn_apply(const fdm_gn_apply_args* a, void* stream) {
   p.N = a->N; p.HW = a->HW; p.Ca = a->Ca; p.Cb = a->xb ? a->Cb : 0; p.C = p.Ca + p.Cb; p.T = a->T > 0 ? a->T : 1;
   p.film_stride = a->film_stride; p.film_off = a->film_off; p.silu = a->silu; p.eps = a->eps;
   p.film_add = (a->film != nullptr && a->film_add) ? 1 : 0;
+  p.inv_cnt = 1.0 / ((double)(p.C / 32) * (double)a->HW);
   FDM_REQUIRE(p.C % 32 == 0 && p.Ca % 4 == 0 && p.Cb % 4 == 0 && p.C <= 4096, FDM_ERR_UNSUPPORTED);
   FDM_REQUIRE(a->N > 0 && a->HW > 0, FDM_ERR_BAD_ARG);
   const int quads = p.C / 4;
