@@ -44,6 +44,7 @@ struct TcParams {
   // residual = GroupNorm of `resid` recomputed here (0: plain residual; 2: temporal GN from rn_tstats; 3: per-frame GN from rn_stats)
   int resid_norm, rn_T;
   float rn_eps;
+  double rn_inv_cnt;  // 1 / (4 * HWo): reciprocal element count of a GroupNorm group, divided on the host
   const float* rn_tstats;
   const double* rn_stats;
   const float* rn_gamma;
@@ -233,10 +234,10 @@ __global__ void __launch_bounds__(TC_THREADS, RN ? 3 : 0) conv_tc_kernel(const _
             const float4 bt = __ldg(reinterpret_cast<const float4*>(p.rn_beta + col));
             const double2* st = reinterpret_cast<const double2*>(p.rn_stats + ((size_t)rn_n[hh] * p.Cout + col) * 2);
             const double2 s0 = st[0], s1_ = st[1], s2_ = st[2], s3 = st[3];
-            const double cnt = 4.0 * (double)p.HWo;
-            const double mean = (s0.x + s1_.x + s2_.x + s3.x) / cnt;
-            const double var = fmax((s0.y + s1_.y + s2_.y + s3.y) / cnt - mean * mean, 0.0);
-            const float mf = (float)mean, rs = (float)(1.0 / sqrt(var + (double)p.rn_eps));
+            // fp64 only where it matters (E[x^2] - mean^2); no fp64 division / square root on the epilogue's critical path
+            const double mean = (s0.x + s1_.x + s2_.x + s3.x) * p.rn_inv_cnt;
+            const double var = fmax((s0.y + s1_.y + s2_.y + s3.y) * p.rn_inv_cnt - mean * mean, 0.0);
+            const float mf = (float)mean, rs = rsqrtf((float)var + p.rn_eps);
             mu = make_float4(gm.x * rs, gm.y * rs, gm.z * rs, gm.w * rs);
             ad = make_float4(bt.x - mf * mu.x, bt.y - mf * mu.y, bt.z - mf * mu.z, bt.w - mf * mu.w);
           }
@@ -528,6 +529,7 @@ int conv_tc_launch(const fdm_conv_args* a, cudaStream_t st) {
   p.klast1 = a->a1 ? (a->C1 - (p.kchunks1 - 1) * TC_BK + 15) / 16 : 0;
   p.out_nchw = a->out_nchw;
   p.resid_norm = a->resid_norm; p.rn_T = a->rn_T > 0 ? a->rn_T : 1; p.rn_eps = a->rn_eps;
+  p.rn_inv_cnt = 1.0 / (4.0 * (double)HWo);
   p.rn_tstats = a->rn_tstats; p.rn_stats = a->rn_stats; p.rn_gamma = a->rn_gamma; p.rn_beta = a->rn_beta;
   if (a->resid_norm != 0) {
     FDM_REQUIRE(a->resid_norm == 2 || a->resid_norm == 3, FDM_ERR_BAD_ARG);

@@ -51,6 +51,7 @@ struct NlParams {
   int a_mode;
   int PL, tpv, tiles;  // a_mode 2: pixels per tile, tiles per video
   float eps;
+  double inv_cnt;  // 1 / (4 * HW), divided on the host
   long long* trace;  // debug: per-CTA phase timestamps (clock64), NULL in production (fdm_debug_nl_trace)
 };
 
@@ -88,14 +89,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // per-frame GroupNorm scale / shift of the 4 channels [c, c+4) (= one group at C = 128) from the fp64 sums
-__device__ __forceinline__ void nl_frame_coefs(const double* stats, int n, int c, int HW, float eps, const float4& g4, const float4& b4,
+__device__ __forceinline__ void nl_frame_coefs(const double* stats, int n, int c, double inv_cnt, float eps, const float4& g4, const float4& b4,
                                                float (&mul)[4], float (&add)[4]) {
   const double2* st = reinterpret_cast<const double2*>(stats + ((size_t)n * NL_K + c) * 2);
   const double2 s0 = st[0], s1 = st[1], s2 = st[2], s3 = st[3];
-  const double cnt = 4.0 * (double)HW;
-  const double mean = (s0.x + s1.x + s2.x + s3.x) / cnt;
-  const double var = fmax((s0.y + s1.y + s2.y + s3.y) / cnt - mean * mean, 0.0);
-  const float mf = (float)mean, rs = (float)(1.0 / sqrt(var + (double)eps));
+  const double mean = (s0.x + s1.x + s2.x + s3.x) * inv_cnt;
+  const double var = fmax((s0.y + s1.y + s2.y + s3.y) * inv_cnt - mean * mean, 0.0);
+  const float mf = (float)mean, rs = rsqrtf((float)var + eps);  // fp64 only for E[x^2] - mean^2
   mul[0] = g4.x * rs; mul[1] = g4.y * rs; mul[2] = g4.z * rs; mul[3] = g4.w * rs;
   add[0] = b4.x - mf * mul[0]; add[1] = b4.y - mf * mul[1]; add[2] = b4.z - mf * mul[2]; add[3] = b4.w - mf * mul[3];
 }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(NL_WORKERS, 1) nl_qkv_kernel(const __grid_cons
         const float* src = p.x + (size_t)m0 * NL_K + c4;
 #pragma unroll
         for (int i = 0; i < 16; ++i) xr[i] = ok ? __ldg(reinterpret_cast<const float4*>(src + i * NL_K)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) nl_frame_coefs(p.stats, m0 / p.HW, c4, p.HW, p.eps, g4, b4, mul, add);
+        if (ok) nl_frame_coefs(p.stats, m0 / p.HW, c4, p.inv_cnt, p.eps, g4, b4, mul, add);
       } else {
         const int vb = tile / p.tpv, px = (tile - vb * p.tpv) * p.PL + warp;
         const bool ok = warp < p.PL && px < p.HW;
@@ -375,6 +375,7 @@ extern "C" int fdm_norm_linear(const fdm_norm_linear_args* a, void* stream) {
   p.B = a->B; p.T = a->T; p.HW = a->HW; p.Cout = a->Cout; p.NS = a->Cout / 128;
   p.M = a->B * a->T * a->HW;
   p.a_mode = a->a_mode; p.eps = a->eps;
+  p.inv_cnt = 1.0 / (4.0 * (double)a->HW);
   p.trace = g_nl_trace;
   p.PL = 1; p.tpv = 1;
   if (a->a_mode == 2) {
