@@ -3,9 +3,13 @@
 // 4x4 middle block of the 32-px model) feature maps, so L is 16, 64 or 256 and a whole score row fits in TMEM:
 // no streaming softmax is needed.
 //
-//   CTA = (128-query tile, head, frame), 128 threads (thread r <-> query row r <-> TMEM lane r).
+//   CTA = (128-query tile, head, frame).  128 threads (thread r <-> query row r <-> TMEM lane r) for short rows; for L >= SA_SPLIT_MIN_L
+//   256 threads: warps w and w + 4 own the same 32 TMEM lanes and each takes HALF of the score row's columns (the softmax — two TMEM
+//   passes, L exp2 and L/8 shared-memory stores per row — is the longest phase of this one-shot CTA and halves; row max and row sum are
+//   exchanged through shared memory).
 //   1. TMA: Q tile, all K and V rows of this (frame, head) from the packed [N][L][3C] bf16 qkv tensor, 64-channel
-//      boxes in the 128B-swizzled K-major layout (head dims 16/32/48 read only their first F/16 k-steps).
+//      boxes in the 128B-swizzled K-major layout (head dims 16/32/48 read only their first F/16 k-steps).  V has its own barrier:
+//      S = Q K^T starts as soon as Q and K have landed, V is only awaited before O = P V.
 //   2. S = Q K^T       tcgen05.mma  M=128, N=L, K=F       -> TMEM columns [0, L)
 //   3. softmax         each thread reads its row from TMEM twice (max, then exp2/sum), writes P (bf16, unnormalised)
 //                      into shared memory in the swizzled K-major layout (aliasing the dead Q/K tiles)
@@ -13,9 +17,12 @@
 //                      -> TMEM columns [0, F) (aliasing S, which every thread has finished reading)
 //   5. O / rowsum -> bf16 -> out[N][L][C]
 #include "tc_common.cuh"
+#include <cstdlib>
 #include <mutex>
 
 namespace fdm {
+
+constexpr int SA_SPLIT_MIN_L = 128;
 
 struct SaTcParams {
   __nv_bfloat16* out;
@@ -23,6 +30,7 @@ struct SaTcParams {
   int rows;     // TMA box rows = min(L, 128)
   int cf;       // 64-wide channel chunks per head = ceil(F / 64)
   int tmem_cols;
+  int vbar;     // V on its own barrier (S = Q K^T starts when Q and K have landed)
   float scale_log2e;
   float* lse;   // optional [N][heads][L]: natural-log sum-exp of each scaled score row (saved for the backward pass)
   float* attn_mean;  // optional [N][L][L]: += softmax weights / heads (attention-map logging, rpe.py:128-130)
@@ -44,14 +52,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tq, const SaTcParams p) {
+__global__ void __launch_bounds__(256) attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tq, const SaTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bar_load, bar_s, bar_o;
+  __shared__ __align__(8) uint64_t bar_load, bar_v, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
+  __shared__ float xch[2][2][128];  // split rows: [max | sum][column half][row]
 
   pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool split = blockDim.x == 256;
+  const int hh = warp >> 2;                 // column half of this thread (0 when not split)
+  const int row = tid & 127;                // query row inside the tile = TMEM lane
   const int q0 = blockIdx.x * 128, h = blockIdx.y, n = blockIdx.z;
   const int L = p.L, F = p.F, C = p.C;
   const int kv_tile = L * 128;                 // bytes of one 64-channel chunk of K (or V)
@@ -63,6 +75,7 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tq) : "memory");
     mbar_init(&bar_load, 1);
+    mbar_init(&bar_v, 1);
     mbar_init(&bar_s, 1);
     mbar_init(&bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -79,13 +92,26 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
 
   if (tid == 0) {
     const int loads_kv = L / p.rows;
-    mbar_expect_tx(&bar_load, (uint32_t)(p.cf * (p.rows * 128 + 2 * kv_tile)));
-    for (int c = 0; c < p.cf; ++c) {
-      const int ch = h * F + c * 64;
-      tma_load_3d(q_s + c * 16384, &tq, &bar_load, ch, q0, n);
-      for (int j = 0; j < loads_kv; ++j) {
-        tma_load_3d(k_s + c * kv_tile + j * p.rows * 128, &tq, &bar_load, C + ch, j * p.rows, n);
-        tma_load_3d(v_s + c * kv_tile + j * p.rows * 128, &tq, &bar_load, 2 * C + ch, j * p.rows, n);
+    if (p.vbar) {
+      mbar_expect_tx(&bar_load, (uint32_t)(p.cf * (p.rows * 128 + kv_tile)));
+      mbar_expect_tx(&bar_v, (uint32_t)(p.cf * kv_tile));
+      for (int c = 0; c < p.cf; ++c) {
+        const int ch = h * F + c * 64;
+        tma_load_3d(q_s + c * 16384, &tq, &bar_load, ch, q0, n);
+        for (int j = 0; j < loads_kv; ++j) tma_load_3d(k_s + c * kv_tile + j * p.rows * 128, &tq, &bar_load, C + ch, j * p.rows, n);
+      }
+      for (int c = 0; c < p.cf; ++c)
+        for (int j = 0; j < loads_kv; ++j)
+          tma_load_3d(v_s + c * kv_tile + j * p.rows * 128, &tq, &bar_v, 2 * C + h * F + c * 64, j * p.rows, n);
+    } else {
+      mbar_expect_tx(&bar_load, (uint32_t)(p.cf * (p.rows * 128 + 2 * kv_tile)));
+      for (int c = 0; c < p.cf; ++c) {
+        const int ch = h * F + c * 64;
+        tma_load_3d(q_s + c * 16384, &tq, &bar_load, ch, q0, n);
+        for (int j = 0; j < loads_kv; ++j) {
+          tma_load_3d(k_s + c * kv_tile + j * p.rows * 128, &tq, &bar_load, C + ch, j * p.rows, n);
+          tma_load_3d(v_s + c * kv_tile + j * p.rows * 128, &tq, &bar_load, 2 * C + ch, j * p.rows, n);
+        }
       }
     }
     mbar_wait(&bar_load, 0);
@@ -105,11 +131,12 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
   mbar_wait(&bar_s, 0);
   tcgen05_fence_after();
 
-  // ---- softmax over this thread's row
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  // ---- softmax over this thread's row (split: its half of the row's columns)
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int c_lo = split ? hh * (L >> 1) : 0, c_hi = split ? c_lo + (L >> 1) : L;
   float mx = -INFINITY;
   if (L >= 32) {
-    for (int c = 0; c < L; c += 32) {
+    for (int c = c_lo; c < c_hi; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + c, v);
 #pragma unroll
@@ -123,12 +150,17 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
   }
   // every thread of the CTA must be done READING Q/K through the tensor core before P overwrites them: S is complete
   // (bar_s), so the MMAs have retired; nothing else reads Q/K.
+  if (split) {
+    xch[0][hh][row] = mx;
+    __syncthreads();
+    mx = fmaxf(xch[0][0][row], xch[0][1][row]);
+  }
   const float mneg = -mx * p.scale_log2e;
   float sum = 0.f;
-  uint8_t* prow = p_s + tid * 128;
-  const int sw = tid & 7;
+  uint8_t* prow = p_s + row * 128;
+  const int sw = row & 7;
   if (L >= 32) {
-    for (int c = 0; c < L; c += 32) {
+    for (int c = c_lo; c < c_hi; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(trow + c, v);
       float e[32];
@@ -162,14 +194,20 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
       *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = w;
     }
   }
+  if (split) xch[1][hh][row] = sum;  // read after the barrier in front of the PV MMAs (the logging variant syncs here itself)
   if (p.attn_mean != nullptr) {
     // materialising variant (logging path): third pass over the score row while S is still in TMEM — the normalised weights,
     // averaged over the heads by fp32 atomics (the head CTAs of a frame add into the same [L][L] map)
-    const float w = 1.f / (sum * (float)p.heads);
-    const int qq = q0 + tid;
+    float tot = sum;
+    if (split) {
+      __syncthreads();
+      tot = xch[1][0][row] + xch[1][1][row];
+    }
+    const float w = 1.f / (tot * (float)p.heads);
+    const int qq = q0 + row;
     float* arow = p.attn_mean + ((size_t)n * L + (qq < L ? qq : 0)) * L;
     if (L >= 32) {
-      for (int c = 0; c < L; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(trow + c, v);
         if (qq < L) {
@@ -189,7 +227,9 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
+  if (split) sum = xch[1][0][row] + xch[1][1][row];
   if (tid == 0) {
+    if (p.vbar) mbar_wait(&bar_v, 0);
     tcgen05_fence_after();
     // ---- O = P V   (N chunks of <= 64 head dims; K = L keys in steps of 16)
     for (int c = 0; c < p.cf; ++c) {
@@ -204,10 +244,11 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
     umma_commit(&bar_o);
   }
   __syncwarp();
+  if (hh == 0) {  // the output tile is F <= 128 columns: drained by the first four warps
   mbar_wait(&bar_o, 0);
   tcgen05_fence_after();
   const float inv = 1.f / sum;
-  const int q = q0 + tid;
+  const int q = q0 + row;
   if (p.lse != nullptr && q < L) p.lse[((size_t)n * p.heads + h) * L + q] = mx * p.scale_log2e * 0.6931471805599453f + logf(sum);
   // O / rowsum -> bf16 -> out, 32 head dims (64 bytes per row) at a time through the warp's staging slice (p_s is dead: the PV
   // MMAs have retired), 4 lanes per row (see warp_store_rows64)
@@ -242,6 +283,7 @@ __global__ void __launch_bounds__(128) attn_spatial_tc_kernel(const __grid_const
       return (q0 + warp * 32 + r < L) ? reinterpret_cast<uint8_t*>(p.out + (row0 + r) * C + h * F + f) : nullptr;
     }, two ? 4 : 2);
   }
+  }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -270,6 +312,8 @@ int attn_spatial_tc_launch(const fdm_attn_spatial_args* a, cudaStream_t st) {
   p.tmem_cols = pow2_at_least(L > F ? L : F, 32);
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)F);
   p.lse = a->lse;
+  static const int vbar = [] { const char* e = getenv("FDM_SA_VBAR"); return e ? atoi(e) : 1; }();  // A/B switch; default on
+  p.vbar = vbar;
   p.attn_mean = a->attn_mean;
   EncodeTiledFn enc = get_tensormap_encoder();
   FDM_REQUIRE(enc != nullptr, FDM_ERR_UNSUPPORTED);
@@ -296,7 +340,13 @@ int attn_spatial_tc_launch(const fdm_attn_spatial_args* a, cudaStream_t st) {
   }
   FDM_REQUIRE(smem <= 200 * 1024, FDM_ERR_UNSUPPORTED);
   dim3 grid((L + 127) / 128, a->heads, a->N);
-  fdm::launch(attn_spatial_tc_kernel, dim3(grid), dim3(128), smem, st, tq, p);
+  // rows of >= SA_SPLIT_MIN_L keys: two threads per query row (256-thread CTAs).  FDM_SA_SPLIT_MIN_L overrides (A/B; 0 = never).
+  static const int split_min_l = [] {
+    const char* e = getenv("FDM_SA_SPLIT_MIN_L");
+    const int v = e ? atoi(e) : SA_SPLIT_MIN_L;
+    return v <= 0 ? 1 << 30 : (v < 64 ? 64 : v);
+  }();
+  fdm::launch(attn_spatial_tc_kernel, dim3(grid), dim3(L >= split_min_l ? 256 : 128), smem, st, tq, p);
   return check_launch();
 }
 
